@@ -26,6 +26,9 @@ CX, CY, CZ, H = -0.01, 0.015, -0.2, 0.2
 X0, X1 = CX - H, CX + H
 Y0, Y1 = CY - H, CY + H
 Z0, Z1 = CZ - H, CZ + H
+# objects float 1e-3 above the floor: coplanar faces would make the closest hit a coin flip between
+# implementations (z-fighting), and 1e-3 is 10x the reference's tmin (shader.cu:114)
+LIFT = 1e-3
 
 
 def fmt(x):
@@ -130,10 +133,10 @@ def main():
     W("back.obj", quad((X0, Y0, Z0), (X1, Y0, Z0), (X1, Y1, Z0), (X0, Y1, Z0), (0, 0, 1)), "back wall, normal +z")
     W("right.obj", quad((X1, Y0, Z0), (X1, Y0, Z1), (X1, Y1, Z1), (X1, Y1, Z0), (-1, 0, 0)), "right wall, normal -x")
     W("left.obj", quad((X0, Y0, Z1), (X0, Y0, Z0), (X0, Y1, Z0), (X0, Y1, Z1), (1, 0, 0)), "left wall, normal +x")
-    W("large_box.obj", box(-0.08, -0.27, 0.12, 0.24, 0.12, Y0, 17.0), "tall block")
-    W("small_box.obj", box(0.07, -0.13, 0.12, 0.12, 0.12, Y0, -17.0), "short block (glass in the README scene)")
-    W("sphere.obj", uv_sphere((-0.10, Y0 + 0.05, -0.09), 0.05), "uv sphere 32x16, smooth normals")
-    ly, lh = Y1 - 1e-4, 0.05
+    W("large_box.obj", box(-0.08, -0.27, 0.12, 0.24, 0.12, Y0 + LIFT, 17.0), "tall block")
+    W("small_box.obj", box(0.07, -0.13, 0.12, 0.12, 0.12, Y0 + LIFT, -17.0), "short block (glass in the README scene)")
+    W("sphere.obj", uv_sphere((-0.10, Y0 + 0.05 + LIFT, -0.09), 0.05), "uv sphere 32x16, smooth normals")
+    ly, lh = Y1 - 1e-3, 0.05
     W("light.obj", quad((CX - lh, ly, CZ - lh), (CX + lh, ly, CZ - lh), (CX + lh, ly, CZ + lh), (CX - lh, ly, CZ + lh),
                         (0, -1, 0)), "area light 0.1 x 0.1 just below the ceiling, normal -y")
 
