@@ -1,0 +1,186 @@
+/* include/lisa_rt.h — C ABI of the B200-native render path (liblisa_rt.so).
+ *
+ * This is the drop-in boundary for the render path of gaetanserre/LiSA: the
+ * four seams the reference's own `main` crosses, flattened to
+ * `extern "C"`, plain pointers and sizes.  No C++ types, no CUDA/torch types
+ * in any signature.  Reference file:line are relative to the reference root.
+ *
+ *   B1 scene hand-off   RendererParams SceneParser::get_params()
+ *                       src/LiSA/include/scene_parser.hh:13, structs.hh:90-103
+ *                       -> lisa_scene_desc (field-for-field, same layouts)
+ *   B2 backend lifetime OptixWrapper(const RendererParams&) / ~OptixWrapper()
+ *                       src/LiSA/include/optix_wrapper.hh:3-20, optix_wrapper.cc:24-37
+ *                       -> lisa_create / lisa_destroy
+ *   B3 render           render() / display() / launchSubframe()
+ *                       src/LiSA/src/render.cc:133-148, 75-131, 35-58
+ *                       -> lisa_render_subframes, lisa_read_*, lisa_write_ppm
+ *   B4 BSDF interface   bounce / BRDF / BTDF, src/LiSA/src/bsdfs/lambertian.cu:7-27
+ *                       -> device header lisa_b200/csrc/bsdf/lambertian.cuh
+ *                          (compile-time seam, as in the reference)
+ *
+ * Error convention: every int-returning function returns LISA_OK (0) or a
+ * negative lisa_status; lisa_last_error() gives the message of the calling
+ * thread's last failure.  The reference throws sutil::Exception instead
+ * (src/sutil/Exception.h:167-177); the host front-end (lisa_b200/host)
+ * converts a failure back into the reference's abort-with-message behaviour.
+ * There is NO CPU fallback: without a CUDA device lisa_create fails with
+ * LISA_ERR_CUDA.
+ *
+ * Threading: one lisa_ctx is used from one host thread at a time.  All device
+ * work of a context runs on the context's own CUDA stream on its device.
+ */
+#ifndef LISA_RT_H
+#define LISA_RT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LISA_RT_VERSION 1
+
+typedef enum lisa_status {
+  LISA_OK            = 0,
+  LISA_ERR_ARG       = -1, /* null pointer, inconsistent sizes, index out of range */
+  LISA_ERR_CUDA      = -2, /* CUDA runtime failure (message holds cudaGetErrorString) */
+  LISA_ERR_NOMEM     = -3,
+  LISA_ERR_IO        = -4,
+  LISA_ERR_STATE     = -5
+} lisa_status;
+
+/* src/LiSA/include/structs.hh:16-23 — identical 40-byte layout. alpha < 1 marks a
+ * dielectric whose parameter is the IOR `n`; otherwise `roughness` is used
+ * (structs.hh:41-52).  Fields the reference leaves uninitialised must be zero. */
+typedef struct lisa_material {
+  float   roughness;
+  float   alpha;
+  float   n;
+  float   diffuse_color[3];
+  uint8_t emit;
+  uint8_t _pad[3];
+  float   emission_color[3];
+} lisa_material;
+
+/* src/LiSA/include/structs.hh:54-58 */
+typedef struct lisa_camera {
+  float eye[3];
+  float look_at[3];
+  float fov; /* vertical, degrees */
+} lisa_camera;
+
+/* src/LiSA/include/structs.hh:90-103 (RendererParams).  float3 = 3 packed floats.
+ * The arrays are only read during lisa_create (copy semantics). */
+typedef struct lisa_scene_desc {
+  const float*         vertices;     /* num_vertices * 3 floats; triangle t = vertices 3t, 3t+1, 3t+2 */
+  const float*         normals;      /* num_vertices * 3 floats */
+  const lisa_material* materials;    /* num_materials */
+  const int32_t*       mat_indices;  /* ONE per triangle (num_vertices / 3); the reference over-reads this (Q11) */
+  int32_t              num_vertices; /* 3 * triangles */
+  int32_t              num_materials;
+  uint32_t             width, height;
+  lisa_camera          camera;
+  uint32_t             num_samples;
+  uint32_t             num_bounces;
+  const char*          output_image; /* may be NULL; only lisa_write_ppm(ctx, NULL) uses it */
+} lisa_scene_desc;
+
+enum { LISA_SHADOW_CLOSEST = 0, LISA_SHADOW_FIRST_FOUND = 1 };
+enum { LISA_BVH_WIDE8 = 0, LISA_BVH_BINARY = 1 };
+
+typedef struct lisa_options {
+  uint32_t struct_size;   /* sizeof(lisa_options) */
+  int32_t  device;        /* CUDA device ordinal; -1 = current device */
+  uint32_t shadow_mode;   /* LISA_SHADOW_CLOSEST (default): the closest hit of a shadow ray decides.
+                             LISA_SHADOW_FIRST_FOUND: the first hit found in traversal order decides, which is
+                             what the reference asks OptiX for (shader.cu:69) and is traversal-order dependent. */
+  uint32_t bvh_kind;      /* LISA_BVH_WIDE8 (default) compressed 8-wide; LISA_BVH_BINARY for ablation */
+  uint32_t max_chains;    /* upper bound on concurrently resident (pixel, subframe) sample chains; 0 = auto */
+  uint32_t flags;         /* reserved, 0 */
+} lisa_options;
+
+typedef struct lisa_stats {
+  uint32_t struct_size;
+  uint32_t num_triangles, num_emitter_triangles;
+  uint32_t bvh_nodes, bvh_emitter_nodes; /* nodes of the traversal BVH(s) */
+  uint64_t bvh_bytes, triangle_bytes;    /* device bytes of nodes / of packed triangles (intersection + shading) */
+  float    upload_ms, bvh_build_ms;      /* lisa_create: H2D copy; device BVH build (CUDA events) */
+  /* cumulative since lisa_create / lisa_reset_accum */
+  uint64_t samples, radiance_rays, shadow_rays, null_directions;
+  uint64_t kernel_launches, iterations;
+  double   render_ms;                    /* sum over lisa_render_subframes calls, CUDA events on the ctx stream */
+  /* last lisa_render_subframes call only */
+  double   last_render_ms;
+  uint64_t last_samples, last_radiance_rays, last_shadow_rays, last_kernel_launches;
+  double   last_extend_ms, last_shadow_ms; /* per-stage device time, only when LISA_PROFILE_STAGES=1 */
+  uint64_t state_bytes;                  /* device bytes of chain state + queues */
+  uint32_t subframes_accumulated;
+  uint32_t _reserved;
+} lisa_stats;
+
+typedef struct lisa_ctx lisa_ctx;
+
+/* B2.  Uploads the soup, builds the BVH on the device, derives the camera frame
+ * (src/sutil/Camera.cpp:34-45 with up = (0,1,0), aspect = width/height,
+ * optix_wrapper.cc:433-442) and allocates the accumulators. */
+int  lisa_create(const lisa_scene_desc* scene, const lisa_options* options /* may be NULL */, lisa_ctx** out);
+void lisa_destroy(lisa_ctx* ctx);
+const char* lisa_last_error(void);
+int  lisa_version(void);
+
+/* B3.  Renders subframes first .. first+count-1, each with spp samples per pixel, seeded
+ * tea<16>(pixel, subframe) exactly as shader.cu:141, and merges them into the accumulators with equal
+ * weights (what the reference's running mean, shader.cu:160-164, converges to).
+ *   reference `-s`  ==  lisa_render_subframes(ctx, 0, 1, num_samples)            (render.cc:140)
+ *   reference `-d`  ==  for f = 0.. : lisa_render_subframes(ctx, f, 1, min(16, num_samples))
+ * Blocking: returns when the accumulators on the device are final. */
+int lisa_render_subframes(lisa_ctx* ctx, uint32_t first_subframe, uint32_t count, uint32_t spp_per_subframe);
+int lisa_reset_accum(lisa_ctx* ctx);
+
+/* Linear mean radiance, W*H*4 floats (r, g, b, 1), row 0 = image BOTTOM like the reference's accum_buffer. */
+int lisa_read_accum(lisa_ctx* ctx, float* rgba);
+/* sRGB-quantised frame exactly as make_color (src/cuda/helpers.h:129-138), W*H*4 bytes, row 0 = bottom. */
+int lisa_read_rgba8(lisa_ctx* ctx, uint8_t* rgba);
+/* Vertically flipped binary PPM as sutil::saveImage/savePPM (src/sutil/sutil.cpp:523-554, 97-117).
+ * path == NULL uses scene->output_image. */
+int lisa_write_ppm(lisa_ctx* ctx, const char* path);
+int lisa_get_stats(lisa_ctx* ctx, lisa_stats* stats /* struct_size set by caller */);
+
+/* Multi-GPU plumbing: every rank renders a disjoint subframe set into its own sums; the
+ * caller reduces the sum buffers (one NCCL reduce) and the root reads the image.  The buffer holds W*H
+ * float4 = (sum of subframe means .xyz, number of subframes .w) and lives on the context's device. */
+void*  lisa_accum_device_ptr(lisa_ctx* ctx);
+size_t lisa_accum_bytes(lisa_ctx* ctx);
+int    lisa_device(lisa_ctx* ctx);
+int    lisa_sync(lisa_ctx* ctx);
+
+/* Diagnostics used by the parity tests (not part of the reference surface).
+ * Batched queries against the context's BVH; host arrays; n rays.  org/dir: n*3 floats.
+ * prim: index of the hit triangle IN THE CALLER'S ORDER (mat_indices order) or -1; t, u, v optional. */
+int lisa_trace_closest(lisa_ctx* ctx, const float* org, const float* dir, uint32_t n, float tmin, float tmax,
+                       int32_t* prim, float* t /* may be NULL */);
+/* outcome per ray: 0 miss, 1 emitter decides (light = material index), 2 non-emitter decides. */
+int lisa_trace_shadow(lisa_ctx* ctx, const float* org, const float* dir, uint32_t n, float tmin, float tmax,
+                      int32_t* outcome, int32_t* light /* may be NULL */);
+/* First camera ray of every pixel of `subframe` as raygen builds it (shader.cu:141-152):
+ * dirs W*H*3 floats, seeds_after W*H (state after the two jitter draws). */
+int lisa_primary_rays(lisa_ctx* ctx, uint32_t subframe, float* dirs, uint32_t* seeds_after);
+/* Evaluates the device helpers on the GPU for known-answer tests.  `what`:
+ *   0 tea16(in_u[2i], in_u[2i+1])                        -> out_u[i]
+ *   1 rnd x3 from seed in_u[i]                            -> out_f[3i..], out_u[i] = seed after
+ *   2 hemisphere(N = in_f[3i..], seed in_u[i])            -> out_f[3i..], out_u[i]
+ *   3 BTDF/fresnel(cos = in_f[2i], eta = in_f[2i+1])      -> out_f[i]
+ *   4 refract(cosI, dir, N, eta = in_f[8i..8i+7])         -> out_f[3i..]
+ *   5 bounce(dir, N, roughness = in_f[7i..], seed in_u[i])-> out_f[3i..], out_u[i]
+ *   6 BRDF(N, L = in_f[6i..])                             -> out_f[i]
+ *   7 make_color(rgb = in_f[3i..])                        -> out_u[i] = r | g<<8 | b<<16 | a<<24
+ *   8 shading normal(P, n1,n2,n3, v1,v2,v3 = in_f[21i..]) -> out_f[3i..]
+ * Returns LISA_ERR_ARG for an unknown selector. */
+int lisa_kat_eval(int device, int what, uint32_t n, const float* in_f, const uint32_t* in_u, float* out_f,
+                  uint32_t* out_u);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LISA_RT_H */

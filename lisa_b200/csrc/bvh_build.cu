@@ -1,0 +1,489 @@
+// lisa_b200/csrc/bvh_build.cu — GPU BVH builder (replaces optixAccelBuild, src/LiSA/src/optix_wrapper.cc:132-145).
+//
+// Pipeline (all on the device, one stream):
+//   1. k_centroid_bounds   scene bounds of triangle centroids (block reduce + ordered-int atomics)
+//   2. k_morton            63-bit Morton key per triangle; bit 63 = "triangle emits", so one sort also
+//                          partitions the soup into non-emitters | emitters
+//   3. radix sort          (key, triangle id) pairs                           [cub::DeviceRadixSort]
+//   4. k_karras            LBVH hierarchy per partition (Karras 2012), one thread per internal node
+//   5. k_refit             leaf boxes + bottom-up box refit with arrival counters
+//   6a. k_emit_binary      binary traversal nodes (ablation path)          -- or --
+//   6b. k_collapse8        level-by-level collapse into compressed 8-wide nodes (Ylitie et al. 2017):
+//                          greedy largest-area child opening, octant-affinity slot assignment,
+//                          8-bit box quantisation, leaf triangles made contiguous per node
+//   7. k_pack_triangles    soup -> (tri_v, tri_n) float4 arrays in final leaf order
+// Algorithmic bytes per triangle: 72 read soup + 12 key/id + sort 8 passes x 24 +
+// 2 x 80 hierarchy/refit + ~40 collapse + 96 packed write.
+#include <cub/device/device_radix_sort.cuh>
+#include <cfloat>
+#include <cstdio>
+
+#include "build.h"
+#include "common.cuh"
+
+namespace lisa {
+
+#define CK(x)                                                              \
+  do {                                                                     \
+    cudaError_t e_ = (x);                                                  \
+    if (e_ != cudaSuccess) { snprintf(err, errlen, "%s: %s", #x, cudaGetErrorString(e_)); return -2; } \
+  } while (0)
+
+__device__ __forceinline__ int   f2ord(float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
+__device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+struct BoundsAcc { int lo[3], hi[3]; unsigned int n_emit; };
+
+__global__ void k_init_bounds(BoundsAcc* b) {
+  for (int a = 0; a < 3; a++) { b->lo[a] = f2ord(FLT_MAX); b->hi[a] = f2ord(-FLT_MAX); }
+  b->n_emit = 0;
+}
+
+__global__ void k_centroid_bounds(const float* __restrict__ verts, int ntris, BoundsAcc* acc) {
+  float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < ntris; t += gridDim.x * blockDim.x) {
+    const float* p = verts + 9ll * t;
+    for (int a = 0; a < 3; a++) {
+      float c = (p[a] + p[3 + a] + p[6 + a]) * (1.0f / 3.0f);
+      lo[a] = fminf(lo[a], c); hi[a] = fmaxf(hi[a], c);
+    }
+  }
+  for (int a = 0; a < 3; a++) {
+    for (int o = 16; o; o >>= 1) {
+      lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+      hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+    }
+    if ((threadIdx.x & 31) == 0) { atomicMin(&acc->lo[a], f2ord(lo[a])); atomicMax(&acc->hi[a], f2ord(hi[a])); }
+  }
+}
+
+__device__ __forceinline__ unsigned long long expand21(unsigned long long v) {
+  v &= 0x1fffffull;
+  v = (v | v << 32) & 0x1f00000000ffffull;
+  v = (v | v << 16) & 0x1f0000ff0000ffull;
+  v = (v | v << 8) & 0x100f00f00f00f00full;
+  v = (v | v << 4) & 0x10c30c30c30c30c3ull;
+  v = (v | v << 2) & 0x1249249249249249ull;
+  return v;
+}
+
+__global__ void k_morton(const float* __restrict__ verts, const int* __restrict__ mat_idx,
+                         const unsigned char* __restrict__ mat_emit, int num_mats, int ntris, const BoundsAcc* acc,
+                         unsigned long long* keys, unsigned int* ids, unsigned int* n_emit) {
+  int          t    = blockIdx.x * blockDim.x + threadIdx.x;
+  bool         emit = false;
+  if (t < ntris) {
+    const float* p = verts + 9ll * t;
+    unsigned long long q[3];
+    for (int a = 0; a < 3; a++) {
+      float lo = ord2f(acc->lo[a]), hi = ord2f(acc->hi[a]);
+      float c  = (p[a] + p[3 + a] + p[6 + a]) * (1.0f / 3.0f);
+      float e  = hi - lo;
+      float x  = e > 0.0f ? (c - lo) / e : 0.0f;
+      x        = fminf(fmaxf(x, 0.0f), 1.0f);
+      q[a]     = (unsigned long long)fminf(x * 2097152.0f, 2097151.0f);
+    }
+    int m = mat_idx[t];
+    emit  = (m >= 0 && m < num_mats) ? (mat_emit[m] != 0) : false;
+    unsigned long long k = (expand21(q[0]) << 2) | (expand21(q[1]) << 1) | expand21(q[2]);
+    keys[t] = k | (emit ? (1ull << 63) : 0ull);
+    ids[t]  = (unsigned int)t;
+  }
+  unsigned int m = __ballot_sync(0xffffffffu, emit);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_emit, __popc(m));
+}
+
+// ---- Karras 2012 -------------------------------------------------------------------------------
+__device__ __forceinline__ int delta(const unsigned long long* __restrict__ keys, int n, int i, int j) {
+  if (j < 0 || j >= n) return -1;
+  unsigned long long a = keys[i], b = keys[j];
+  if (a == b) return 64 + __clz((unsigned)i ^ (unsigned)j);
+  return __clzll((long long)(a ^ b));
+}
+
+// Node ids inside one partition with n leaves: internal 0..n-2, leaf j -> (n-1)+j.  Arrays are the partition's slices.
+__global__ void k_karras(const unsigned long long* __restrict__ keys, int n, int2* child, int* parent, int2* range) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n - 1) return;
+  int d     = (delta(keys, n, i, i + 1) - delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+  int dmin  = delta(keys, n, i, i - d);
+  int lmax  = 2;
+  while (delta(keys, n, i, i + lmax * d) > dmin) lmax <<= 1;
+  int l = 0;
+  for (int t = lmax >> 1; t >= 1; t >>= 1)
+    if (delta(keys, n, i, i + (l + t) * d) > dmin) l += t;
+  int j     = i + l * d;
+  int dnode = delta(keys, n, i, j);
+  int s     = 0;
+  int t     = l;
+  do {
+    t = (t + 1) >> 1;
+    if (delta(keys, n, i, i + (s + t) * d) > dnode) s += t;
+  } while (t > 1);
+  int gamma = i + s * d + min(d, 0);
+  int lo = min(i, j), hi = max(i, j);
+  int left  = (lo == gamma) ? (n - 1) + gamma : gamma;
+  int right = (hi == gamma + 1) ? (n - 1) + gamma + 1 : gamma + 1;
+  child[i]  = make_int2(left, right);
+  range[i]  = make_int2(lo, hi);
+  parent[left]  = i;
+  parent[right] = i;
+  if (i == 0) parent[0] = -1;
+}
+
+// Leaf boxes, then bottom-up refit.  box_lo/box_hi: 2n-1 entries per partition.
+__global__ void k_refit(const float* __restrict__ verts, const unsigned int* __restrict__ ids, int n,
+                        const int2* __restrict__ child, const int* __restrict__ parent, float4* box_lo, float4* box_hi,
+                        int* flags) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const float* p  = verts + 9ll * ids[j];
+  float3       lo = f3(fminf(p[0], fminf(p[3], p[6])), fminf(p[1], fminf(p[4], p[7])), fminf(p[2], fminf(p[5], p[8])));
+  float3       hi = f3(fmaxf(p[0], fmaxf(p[3], p[6])), fmaxf(p[1], fmaxf(p[4], p[7])), fmaxf(p[2], fmaxf(p[5], p[8])));
+  int          me = (n - 1) + j;
+  box_lo[me] = make_float4(lo.x, lo.y, lo.z, 0.0f);
+  box_hi[me] = make_float4(hi.x, hi.y, hi.z, 0.0f);
+  if (n == 1) return;
+  int cur = parent[me];
+  while (cur >= 0) {
+    __threadfence();
+    if (atomicAdd(&flags[cur], 1) == 0) return;  // first arrival: the sibling will continue
+    int2   c  = child[cur];
+    float4 l0 = __ldcg(box_lo + c.x), h0 = __ldcg(box_hi + c.x), l1 = __ldcg(box_lo + c.y), h1 = __ldcg(box_hi + c.y);
+    box_lo[cur] = make_float4(fminf(l0.x, l1.x), fminf(l0.y, l1.y), fminf(l0.z, l1.z), 0.0f);
+    box_hi[cur] = make_float4(fmaxf(h0.x, h1.x), fmaxf(h0.y, h1.y), fmaxf(h0.z, h1.z), 0.0f);
+    cur = parent[cur];
+  }
+}
+
+// ---- binary traversal nodes -----------------------------------------------------------------------
+// One node per internal Karras node; tri_base = first final triangle index of the partition.
+__global__ void k_emit_binary(int n, const int2* __restrict__ child, const float4* __restrict__ box_lo,
+                              const float4* __restrict__ box_hi, int node_base, int tri_base, float4* out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= max(n - 1, 1)) return;
+  float4* o = out + 4ll * (node_base + i);
+  if (n == 1) {  // single triangle: child 0 = the leaf, child 1 = empty box
+    float4 l = box_lo[0], h = box_hi[0];
+    o[0] = make_float4(l.x, h.x, l.y, h.y);
+    o[1] = make_float4(FLT_MAX, -FLT_MAX, FLT_MAX, -FLT_MAX);
+    o[2] = make_float4(l.z, h.z, FLT_MAX, -FLT_MAX);
+    o[3] = make_float4(__int_as_float(~tri_base), __int_as_float(~tri_base), 0.0f, 0.0f);
+    return;
+  }
+  int2   c  = child[i];
+  float4 l0 = box_lo[c.x], h0 = box_hi[c.x], l1 = box_lo[c.y], h1 = box_hi[c.y];
+  o[0] = make_float4(l0.x, h0.x, l0.y, h0.y);
+  o[1] = make_float4(l1.x, h1.x, l1.y, h1.y);
+  o[2] = make_float4(l0.z, h0.z, l1.z, h1.z);
+  int e0 = c.x >= n - 1 ? ~(tri_base + (c.x - (n - 1))) : node_base + c.x;
+  int e1 = c.y >= n - 1 ? ~(tri_base + (c.y - (n - 1))) : node_base + c.y;
+  o[3] = make_float4(__int_as_float(e0), __int_as_float(e1), 0.0f, 0.0f);
+}
+
+// ---- collapse to compressed 8-wide nodes --------------------------------------------------------
+#define LEAF_MAX 3
+struct WorkItem { int node2; int out; };  // binary node to expand -> index of the wide node to write
+
+__device__ __forceinline__ float half_area(const float4& lo, const float4& hi) {
+  float dx = hi.x - lo.x, dy = hi.y - lo.y, dz = hi.z - lo.z;
+  return dx * dy + dy * dz + dz * dx;
+}
+__device__ __forceinline__ int node_count(int node, int n, const int2* __restrict__ range) {
+  if (node >= n - 1) return 1;
+  int2 r = range[node];
+  return r.y - r.x + 1;
+}
+__device__ __forceinline__ int node_first(int node, int n, const int2* __restrict__ range) {
+  return node >= n - 1 ? node - (n - 1) : range[node].x;
+}
+
+// counters: [0] next free wide node, [1] next free final triangle slot, [2] items in the output queue
+__global__ void k_collapse8(const WorkItem* __restrict__ in, int n_in, WorkItem* out_q, int n, const int2* __restrict__ child,
+                            const int2* __restrict__ range, const float4* __restrict__ box_lo,
+                            const float4* __restrict__ box_hi, int* counters, float4* nodes,
+                            unsigned int* final_to_sorted, int sorted_base) {
+  int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= n_in) return;
+  const WorkItem item = in[w];
+  int            ch[8];
+  int            nc = 0;
+  float4         plo, phi;
+  if (n == 1) {  // degenerate partition: one triangle, no binary internal node
+    ch[nc++] = 0;
+    plo = box_lo[0]; phi = box_hi[0];
+  } else {
+    int2 c = child[item.node2];
+    ch[nc++] = c.x; ch[nc++] = c.y;
+    plo = box_lo[item.node2]; phi = box_hi[item.node2];
+    while (nc < 8) {
+      int   best = -1;
+      float ba   = -1.0f;
+      for (int k = 0; k < nc; k++) {
+        if (node_count(ch[k], n, range) <= LEAF_MAX) continue;  // stays a leaf
+        float a = half_area(box_lo[ch[k]], box_hi[ch[k]]);
+        if (a > ba) { ba = a; best = k; }
+      }
+      if (best < 0) break;
+      int2 c2  = child[ch[best]];
+      ch[best] = c2.x;
+      ch[nc++] = c2.y;
+    }
+  }
+  // octant-affinity slot assignment (greedy): slot bit 4/2/1 set = child lies on the +x/+y/+z side
+  const float3 pc = f3((plo.x + phi.x) * 0.5f, (plo.y + phi.y) * 0.5f, (plo.z + phi.z) * 0.5f);
+  float3 rel[8];
+  for (int k = 0; k < nc; k++) {
+    float4 l = box_lo[ch[k]], h = box_hi[ch[k]];
+    rel[k] = f3((l.x + h.x) * 0.5f - pc.x, (l.y + h.y) * 0.5f - pc.y, (l.z + h.z) * 0.5f - pc.z);
+  }
+  int slot_child[8];
+  for (int s = 0; s < 8; s++) slot_child[s] = -1;
+  unsigned int child_done = 0, slot_done = 0;
+  for (int it = 0; it < nc; it++) {
+    float bc = -FLT_MAX;
+    int   bk = -1, bs = -1;
+    for (int k = 0; k < nc; k++) {
+      if (child_done >> k & 1) continue;
+      for (int s = 0; s < 8; s++) {
+        if (slot_done >> s & 1) continue;
+        float c = ((s & 4) ? rel[k].x : -rel[k].x) + ((s & 2) ? rel[k].y : -rel[k].y) + ((s & 1) ? rel[k].z : -rel[k].z);
+        if (c > bc) { bc = c; bk = k; bs = s; }
+      }
+    }
+    slot_child[bs] = ch[bk];
+    child_done |= 1u << bk;
+    slot_done |= 1u << bs;
+  }
+  // quantisation frame
+  int   ex[3];
+  float scale[3];
+  const float plo3[3] = {plo.x, plo.y, plo.z}, phi3[3] = {phi.x, phi.y, phi.z};
+  for (int a = 0; a < 3; a++) {
+    float ext = (phi3[a] - plo3[a]) * (1.0f / 255.0f);
+    int   e   = -126;
+    if (ext > 0.0f) {
+      frexpf(ext, &e);  // ext = m * 2^e with m in [0.5, 1) => 2^e >= ext
+      e = max(e, -126);
+    }
+    e = min(e, 126);
+    ex[a]    = e;
+    scale[a] = __int_as_float((127 - e) << 23);  // 2^-e, exact
+  }
+  // counts
+  int n_inner = 0, n_tri = 0;
+  for (int s = 0; s < 8; s++) {
+    if (slot_child[s] < 0) continue;
+    int cnt = node_count(slot_child[s], n, range);
+    if (cnt <= LEAF_MAX) n_tri += cnt; else n_inner++;
+  }
+  int child_base = n_inner ? atomicAdd(&counters[0], n_inner) : 0;
+  int tri_base   = n_tri ? atomicAdd(&counters[1], n_tri) : 0;
+  int q_base     = n_inner ? atomicAdd(&counters[2], n_inner) : 0;
+  unsigned int imask = 0;
+  unsigned int meta[8], qlo[3][8], qhi[3][8];
+  int k_inner = 0, tri_off = 0;
+  for (int s = 0; s < 8; s++) {
+    meta[s] = 0;
+    for (int a = 0; a < 3; a++) { qlo[a][s] = 255; qhi[a][s] = 0; }  // empty: inverted box, never hit
+    int c = slot_child[s];
+    if (c < 0) continue;
+    float4 l = box_lo[c], h = box_hi[c];
+    const float l3[3] = {l.x, l.y, l.z}, h3[3] = {h.x, h.y, h.z};
+    for (int a = 0; a < 3; a++) {
+      float step = __int_as_float((ex[a] + 127) << 23);  // 2^e, exact
+      int   ql = (int)floorf((l3[a] - plo3[a]) * scale[a]);
+      int   qh = (int)ceilf((h3[a] - plo3[a]) * scale[a]);
+      ql = max(0, min(255, ql)); qh = max(0, min(255, qh));
+      while (ql > 0 && plo3[a] + (float)ql * step > l3[a]) ql--;     // stay conservative under rounding
+      while (qh < 255 && plo3[a] + (float)qh * step < h3[a]) qh++;
+      qlo[a][s] = (unsigned)ql; qhi[a][s] = (unsigned)qh;
+    }
+    int cnt = node_count(c, n, range);
+    if (cnt <= LEAF_MAX) {
+      meta[s]   = (((1u << cnt) - 1u) << 5) | (unsigned)tri_off;
+      int first = node_first(c, n, range);
+      for (int k = 0; k < cnt; k++) final_to_sorted[tri_base + tri_off + k] = (unsigned)(sorted_base + first + k);
+      tri_off += cnt;
+    } else {
+      meta[s] = (1u << 5) | (24u + (unsigned)s);
+      imask |= 1u << s;
+      out_q[q_base + k_inner] = WorkItem{c, child_base + k_inner};
+      k_inner++;
+    }
+  }
+  auto pack4 = [](const unsigned int* v) { return v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24); };
+  float4* o = nodes + 5ll * item.out;
+  unsigned int eim = (unsigned)(ex[0] + 127) | ((unsigned)(ex[1] + 127) << 8) | ((unsigned)(ex[2] + 127) << 16) | (imask << 24);
+  o[0] = make_float4(plo.x, plo.y, plo.z, __uint_as_float(eim));
+  o[1] = make_float4(__uint_as_float((unsigned)child_base), __uint_as_float((unsigned)tri_base),
+                     __uint_as_float(pack4(meta)), __uint_as_float(pack4(meta + 4)));
+  o[2] = make_float4(__uint_as_float(pack4(qlo[0])), __uint_as_float(pack4(qlo[0] + 4)), __uint_as_float(pack4(qlo[1])),
+                     __uint_as_float(pack4(qlo[1] + 4)));
+  o[3] = make_float4(__uint_as_float(pack4(qlo[2])), __uint_as_float(pack4(qlo[2] + 4)), __uint_as_float(pack4(qhi[0])),
+                     __uint_as_float(pack4(qhi[0] + 4)));
+  o[4] = make_float4(__uint_as_float(pack4(qhi[1])), __uint_as_float(pack4(qhi[1] + 4)), __uint_as_float(pack4(qhi[2])),
+                     __uint_as_float(pack4(qhi[2] + 4)));
+}
+
+__global__ void k_iota_sorted(unsigned int* final_to_sorted, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) final_to_sorted[i] = (unsigned)i;
+}
+
+// final order -> packed float4 arrays
+__global__ void k_pack_triangles(const float* __restrict__ verts, const float* __restrict__ normals,
+                                 const int* __restrict__ mat_idx, const unsigned int* __restrict__ sorted_ids,
+                                 const unsigned int* __restrict__ final_to_sorted, int ntris, float4* tri_v,
+                                 float4* tri_n, int* final_to_orig) {
+  int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= ntris) return;
+  unsigned int t = sorted_ids[final_to_sorted[f]];
+  const float* p = verts + 9ll * t;
+  const float* q = normals + 9ll * t;
+  tri_v[3ll * f + 0] = make_float4(p[0], p[1], p[2], __int_as_float(mat_idx[t]));
+  tri_v[3ll * f + 1] = make_float4(p[3], p[4], p[5], 0.0f);
+  tri_v[3ll * f + 2] = make_float4(p[6], p[7], p[8], 0.0f);
+  tri_n[3ll * f + 0] = make_float4(q[0], q[1], q[2], __int_as_float((int)t));
+  tri_n[3ll * f + 1] = make_float4(q[3], q[4], q[5], 0.0f);
+  tri_n[3ll * f + 2] = make_float4(q[6], q[7], q[8], 0.0f);
+  final_to_orig[f] = (int)t;
+}
+
+static inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
+
+int build_bvh(const BuildInput& in, BuildOutput* out, cudaStream_t st, char* err, size_t errlen) {
+  const int T = in.num_tris;
+  memset(out, 0, sizeof(*out));
+  out->root_other = out->root_emit = -1;
+  if (T == 0) return 0;
+
+  BoundsAcc*          d_acc;
+  unsigned long long *d_keys, *d_keys2;
+  unsigned int *      d_ids, *d_ids2, *d_final_to_sorted;
+  CK(cudaMalloc(&d_acc, sizeof(BoundsAcc)));
+  CK(cudaMalloc(&d_keys, sizeof(unsigned long long) * T));
+  CK(cudaMalloc(&d_keys2, sizeof(unsigned long long) * T));
+  CK(cudaMalloc(&d_ids, sizeof(unsigned int) * T));
+  CK(cudaMalloc(&d_ids2, sizeof(unsigned int) * T));
+  CK(cudaMalloc(&d_final_to_sorted, sizeof(unsigned int) * T));
+
+  k_init_bounds<<<1, 1, 0, st>>>(d_acc);
+  k_centroid_bounds<<<min(cdiv(T, 256), 148 * 8), 256, 0, st>>>(in.d_verts, T, d_acc);
+  k_morton<<<cdiv(T, 256), 256, 0, st>>>(in.d_verts, in.d_mat_idx, in.d_mat_emit, in.num_mats, T, d_acc, d_keys, d_ids,
+                                         &d_acc->n_emit);
+  size_t tmp_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_keys, d_keys2, d_ids, d_ids2, T, 0, 64, st);
+  void* d_tmp;
+  CK(cudaMalloc(&d_tmp, tmp_bytes ? tmp_bytes : 16));
+  CK(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_keys, d_keys2, d_ids, d_ids2, T, 0, 64, st));
+  BoundsAcc h_acc;
+  CK(cudaMemcpyAsync(&h_acc, d_acc, sizeof(h_acc), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  const int n_emit = (int)h_acc.n_emit, n_other = T - n_emit;
+  out->num_emit_tris = n_emit;
+
+  // hierarchy storage for both partitions: partition p uses node slice [base_p, base_p + 2 n_p - 1)
+  int2 *  d_child, *d_range;
+  int *   d_parent, *d_flags;
+  float4 *d_lo, *d_hi;
+  const size_t NN = 2ull * T + 2;
+  CK(cudaMalloc(&d_child, sizeof(int2) * NN));
+  CK(cudaMalloc(&d_range, sizeof(int2) * NN));
+  CK(cudaMalloc(&d_parent, sizeof(int) * NN));
+  CK(cudaMalloc(&d_flags, sizeof(int) * NN));
+  CK(cudaMalloc(&d_lo, sizeof(float4) * NN));
+  CK(cudaMalloc(&d_hi, sizeof(float4) * NN));
+  CK(cudaMemsetAsync(d_flags, 0, sizeof(int) * NN, st));
+
+  struct Part { int n, sorted_base, slice; } parts[2] = {{n_other, 0, 0}, {n_emit, n_other, 2 * n_other + 1}};
+  for (int p = 0; p < 2; p++) {
+    const Part& P = parts[p];
+    if (P.n == 0) continue;
+    if (P.n > 1)
+      k_karras<<<cdiv(P.n - 1, 256), 256, 0, st>>>(d_keys2 + P.sorted_base, P.n, d_child + P.slice, d_parent + P.slice,
+                                                   d_range + P.slice);
+    k_refit<<<cdiv(P.n, 256), 256, 0, st>>>(in.d_verts, d_ids2 + P.sorted_base, P.n, d_child + P.slice,
+                                            d_parent + P.slice, d_lo + P.slice, d_hi + P.slice, d_flags + P.slice);
+  }
+
+  float4* d_nodes = nullptr;
+  int     total_nodes = 0;
+  if (!in.wide) {
+    int nn[2] = {n_other ? max(n_other - 1, 1) : 0, n_emit ? max(n_emit - 1, 1) : 0};
+    total_nodes = nn[0] + nn[1];
+    CK(cudaMalloc(&d_nodes, sizeof(float4) * 4 * (size_t)max(total_nodes, 1)));
+    int base = 0;
+    for (int p = 0; p < 2; p++) {
+      const Part& P = parts[p];
+      if (P.n == 0) continue;
+      k_emit_binary<<<cdiv(nn[p], 256), 256, 0, st>>>(P.n, d_child + P.slice, d_lo + P.slice, d_hi + P.slice, base,
+                                                      P.sorted_base, d_nodes);
+      (p == 0 ? out->root_other : out->root_emit) = base;
+      (p == 0 ? out->nodes_other : out->nodes_emit) = nn[p];
+      base += nn[p];
+    }
+    k_iota_sorted<<<cdiv(T, 256), 256, 0, st>>>(d_final_to_sorted, T);
+  } else {
+    // every wide node has >= 2 children except degenerate roots, so #wide nodes <= #binary internal nodes + 2
+    const size_t max_nodes = (size_t)T + 4;
+    CK(cudaMalloc(&d_nodes, sizeof(float4) * 5 * max_nodes));
+    WorkItem *d_q[2];
+    int*      d_counters;
+    CK(cudaMalloc(&d_q[0], sizeof(WorkItem) * max_nodes));
+    CK(cudaMalloc(&d_q[1], sizeof(WorkItem) * max_nodes));
+    CK(cudaMalloc(&d_counters, sizeof(int) * 4));
+    int node_next = 0, tri_next = 0;
+    for (int p = 0; p < 2; p++) {
+      const Part& P = parts[p];
+      if (P.n == 0) continue;
+      const int root = node_next++;
+      (p == 0 ? out->root_other : out->root_emit) = root;
+      WorkItem h_item = {0, root};
+      CK(cudaMemcpyAsync(d_q[0], &h_item, sizeof(h_item), cudaMemcpyHostToDevice, st));
+      int n_in = 1, cur = 0;
+      const int nodes_before = node_next - 1;
+      while (n_in > 0) {
+        int h_cnt[4] = {node_next, tri_next, 0, 0};
+        CK(cudaMemcpyAsync(d_counters, h_cnt, sizeof(h_cnt), cudaMemcpyHostToDevice, st));
+        k_collapse8<<<cdiv(n_in, 128), 128, 0, st>>>(d_q[cur], n_in, d_q[cur ^ 1], P.n, d_child + P.slice, d_range + P.slice,
+                                                     d_lo + P.slice, d_hi + P.slice, d_counters, d_nodes,
+                                                     d_final_to_sorted, P.sorted_base);
+        CK(cudaMemcpyAsync(h_cnt, d_counters, sizeof(h_cnt), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        node_next = h_cnt[0]; tri_next = h_cnt[1]; n_in = h_cnt[2];
+        cur ^= 1;
+      }
+      (p == 0 ? out->nodes_other : out->nodes_emit) = node_next - nodes_before;
+      if (tri_next != P.sorted_base + P.n) {
+        snprintf(err, errlen, "bvh collapse: partition %d placed %d of %d triangles", p, tri_next - P.sorted_base, P.n);
+        return -5;
+      }
+    }
+    total_nodes = node_next;
+    cudaFree(d_q[0]); cudaFree(d_q[1]); cudaFree(d_counters);
+  }
+
+  float4 *d_tri_v, *d_tri_n;
+  int*    d_final_to_orig;
+  CK(cudaMalloc(&d_tri_v, sizeof(float4) * 3 * (size_t)T));
+  CK(cudaMalloc(&d_tri_n, sizeof(float4) * 3 * (size_t)T));
+  CK(cudaMalloc(&d_final_to_orig, sizeof(int) * (size_t)T));
+  k_pack_triangles<<<cdiv(T, 256), 256, 0, st>>>(in.d_verts, in.d_normals, in.d_mat_idx, d_ids2, d_final_to_sorted, T,
+                                                 d_tri_v, d_tri_n, d_final_to_orig);
+  CK(cudaStreamSynchronize(st));
+  CK(cudaGetLastError());
+
+  cudaFree(d_acc); cudaFree(d_keys); cudaFree(d_keys2); cudaFree(d_ids); cudaFree(d_ids2); cudaFree(d_final_to_sorted);
+  cudaFree(d_tmp); cudaFree(d_child); cudaFree(d_range); cudaFree(d_parent); cudaFree(d_flags); cudaFree(d_lo); cudaFree(d_hi);
+
+  out->d_nodes = d_nodes;
+  out->num_nodes = total_nodes;
+  out->node_bytes = (size_t)total_nodes * (in.wide ? 80 : 64);
+  out->d_tri_v = d_tri_v;
+  out->d_tri_n = d_tri_n;
+  out->d_final_to_orig = d_final_to_orig;
+  return 0;
+}
+
+}  // namespace lisa

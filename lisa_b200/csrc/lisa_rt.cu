@@ -1,0 +1,520 @@
+// lisa_b200/csrc/lisa_rt.cu — implementation of the C ABI in include/lisa_rt.h.
+//
+// Host-side driver of the render path: scene upload, device BVH build (bvh_build.cu), camera frame,
+// the wavefront iteration loop (wavefront.cu) and read-back.  It stands where the reference has
+// OptixWrapper (src/LiSA/src/optix_wrapper.cc) and launchSubframe/render (src/LiSA/src/render.cc).
+// There is no CPU path: every entry point that computes needs a CUDA device.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/lisa_rt.h"
+#include "build.h"
+#include "scene.cuh"
+#include "wavefront.cuh"
+
+using namespace lisa;
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CU(x)                                                                                   \
+  do {                                                                                          \
+    cudaError_t e_ = (x);                                                                       \
+    if (e_ != cudaSuccess) return fail(LISA_ERR_CUDA, "%s: %s", #x, cudaGetErrorString(e_));    \
+  } while (0)
+
+struct lisa_ctx {
+  int          device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t  ev0 = nullptr, ev1 = nullptr;
+  DScene       scene{};
+  DCamera      cam{};
+  BuildOutput  bvh{};
+  DMaterial*   d_mats = nullptr;
+  float4*      d_accum = nullptr;   // W*H float4: sum of subframe means | subframe count
+  float4*      d_mean = nullptr;    // scratch for read-back
+  uint32_t*    d_rgba8 = nullptr;
+  DState       state{};
+  size_t       state_chains = 0;    // capacity of the state arrays, in chains
+  uint32_t     max_chains = 0;
+  unsigned long long* h_stats = nullptr;  // pinned mirror of state.stats
+  LaunchCfg    cfg{};
+  lisa_stats   stats{};
+  uint32_t     width = 0, height = 0, num_samples = 0, num_bounces = 0;
+  std::string  output_image;
+  bool         profile_stages = false;
+};
+
+extern "C" const char* lisa_last_error(void) { return g_err; }
+extern "C" int         lisa_version(void) { return LISA_RT_VERSION; }
+
+// src/sutil/Camera.cpp:34-45 with up = (0,1,0) and aspect = width/height (optix_wrapper.cc:433-442)
+static void camera_frame(const lisa_camera& c, uint32_t w, uint32_t h, DCamera* out) {
+  auto  sub = [](const float* a, const float* b, float* r) { for (int i = 0; i < 3; i++) r[i] = a[i] - b[i]; };
+  auto  crs = [](const float* a, const float* b, float* r) {
+    r[0] = a[1] * b[2] - a[2] * b[1]; r[1] = a[2] * b[0] - a[0] * b[2]; r[2] = a[0] * b[1] - a[1] * b[0];
+  };
+  auto  len = [](const float* a) { return sqrtf(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]); };
+  auto  nrm = [&](float* a) { float inv = 1.0f / len(a); for (int i = 0; i < 3; i++) a[i] *= inv; };
+  float W[3], U[3], V[3];
+  const float up[3] = {0.0f, 1.0f, 0.0f};
+  sub(c.look_at, c.eye, W);
+  const float wlen = len(W);
+  crs(W, up, U); nrm(U);
+  crs(U, W, V); nrm(V);
+  const float vlen = wlen * tanf(0.5f * c.fov * (float)M_PI / 180.0f);
+  for (int i = 0; i < 3; i++) V[i] *= vlen;
+  const float ulen = vlen * ((float)w / (float)h);
+  for (int i = 0; i < 3; i++) U[i] *= ulen;
+  out->eye = make_float3(c.eye[0], c.eye[1], c.eye[2]);
+  out->U = make_float3(U[0], U[1], U[2]);
+  out->V = make_float3(V[0], V[1], V[2]);
+  out->W = make_float3(W[0], W[1], W[2]);
+  out->width = w; out->height = h;
+}
+
+static void free_state(lisa_ctx* c) {
+  cudaFree(c->state.o); cudaFree(c->state.d); cudaFree(c->state.a); cudaFree(c->state.c); cudaFree(c->state.n);
+  cudaFree(c->state.sum); cudaFree(c->state.shadow_q);
+  c->state.o = c->state.d = c->state.a = c->state.c = c->state.n = c->state.sum = nullptr;
+  c->state.shadow_q = nullptr;
+  c->state_chains = 0;
+}
+
+static int ensure_state(lisa_ctx* c, size_t chains) {
+  if (chains <= c->state_chains) return LISA_OK;
+  free_state(c);
+  CU(cudaMalloc(&c->state.o, sizeof(float4) * chains));
+  CU(cudaMalloc(&c->state.d, sizeof(float4) * chains));
+  CU(cudaMalloc(&c->state.a, sizeof(float4) * chains));
+  CU(cudaMalloc(&c->state.c, sizeof(float4) * chains));
+  CU(cudaMalloc(&c->state.n, sizeof(float4) * chains));
+  CU(cudaMalloc(&c->state.sum, sizeof(float4) * chains));
+  CU(cudaMalloc(&c->state.shadow_q, sizeof(int) * chains));
+  c->state_chains = chains;
+  c->stats.state_bytes = chains * (6 * sizeof(float4) + sizeof(int));
+  return LISA_OK;
+}
+
+extern "C" void lisa_destroy(lisa_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  free_state(c);
+  cudaFree(c->state.ring); cudaFree(c->state.stats);
+  cudaFree(c->bvh.d_nodes); cudaFree(c->bvh.d_tri_v); cudaFree(c->bvh.d_tri_n); cudaFree(c->bvh.d_final_to_orig);
+  cudaFree(c->d_mats); cudaFree(c->d_accum); cudaFree(c->d_mean); cudaFree(c->d_rgba8);
+  if (c->h_stats) cudaFreeHost(c->h_stats);
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+static int create_impl(const lisa_scene_desc* sd, const lisa_options* opt, lisa_ctx* c) {
+  lisa_options o{};
+  o.struct_size = sizeof(o);
+  o.device = -1;
+  if (opt) memcpy(&o, opt, std::min<size_t>(opt->struct_size ? opt->struct_size : sizeof(o), sizeof(o)));
+  if (const char* e = getenv("LISA_BVH")) o.bvh_kind = !strcmp(e, "binary") ? LISA_BVH_BINARY : LISA_BVH_WIDE8;
+  if (const char* e = getenv("LISA_SHADOW")) o.shadow_mode = !strcmp(e, "first") ? LISA_SHADOW_FIRST_FOUND : LISA_SHADOW_CLOSEST;
+  if (const char* e = getenv("LISA_MAX_CHAINS")) o.max_chains = (uint32_t)strtoul(e, nullptr, 10);
+  c->profile_stages = getenv("LISA_PROFILE_STAGES") && atoi(getenv("LISA_PROFILE_STAGES"));
+
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(LISA_ERR_CUDA, "no CUDA device (%s): lisa_rt has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+  if (o.device >= 0) { CU(cudaSetDevice(o.device)); }
+  CU(cudaGetDevice(&c->device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, c->device));
+  CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CU(cudaEventCreate(&c->ev0));
+  CU(cudaEventCreate(&c->ev1));
+  if (configure_kernels(g_err, sizeof(g_err))) return LISA_ERR_CUDA;
+
+  const int T = sd->num_vertices / 3;
+  c->width = sd->width; c->height = sd->height;
+  c->num_samples = sd->num_samples; c->num_bounces = sd->num_bounces;
+  if (sd->output_image) c->output_image = sd->output_image;
+  camera_frame(sd->camera, sd->width, sd->height, &c->cam);
+
+  // ---- upload (Q11: one material index per triangle; Q12: the caller zero-fills unused material fields)
+  cudaEvent_t t0, t1, t2;
+  CU(cudaEventCreate(&t0)); CU(cudaEventCreate(&t1)); CU(cudaEventCreate(&t2));
+  float *d_verts = nullptr, *d_normals = nullptr;
+  int*   d_mat_idx = nullptr;
+  unsigned char* d_emit = nullptr;
+  std::vector<DMaterial>     mats((size_t)std::max(sd->num_materials, 1));
+  std::vector<unsigned char> emit((size_t)std::max(sd->num_materials, 1), 0);
+  int first_light = -1, single_light = 1;
+  for (int i = 0; i < sd->num_materials; i++) {
+    const lisa_material& m = sd->materials[i];
+    mats[i].a = make_float4(m.diffuse_color[0], m.diffuse_color[1], m.diffuse_color[2], m.roughness);
+    mats[i].b = make_float4(m.emission_color[0], m.emission_color[1], m.emission_color[2], m.n);
+    mats[i].c = make_float4(m.alpha, m.emit ? 1.0f : 0.0f, 0.0f, 0.0f);
+    emit[i]   = m.emit ? 1 : 0;
+    if (m.emit) { if (first_light < 0) first_light = i; else single_light = 0; }
+  }
+  CU(cudaEventRecord(t0, c->stream));
+  const size_t vb = sizeof(float) * 9 * (size_t)std::max(T, 1);
+  CU(cudaMalloc(&d_verts, vb)); CU(cudaMalloc(&d_normals, vb));
+  CU(cudaMalloc(&d_mat_idx, sizeof(int) * (size_t)std::max(T, 1)));
+  CU(cudaMalloc(&d_emit, emit.size()));
+  CU(cudaMalloc(&c->d_mats, sizeof(DMaterial) * mats.size()));
+  if (T) {
+    CU(cudaMemcpyAsync(d_verts, sd->vertices, sizeof(float) * 9 * (size_t)T, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d_normals, sd->normals, sizeof(float) * 9 * (size_t)T, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d_mat_idx, sd->mat_indices, sizeof(int) * (size_t)T, cudaMemcpyHostToDevice, c->stream));
+  }
+  CU(cudaMemcpyAsync(d_emit, emit.data(), emit.size(), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(c->d_mats, mats.data(), sizeof(DMaterial) * mats.size(), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaEventRecord(t1, c->stream));
+
+  // ---- BVH
+  BuildInput bi{d_verts, d_normals, d_mat_idx, d_emit, T, sd->num_materials, o.bvh_kind == LISA_BVH_WIDE8 ? 1 : 0};
+  int rc = build_bvh(bi, &c->bvh, c->stream, g_err, sizeof(g_err));
+  CU(cudaEventRecord(t2, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  cudaFree(d_verts); cudaFree(d_normals); cudaFree(d_mat_idx); cudaFree(d_emit);
+  if (rc) return rc;
+  cudaEventElapsedTime(&c->stats.upload_ms, t0, t1);
+  cudaEventElapsedTime(&c->stats.bvh_build_ms, t1, t2);
+  cudaEventDestroy(t0); cudaEventDestroy(t1); cudaEventDestroy(t2);
+
+  c->scene.tri_v = c->bvh.d_tri_v;
+  c->scene.tri_n = c->bvh.d_tri_n;
+  c->scene.mats = c->d_mats;
+  c->scene.bvh = c->bvh.d_nodes;
+  c->scene.root_other = c->bvh.root_other;
+  c->scene.root_emit = c->bvh.root_emit;
+  c->scene.wide = bi.wide;
+  c->scene.num_tris = T;
+  c->scene.num_mats = sd->num_materials;
+  c->scene.single_light = single_light;
+  c->scene.shadow_first_found = o.shadow_mode == LISA_SHADOW_FIRST_FOUND;
+
+  c->stats.struct_size = sizeof(lisa_stats);
+  c->stats.num_triangles = (uint32_t)T;
+  c->stats.num_emitter_triangles = (uint32_t)c->bvh.num_emit_tris;
+  c->stats.bvh_nodes = (uint32_t)c->bvh.num_nodes;
+  c->stats.bvh_emitter_nodes = (uint32_t)c->bvh.nodes_emit;
+  c->stats.bvh_bytes = c->bvh.node_bytes;
+  c->stats.triangle_bytes = (uint64_t)T * 96;
+
+  // ---- accumulators, counters
+  const size_t npix = (size_t)c->width * c->height;
+  CU(cudaMalloc(&c->d_accum, sizeof(float4) * std::max<size_t>(npix, 1)));
+  CU(cudaMemsetAsync(c->d_accum, 0, sizeof(float4) * npix, c->stream));
+  CU(cudaMalloc(&c->state.ring, sizeof(unsigned int) * 12));
+  CU(cudaMalloc(&c->state.stats, sizeof(unsigned long long) * 8));
+  CU(cudaMemsetAsync(c->state.stats, 0, sizeof(unsigned long long) * 8, c->stream));
+  CU(cudaMallocHost(&c->h_stats, sizeof(unsigned long long) * 8));
+  memset(c->h_stats, 0, sizeof(unsigned long long) * 8);
+
+  c->cfg.sm_count = prop.multiProcessorCount;
+  c->cfg.extend_block = 256;
+  c->cfg.shadow_block = 256;
+  c->cfg.shadow_blocks_per_sm = 4;
+  if (const char* e2 = getenv("LISA_SHADOW_BLOCKS_PER_SM")) c->cfg.shadow_blocks_per_sm = std::max(1, atoi(e2));
+  // default residency: enough chains to fill the machine several times over, bounded so the state stays
+  // a small fraction of HBM (112 B per chain)
+  c->max_chains = o.max_chains ? o.max_chains : (4u << 20);
+  CU(cudaStreamSynchronize(c->stream));
+  return LISA_OK;
+}
+
+extern "C" int lisa_create(const lisa_scene_desc* sd, const lisa_options* opt, lisa_ctx** out) {
+  if (!sd || !out) return fail(LISA_ERR_ARG, "lisa_create: null argument");
+  *out = nullptr;
+  if (sd->num_vertices < 0 || sd->num_vertices % 3) return fail(LISA_ERR_ARG, "num_vertices (%d) must be a non-negative multiple of 3", sd->num_vertices);
+  if (sd->num_vertices && (!sd->vertices || !sd->normals || !sd->mat_indices)) return fail(LISA_ERR_ARG, "null geometry array");
+  if (sd->num_materials < 0 || (sd->num_materials && !sd->materials)) return fail(LISA_ERR_ARG, "bad materials");
+  if (!sd->width || !sd->height) return fail(LISA_ERR_ARG, "width and height must be positive");
+  if ((uint64_t)sd->width * sd->height > (1ull << 31)) return fail(LISA_ERR_ARG, "image too large");
+  if (sd->num_materials > 65535) return fail(LISA_ERR_ARG, "at most 65535 materials");
+  const int T = sd->num_vertices / 3;
+  for (int t = 0; t < T; t++)
+    if (sd->mat_indices[t] < 0 || sd->mat_indices[t] >= sd->num_materials)
+      return fail(LISA_ERR_ARG, "triangle %d: material index %d out of range [0, %d)", t, sd->mat_indices[t], sd->num_materials);
+  lisa_ctx* c = new lisa_ctx();
+  int rc = create_impl(sd, opt, c);
+  if (rc != LISA_OK) {
+    std::string keep = g_err;
+    lisa_destroy(c);
+    snprintf(g_err, sizeof(g_err), "%s", keep.c_str());
+    return rc;
+  }
+  *out = c;
+  return LISA_OK;
+}
+
+extern "C" int lisa_reset_accum(lisa_ctx* c) {
+  if (!c) return fail(LISA_ERR_ARG, "null ctx");
+  CU(cudaSetDevice(c->device));
+  CU(cudaMemsetAsync(c->d_accum, 0, sizeof(float4) * (size_t)c->width * c->height, c->stream));
+  CU(cudaMemsetAsync(c->state.stats, 0, sizeof(unsigned long long) * 8, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  lisa_stats keep = c->stats;
+  c->stats.samples = c->stats.radiance_rays = c->stats.shadow_rays = c->stats.null_directions = 0;
+  c->stats.kernel_launches = c->stats.iterations = 0;
+  c->stats.render_ms = 0;
+  c->stats.subframes_accumulated = 0;
+  (void)keep;
+  return LISA_OK;
+}
+
+// Runs one tile (pixel range x subframe range) to completion.
+static int run_tile(lisa_ctx* c, const Tile& t, uint64_t* launches, uint64_t* iterations) {
+  int rc = ensure_state(c, t.n_chains);
+  if (rc) return rc;
+  launch_init_chains(c->state, c->cam, t, c->stream);
+  (*launches)++;
+  // Every chain needs between spp and spp*bounces iterations; poll the finished-chain counter in bursts.
+  uint32_t iter = 0;
+  const uint64_t max_iter = (uint64_t)t.spp * std::max(t.bounces, 1u) + 2;
+  // a sample takes at least one iteration, so nothing can finish before spp iterations
+  uint32_t burst = std::max<uint32_t>(1, t.spp);
+  while (true) {
+    for (uint32_t k = 0; k < burst; k++, iter++) {
+      launch_extend(c->scene, c->state, c->cam, t, iter, c->cfg, c->stream);
+      launch_shadow(c->scene, c->state, t, iter, c->cfg, c->stream);
+      *launches += 2;
+    }
+    CU(cudaMemcpyAsync(c->h_stats, c->state.stats, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (c->h_stats[4] >= t.n_chains) break;
+    if (iter > max_iter) return fail(LISA_ERR_STATE, "wavefront did not converge after %u iterations (%llu of %u chains done)", iter,
+                                     (unsigned long long)c->h_stats[4], t.n_chains);
+    // iterations after the last chain finished are near-free (every thread exits on its sample count)
+    burst = std::max<uint32_t>(8, t.spp / 16);
+  }
+  *iterations += iter;
+  launch_finalize(c->state, c->cam, t, c->d_accum, c->stream);
+  (*launches)++;
+  return LISA_OK;
+}
+
+extern "C" int lisa_render_subframes(lisa_ctx* c, uint32_t first, uint32_t count, uint32_t spp) {
+  if (!c) return fail(LISA_ERR_ARG, "null ctx");
+  if (!count || !spp) return fail(LISA_ERR_ARG, "count and spp must be positive");
+  CU(cudaSetDevice(c->device));
+  const uint64_t npix = (uint64_t)c->width * c->height;
+  unsigned long long before[8];
+  CU(cudaMemcpyAsync(c->h_stats, c->state.stats, sizeof(before), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  memcpy(before, c->h_stats, sizeof(before));
+  uint64_t launches = 0, iterations = 0;
+  CU(cudaEventRecord(c->ev0, c->stream));
+  if (c->num_bounces == 0) {
+    // shader.cu:110: zero bounces trace nothing; every sample is black
+  } else {
+    // tiles: as many whole subframes as fit in max_chains, else pixel ranges of one subframe
+    const uint64_t cap = std::max<uint64_t>(c->max_chains, 1024);
+    if (npix <= cap) {
+      const uint32_t per = (uint32_t)std::max<uint64_t>(1, cap / npix);
+      for (uint32_t f = 0; f < count; f += per) {
+        Tile t{0, (uint32_t)npix, first + f, std::min(per, count - f), spp, c->num_bounces, 0};
+        t.n_chains = t.npix * t.nf;
+        int rc = run_tile(c, t, &launches, &iterations);
+        if (rc) return rc;
+      }
+    } else {
+      for (uint32_t f = 0; f < count; f++)
+        for (uint64_t p0 = 0; p0 < npix; p0 += cap) {
+          Tile t{(uint32_t)p0, (uint32_t)std::min<uint64_t>(cap, npix - p0), first + f, 1, spp, c->num_bounces, 0};
+          t.n_chains = t.npix;
+          int rc = run_tile(c, t, &launches, &iterations);
+          if (rc) return rc;
+        }
+    }
+  }
+  CU(cudaEventRecord(c->ev1, c->stream));
+  CU(cudaMemcpyAsync(c->h_stats, c->state.stats, sizeof(before), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaGetLastError());
+  float ms = 0;
+  cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+  lisa_stats& s = c->stats;
+  s.last_render_ms = ms;
+  s.render_ms += ms;
+  s.last_radiance_rays = c->h_stats[0] - before[0];
+  s.last_shadow_rays = c->h_stats[1] - before[1];
+  s.last_samples = npix * count * spp;
+  s.last_kernel_launches = launches;
+  s.radiance_rays = c->h_stats[0];
+  s.shadow_rays = c->h_stats[1];
+  s.null_directions = c->h_stats[3];
+  s.samples += npix * count * spp;
+  s.kernel_launches += launches;
+  s.iterations += iterations;
+  s.subframes_accumulated += count;
+  return LISA_OK;
+}
+
+static int resolve(lisa_ctx* c, bool want_mean, bool want_rgba) {
+  const size_t npix = (size_t)c->width * c->height;
+  if (want_mean && !c->d_mean) CU(cudaMalloc(&c->d_mean, sizeof(float4) * npix));
+  if (want_rgba && !c->d_rgba8) CU(cudaMalloc(&c->d_rgba8, sizeof(uint32_t) * npix));
+  launch_resolve(c->d_accum, (uint32_t)npix, want_mean ? c->d_mean : nullptr, want_rgba ? c->d_rgba8 : nullptr, c->stream);
+  return LISA_OK;
+}
+
+extern "C" int lisa_read_accum(lisa_ctx* c, float* rgba) {
+  if (!c || !rgba) return fail(LISA_ERR_ARG, "null argument");
+  CU(cudaSetDevice(c->device));
+  int rc = resolve(c, true, false);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(rgba, c->d_mean, sizeof(float4) * (size_t)c->width * c->height, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return LISA_OK;
+}
+
+extern "C" int lisa_read_rgba8(lisa_ctx* c, uint8_t* rgba) {
+  if (!c || !rgba) return fail(LISA_ERR_ARG, "null argument");
+  CU(cudaSetDevice(c->device));
+  int rc = resolve(c, false, true);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(rgba, c->d_rgba8, sizeof(uint32_t) * (size_t)c->width * c->height, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return LISA_OK;
+}
+
+extern "C" int lisa_write_ppm(lisa_ctx* c, const char* path) {
+  if (!c) return fail(LISA_ERR_ARG, "null ctx");
+  if (!path) path = c->output_image.c_str();
+  if (!path || !*path) return fail(LISA_ERR_ARG, "no output path");
+  std::vector<uint8_t> px((size_t)c->width * c->height * 4);
+  int rc = lisa_read_rgba8(c, px.data());
+  if (rc) return rc;
+  FILE* f = fopen(path, "wb");
+  if (!f) return fail(LISA_ERR_IO, "cannot open %s for writing", path);
+  // sutil::savePPM (sutil.cpp:97-117) after saveImage's flip and alpha drop (sutil.cpp:523-554)
+  fprintf(f, "P6\n%u %u\n255\n", c->width, c->height);
+  std::vector<uint8_t> row((size_t)c->width * 3);
+  for (int y = (int)c->height - 1; y >= 0; y--) {
+    const uint8_t* src = px.data() + (size_t)y * c->width * 4;
+    for (uint32_t x = 0; x < c->width; x++) { row[3 * x] = src[4 * x]; row[3 * x + 1] = src[4 * x + 1]; row[3 * x + 2] = src[4 * x + 2]; }
+    if (fwrite(row.data(), 1, row.size(), f) != row.size()) { fclose(f); return fail(LISA_ERR_IO, "short write to %s", path); }
+  }
+  fclose(f);
+  return LISA_OK;
+}
+
+extern "C" int lisa_get_stats(lisa_ctx* c, lisa_stats* out) {
+  if (!c || !out) return fail(LISA_ERR_ARG, "null argument");
+  uint32_t sz = out->struct_size ? std::min<uint32_t>(out->struct_size, sizeof(lisa_stats)) : sizeof(lisa_stats);
+  c->stats.struct_size = sizeof(lisa_stats);
+  memcpy(out, &c->stats, sz);
+  return LISA_OK;
+}
+
+extern "C" void*  lisa_accum_device_ptr(lisa_ctx* c) { return c ? (void*)c->d_accum : nullptr; }
+extern "C" size_t lisa_accum_bytes(lisa_ctx* c) { return c ? sizeof(float4) * (size_t)c->width * c->height : 0; }
+extern "C" int    lisa_device(lisa_ctx* c) { return c ? c->device : -1; }
+extern "C" int    lisa_sync(lisa_ctx* c) {
+  if (!c) return fail(LISA_ERR_ARG, "null ctx");
+  CU(cudaSetDevice(c->device));
+  CU(cudaStreamSynchronize(c->stream));
+  return LISA_OK;
+}
+
+// ---- diagnostics ---------------------------------------------------------------------------------
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  ~DevBuf() { cudaFree(p); }
+  cudaError_t alloc(size_t n) { return cudaMalloc(&p, sizeof(T) * std::max<size_t>(n, 1)); }
+};
+
+extern "C" int lisa_trace_closest(lisa_ctx* c, const float* org, const float* dir, uint32_t n, float tmin, float tmax,
+                                  int32_t* prim, float* t) {
+  if (!c || !org || !dir || !prim) return fail(LISA_ERR_ARG, "null argument");
+  CU(cudaSetDevice(c->device));
+  DevBuf<float> d_o, d_d, d_t;
+  DevBuf<int>   d_p;
+  CU(d_o.alloc(3ull * n)); CU(d_d.alloc(3ull * n)); CU(d_t.alloc(n)); CU(d_p.alloc(n));
+  CU(cudaMemcpyAsync(d_o.p, org, sizeof(float) * 3ull * n, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(d_d.p, dir, sizeof(float) * 3ull * n, cudaMemcpyHostToDevice, c->stream));
+  launch_trace_closest(c->scene, d_o.p, d_d.p, n, tmin, tmax, d_p.p, d_t.p, c->stream);
+  std::vector<int> fp(n);
+  CU(cudaMemcpyAsync(fp.data(), d_p.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+  if (t) CU(cudaMemcpyAsync(t, d_t.p, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+  std::vector<int> f2o((size_t)c->scene.num_tris);
+  if (c->scene.num_tris)
+    CU(cudaMemcpyAsync(f2o.data(), c->bvh.d_final_to_orig, sizeof(int) * f2o.size(), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaGetLastError());
+  for (uint32_t i = 0; i < n; i++) prim[i] = fp[i] >= 0 ? f2o[fp[i]] : -1;
+  return LISA_OK;
+}
+
+extern "C" int lisa_trace_shadow(lisa_ctx* c, const float* org, const float* dir, uint32_t n, float tmin, float tmax,
+                                 int32_t* outcome, int32_t* light) {
+  if (!c || !org || !dir || !outcome) return fail(LISA_ERR_ARG, "null argument");
+  CU(cudaSetDevice(c->device));
+  DevBuf<float> d_o, d_d;
+  DevBuf<int>   d_oc, d_l;
+  CU(d_o.alloc(3ull * n)); CU(d_d.alloc(3ull * n)); CU(d_oc.alloc(n)); CU(d_l.alloc(n));
+  CU(cudaMemcpyAsync(d_o.p, org, sizeof(float) * 3ull * n, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(d_d.p, dir, sizeof(float) * 3ull * n, cudaMemcpyHostToDevice, c->stream));
+  launch_trace_shadow(c->scene, d_o.p, d_d.p, n, tmin, tmax, d_oc.p, d_l.p, c->stream);
+  CU(cudaMemcpyAsync(outcome, d_oc.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+  if (light) CU(cudaMemcpyAsync(light, d_l.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaGetLastError());
+  return LISA_OK;
+}
+
+extern "C" int lisa_primary_rays(lisa_ctx* c, uint32_t subframe, float* dirs, uint32_t* seeds_after) {
+  if (!c || !dirs || !seeds_after) return fail(LISA_ERR_ARG, "null argument");
+  CU(cudaSetDevice(c->device));
+  const size_t npix = (size_t)c->width * c->height;
+  DevBuf<float>    d_d;
+  DevBuf<uint32_t> d_s;
+  CU(d_d.alloc(3 * npix)); CU(d_s.alloc(npix));
+  launch_primary_rays(c->cam, subframe, d_d.p, d_s.p, c->stream);
+  CU(cudaMemcpyAsync(dirs, d_d.p, sizeof(float) * 3 * npix, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(seeds_after, d_s.p, sizeof(uint32_t) * npix, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaGetLastError());
+  return LISA_OK;
+}
+
+extern "C" int lisa_kat_eval(int device, int what, uint32_t n, const float* in_f, const uint32_t* in_u, float* out_f,
+                             uint32_t* out_u) {
+  static const int fin[9] = {0, 0, 3, 2, 8, 7, 6, 3, 21}, uin[9] = {2, 1, 1, 0, 0, 1, 0, 0, 0};
+  static const int fout[9] = {0, 3, 3, 1, 3, 3, 1, 0, 3}, uout[9] = {1, 1, 1, 0, 0, 1, 0, 1, 0};
+  if (what < 0 || what > 8) return fail(LISA_ERR_ARG, "unknown KAT selector %d", what);
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(LISA_ERR_CUDA, "no CUDA device: lisa_rt has no CPU fallback");
+  if (device >= 0) CU(cudaSetDevice(device));
+  DevBuf<float>    d_if, d_of;
+  DevBuf<uint32_t> d_iu, d_ou;
+  CU(d_if.alloc((size_t)fin[what] * n)); CU(d_iu.alloc((size_t)uin[what] * n));
+  CU(d_of.alloc((size_t)fout[what] * n)); CU(d_ou.alloc((size_t)uout[what] * n));
+  if (fin[what] && in_f) CU(cudaMemcpy(d_if.p, in_f, sizeof(float) * fin[what] * (size_t)n, cudaMemcpyHostToDevice));
+  if (uin[what] && in_u) CU(cudaMemcpy(d_iu.p, in_u, sizeof(uint32_t) * uin[what] * (size_t)n, cudaMemcpyHostToDevice));
+  if (launch_kat(what, n, d_if.p, d_iu.p, d_of.p, d_ou.p, 0)) return fail(LISA_ERR_ARG, "unknown KAT selector %d", what);
+  CU(cudaDeviceSynchronize());
+  CU(cudaGetLastError());
+  if (fout[what] && out_f) CU(cudaMemcpy(out_f, d_of.p, sizeof(float) * fout[what] * (size_t)n, cudaMemcpyDeviceToHost));
+  if (uout[what] && out_u) CU(cudaMemcpy(out_u, d_ou.p, sizeof(uint32_t) * uout[what] * (size_t)n, cudaMemcpyDeviceToHost));
+  return LISA_OK;
+}

@@ -1,0 +1,285 @@
+// lisa_b200/csrc/traverse.cuh — ray/triangle test and BVH traversal (device code).
+//
+// Replaces what the reference gets from the closed-source OptiX runtime through optixTrace
+// (src/LiSA/src/shader.cu:62,86): closest-hit and shadow queries over one triangle soup.
+//   * ray/triangle: watertight test of Woop, Benthin, Wald (JCGT 2013): shear the triangle into
+//     ray space, three edge functions computed WITHOUT fma contraction so that the two triangles
+//     sharing an edge see exactly opposite values, double-precision fallback on a zero edge value;
+//     no culling (the reference never culls), t in units of |dir| (directions are not unit, Q5).
+//   * BVH: binary LBVH nodes (64 B, both child boxes in one node) or the compressed 8-wide nodes
+//     of Ylitie, Karras, Laine (HPG 2017; 80 B, 8-bit quantised child boxes, octant-ordered
+//     traversal with a (node-group, hit-mask) stack).
+//   * traversal stack: the first entries live in shared memory ([entry][thread] layout, so a warp
+//     touches 32 consecutive banks), deeper levels spill to a per-thread local array.
+#pragma once
+#include "common.cuh"
+
+namespace lisa {
+
+struct Hit {
+  float t;
+  float u, v;  // barycentric weights of vertex 1 and vertex 2 (vertex 0 has 1-u-v)
+  int   prim;  // index into the packed triangle arrays, -1 = miss
+};
+
+// ------------------------------------------------------------------------------------------------
+// Watertight ray/triangle
+// ------------------------------------------------------------------------------------------------
+struct RayPre {
+  float3 o;
+  int    kz;
+  float  Sx, Sy, Sz;
+};
+
+__device__ __forceinline__ float3 perm3(const float3& v, int kz) {
+  // (v[kx], v[ky], v[kz]) with kx = (kz+1)%3, ky = (kz+2)%3 (a pure rotation: winding is irrelevant without culling)
+  return f3(kz == 0 ? v.y : (kz == 1 ? v.z : v.x), kz == 0 ? v.z : (kz == 1 ? v.x : v.y),
+            kz == 0 ? v.x : (kz == 1 ? v.y : v.z));
+}
+
+__device__ __forceinline__ RayPre ray_precompute(const float3& o, const float3& d) {
+  RayPre r;
+  r.o      = o;
+  float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
+  r.kz     = (ax > ay) ? (ax > az ? 0 : 2) : (ay > az ? 1 : 2);
+  float3 p = perm3(d, r.kz);
+  r.Sz     = 1.0f / p.z;
+  r.Sx     = p.x * r.Sz;
+  r.Sy     = p.y * r.Sz;
+  return r;
+}
+
+// Returns true and updates (t, u, v) when the triangle is hit with tmin < t < tmax.
+__device__ __forceinline__ bool intersect_tri(const RayPre& r, const float3& v0, const float3& v1, const float3& v2,
+                                              float tmin, float tmax, float& t_out, float& u_out, float& v_out) {
+  const float3 A = perm3(v0 - r.o, r.kz), B = perm3(v1 - r.o, r.kz), C = perm3(v2 - r.o, r.kz);
+  const float  Ax = A.x - r.Sx * A.z, Ay = A.y - r.Sy * A.z;
+  const float  Bx = B.x - r.Sx * B.z, By = B.y - r.Sy * B.z;
+  const float  Cx = C.x - r.Sx * C.z, Cy = C.y - r.Sy * C.z;
+  // edge functions: explicit round-to-nearest mul/sub, never contracted to fma
+  float U = __fsub_rn(__fmul_rn(Cx, By), __fmul_rn(Cy, Bx));
+  float V = __fsub_rn(__fmul_rn(Ax, Cy), __fmul_rn(Ay, Cx));
+  float W = __fsub_rn(__fmul_rn(Bx, Ay), __fmul_rn(By, Ax));
+  if (U == 0.0f || V == 0.0f || W == 0.0f) {
+    U = (float)((double)Cx * (double)By - (double)Cy * (double)Bx);
+    V = (float)((double)Ax * (double)Cy - (double)Ay * (double)Cx);
+    W = (float)((double)Bx * (double)Ay - (double)By * (double)Ax);
+  }
+  if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) return false;
+  const float det = U + V + W;
+  if (det == 0.0f) return false;
+  const float T   = U * (r.Sz * A.z) + V * (r.Sz * B.z) + W * (r.Sz * C.z);
+  const float rcp = 1.0f / det;
+  const float t   = T * rcp;
+  if (!(t > tmin && t < tmax)) return false;
+  t_out = t;
+  u_out = V * rcp;
+  v_out = W * rcp;
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Traversal stack: NS entries in shared memory, NL more in local memory
+// ------------------------------------------------------------------------------------------------
+template <typename T, int NS, int NL>
+struct TravStack {
+  T*  sm;      // this thread's column of the block's shared array
+  int stride;  // = blockDim.x
+  T   loc[NL];
+  int sp;
+  __device__ __forceinline__ TravStack(T* smem_base) : sm(smem_base + threadIdx.x), stride(blockDim.x), sp(0) {}
+  __device__ __forceinline__ void push(const T& v) {
+    if (sp < NS) sm[sp * stride] = v;
+    else if (sp < NS + NL) loc[sp - NS] = v;
+    sp++;  // beyond NS+NL entries are dropped (cannot happen: builders bound the depth, see bvh_build.cu)
+  }
+  __device__ __forceinline__ T pop() {
+    sp--;
+    return sp < NS ? sm[sp * stride] : loc[sp - NS];
+  }
+  __device__ __forceinline__ bool empty() const { return sp == 0; }
+  __device__ __forceinline__ void clear() { sp = 0; }
+};
+
+#define LISA_STACK_SM 12
+#define LISA_STACK_LOC 52
+typedef TravStack<uint2, LISA_STACK_SM, LISA_STACK_LOC> Stack;
+// bytes of dynamic shared memory a traversal kernel needs per thread
+#define LISA_STACK_SMEM_PER_THREAD (LISA_STACK_SM * 8)
+
+__device__ __forceinline__ float3 safe_rcp_dir(const float3& d) {
+  const float eps = 1e-30f;
+  return f3(1.0f / (fabsf(d.x) > eps ? d.x : copysignf(eps, d.x)), 1.0f / (fabsf(d.y) > eps ? d.y : copysignf(eps, d.y)),
+            1.0f / (fabsf(d.z) > eps ? d.z : copysignf(eps, d.z)));
+}
+
+// ------------------------------------------------------------------------------------------------
+// Binary BVH (ablation path).  Node = 4 x float4:
+//   n0 = (c0.lo.x, c0.hi.x, c0.lo.y, c0.hi.y)   n1 = (c1.lo.x, c1.hi.x, c1.lo.y, c1.hi.y)
+//   n2 = (c0.lo.z, c0.hi.z, c1.lo.z, c1.hi.z)   n3 = (child0, child1, -, -) as int bits
+// child >= 0: node index; child < 0: leaf holding the single triangle ~child; INT_MIN-free.
+// ------------------------------------------------------------------------------------------------
+template <bool ANY>
+__device__ __forceinline__ bool bvh2_trace(const float4* __restrict__ nodes, const float4* __restrict__ tri_v, int root,
+                                           const float3& o, const float3& d, float tmin, float tmax, Hit& hit,
+                                           Stack& stack, uint32_t& n_nodes, uint32_t& n_tris) {
+  hit.prim = -1;
+  hit.t    = tmax;
+  if (root < 0) return false;
+  const RayPre pre  = ray_precompute(o, d);
+  const float3 idir = safe_rcp_dir(d);
+  const float3 ood  = f3(o.x * idir.x, o.y * idir.y, o.z * idir.z);
+  stack.clear();
+  int cur = root;
+  while (true) {
+    if (cur >= 0) {
+      const float4 n0 = __ldg(nodes + 4 * cur), n1 = __ldg(nodes + 4 * cur + 1), n2 = __ldg(nodes + 4 * cur + 2),
+                   n3 = __ldg(nodes + 4 * cur + 3);
+      n_nodes++;
+      // slab test, both children
+      const float c0lox = n0.x * idir.x - ood.x, c0hix = n0.y * idir.x - ood.x;
+      const float c0loy = n0.z * idir.y - ood.y, c0hiy = n0.w * idir.y - ood.y;
+      const float c0loz = n2.x * idir.z - ood.z, c0hiz = n2.y * idir.z - ood.z;
+      const float c1lox = n1.x * idir.x - ood.x, c1hix = n1.y * idir.x - ood.x;
+      const float c1loy = n1.z * idir.y - ood.y, c1hiy = n1.w * idir.y - ood.y;
+      const float c1loz = n2.z * idir.z - ood.z, c1hiz = n2.w * idir.z - ood.z;
+      const float t0n = fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), tmin));
+      const float t0f = fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), hit.t));
+      const float t1n = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), tmin));
+      const float t1f = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), hit.t));
+      const bool  h0 = t0n <= t0f * 1.0000004f, h1 = t1n <= t1f * 1.0000004f;
+      int         c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
+      if (h0 && h1) {
+        if (t1n < t0n) { int t = c0; c0 = c1; c1 = t; }
+        stack.push(make_uint2((uint32_t)c1, 0u));
+        cur = c0;
+        continue;
+      } else if (h0) { cur = c0; continue; }
+      else if (h1) { cur = c1; continue; }
+    } else {
+      const int    ti = ~cur;
+      const float4 a = __ldg(tri_v + 3 * ti), b = __ldg(tri_v + 3 * ti + 1), c = __ldg(tri_v + 3 * ti + 2);
+      n_tris++;
+      float t, u, v;
+      if (intersect_tri(pre, f3(a), f3(b), f3(c), tmin, hit.t, t, u, v)) {
+        hit.t = t; hit.u = u; hit.v = v; hit.prim = ti;
+        if (ANY) return true;
+      }
+    }
+    if (stack.empty()) break;
+    cur = (int)stack.pop().x;
+  }
+  return hit.prim >= 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Compressed 8-wide BVH.  Node = 5 x float4 (80 B):
+//   w0 = (p.x, p.y, p.z, [ex | ey<<8 | ez<<16 | imask<<24])
+//   w1 = (child_base, tri_base, meta[0..3], meta[4..7])
+//   w2 = (qlo_x[0..3], qlo_x[4..7], qlo_y[0..3], qlo_y[4..7])
+//   w3 = (qlo_z[0..3], qlo_z[4..7], qhi_x[0..3], qhi_x[4..7])
+//   w4 = (qhi_y[0..3], qhi_y[4..7], qhi_z[0..3], qhi_z[4..7])
+// meta[i]: 0 empty | internal: 0b001_11sss (sss = slot i) | leaf: unary triangle count in the top
+// 3 bits (1: 001, 2: 011, 3: 111) and the offset of its first triangle from tri_base in the low 5.
+// Child boxes: lo = p + qlo * 2^e, hi = p + qhi * 2^e per axis.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t sign_extend_s8x4(uint32_t x) {
+  // each byte with bit 7 set becomes 0xff, else 0x00
+  uint32_t r;
+  asm("prmt.b32 %0, %1, 0x0, 0x0000BA98;" : "=r"(r) : "r"(x));
+  return r;
+}
+__device__ __forceinline__ uint32_t extract_byte(uint32_t x, uint32_t i) { return (x >> (i * 8)) & 0xffu; }
+
+template <bool ANY>
+__device__ __forceinline__ bool bvh8_trace(const float4* __restrict__ nodes, const float4* __restrict__ tri_v, int root,
+                                           const float3& o, const float3& d, float tmin, float tmax, Hit& hit,
+                                           Stack& stack, uint32_t& n_nodes, uint32_t& n_tris) {
+  hit.prim = -1;
+  hit.t    = tmax;
+  if (root < 0) return false;
+  const RayPre pre  = ray_precompute(o, d);
+  const float3 idir = safe_rcp_dir(d);
+  // octant: bit set where the direction is NON-negative (paper's oct_inv = 7 - oct)
+  const uint32_t oct_inv  = (d.x < 0.0f ? 0u : 4u) | (d.y < 0.0f ? 0u : 2u) | (d.z < 0.0f ? 0u : 1u);
+  const uint32_t oct_inv4 = oct_inv * 0x01010101u;
+  stack.clear();
+  uint2 node_group = make_uint2((uint32_t)root, 0x80000000u);  // one "internal child" pending: the root
+  uint2 tri_group  = make_uint2(0u, 0u);
+  while (true) {
+    if (node_group.y & 0xff000000u) {
+      const uint32_t hits_imask      = node_group.y;
+      const uint32_t child_bit_index = 31u - __clz(hits_imask);
+      const uint32_t child_base      = node_group.x;
+      node_group.y &= ~(1u << child_bit_index);
+      if (node_group.y & 0xff000000u) stack.push(node_group);
+      const uint32_t slot_index     = (child_bit_index - 24u) ^ (oct_inv4 & 0xffu);
+      const uint32_t relative_index = __popc(hits_imask & ~(0xffffffffu << slot_index) & 0xffu);
+      const uint32_t ni             = child_base + relative_index;
+
+      const float4 w0 = __ldg(nodes + 5 * ni), w1 = __ldg(nodes + 5 * ni + 1), w2 = __ldg(nodes + 5 * ni + 2),
+                   w3 = __ldg(nodes + 5 * ni + 3), w4 = __ldg(nodes + 5 * ni + 4);
+      n_nodes++;
+      const uint32_t eimask = __float_as_uint(w0.w);
+      const float    sx = __uint_as_float((eimask & 0xffu) << 23), sy = __uint_as_float(((eimask >> 8) & 0xffu) << 23),
+                     sz = __uint_as_float(((eimask >> 16) & 0xffu) << 23);
+      const float3 adir = f3(sx * idir.x, sy * idir.y, sz * idir.z);
+      const float3 org  = f3((w0.x - o.x) * idir.x, (w0.y - o.y) * idir.y, (w0.z - o.z) * idir.z);
+      node_group.x = __float_as_uint(w1.x);
+      tri_group.x  = __float_as_uint(w1.y);
+      uint32_t hitmask = 0;
+#pragma unroll
+      for (int half = 0; half < 2; half++) {
+        const uint32_t meta4 = __float_as_uint(half == 0 ? w1.z : w1.w);
+        const uint32_t is_inner4   = (meta4 & (meta4 << 1)) & 0x10101010u;
+        const uint32_t inner_mask4 = sign_extend_s8x4(is_inner4 << 3);
+        const uint32_t bit_index4  = (meta4 ^ (oct_inv4 & inner_mask4)) & 0x1f1f1f1fu;
+        const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
+        const uint32_t qlox = __float_as_uint(half == 0 ? w2.x : w2.y), qloy = __float_as_uint(half == 0 ? w2.z : w2.w);
+        const uint32_t qloz = __float_as_uint(half == 0 ? w3.x : w3.y), qhix = __float_as_uint(half == 0 ? w3.z : w3.w);
+        const uint32_t qhiy = __float_as_uint(half == 0 ? w4.x : w4.y), qhiz = __float_as_uint(half == 0 ? w4.z : w4.w);
+        // near/far planes per axis depend on the direction sign
+        const uint32_t nx = d.x < 0.0f ? qhix : qlox, fx = d.x < 0.0f ? qlox : qhix;
+        const uint32_t ny = d.y < 0.0f ? qhiy : qloy, fy = d.y < 0.0f ? qloy : qhiy;
+        const uint32_t nz = d.z < 0.0f ? qhiz : qloz, fz = d.z < 0.0f ? qloz : qhiz;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const float tnx = (float)extract_byte(nx, j) * adir.x + org.x, tfx = (float)extract_byte(fx, j) * adir.x + org.x;
+          const float tny = (float)extract_byte(ny, j) * adir.y + org.y, tfy = (float)extract_byte(fy, j) * adir.y + org.y;
+          const float tnz = (float)extract_byte(nz, j) * adir.z + org.z, tfz = (float)extract_byte(fz, j) * adir.z + org.z;
+          const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
+          const float tf = fminf(fminf(tfx, tfy), fminf(tfz, hit.t));
+          if (tn <= tf * 1.0000004f) {
+            const uint32_t child_bits = extract_byte(child_bits4, j);
+            const uint32_t bit_index  = extract_byte(bit_index4, j);
+            hitmask |= child_bits << bit_index;
+          }
+        }
+      }
+      node_group.y = (hitmask & 0xff000000u) | (eimask >> 24);
+      tri_group.y  = hitmask & 0x00ffffffu;
+    } else {
+      tri_group  = node_group;
+      node_group = make_uint2(0u, 0u);
+    }
+    while (tri_group.y) {
+      const uint32_t k = __ffs(tri_group.y) - 1u;
+      tri_group.y &= tri_group.y - 1u;
+      const int    ti = (int)(tri_group.x + k);
+      const float4 a = __ldg(tri_v + 3 * ti), b = __ldg(tri_v + 3 * ti + 1), c = __ldg(tri_v + 3 * ti + 2);
+      n_tris++;
+      float t, u, v;
+      if (intersect_tri(pre, f3(a), f3(b), f3(c), tmin, hit.t, t, u, v)) {
+        hit.t = t; hit.u = u; hit.v = v; hit.prim = ti;
+        if (ANY) return true;
+      }
+    }
+    if ((node_group.y & 0xff000000u) == 0u) {
+      if (stack.empty()) break;
+      node_group = stack.pop();
+    }
+  }
+  return hit.prim >= 0;
+}
+
+}  // namespace lisa

@@ -1,0 +1,472 @@
+// lisa_b200/csrc/wavefront.cu — wavefront path tracing kernels (sm_100a).
+//
+// Replaces the reference's single OptiX megakernel launch (src/LiSA/src/shader.cu, 5 programs,
+// one thread per pixel looping samples x bounces x <=30 shadow tries) by two stages that run once per
+// "iteration" over SoA chain state in HBM (DState, wavefront.cuh):
+//
+//   k_extend  one thread per chain.  Regenerates a camera ray when the previous sample ended
+//             (__raygen__rg, shader.cu:141-152), traces the radiance ray (closest hit,
+//             trace_radiance shader.cu:77-98), and runs the material dispatch of
+//             __closesthit__radiance / __miss__radiance (shader.cu:189-194, 211-246): miss and emitter
+//             end the sample, a dielectric produces the next direction in place, an opaque hit
+//             stores P, N, attenuation and is appended to the shadow queue by warp-ballot +
+//             prefix-popcount compaction (one atomicAdd per warp).
+//   k_shadow  persistent CTAs; every LANE pulls opaque hits from the shadow queue and runs
+//             shoot_ray_to_light (shader.cu:196-209): up to 30 hemisphere tries, each a shadow query;
+//             a lane that finishes its job (light found or 30 failures) does the BSDF bounce
+//             (lambertian.cu:7-13), writes the chain back and immediately fetches another job, so the
+//             1..30-try spread does not idle lanes (dynamic fetch, warp-local batches of the queue).
+//
+// Every chain owns its LCG stream, so the order in which chains are processed never changes a result:
+// images are bit-reproducible run to run and independent of queue order.
+#include <cstdio>
+
+#include "bsdf/lambertian.cuh"
+#include "traverse.cuh"
+#include "wavefront.cuh"
+
+namespace lisa {
+
+// flags word (DState::c .w)
+#define F_BOUNCE_MASK 0x000000ffu
+#define F_STICKY 0x00000100u  // RayState::hit carried across bounces of one sample (Q1)
+#define F_NEW 0x00000200u     // previous sample ended: regenerate a camera ray
+#define F_LIGHT_SHIFT 16      // material id of the last light found (RayState::material)
+
+#define FULL 0xffffffffu
+#define SHADOW_BATCH 32
+
+enum { ST_RADIANCE = 0, ST_SHADOW = 1, ST_SAMPLES = 2, ST_NULLDIR = 3, ST_CHAINS_DONE = 4, ST_NODES = 5, ST_TRIS = 6 };
+
+__device__ __forceinline__ void warp_add(unsigned long long* p, uint32_t v) {
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  if (lane_id() == 0 && v) atomicAdd(p, (unsigned long long)v);
+}
+
+template <bool WIDE, bool ANY>
+__device__ __forceinline__ bool trace_one(const DScene& sc, int root, const float3& o, const float3& d, float tmin, float tmax,
+                                          Hit& h, Stack& stack, uint32_t& nn, uint32_t& nt) {
+  if (WIDE) return bvh8_trace<ANY>(sc.bvh, sc.tri_v, root, o, d, tmin, tmax, h, stack, nn, nt);
+  return bvh2_trace<ANY>(sc.bvh, sc.tri_v, root, o, d, tmin, tmax, h, stack, nn, nt);
+}
+
+// closest hit over emitters and non-emitters (trace_radiance)
+template <bool WIDE>
+__device__ __forceinline__ Hit closest_hit(const DScene& sc, const float3& o, const float3& d, float tmin, float tmax,
+                                           Stack& stack, uint32_t& nn, uint32_t& nt) {
+  Hit he, ho;
+  trace_one<WIDE, false>(sc, sc.root_emit, o, d, tmin, tmax, he, stack, nn, nt);
+  trace_one<WIDE, false>(sc, sc.root_other, o, d, tmin, he.t, ho, stack, nn, nt);
+  return ho.prim >= 0 ? ho : he;
+}
+
+// Shadow query (trace_occlusion + the two occlusion programs, shader.cu:53-74,172-184).
+// Returns 0 miss, 1 the deciding hit is an emitter (light = its material), 2 it is not.
+template <bool WIDE>
+__device__ __forceinline__ int shadow_query(const DScene& sc, const float3& o, const float3& d, float tmin, float tmax,
+                                            int& light, Stack& stack, uint32_t& nn, uint32_t& nt) {
+  Hit he, ho;
+  if (sc.shadow_first_found) {
+    if (trace_one<WIDE, true>(sc, sc.root_emit, o, d, tmin, tmax, he, stack, nn, nt)) {
+      light = __float_as_int(__ldg(sc.tri_v + 3 * he.prim).w);
+      return 1;
+    }
+    return trace_one<WIDE, true>(sc, sc.root_other, o, d, tmin, tmax, ho, stack, nn, nt) ? 2 : 0;
+  }
+  trace_one<WIDE, false>(sc, sc.root_emit, o, d, tmin, tmax, he, stack, nn, nt);           // closest emitter
+  if (trace_one<WIDE, true>(sc, sc.root_other, o, d, tmin, he.t, ho, stack, nn, nt)) return 2;  // any occluder in front
+  if (he.prim < 0) return 0;
+  light = __float_as_int(__ldg(sc.tri_v + 3 * he.prim).w);
+  return 1;
+}
+
+__device__ __forceinline__ float3 shading_normal(const DScene& sc, const Hit& h) {
+  // barycentric_normal (maths.cu:33-57) with the barycentrics of the intersection test
+  const float4 n0 = __ldg(sc.tri_n + 3 * h.prim), n1 = __ldg(sc.tri_n + 3 * h.prim + 1), n2 = __ldg(sc.tri_n + 3 * h.prim + 2);
+  const float  w0 = 1.0f - h.u - h.v;
+  return normalize(w0 * f3(n0) + h.u * f3(n1) + h.v * f3(n2));
+}
+
+// camera ray of pixel p for the chain's next sample (shader.cu:149-152)
+__device__ __forceinline__ float3 camera_ray(const DCamera& cam, uint32_t p, uint32_t& seed) {
+  const uint32_t x = p % cam.width, y = p / cam.width;
+  const float    jx = rng(seed), jy = rng(seed);
+  const float    dx = (2.0f * (float)x + jx) / (float)cam.width - 1.0f;
+  const float    dy = (2.0f * (float)y + jy) / (float)cam.height - 1.0f;
+  return normalize(dx * cam.U + dy * cam.V + cam.W);
+}
+
+__device__ __forceinline__ uint32_t chain_seed(const DCamera& cam, uint32_t p, uint32_t subframe) {
+  const uint32_t x = p % cam.width, y = p / cam.width;
+  // shader.cu:141 — the pixel index is formed in float
+  return tea16((uint32_t)((float)y * (float)cam.width + (float)x), subframe);
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void k_init_chains(DState s, DCamera cam, Tile t) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) {
+    for (int k = 0; k < 12; k++) s.ring[k] = 0;
+    s.stats[ST_CHAINS_DONE] = 0;
+  }
+  if (i >= t.n_chains) return;
+  const uint32_t p = t.pix0 + i % t.npix, f = t.f0 + i / t.npix;
+  s.a[i]   = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(chain_seed(cam, p, f)));
+  s.c[i]   = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(F_NEW));
+  s.sum[i] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(0u));
+}
+
+// ------------------------------------------------------------------------------------------------
+template <bool WIDE>
+__global__ void __launch_bounds__(256) k_extend(DScene sc, DState s, DCamera cam, Tile t, uint32_t iter) {
+  extern __shared__ uint2 smem_stack[];
+  Stack          stack(smem_stack);
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned int*  ring = s.ring + 4 * (iter % 3);
+  if (i == 0) {  // reset the counter block of the NEXT iteration (its last user finished two iterations ago)
+    unsigned int* nxt = s.ring + 4 * ((iter + 1) % 3);
+    nxt[0] = 0; nxt[1] = 0;
+  }
+  uint32_t n_rad = 0, n_null = 0, n_samp = 0, n_done = 0, nn = 0, nt = 0;
+  bool     push = false;
+  if (i < t.n_chains) {
+    float4   sum4 = s.sum[i];
+    uint32_t done = __float_as_uint(sum4.w);
+    if (done < t.spp) {
+      float4   a4 = s.a[i], c4 = s.c[i];
+      uint32_t flags = __float_as_uint(c4.w), seed = __float_as_uint(a4.w);
+      float3   o, d, atten, color;
+      const bool fresh = flags & F_NEW;
+      if (fresh) {
+        d = camera_ray(cam, t.pix0 + i % t.npix, seed);
+        o = cam.eye;
+        atten = f3(1.0f, 1.0f, 1.0f);
+        color = f3(0.0f, 0.0f, 0.0f);
+        flags = 0;
+      } else {
+        o = f3(s.o[i]); d = f3(s.d[i]);
+        atten = f3(a4); color = f3(c4);
+      }
+      bool finished = false;
+      if (d.x == 0.0f && d.y == 0.0f && d.z == 0.0f) {  // Q7: refract() returned the null vector: treated as a miss
+        n_null++;
+        finished = true;
+      } else {
+        n_rad++;
+        const Hit h = closest_hit<WIDE>(sc, o, d, LISA_TMIN, LISA_TMAX, stack, nn, nt);
+        if (h.prim < 0) {
+          finished = true;  // __miss__radiance: background is 0 (optix_wrapper.cc:354)
+        } else {
+          const int       mid = __float_as_int(__ldg(sc.tri_v + 3 * h.prim).w);
+          const DMaterial m   = load_material(sc.mats, mid);
+          if (m.emit()) {  // shader.cu:216-218
+            color = color + m.emission() * atten;
+            finished = true;
+          } else {
+            const float3 P = o + h.t * d;  // shader.cu:221
+            const float3 N = shading_normal(sc, h);
+            uint32_t bounce = (flags & F_BOUNCE_MASK);
+            if (m.alpha() < 1.0f) {  // dielectric, shader.cu:226-246
+              float  cosI = dot(d, N), eta;
+              float3 Nn;
+              if (cosI < 0.0f) { cosI = -cosI; eta = 1.0f / m.ior(); Nn = N; }
+              else { atten = atten * m.diffuse(); eta = m.ior(); Nn = -N; }
+              float3 nd;
+              if (eta == 1.0f) nd = d;
+              else if (rnd(seed) <= bsdf::BTDF(cosI, eta)) nd = reflect(d, Nn);
+              else nd = refract(cosI, d, Nn, eta);
+              bounce++;
+              if (bounce >= t.bounces) finished = true;
+              else {
+                flags = (flags & ~F_BOUNCE_MASK) | bounce;
+                s.o[i] = make_float4(P.x, P.y, P.z, 0.0f);
+                s.d[i] = make_float4(nd.x, nd.y, nd.z, 0.0f);
+                s.a[i] = make_float4(atten.x, atten.y, atten.z, __uint_as_float(seed));
+                s.c[i] = make_float4(color.x, color.y, color.z, __uint_as_float(flags));
+              }
+            } else {  // opaque, shader.cu:248-253: light sampling + bounce happen in k_shadow
+              atten = atten * m.diffuse();
+              s.o[i] = make_float4(P.x, P.y, P.z, 0.0f);
+              if (fresh) s.d[i] = make_float4(d.x, d.y, d.z, 0.0f);
+              s.n[i] = make_float4(N.x, N.y, N.z, __int_as_float(mid));
+              s.a[i] = make_float4(atten.x, atten.y, atten.z, __uint_as_float(seed));
+              s.c[i] = make_float4(color.x, color.y, color.z, __uint_as_float(flags));
+              push = true;
+            }
+          }
+        }
+      }
+      if (finished) {
+        done++;
+        n_samp++;
+        s.sum[i] = make_float4(sum4.x + color.x, sum4.y + color.y, sum4.z + color.z, __uint_as_float(done));
+        s.a[i]   = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(seed));
+        s.c[i]   = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(F_NEW));
+        if (done == t.spp) n_done++;
+      }
+    }
+  }
+  // stream compaction into the shadow queue: ballot + prefix popcount, one atomic per warp
+  const unsigned m = __ballot_sync(FULL, push);
+  if (m) {
+    unsigned base = 0;
+    const int leader = __ffs(m) - 1;
+    if ((int)lane_id() == leader) base = atomicAdd(&ring[0], __popc(m));
+    base = __shfl_sync(FULL, base, leader);
+    if (push) s.shadow_q[base + __popc(m & lanemask_lt())] = (int)i;
+  }
+  warp_add(&s.stats[ST_RADIANCE], n_rad);
+  warp_add(&s.stats[ST_SAMPLES], n_samp);
+  warp_add(&s.stats[ST_NULLDIR], n_null);
+  warp_add(&s.stats[ST_CHAINS_DONE], n_done);
+#ifdef LISA_COUNT_TRAVERSAL
+  warp_add(&s.stats[ST_NODES], nn);
+  warp_add(&s.stats[ST_TRIS], nt);
+#endif
+}
+
+// ------------------------------------------------------------------------------------------------
+template <bool WIDE>
+__global__ void __launch_bounds__(256) k_shadow(DScene sc, DState s, Tile t, uint32_t iter) {
+  extern __shared__ uint2 smem_stack[];
+  Stack               stack(smem_stack);
+  unsigned int*       ring = s.ring + 4 * (iter % 3);
+  const unsigned int  qn   = ring[0];
+  const unsigned      lane = lane_id();
+  int      job = -1;
+  float3   P = f3(0, 0, 0), N = f3(0, 0, 0);
+  uint32_t seed = 0, flags = 0, tries = 0;
+  int      mid = 0;
+  unsigned wnext = 0, wend = 0;  // warp-local slice of the queue
+  bool     exhausted = (qn == 0);
+  uint32_t n_sh = 0, n_samp = 0, n_done = 0, nn = 0, nt = 0;
+  while (true) {
+    const bool     need     = job < 0;
+    const unsigned needmask = __ballot_sync(FULL, need);
+    if (needmask) {
+      if (wnext == wend && !exhausted) {
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(&ring[1], SHADOW_BATCH);
+        base = __shfl_sync(FULL, base, 0);
+        wnext = min(base, qn);
+        wend  = min(base + SHADOW_BATCH, qn);
+        if (base + SHADOW_BATCH >= qn) exhausted = true;
+      }
+      const unsigned avail = wend - wnext, cnt = __popc(needmask), rank = __popc(needmask & lanemask_lt());
+      if (need && rank < avail) {
+        job = s.shadow_q[wnext + rank];
+        const float4 o4 = s.o[job], n4 = s.n[job], a4 = s.a[job], c4 = s.c[job];
+        P = f3(o4); N = f3(n4);
+        mid   = __float_as_int(n4.w);
+        seed  = __float_as_uint(a4.w);
+        flags = __float_as_uint(c4.w);
+        tries = 0;
+      }
+      wnext += min(cnt, avail);
+    }
+    if (__ballot_sync(FULL, job >= 0) == 0) break;
+    if (job >= 0) {
+      // one try of shoot_ray_to_light (shader.cu:199-207)
+      const float3 w = shoot_ray_hemisphere(N, seed);
+      int          light = (int)(flags >> F_LIGHT_SHIFT);
+      const int    oc = shadow_query<WIDE>(sc, P, w, LISA_TMIN, LISA_TMAX, light, stack, nn, nt);
+      n_sh++;
+      tries++;
+      if (oc == 0) flags &= ~F_STICKY;                                                       // __miss__occlusion
+      else if (oc == 1) flags = (flags & 0x0000ffffu) | F_STICKY | ((uint32_t)light << F_LIGHT_SHIFT);  // emitter
+      // oc == 2: RayState::hit keeps its previous value (Q1)
+      const bool lit = flags & F_STICKY;
+      if (lit || tries == LISA_SHADOW_TRIES) {
+        const float4    a4 = s.a[job], c4 = s.c[job], d4 = s.d[job];
+        const float3    atten = f3(a4);
+        float3          color = f3(c4);
+        const DMaterial m = load_material(sc.mats, mid);
+        if (lit) {
+          const DMaterial lm = load_material(sc.mats, (int)(flags >> F_LIGHT_SHIFT));
+          color = color + (lm.emission() * bsdf::BRDF(N, w, m)) * atten;  // shader.cu:205,251
+        }
+        const float3 nd = bsdf::bounce(f3(d4), N, seed, m);  // shader.cu:252 (drawn even after the last bounce)
+        uint32_t bounce = (flags & F_BOUNCE_MASK) + 1;
+        if (bounce >= t.bounces) {
+          float4   sum4 = s.sum[job];
+          uint32_t done = __float_as_uint(sum4.w) + 1;
+          s.sum[job] = make_float4(sum4.x + color.x, sum4.y + color.y, sum4.z + color.z, __uint_as_float(done));
+          s.a[job]   = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(seed));
+          s.c[job]   = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(F_NEW));
+          n_samp++;
+          if (done == t.spp) n_done++;
+        } else {
+          flags = (flags & ~F_BOUNCE_MASK) | bounce;
+          s.d[job] = make_float4(nd.x, nd.y, nd.z, 0.0f);
+          s.a[job] = make_float4(atten.x, atten.y, atten.z, __uint_as_float(seed));
+          s.c[job] = make_float4(color.x, color.y, color.z, __uint_as_float(flags));
+        }
+        job = -1;
+      }
+    }
+  }
+  warp_add(&s.stats[ST_SHADOW], n_sh);
+  warp_add(&s.stats[ST_SAMPLES], n_samp);
+  warp_add(&s.stats[ST_CHAINS_DONE], n_done);
+#ifdef LISA_COUNT_TRAVERSAL
+  warp_add(&s.stats[ST_NODES], nn);
+  warp_add(&s.stats[ST_TRIS], nt);
+#endif
+}
+
+// ------------------------------------------------------------------------------------------------
+// Chain sums -> accumulators.  accum.xyz += mean of every subframe of the tile, accum.w += subframes,
+// in subframe order (fixed order => deterministic sums).
+__global__ void k_finalize(DState s, Tile t, float4* accum) {
+  uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= t.npix) return;
+  float4 acc = accum[t.pix0 + k];
+  for (uint32_t f = 0; f < t.nf; f++) {
+    const float4 sm = s.sum[f * t.npix + k];
+    const float  inv = 1.0f / (float)t.spp;  // shader.cu:158
+    acc.x += sm.x * inv; acc.y += sm.y * inv; acc.z += sm.z * inv; acc.w += 1.0f;
+  }
+  accum[t.pix0 + k] = acc;
+}
+
+// accumulators -> mean image (float4, alpha 1) and/or sRGB8 (shader.cu:165-166)
+__global__ void k_resolve(const float4* __restrict__ accum, uint32_t npix, float4* mean_out, uint32_t* rgba8_out) {
+  uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npix) return;
+  const float4 a   = accum[p];
+  const float  inv = a.w > 0.0f ? 1.0f / a.w : 0.0f;
+  const float3 m   = f3(a.x * inv, a.y * inv, a.z * inv);
+  if (mean_out) mean_out[p] = make_float4(m.x, m.y, m.z, 1.0f);
+  if (rgba8_out) rgba8_out[p] = make_color(m);
+}
+
+// ------------------------------------------------------------------------------------------------
+// diagnostics
+template <bool WIDE>
+__global__ void k_trace_closest(DScene sc, const float* __restrict__ org, const float* __restrict__ dir, uint32_t n, float tmin,
+                                float tmax, int* prim, float* tt) {
+  extern __shared__ uint2 smem_stack[];
+  Stack    stack(smem_stack);
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t nn = 0, nt = 0;
+  float3   o = f3(org[3 * i], org[3 * i + 1], org[3 * i + 2]), d = f3(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]);
+  Hit      h = closest_hit<WIDE>(sc, o, d, tmin, tmax, stack, nn, nt);
+  prim[i] = h.prim;
+  if (tt) tt[i] = h.t;
+}
+template <bool WIDE>
+__global__ void k_trace_shadow(DScene sc, const float* __restrict__ org, const float* __restrict__ dir, uint32_t n, float tmin,
+                               float tmax, int* outcome, int* light) {
+  extern __shared__ uint2 smem_stack[];
+  Stack    stack(smem_stack);
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t nn = 0, nt = 0;
+  float3   o = f3(org[3 * i], org[3 * i + 1], org[3 * i + 2]), d = f3(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]);
+  int      l = -1;
+  int      oc = shadow_query<WIDE>(sc, o, d, tmin, tmax, l, stack, nn, nt);
+  outcome[i] = oc;
+  if (light) light[i] = oc == 1 ? l : -1;
+}
+__global__ void k_primary_rays(DCamera cam, uint32_t subframe, float* dirs, uint32_t* seeds) {
+  uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= cam.width * cam.height) return;
+  uint32_t seed = chain_seed(cam, p, subframe);
+  float3   d    = camera_ray(cam, p, seed);
+  dirs[3 * p] = d.x; dirs[3 * p + 1] = d.y; dirs[3 * p + 2] = d.z;
+  seeds[p] = seed;
+}
+__global__ void k_kat(int what, uint32_t n, const float* __restrict__ in_f, const uint32_t* __restrict__ in_u, float* out_f,
+                      uint32_t* out_u) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  DMaterial m;
+  m.a = m.b = m.c = make_float4(0, 0, 0, 0);
+  switch (what) {
+    case 0: out_u[i] = tea16(in_u[2 * i], in_u[2 * i + 1]); break;
+    case 1: { uint32_t s = in_u[i]; out_f[3 * i] = rnd(s); out_f[3 * i + 1] = rnd(s); out_f[3 * i + 2] = rnd(s); out_u[i] = s; } break;
+    case 2: { uint32_t s = in_u[i]; float3 h = shoot_ray_hemisphere(f3(in_f[3 * i], in_f[3 * i + 1], in_f[3 * i + 2]), s);
+              out_f[3 * i] = h.x; out_f[3 * i + 1] = h.y; out_f[3 * i + 2] = h.z; out_u[i] = s; } break;
+    case 3: out_f[i] = bsdf::BTDF(in_f[2 * i], in_f[2 * i + 1]); break;
+    case 4: { const float* p = in_f + 8 * i; float3 r = refract(p[0], f3(p[1], p[2], p[3]), f3(p[4], p[5], p[6]), p[7]);
+              out_f[3 * i] = r.x; out_f[3 * i + 1] = r.y; out_f[3 * i + 2] = r.z; } break;
+    case 5: { const float* p = in_f + 7 * i; uint32_t s = in_u[i]; m.a.w = p[6];
+              float3 r = bsdf::bounce(f3(p[0], p[1], p[2]), f3(p[3], p[4], p[5]), s, m);
+              out_f[3 * i] = r.x; out_f[3 * i + 1] = r.y; out_f[3 * i + 2] = r.z; out_u[i] = s; } break;
+    case 6: { const float* p = in_f + 6 * i; out_f[i] = bsdf::BRDF(f3(p[0], p[1], p[2]), f3(p[3], p[4], p[5]), m); } break;
+    case 7: out_u[i] = make_color(f3(in_f[3 * i], in_f[3 * i + 1], in_f[3 * i + 2])); break;
+    case 8: {  // shading normal at P: watertight-test barycentrics of a ray through P, then interpolation
+      const float* p = in_f + 21 * i;
+      float3 P = f3(p[0], p[1], p[2]);
+      float3 v0 = f3(p[12], p[13], p[14]), v1 = f3(p[15], p[16], p[17]), v2 = f3(p[18], p[19], p[20]);
+      float3 gn = normalize(cross(v1 - v0, v2 - v0));
+      float3 o = P + gn, d = -gn;
+      RayPre pre = ray_precompute(o, d);
+      float t = 0, u = 0, v = 0;
+      intersect_tri(pre, v0, v1, v2, 0.0f, 1e30f, t, u, v);
+      float3 nrm = normalize((1.0f - u - v) * f3(p[3], p[4], p[5]) + u * f3(p[6], p[7], p[8]) + v * f3(p[9], p[10], p[11]));
+      out_f[3 * i] = nrm.x; out_f[3 * i + 1] = nrm.y; out_f[3 * i + 2] = nrm.z;
+    } break;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+static inline unsigned cdiv(unsigned a, unsigned b) { return (a + b - 1) / b; }
+static inline size_t   stack_smem(int block) { return (size_t)block * LISA_STACK_SMEM_PER_THREAD; }
+
+int configure_kernels(char* err, size_t errlen) {
+  cudaError_t e = cudaSuccess;
+  const int   smem = (int)stack_smem(256);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_extend<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_extend<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_shadow<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_shadow<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) { snprintf(err, errlen, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -2; }
+  return 0;
+}
+
+void launch_init_chains(const DState& s, const DCamera& cam, const Tile& t, cudaStream_t st) {
+  k_init_chains<<<cdiv(t.n_chains, 256), 256, 0, st>>>(s, cam, t);
+}
+void launch_extend(const DScene& sc, const DState& s, const DCamera& cam, const Tile& t, uint32_t iter, const LaunchCfg& cfg,
+                   cudaStream_t st) {
+  const int b = cfg.extend_block;
+  if (sc.wide) k_extend<true><<<cdiv(t.n_chains, b), b, stack_smem(b), st>>>(sc, s, cam, t, iter);
+  else k_extend<false><<<cdiv(t.n_chains, b), b, stack_smem(b), st>>>(sc, s, cam, t, iter);
+}
+void launch_shadow(const DScene& sc, const DState& s, const Tile& t, uint32_t iter, const LaunchCfg& cfg, cudaStream_t st) {
+  const int b = cfg.shadow_block;
+  unsigned  grid = (unsigned)(cfg.sm_count * cfg.shadow_blocks_per_sm);
+  grid = min(grid, max(1u, cdiv(t.n_chains, SHADOW_BATCH * (b / 32)) ));
+  if (sc.wide) k_shadow<true><<<grid, b, stack_smem(b), st>>>(sc, s, t, iter);
+  else k_shadow<false><<<grid, b, stack_smem(b), st>>>(sc, s, t, iter);
+}
+void launch_finalize(const DState& s, const DCamera&, const Tile& t, float4* accum, cudaStream_t st) {
+  k_finalize<<<cdiv(t.npix, 256), 256, 0, st>>>(s, t, accum);
+}
+void launch_resolve(const float4* accum, uint32_t npix, float4* mean_out, uint32_t* rgba8_out, cudaStream_t st) {
+  k_resolve<<<cdiv(npix, 256), 256, 0, st>>>(accum, npix, mean_out, rgba8_out);
+}
+void launch_trace_closest(const DScene& sc, const float* d_org, const float* d_dir, uint32_t n, float tmin, float tmax,
+                          int* d_prim, float* d_t, cudaStream_t st) {
+  if (!n) return;
+  if (sc.wide) k_trace_closest<true><<<cdiv(n, 128), 128, stack_smem(128), st>>>(sc, d_org, d_dir, n, tmin, tmax, d_prim, d_t);
+  else k_trace_closest<false><<<cdiv(n, 128), 128, stack_smem(128), st>>>(sc, d_org, d_dir, n, tmin, tmax, d_prim, d_t);
+}
+void launch_trace_shadow(const DScene& sc, const float* d_org, const float* d_dir, uint32_t n, float tmin, float tmax,
+                         int* d_outcome, int* d_light, cudaStream_t st) {
+  if (!n) return;
+  if (sc.wide) k_trace_shadow<true><<<cdiv(n, 128), 128, stack_smem(128), st>>>(sc, d_org, d_dir, n, tmin, tmax, d_outcome, d_light);
+  else k_trace_shadow<false><<<cdiv(n, 128), 128, stack_smem(128), st>>>(sc, d_org, d_dir, n, tmin, tmax, d_outcome, d_light);
+}
+void launch_primary_rays(const DCamera& cam, uint32_t subframe, float* d_dirs, uint32_t* d_seeds, cudaStream_t st) {
+  k_primary_rays<<<cdiv(cam.width * cam.height, 256), 256, 0, st>>>(cam, subframe, d_dirs, d_seeds);
+}
+int launch_kat(int what, uint32_t n, const float* in_f, const uint32_t* in_u, float* out_f, uint32_t* out_u, cudaStream_t st) {
+  if (what < 0 || what > 8) return -1;
+  if (n) k_kat<<<cdiv(n, 128), 128, 0, st>>>(what, n, in_f, in_u, out_f, out_u);
+  return 0;
+}
+
+}  // namespace lisa

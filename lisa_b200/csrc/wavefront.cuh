@@ -1,0 +1,58 @@
+// lisa_b200/csrc/wavefront.cuh — host-visible declarations of the wavefront path tracer (wavefront.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "scene.cuh"
+
+namespace lisa {
+
+// Per-chain state, structure of arrays of 16-byte words.  A "chain" is one (pixel, subframe) sample
+// sequence: the reference's per-thread loop `for i < samples_per_launch` (shader.cu:147-155) with its
+// strictly sequential LCG stream seeded by tea<16>(pixel, subframe) (shader.cu:141).
+struct DState {
+  float4* o;    // ray origin .xyz (hit point P after the extend stage)
+  float4* d;    // ray direction .xyz (not unit, Q5)
+  float4* a;    // attenuation .xyz | LCG state in .w
+  float4* c;    // radiance of the sample in flight .xyz | flags in .w (see F_* in wavefront.cu)
+  float4* n;    // shading normal .xyz | material id in .w   (extend -> shadow stage hand-off)
+  float4* sum;  // sum of finished samples .xyz | number of finished samples in .w
+  int*    shadow_q;  // chain ids with an opaque hit waiting for light sampling
+  // ring of 3 per-iteration counter blocks {shadow queue length, shadow queue fetch cursor, -, -}
+  unsigned int* ring;
+  // cumulative: [0] radiance rays [1] shadow rays [2] samples [3] null directions [4] finished chains
+  // [5] nodes visited [6] triangles tested (only counted when LISA_COUNT_TRAVERSAL is compiled in)
+  unsigned long long* stats;
+};
+
+struct Tile {
+  uint32_t pix0, npix;      // pixel range of the tile (pixel id = y*W + x)
+  uint32_t f0, nf;          // subframe range
+  uint32_t spp;             // samples per chain
+  uint32_t bounces;
+  uint32_t n_chains;        // npix * nf
+};
+
+struct LaunchCfg {
+  int sm_count;
+  int extend_block, shadow_block;
+  int shadow_blocks_per_sm;
+};
+
+void launch_init_chains(const DState& s, const DCamera& cam, const Tile& t, cudaStream_t st);
+void launch_extend(const DScene& sc, const DState& s, const DCamera& cam, const Tile& t, uint32_t iter, const LaunchCfg& cfg,
+                   cudaStream_t st);
+void launch_shadow(const DScene& sc, const DState& s, const Tile& t, uint32_t iter, const LaunchCfg& cfg, cudaStream_t st);
+void launch_finalize(const DState& s, const DCamera& cam, const Tile& t, float4* accum, cudaStream_t st);
+void launch_resolve(const float4* accum, uint32_t npix, float4* mean_out, uint32_t* rgba8_out, cudaStream_t st);
+int  configure_kernels(char* err, size_t errlen);
+
+// diagnostics
+void launch_trace_closest(const DScene& sc, const float* d_org, const float* d_dir, uint32_t n, float tmin, float tmax,
+                          int* d_prim, float* d_t, cudaStream_t st);
+void launch_trace_shadow(const DScene& sc, const float* d_org, const float* d_dir, uint32_t n, float tmin, float tmax,
+                         int* d_outcome, int* d_light, cudaStream_t st);
+void launch_primary_rays(const DCamera& cam, uint32_t subframe, float* d_dirs, uint32_t* d_seeds, cudaStream_t st);
+int  launch_kat(int what, uint32_t n, const float* in_f, const uint32_t* in_u, float* out_f, uint32_t* out_u, cudaStream_t st);
+
+}  // namespace lisa

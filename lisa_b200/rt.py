@@ -1,0 +1,264 @@
+"""ctypes binding of liblisa_rt.so — the C ABI declared in include/lisa_rt.h.
+
+Nothing here computes: every call goes to the CUDA library.  Importing this module without the built
+library raises (the product has no CPU or PyTorch fallback).
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_DIR, "liblisa_rt.so")
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        "lisa_b200: %s is missing — build it with `make -C lisa_b200` (or __graft_entry__.build()); "
+        "there is no CPU fallback" % LIB_PATH)
+
+_L = ctypes.CDLL(LIB_PATH)
+
+LISA_OK = 0
+SHADOW_CLOSEST, SHADOW_FIRST_FOUND = 0, 1
+BVH_WIDE8, BVH_BINARY = 0, 1
+
+
+class Material(ctypes.Structure):
+    _fields_ = [("roughness", ctypes.c_float), ("alpha", ctypes.c_float), ("n", ctypes.c_float),
+                ("diffuse_color", ctypes.c_float * 3), ("emit", ctypes.c_uint8), ("_pad", ctypes.c_uint8 * 3),
+                ("emission_color", ctypes.c_float * 3)]
+
+
+class Camera(ctypes.Structure):
+    _fields_ = [("eye", ctypes.c_float * 3), ("look_at", ctypes.c_float * 3), ("fov", ctypes.c_float)]
+
+
+class SceneDesc(ctypes.Structure):
+    _fields_ = [("vertices", ctypes.c_void_p), ("normals", ctypes.c_void_p), ("materials", ctypes.c_void_p),
+                ("mat_indices", ctypes.c_void_p), ("num_vertices", ctypes.c_int32), ("num_materials", ctypes.c_int32),
+                ("width", ctypes.c_uint32), ("height", ctypes.c_uint32), ("camera", Camera),
+                ("num_samples", ctypes.c_uint32), ("num_bounces", ctypes.c_uint32), ("output_image", ctypes.c_char_p)]
+
+
+class Options(ctypes.Structure):
+    _fields_ = [("struct_size", ctypes.c_uint32), ("device", ctypes.c_int32), ("shadow_mode", ctypes.c_uint32),
+                ("bvh_kind", ctypes.c_uint32), ("max_chains", ctypes.c_uint32), ("flags", ctypes.c_uint32)]
+
+
+class Stats(ctypes.Structure):
+    _fields_ = [("struct_size", ctypes.c_uint32), ("num_triangles", ctypes.c_uint32),
+                ("num_emitter_triangles", ctypes.c_uint32), ("bvh_nodes", ctypes.c_uint32),
+                ("bvh_emitter_nodes", ctypes.c_uint32), ("bvh_bytes", ctypes.c_uint64), ("triangle_bytes", ctypes.c_uint64),
+                ("upload_ms", ctypes.c_float), ("bvh_build_ms", ctypes.c_float),
+                ("samples", ctypes.c_uint64), ("radiance_rays", ctypes.c_uint64), ("shadow_rays", ctypes.c_uint64),
+                ("null_directions", ctypes.c_uint64), ("kernel_launches", ctypes.c_uint64), ("iterations", ctypes.c_uint64),
+                ("render_ms", ctypes.c_double), ("last_render_ms", ctypes.c_double),
+                ("last_samples", ctypes.c_uint64), ("last_radiance_rays", ctypes.c_uint64),
+                ("last_shadow_rays", ctypes.c_uint64), ("last_kernel_launches", ctypes.c_uint64),
+                ("last_extend_ms", ctypes.c_double), ("last_shadow_ms", ctypes.c_double),
+                ("state_bytes", ctypes.c_uint64), ("subframes_accumulated", ctypes.c_uint32), ("_reserved", ctypes.c_uint32)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_ if not k.startswith("_")}
+
+
+assert ctypes.sizeof(Material) == 40
+
+_vp = ctypes.c_void_p
+_L.lisa_last_error.restype = ctypes.c_char_p
+_L.lisa_version.restype = ctypes.c_int
+_L.lisa_create.argtypes = [ctypes.POINTER(SceneDesc), ctypes.POINTER(Options), ctypes.POINTER(_vp)]
+_L.lisa_destroy.argtypes = [_vp]
+_L.lisa_destroy.restype = None
+_L.lisa_render_subframes.argtypes = [_vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32]
+_L.lisa_reset_accum.argtypes = [_vp]
+_L.lisa_read_accum.argtypes = [_vp, _vp]
+_L.lisa_read_rgba8.argtypes = [_vp, _vp]
+_L.lisa_write_ppm.argtypes = [_vp, ctypes.c_char_p]
+_L.lisa_get_stats.argtypes = [_vp, ctypes.POINTER(Stats)]
+_L.lisa_accum_device_ptr.argtypes = [_vp]
+_L.lisa_accum_device_ptr.restype = _vp
+_L.lisa_accum_bytes.argtypes = [_vp]
+_L.lisa_accum_bytes.restype = ctypes.c_size_t
+_L.lisa_device.argtypes = [_vp]
+_L.lisa_sync.argtypes = [_vp]
+_L.lisa_trace_closest.argtypes = [_vp, _vp, _vp, ctypes.c_uint32, ctypes.c_float, ctypes.c_float, _vp, _vp]
+_L.lisa_trace_shadow.argtypes = [_vp, _vp, _vp, ctypes.c_uint32, ctypes.c_float, ctypes.c_float, _vp, _vp]
+_L.lisa_primary_rays.argtypes = [_vp, ctypes.c_uint32, _vp, _vp]
+_L.lisa_kat_eval.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_uint32, _vp, _vp, _vp, _vp]
+
+EXPORTS = ["lisa_create", "lisa_destroy", "lisa_last_error", "lisa_version", "lisa_render_subframes",
+           "lisa_reset_accum", "lisa_read_accum", "lisa_read_rgba8", "lisa_write_ppm", "lisa_get_stats",
+           "lisa_accum_device_ptr", "lisa_accum_bytes", "lisa_device", "lisa_sync", "lisa_trace_closest",
+           "lisa_trace_shadow", "lisa_primary_rays", "lisa_kat_eval"]
+
+
+class LisaError(RuntimeError):
+    def __init__(self, code):
+        self.code = code
+        super().__init__("lisa_rt error %d: %s" % (code, _L.lisa_last_error().decode("utf-8", "replace")))
+
+
+def _check(rc):
+    if rc != LISA_OK:
+        raise LisaError(rc)
+
+
+def library():
+    return _L
+
+
+def pack_materials(mats):
+    """list of dicts (emit, alpha, diffuse, roughness | n, emission) -> ctypes array of lisa_material."""
+    arr = (Material * max(len(mats), 1))()
+    for i, m in enumerate(mats):
+        arr[i].roughness = m.get("roughness", 0.0)
+        arr[i].alpha = m.get("alpha", 1.0)
+        arr[i].n = m.get("n", 0.0)
+        arr[i].diffuse_color[:] = m.get("diffuse", (0.0, 0.0, 0.0))
+        arr[i].emit = 1 if m.get("emit") else 0
+        arr[i].emission_color[:] = m.get("emission", (0.0, 0.0, 0.0))
+    return arr
+
+
+class Renderer:
+    """One lisa_ctx: OptixWrapper + render() of the reference behind the C ABI."""
+
+    def __init__(self, vertices, normals, mat_indices, materials, width, height, eye, look_at, fov, num_samples=1,
+                 num_bounces=7, output_image=None, device=-1, shadow_mode=SHADOW_CLOSEST, bvh_kind=BVH_WIDE8, max_chains=0):
+        self._v = np.ascontiguousarray(vertices, dtype=np.float32).reshape(-1, 3)
+        self._n = np.ascontiguousarray(normals, dtype=np.float32).reshape(-1, 3)
+        self._m = np.ascontiguousarray(mat_indices, dtype=np.int32).reshape(-1)
+        if isinstance(materials, (bytes, bytearray)):
+            nm = len(materials) // 40
+            self._mats = (Material * max(nm, 1)).from_buffer_copy(bytes(materials).ljust(40, b"\0"))
+        else:
+            nm = len(materials)
+            self._mats = pack_materials(materials)
+        sd = SceneDesc()
+        sd.vertices = self._v.ctypes.data
+        sd.normals = self._n.ctypes.data
+        sd.materials = ctypes.cast(self._mats, _vp)
+        sd.mat_indices = self._m.ctypes.data
+        sd.num_vertices = self._v.shape[0]
+        sd.num_materials = nm
+        sd.width, sd.height = width, height
+        sd.camera.eye[:] = [float(x) for x in eye]
+        sd.camera.look_at[:] = [float(x) for x in look_at]
+        sd.camera.fov = float(fov)
+        sd.num_samples, sd.num_bounces = num_samples, num_bounces
+        sd.output_image = output_image.encode() if output_image else None
+        opt = Options(ctypes.sizeof(Options), device, shadow_mode, bvh_kind, max_chains, 0)
+        self.width, self.height = width, height
+        self.num_samples, self.num_bounces = num_samples, num_bounces
+        self._h = _vp()
+        _check(_L.lisa_create(ctypes.byref(sd), ctypes.byref(opt), ctypes.byref(self._h)))
+
+    @classmethod
+    def from_scene(cls, sc, **kw):
+        """sc: dict with vertices, normals, mat_indices, materials(_packed), width, height, camera, num_samples, num_bounces."""
+        cam = sc["camera"]
+        args = dict(width=sc["width"], height=sc["height"], eye=cam["eye"], look_at=cam["look_at"], fov=cam["fov"],
+                    num_samples=sc["num_samples"], num_bounces=sc["num_bounces"], output_image=sc.get("output_image"))
+        args.update(kw)
+        mats = sc["materials_packed"] if "materials_packed" in sc else sc["materials"]
+        return cls(sc["vertices"], sc["normals"], sc["mat_indices"], mats, **args)
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            _L.lisa_destroy(self._h)
+            self._h = _vp()
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def render_subframes(self, first=0, count=1, spp=None):
+        _check(_L.lisa_render_subframes(self._h, first, count, self.num_samples if spp is None else spp))
+
+    def render(self):
+        """The reference's `-s` path: one subframe (index 0) of num_samples spp (render.cc:133-148)."""
+        self.reset()
+        self.render_subframes(0, 1, self.num_samples)
+
+    def reset(self):
+        _check(_L.lisa_reset_accum(self._h))
+
+    def read_accum(self):
+        out = np.empty((self.height, self.width, 4), dtype=np.float32)
+        _check(_L.lisa_read_accum(self._h, out.ctypes.data))
+        return out
+
+    def read_rgba8(self):
+        out = np.empty((self.height, self.width, 4), dtype=np.uint8)
+        _check(_L.lisa_read_rgba8(self._h, out.ctypes.data))
+        return out
+
+    def write_ppm(self, path=None):
+        _check(_L.lisa_write_ppm(self._h, path.encode() if path else None))
+
+    def stats(self):
+        s = Stats()
+        s.struct_size = ctypes.sizeof(Stats)
+        _check(_L.lisa_get_stats(self._h, ctypes.byref(s)))
+        return s.as_dict()
+
+    def accum_device_ptr(self):
+        return _L.lisa_accum_device_ptr(self._h)
+
+    def accum_bytes(self):
+        return _L.lisa_accum_bytes(self._h)
+
+    def device(self):
+        return _L.lisa_device(self._h)
+
+    def sync(self):
+        _check(_L.lisa_sync(self._h))
+
+    def trace_closest(self, org, dirs, tmin=1e-4, tmax=1e16):
+        org = np.ascontiguousarray(org, dtype=np.float32).reshape(-1, 3)
+        dirs = np.ascontiguousarray(dirs, dtype=np.float32).reshape(-1, 3)
+        n = org.shape[0]
+        prim = np.empty(n, dtype=np.int32)
+        t = np.empty(n, dtype=np.float32)
+        _check(_L.lisa_trace_closest(self._h, org.ctypes.data, dirs.ctypes.data, n, tmin, tmax, prim.ctypes.data, t.ctypes.data))
+        return prim, t
+
+    def trace_shadow(self, org, dirs, tmin=1e-4, tmax=1e16):
+        org = np.ascontiguousarray(org, dtype=np.float32).reshape(-1, 3)
+        dirs = np.ascontiguousarray(dirs, dtype=np.float32).reshape(-1, 3)
+        n = org.shape[0]
+        oc = np.empty(n, dtype=np.int32)
+        light = np.empty(n, dtype=np.int32)
+        _check(_L.lisa_trace_shadow(self._h, org.ctypes.data, dirs.ctypes.data, n, tmin, tmax, oc.ctypes.data, light.ctypes.data))
+        return oc, light
+
+    def primary_rays(self, subframe=0):
+        d = np.empty((self.height, self.width, 3), dtype=np.float32)
+        s = np.empty((self.height, self.width), dtype=np.uint32)
+        _check(_L.lisa_primary_rays(self._h, subframe, d.ctypes.data, s.ctypes.data))
+        return d, s
+
+
+_KAT_SHAPES = {0: (0, 2, 0, 1), 1: (0, 1, 3, 1), 2: (3, 1, 3, 1), 3: (2, 0, 1, 0), 4: (8, 0, 3, 0), 5: (7, 1, 3, 1),
+               6: (6, 0, 1, 0), 7: (3, 0, 0, 1), 8: (21, 0, 3, 0)}
+
+
+def kat_eval(what, in_f=None, in_u=None, device=-1):
+    """Evaluate a device helper on the GPU (lisa_kat_eval).  Returns (out_f, out_u)."""
+    fi, ui, fo, uo = _KAT_SHAPES[what]
+    if fi:
+        in_f = np.ascontiguousarray(in_f, dtype=np.float32).reshape(-1, fi)
+        n = in_f.shape[0]
+    if ui:
+        in_u = np.ascontiguousarray(in_u, dtype=np.uint32).reshape(-1, ui)
+        n = in_u.shape[0]
+    out_f = np.zeros((n, max(fo, 1)), dtype=np.float32)
+    out_u = np.zeros((n, max(uo, 1)), dtype=np.uint32)
+    _check(_L.lisa_kat_eval(device, what, n, in_f.ctypes.data if fi else None, in_u.ctypes.data if ui else None,
+                            out_f.ctypes.data, out_u.ctypes.data))
+    return out_f, out_u
