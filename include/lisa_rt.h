@@ -88,6 +88,7 @@ typedef struct lisa_scene_desc {
 
 enum { LISA_SHADOW_CLOSEST = 0, LISA_SHADOW_FIRST_FOUND = 1 };
 enum { LISA_BVH_WIDE8 = 0, LISA_BVH_BINARY = 1 };
+enum { LISA_FLAG_PROFILE_STAGES = 1 };
 
 typedef struct lisa_options {
   uint32_t struct_size;   /* sizeof(lisa_options) */
@@ -97,7 +98,7 @@ typedef struct lisa_options {
                              what the reference asks OptiX for (shader.cu:69) and is traversal-order dependent. */
   uint32_t bvh_kind;      /* LISA_BVH_WIDE8 (default) compressed 8-wide; LISA_BVH_BINARY for ablation */
   uint32_t max_chains;    /* upper bound on concurrently resident (pixel, subframe) sample chains; 0 = auto */
-  uint32_t flags;         /* reserved, 0 */
+  uint32_t flags;         /* LISA_FLAG_* */
 } lisa_options;
 
 typedef struct lisa_stats {
@@ -113,10 +114,14 @@ typedef struct lisa_stats {
   /* last lisa_render_subframes call only */
   double   last_render_ms;
   uint64_t last_samples, last_radiance_rays, last_shadow_rays, last_kernel_launches;
-  double   last_extend_ms, last_shadow_ms; /* per-stage device time, only when LISA_PROFILE_STAGES=1 */
+  double   last_extend_ms, last_shadow_ms; /* per-stage device time (CUDA events around every launch of the stage),
+                                              only when options.flags & LISA_FLAG_PROFILE_STAGES or LISA_PROFILE_STAGES=1 */
   uint64_t state_bytes;                  /* device bytes of chain state + queues */
   uint32_t subframes_accumulated;
   uint32_t _reserved;
+  uint64_t last_extend_launches, last_shadow_launches, last_shadow_jobs; /* jobs = opaque hits light-sampled */
+  uint64_t nodes_visited, triangles_tested;           /* cumulative traversal work (both stages) */
+  uint64_t last_nodes_visited, last_triangles_tested;
 } lisa_stats;
 
 typedef struct lisa_ctx lisa_ctx;

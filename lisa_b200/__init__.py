@@ -6,4 +6,4 @@ the reference's ``SceneParser``, ``parse_obj``, ``render`` and ``display``) and 
 This Python package is only the ctypes binding the tests and ``bench.py`` use; it raises at import of
 ``lisa_b200.rt`` if the CUDA library has not been built (there is no CPU fallback).
 """
-__all__ = ["rt", "host", "dist"]
+__all__ = ["rt", "frontend", "dist"]

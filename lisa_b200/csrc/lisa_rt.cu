@@ -58,7 +58,31 @@ struct lisa_ctx {
   uint32_t     width = 0, height = 0, num_samples = 0, num_bounces = 0;
   std::string  output_image;
   bool         profile_stages = false;
+  std::vector<cudaEvent_t> ev_pool;  // stage profiling: 3 events per iteration (extend start, shadow start, shadow end)
+  size_t       ev_used = 0;
+  double       stage_ms[2] = {0, 0};
+  uint64_t     stage_launches[2] = {0, 0};
 };
+
+static cudaEvent_t next_event(lisa_ctx* c) {
+  if (c->ev_used == c->ev_pool.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    c->ev_pool.push_back(e);
+  }
+  return c->ev_pool[c->ev_used++];
+}
+// events were recorded as triples (extend start, shadow start, shadow end); call after a stream sync
+static void drain_stage_events(lisa_ctx* c) {
+  for (size_t i = 0; i + 2 < c->ev_used + 0 && i + 2 < c->ev_pool.size() + 0; i += 3) {
+    float a = 0, b = 0;
+    cudaEventElapsedTime(&a, c->ev_pool[i], c->ev_pool[i + 1]);
+    cudaEventElapsedTime(&b, c->ev_pool[i + 1], c->ev_pool[i + 2]);
+    c->stage_ms[0] += a; c->stage_ms[1] += b;
+    c->stage_launches[0]++; c->stage_launches[1]++;
+  }
+  c->ev_used = 0;
+}
 
 extern "C" const char* lisa_last_error(void) { return g_err; }
 extern "C" int         lisa_version(void) { return LISA_RT_VERSION; }
@@ -122,6 +146,7 @@ extern "C" void lisa_destroy(lisa_ctx* c) {
   if (c->h_stats) cudaFreeHost(c->h_stats);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
+  for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -134,7 +159,7 @@ static int create_impl(const lisa_scene_desc* sd, const lisa_options* opt, lisa_
   if (const char* e = getenv("LISA_BVH")) o.bvh_kind = !strcmp(e, "binary") ? LISA_BVH_BINARY : LISA_BVH_WIDE8;
   if (const char* e = getenv("LISA_SHADOW")) o.shadow_mode = !strcmp(e, "first") ? LISA_SHADOW_FIRST_FOUND : LISA_SHADOW_CLOSEST;
   if (const char* e = getenv("LISA_MAX_CHAINS")) o.max_chains = (uint32_t)strtoul(e, nullptr, 10);
-  c->profile_stages = getenv("LISA_PROFILE_STAGES") && atoi(getenv("LISA_PROFILE_STAGES"));
+  c->profile_stages = (o.flags & LISA_FLAG_PROFILE_STAGES) || (getenv("LISA_PROFILE_STAGES") && atoi(getenv("LISA_PROFILE_STAGES")));
 
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -293,12 +318,16 @@ static int run_tile(lisa_ctx* c, const Tile& t, uint64_t* launches, uint64_t* it
   uint32_t burst = std::max<uint32_t>(1, t.spp);
   while (true) {
     for (uint32_t k = 0; k < burst; k++, iter++) {
+      if (c->profile_stages) cudaEventRecord(next_event(c), c->stream);
       launch_extend(c->scene, c->state, c->cam, t, iter, c->cfg, c->stream);
+      if (c->profile_stages) cudaEventRecord(next_event(c), c->stream);
       launch_shadow(c->scene, c->state, t, iter, c->cfg, c->stream);
+      if (c->profile_stages) cudaEventRecord(next_event(c), c->stream);
       *launches += 2;
     }
     CU(cudaMemcpyAsync(c->h_stats, c->state.stats, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    if (c->profile_stages) drain_stage_events(c);
     if (c->h_stats[4] >= t.n_chains) break;
     if (iter > max_iter) return fail(LISA_ERR_STATE, "wavefront did not converge after %u iterations (%llu of %u chains done)", iter,
                                      (unsigned long long)c->h_stats[4], t.n_chains);
@@ -321,6 +350,8 @@ extern "C" int lisa_render_subframes(lisa_ctx* c, uint32_t first, uint32_t count
   CU(cudaStreamSynchronize(c->stream));
   memcpy(before, c->h_stats, sizeof(before));
   uint64_t launches = 0, iterations = 0;
+  c->stage_ms[0] = c->stage_ms[1] = 0;
+  c->stage_launches[0] = c->stage_launches[1] = 0;
   CU(cudaEventRecord(c->ev0, c->stream));
   if (c->num_bounces == 0) {
     // shader.cu:110: zero bounces trace nothing; every sample is black
@@ -358,6 +389,15 @@ extern "C" int lisa_render_subframes(lisa_ctx* c, uint32_t first, uint32_t count
   s.last_shadow_rays = c->h_stats[1] - before[1];
   s.last_samples = npix * count * spp;
   s.last_kernel_launches = launches;
+  s.last_extend_ms = c->stage_ms[0];
+  s.last_shadow_ms = c->stage_ms[1];
+  s.last_extend_launches = c->profile_stages ? c->stage_launches[0] : iterations;
+  s.last_shadow_launches = c->profile_stages ? c->stage_launches[1] : iterations;
+  s.last_shadow_jobs = c->h_stats[7] - before[7];
+  s.last_nodes_visited = c->h_stats[5] - before[5];
+  s.last_triangles_tested = c->h_stats[6] - before[6];
+  s.nodes_visited = c->h_stats[5];
+  s.triangles_tested = c->h_stats[6];
   s.radiance_rays = c->h_stats[0];
   s.shadow_rays = c->h_stats[1];
   s.null_directions = c->h_stats[3];

@@ -36,7 +36,7 @@ namespace lisa {
 #define FULL 0xffffffffu
 #define SHADOW_BATCH 32
 
-enum { ST_RADIANCE = 0, ST_SHADOW = 1, ST_SAMPLES = 2, ST_NULLDIR = 3, ST_CHAINS_DONE = 4, ST_NODES = 5, ST_TRIS = 6 };
+enum { ST_RADIANCE = 0, ST_SHADOW = 1, ST_SAMPLES = 2, ST_NULLDIR = 3, ST_CHAINS_DONE = 4, ST_NODES = 5, ST_TRIS = 6, ST_JOBS = 7 };
 
 __device__ __forceinline__ void warp_add(unsigned long long* p, uint32_t v) {
   for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
@@ -211,7 +211,10 @@ __global__ void __launch_bounds__(256) k_extend(DScene sc, DState s, DCamera cam
   if (m) {
     unsigned base = 0;
     const int leader = __ffs(m) - 1;
-    if ((int)lane_id() == leader) base = atomicAdd(&ring[0], __popc(m));
+    if ((int)lane_id() == leader) {
+      base = atomicAdd(&ring[0], __popc(m));
+      atomicAdd(&s.stats[ST_JOBS], (unsigned long long)__popc(m));
+    }
     base = __shfl_sync(FULL, base, leader);
     if (push) s.shadow_q[base + __popc(m & lanemask_lt())] = (int)i;
   }
@@ -219,10 +222,8 @@ __global__ void __launch_bounds__(256) k_extend(DScene sc, DState s, DCamera cam
   warp_add(&s.stats[ST_SAMPLES], n_samp);
   warp_add(&s.stats[ST_NULLDIR], n_null);
   warp_add(&s.stats[ST_CHAINS_DONE], n_done);
-#ifdef LISA_COUNT_TRAVERSAL
   warp_add(&s.stats[ST_NODES], nn);
   warp_add(&s.stats[ST_TRIS], nt);
-#endif
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -308,10 +309,8 @@ __global__ void __launch_bounds__(256) k_shadow(DScene sc, DState s, Tile t, uin
   warp_add(&s.stats[ST_SHADOW], n_sh);
   warp_add(&s.stats[ST_SAMPLES], n_samp);
   warp_add(&s.stats[ST_CHAINS_DONE], n_done);
-#ifdef LISA_COUNT_TRAVERSAL
   warp_add(&s.stats[ST_NODES], nn);
   warp_add(&s.stats[ST_TRIS], nt);
-#endif
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -21,7 +21,7 @@ struct DState {
   // ring of 3 per-iteration counter blocks {shadow queue length, shadow queue fetch cursor, -, -}
   unsigned int* ring;
   // cumulative: [0] radiance rays [1] shadow rays [2] samples [3] null directions [4] finished chains
-  // [5] nodes visited [6] triangles tested (only counted when LISA_COUNT_TRAVERSAL is compiled in)
+  // [5] BVH nodes visited [6] triangles tested [7] shadow jobs (opaque hits queued)
   unsigned long long* stats;
 };
 

@@ -1,0 +1,65 @@
+// lisa_b200/host/main.cc — the CLI (src/LiSA/src/main.cc:6-28, include/parse_args.hh:3-16).
+//   lisa -s scene.rto [-d]
+// -s <scene> is mandatory; without it the usage goes to stderr and the exit code is 1.  -d selects the
+// progressive mode (headless here).  Extra, optional: --stats prints one JSON line with the counters of
+// include/lisa_rt.h:lisa_stats; environment variables LISA_BVH/LISA_SHADOW/LISA_MAX_CHAINS select
+// ablation variants (see lisa_rt.cu).
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <iostream>
+#include <string>
+
+#include "render.hh"
+#include "scene_parser.hh"
+
+static char* getCmdOption(char** begin, char** end, const std::string& option) {
+  char** itr = std::find(begin, end, option);
+  if (itr != end && ++itr != end) return *itr;
+  return nullptr;
+}
+static bool cmdOptionExists(char** begin, char** end, const std::string& option) { return std::find(begin, end, option) != end; }
+
+int main(int argc, char** argv) {
+  char* scene_path = nullptr;
+  if (cmdOptionExists(argv, argv + argc, "-s")) scene_path = getCmdOption(argv, argv + argc, "-s");
+  if (!scene_path) {
+    std::cerr << "Missing scene path." << std::endl;
+    std::cerr << "Usage: " << argv[0] << " -s scene_path" << std::endl;
+    return 1;
+  }
+  try {
+    SceneParser     parser(scene_path);
+    lisa_scene_desc params = parser.get_params();
+    lisa_ctx*       ctx = nullptr;
+    if (lisa_create(&params, nullptr, &ctx) != LISA_OK) {
+      // the reference throws sutil::Exception out of OptixWrapper's constructor and aborts
+      std::cerr << "lisa: " << lisa_last_error() << std::endl;
+      return 134;
+    }
+    printf("Starting rendering...\n");
+    if (cmdOptionExists(argv, argv + argc, "-d")) display(ctx, params);
+    else render(ctx, params);
+    if (cmdOptionExists(argv, argv + argc, "--stats")) {
+      lisa_stats s;
+      s.struct_size = sizeof(s);
+      lisa_get_stats(ctx, &s);
+      printf("{\"triangles\": %u, \"bvh_nodes\": %u, \"bvh_build_ms\": %.3f, \"render_ms\": %.3f, \"samples\": %llu, "
+             "\"radiance_rays\": %llu, \"shadow_rays\": %llu, \"msamples_per_s\": %.3f, \"mrays_per_s\": %.3f, "
+             "\"kernel_launches\": %llu}\n",
+             s.num_triangles, s.bvh_nodes, s.bvh_build_ms, s.render_ms, (unsigned long long)s.samples,
+             (unsigned long long)s.radiance_rays, (unsigned long long)s.shadow_rays, s.samples / s.render_ms / 1e3,
+             (s.radiance_rays + s.shadow_rays) / s.render_ms / 1e3, (unsigned long long)s.kernel_launches);
+    }
+    lisa_destroy(ctx);
+  } catch (const SceneError& e) {
+    std::string m = e.what();
+    std::cerr << m;
+    if (m.empty() || m.back() != '\n') std::cerr << std::endl;
+    return e.exit_code & 0xff;
+  } catch (const std::exception& e) {
+    std::cerr << "lisa: " << e.what() << std::endl;
+    return 134;
+  }
+  return 0;
+}

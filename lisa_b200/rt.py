@@ -21,6 +21,7 @@ _L = ctypes.CDLL(LIB_PATH)
 LISA_OK = 0
 SHADOW_CLOSEST, SHADOW_FIRST_FOUND = 0, 1
 BVH_WIDE8, BVH_BINARY = 0, 1
+FLAG_PROFILE_STAGES = 1
 
 
 class Material(ctypes.Structure):
@@ -56,7 +57,11 @@ class Stats(ctypes.Structure):
                 ("last_samples", ctypes.c_uint64), ("last_radiance_rays", ctypes.c_uint64),
                 ("last_shadow_rays", ctypes.c_uint64), ("last_kernel_launches", ctypes.c_uint64),
                 ("last_extend_ms", ctypes.c_double), ("last_shadow_ms", ctypes.c_double),
-                ("state_bytes", ctypes.c_uint64), ("subframes_accumulated", ctypes.c_uint32), ("_reserved", ctypes.c_uint32)]
+                ("state_bytes", ctypes.c_uint64), ("subframes_accumulated", ctypes.c_uint32), ("_reserved", ctypes.c_uint32),
+                ("last_extend_launches", ctypes.c_uint64), ("last_shadow_launches", ctypes.c_uint64),
+                ("last_shadow_jobs", ctypes.c_uint64), ("nodes_visited", ctypes.c_uint64),
+                ("triangles_tested", ctypes.c_uint64), ("last_nodes_visited", ctypes.c_uint64),
+                ("last_triangles_tested", ctypes.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if not k.startswith("_")}
@@ -125,7 +130,8 @@ class Renderer:
     """One lisa_ctx: OptixWrapper + render() of the reference behind the C ABI."""
 
     def __init__(self, vertices, normals, mat_indices, materials, width, height, eye, look_at, fov, num_samples=1,
-                 num_bounces=7, output_image=None, device=-1, shadow_mode=SHADOW_CLOSEST, bvh_kind=BVH_WIDE8, max_chains=0):
+                 num_bounces=7, output_image=None, device=-1, shadow_mode=SHADOW_CLOSEST, bvh_kind=BVH_WIDE8, max_chains=0,
+                 flags=0):
         self._v = np.ascontiguousarray(vertices, dtype=np.float32).reshape(-1, 3)
         self._n = np.ascontiguousarray(normals, dtype=np.float32).reshape(-1, 3)
         self._m = np.ascontiguousarray(mat_indices, dtype=np.int32).reshape(-1)
@@ -148,7 +154,7 @@ class Renderer:
         sd.camera.fov = float(fov)
         sd.num_samples, sd.num_bounces = num_samples, num_bounces
         sd.output_image = output_image.encode() if output_image else None
-        opt = Options(ctypes.sizeof(Options), device, shadow_mode, bvh_kind, max_chains, 0)
+        opt = Options(ctypes.sizeof(Options), device, shadow_mode, bvh_kind, max_chains, flags)
         self.width, self.height = width, height
         self.num_samples, self.num_bounces = num_samples, num_bounces
         self._h = _vp()

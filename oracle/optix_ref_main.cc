@@ -114,13 +114,22 @@ int main(int argc, char** argv) {
     launch(state, d_frame);
   }
   state.params.samples_per_launch = spp;
+  /* --warmup-steps W: W untimed launches of the SAME size (bench.py's warm-up steps) */
+  unsigned warm = opt(argc, argv, "--warmup-steps") ? (unsigned)atoi(opt(argc, argv, "--warmup-steps")) : 0;
+  for (unsigned w = 0; w < warm; w++) {
+    state.params.subframe_index = 1000000u + w;
+    launch(state, d_frame);
+  }
+  std::vector<double> step_ms;
   auto t0                         = std::chrono::steady_clock::now();
   for (unsigned f = 0; f < subframes; f++) {
+    auto ts = std::chrono::steady_clock::now();
     /* the shader merges with lerp(prev, cur, 1/(subframe_index+1)); a run that
      * starts at first>0 therefore needs prev==0 weighting handled by the
      * caller — only first==0 gives a plain mean. */
     state.params.subframe_index = first + f;
     launch(state, d_frame);
+    step_ms.push_back(std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - ts).count());
   }
   double render_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
 
@@ -152,9 +161,11 @@ int main(int argc, char** argv) {
   double samples = (double)npix * spp * subframes;
   printf("{\"impl\": \"optix_ref\", \"width\": %u, \"height\": %u, \"spp\": %u, \"subframes\": %u, \"bounces\": %u, "
          "\"triangles\": %d, \"setup_ms\": %.3f, \"render_ms\": %.3f, \"msamples_per_s\": %.4f, "
-         "\"mean_rgb\": [%.8g, %.8g, %.8g]}\n",
+         "\"mean_rgb\": [%.8g, %.8g, %.8g], \"step_ms\": [",
          state.params.width, state.params.height, spp, subframes, state.params.num_bounces, params.num_vertices / 3,
          setup_ms, render_ms, samples / render_ms / 1e3, sum[0] / npix, sum[1] / npix, sum[2] / npix);
+  for (size_t i = 0; i < step_ms.size(); i++) printf("%s%.3f", i ? ", " : "", step_ms[i]);
+  printf("]}\n");
   fflush(stdout);
   /* skip ~OptixWrapper's teardown ordering issues on error paths: normal return runs it */
   return 0;

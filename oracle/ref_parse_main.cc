@@ -18,6 +18,7 @@ int main(int argc, char** argv) {
   fprintf(f, "{\"width\": %u, \"height\": %u, \"num_samples\": %u, \"num_bounces\": %u, \"output_image\": \"",
           p.width, p.height, p.num_samples, p.num_bounces);
   for (const char* c = p.output_image; *c; c++) {
+    if ((unsigned char)*c < 0x20) { fprintf(f, "\\u%04x", (unsigned)(unsigned char)*c); continue; }
     if (*c == '"' || *c == '\\') fputc('\\', f);
     fputc(*c, f);
   }

@@ -1,0 +1,120 @@
+"""Image parity of the CUDA path, through the C ABI, on the README Cornell scene.
+
+Checker 1: accumulators dumped by the UNMODIFIED reference OptiX renderer on a B200
+(tests/golden/optix_*.npz).  Checker 2: the oracle (oracle/cpu_ref.c) on the same seeded inputs.
+All three use tea<16>(pixel, subframe) + LCG (north_star: "the reference's per-pixel RNG seeding").
+Bars (floating point, stated per test):
+  * equal-spp, per pixel: a pixel whose decisions all agree reproduces the reference to 1e-4 absolute;
+    >= 99.5 % of pixels at 1 spp, >= 95 % at 16 spp, >= 85 % at 64 spp (chains diverge after one
+    differing decision, so the matching fraction decays with spp);
+  * relMSE at equal spp within the Monte-Carlo noise band: relMSE(ours, ref_1024) <= 1.25 x
+    relMSE(ref_64, ref_1024) on 8x8 block means;
+  * means within 1 % of the reference's (north_star: converged mean agrees within 1 %).
+Size-independent properties at the full BASELINE sizes are in test_gpu_properties.py.
+"""
+import numpy as np
+import pytest
+
+from conftest import golden, resized
+
+pytestmark = pytest.mark.gpu
+
+
+def _render(rt, sc, w, spp, first=0, count=1, **kw):
+    R = rt.Renderer.from_scene(resized(sc, w), **kw)
+    R.render_subframes(first, count, spp)
+    return R.read_accum()[..., :3], R.stats()
+
+
+@pytest.mark.parametrize("bvh", [0, 1], ids=["wide8", "binary"])
+def test_1spp_matches_reference_optix(rt, cornell, bvh):
+    acc, st = _render(rt, cornell, 64, 1, bvh_kind=bvh)
+    ref = golden("optix_tiny_1")["accum"]
+    assert (np.abs(acc - ref).max(axis=2) < 1e-4).mean() >= 0.995
+    acc, st = _render(rt, cornell, 512, 1, bvh_kind=bvh)
+    g = golden("optix_c1_1")
+    o = g["crop_origin"]
+    assert (np.abs(acc[o[0]:o[0] + 128, o[1]:o[1] + 128] - g["crop"]).max(axis=2) < 1e-4).mean() >= 0.995
+    np.testing.assert_allclose(acc.reshape(-1, 3).mean(0), g["mean_rgb"], rtol=0.01)
+    b8 = acc.reshape(64, 8, 64, 8, 3).mean(axis=(1, 3))
+    assert np.abs(b8 - g["block8"]).max() < 0.02
+
+
+def test_16spp_and_subframes_match_reference_optix(rt, cornell):
+    acc, _ = _render(rt, cornell, 64, 16)
+    g = golden("optix_tiny_16")
+    assert (np.abs(acc - g["accum"]).max(axis=2) < 1e-4).mean() >= 0.95
+    np.testing.assert_allclose(acc.reshape(-1, 3).mean(0), g["mean_rgb"], rtol=0.01)
+    # display() mode: 4 subframes x 4 spp, equal-weight merge == the reference's running mean
+    acc, _ = _render(rt, cornell, 64, 4, 0, 4)
+    g = golden("optix_tiny_4x4")
+    assert (np.abs(acc - g["accum"]).max(axis=2) < 1e-4).mean() >= 0.95
+    np.testing.assert_allclose(acc.reshape(-1, 3).mean(0), g["mean_rgb"], rtol=0.01)
+
+
+def test_c1_config_against_reference(rt, cornell):
+    """BASELINE configs[0]: 512x512, 64 spp, 7 bounces."""
+    acc, st = _render(rt, cornell, 512, 64)
+    g64, g1024 = golden("optix_c1"), golden("optix_c1_1024")
+    o = g64["crop_origin"]
+    assert (np.abs(acc[o[0]:o[0] + 128, o[1]:o[1] + 128] - g64["crop"]).max(axis=2) < 1e-4).mean() >= 0.85
+    np.testing.assert_allclose(acc.reshape(-1, 3).mean(0), g64["mean_rgb"], rtol=0.01)
+    np.testing.assert_allclose(acc.reshape(-1, 3).mean(0), g1024["mean_rgb"], rtol=0.01)
+    b8 = acc.reshape(64, 8, 64, 8, 3).mean(axis=(1, 3))
+    conv = g1024["block8"]
+    relmse = lambda a: float((((a - conv) ** 2) / (conv ** 2 + 1e-4)).mean())
+    assert relmse(b8) <= 1.25 * relmse(g64["block8"]) + 1e-6
+    assert st["last_samples"] == 512 * 512 * 64
+    rays = (st["last_radiance_rays"] + st["last_shadow_rays"]) / st["last_samples"]
+    assert 60 < rays < 80  # the oracle counts 71.2 rays per sample on this scene
+
+
+def test_converged_mean_within_1_percent(rt, cornell):
+    acc, _ = _render(rt, cornell, 64, 1024)
+    g = golden("optix_tiny_1024")
+    np.testing.assert_allclose(acc.reshape(-1, 3).mean(0), g["mean_rgb"], rtol=0.01)
+    lum = lambda a: a.sum(-1)
+    rel = np.abs(lum(acc) - lum(g["accum"])) / (lum(g["accum"]) + 1e-2)
+    assert np.median(rel) < 0.04 and np.percentile(rel, 99) < 0.5
+
+
+def test_matches_oracle_same_seeds(rt, orc, cornell):
+    """GPU vs the CPU restatement on identical seeded inputs, plus identical ray statistics."""
+    S = orc.Scene(cornell["vertices"], cornell["normals"], cornell["mat_indices"], cornell["materials_packed"])
+    cam = cornell["camera"]
+    for (w, spp, bounces, frac) in ((48, 1, 7, 0.995), (48, 8, 7, 0.97), (40, 4, 1, 0.999), (40, 4, 2, 0.99), (32, 3, 12, 0.98)):
+        ref, cnt = S.render(cam["eye"], cam["look_at"], cam["fov"], w, w, bounces, spp)
+        R = rt.Renderer.from_scene(resized(cornell, w, bounces=bounces))
+        R.render_subframes(0, 1, spp)
+        acc, st = R.read_accum(), R.stats()
+        assert (np.abs(acc[..., :3] - ref[..., :3]).max(axis=2) < 1e-4).mean() >= frac, (w, spp, bounces)
+        assert (acc[..., 3] == 1).all()
+        for k, tol in (("radiance_rays", 0.005), ("shadow_rays", 0.02)):
+            assert abs(st["last_" + k] - cnt[k]) <= tol * cnt[k] + 8, (k, st["last_" + k], cnt[k])
+        assert abs(st["null_directions"] - cnt["null_dirs"]) <= 0.05 * cnt["null_dirs"] + 8
+
+
+def test_primary_rays_bitwise_seeds(rt, orc, cornell):
+    import ctypes
+    R = rt.Renderer.from_scene(resized(cornell, 2000))
+    d, s = R.primary_rays(0)
+    L = orc.lib()
+    cam = cornell["camera"]
+    f3 = lambda v: (ctypes.c_float * 3)(*v)
+    rng = np.random.default_rng(2)
+    for (x, y) in [(0, 0), (1999, 0), (0, 1999), (1999, 1999), (1000, 1000)] + [tuple(rng.integers(0, 2000, 2)) for _ in range(200)]:
+        out = (ctypes.c_float * 3)()
+        sa = ctypes.c_uint32(0)
+        L.orc_primary_ray(f3(cam["eye"]), f3(cam["look_at"]), cam["fov"], 2000, 2000, int(x), int(y), 0, out, ctypes.byref(sa))
+        assert int(s[y, x]) == sa.value                       # seeds: bitwise
+        np.testing.assert_allclose(d[y, x], list(out), rtol=0, atol=3e-7)  # directions: ~1 ulp (rsqrt.approx)
+
+
+
+def test_shadow_policy_sensitivity(rt, cornell):
+    """Q2: closest-hit-decides (default) vs first-found (emitters first): report the mean shift."""
+    a, _ = _render(rt, cornell, 128, 32, shadow_mode=0)
+    b, _ = _render(rt, cornell, 128, 32, shadow_mode=1)
+    shift = b.reshape(-1, 3).mean(0) / a.reshape(-1, 3).mean(0)
+    assert (shift >= 0.999).all()      # ignoring occluders in front of the light can only brighten
+    assert (shift < 1.5).all()

@@ -1,0 +1,116 @@
+"""Size-independent properties of the CUDA path at (and around) BASELINE.json's full sizes, plus the
+output stage (tonemap, PPM) and the host render()/display() drivers."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, resized
+
+pytestmark = pytest.mark.gpu
+
+
+def test_deterministic_and_tiling_invariant(rt, cornell):
+    """Chains own their RNG streams: re-running, or running with a different number of resident chains
+    (different tiles / queue orders), gives bit-identical accumulators."""
+    sc = resized(cornell, 96)
+    imgs = []
+    for mc in (0, 0, 3000, 96 * 96, 2 * 96 * 96 + 5):
+        R = rt.Renderer.from_scene(sc, max_chains=mc)
+        R.render_subframes(0, 3, 4)
+        imgs.append(R.read_accum())
+    for im in imgs[1:]:
+        np.testing.assert_array_equal(imgs[0], im)
+
+
+def test_subframe_additivity(rt, cornell):
+    """render(0..3) == equal-weight merge of render(0..1) and render(2..3): the identity the multi-GPU
+    partition relies on (lisa_b200/dist.py)."""
+    sc = resized(cornell, 64)
+    R = rt.Renderer.from_scene(sc)
+    R.render_subframes(0, 4, 2)
+    full = R.read_accum()
+    R.reset()
+    R.render_subframes(0, 2, 2)
+    a = R.read_accum()
+    R.reset()
+    R.render_subframes(2, 2, 2)
+    b = R.read_accum()
+    np.testing.assert_allclose(full[..., :3], 0.5 * (a[..., :3] + b[..., :3]), rtol=2e-6, atol=1e-7)
+    # accumulating across calls is the same as one call
+    R.reset()
+    R.render_subframes(0, 2, 2)
+    R.render_subframes(2, 2, 2)
+    np.testing.assert_allclose(R.read_accum(), full, rtol=2e-6, atol=1e-7)
+    assert R.stats()["subframes_accumulated"] == 4
+
+
+def test_full_resolution_c2_smoke_properties(rt, cornell):
+    """2000x2000 (BASELINE configs[1] resolution), few spp: energy bounds, black border, ray budget."""
+    sc = resized(cornell, 2000)
+    R = rt.Renderer.from_scene(sc)
+    R.render_subframes(0, 1, 2)
+    acc, st = R.read_accum(), R.stats()
+    assert np.isfinite(acc).all() and (acc[..., :3] >= 0).all()
+    # radiance <= sum over <=7 bounces of emission(1) * brdf(<=1/pi) + one emitter hit  (Q3)
+    assert acc[..., :3].max() <= 1.0 + 7 / np.pi + 1e-3
+    assert acc[:, :60, :3].max() == 0 and acc[:, -60:, :3].max() == 0  # camera sees past the box edges: miss = 0
+    assert st["last_samples"] == 2000 * 2000 * 2
+    assert st["last_radiance_rays"] <= 7 * st["last_samples"]
+    assert st["last_shadow_rays"] <= 30 * st["last_radiance_rays"]
+    np.testing.assert_allclose(acc[..., :3].reshape(-1, 3).mean(0), [0.08631, 0.09263, 0.04085], rtol=0.02)  # OptiX 1024-spp mean
+
+
+def test_zero_bounces_and_one_bounce(rt, cornell):
+    R = rt.Renderer.from_scene(resized(cornell, 32, bounces=0))
+    R.render_subframes(0, 1, 2)
+    assert float(R.read_accum()[..., :3].max()) == 0.0
+    R = rt.Renderer.from_scene(resized(cornell, 64, bounces=1))
+    R.render_subframes(0, 1, 4)
+    a = R.read_accum()[..., :3]
+    assert a.max() <= 1.0 + 1 / np.pi + 1e-4 and a[60, 32].min() > 0.99  # the light itself
+
+
+def test_rgba8_and_ppm(rt, orc, cornell, tmp_path):
+    import ctypes
+    R = rt.Renderer.from_scene(resized(cornell, 80, 48))
+    R.render_subframes(0, 1, 8)
+    acc, px = R.read_accum(), R.read_rgba8()
+    exp = np.zeros_like(px)
+    L = orc.lib()
+    for y in range(48):
+        for x in range(80):
+            o = (ctypes.c_uint8 * 4)()
+            L.orc_make_color((ctypes.c_float * 3)(*acc[y, x, :3]), o)
+            exp[y, x] = list(o)
+    diff = np.abs(px.astype(int) - exp.astype(int))
+    assert diff.max() <= 1 and (diff > 0).mean() < 0.01  # fast-math powf may move a value across one boundary
+    assert (px[..., 3] == 255).all()
+    p = str(tmp_path / "o.ppm")
+    R.write_ppm(p)
+    raw = open(p, "rb").read()
+    hdr = b"P6\n80 48\n255\n"
+    assert raw.startswith(hdr) and len(raw) == len(hdr) + 80 * 48 * 3
+    img = np.frombuffer(raw[len(hdr):], np.uint8).reshape(48, 80, 3)
+    np.testing.assert_array_equal(img, px[::-1, :, :3])  # rows reversed, alpha dropped
+
+
+def test_host_render_and_display(rt, frontend, tmp_path, capfd):
+    """render()/display() of the reference (render.cc:133-148, 75-131) through liblisa_host.so."""
+    os.makedirs(os.path.join(ROOT, "out"), exist_ok=True)
+    sc = frontend.Scene("scenes/cornell_tiny.rto")
+    d = sc.as_dict()
+    out = os.path.join(ROOT, d["output_image"])
+    imgs = []
+    for progressive in (False, True):
+        if os.path.exists(out):
+            os.remove(out)
+        R = rt.Renderer.from_scene(d)
+        frontend.host_render(R, sc, progressive)
+        so = capfd.readouterr().out
+        assert "Rendering finished in " in so
+        assert os.path.exists(out)
+        imgs.append(R.read_accum())
+        assert R.stats()["samples"] == 64 * 64 * 16
+    # -s (1 x 16 spp, subframe 0) and -d (1 x 16 spp, subframe 0) coincide for num_samples = 16
+    np.testing.assert_array_equal(imgs[0], imgs[1])

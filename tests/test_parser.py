@@ -1,0 +1,120 @@
+"""Scene front-end: the product's C++ SceneParser/parse_obj (lisa_b200/host, through include/lisa_host.h)
+and the oracle's Python restatement, both against dumps of the reference's own parser
+(tests/golden/ref_parse_*.json, produced by oracle/ref_parse_main.cc which compiles the reference's
+scene_parser.cc + parse_obj.cc in place).  Covers the grammar quirks listed in SURVEY.md §8a-P."""
+import glob
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT
+
+CASES = sorted(glob.glob(os.path.join(GOLDEN, "ref_parse_*.json")))
+
+
+def _scene_path(name):
+    for d in ("scenes", os.path.join("tests", "golden", "parser_cases")):
+        p = os.path.join(d, name + ".rto")
+        if os.path.exists(os.path.join(ROOT, p)):
+            return p
+    raise FileNotFoundError(name)
+
+
+def _check_against(ref, got):
+    for k in ("width", "height", "num_samples", "num_bounces", "output_image"):
+        assert got[k] == ref[k], k
+    for k in ("eye", "look_at"):
+        np.testing.assert_array_equal(np.float32(got["camera"][k]), np.float32(ref["camera"][k]))
+    assert np.float32(got["camera"]["fov"]) == np.float32(ref["camera"]["fov"])
+    assert got["vertices"].shape[0] == ref["num_vertices"]
+    assert len(got["materials"]) == ref["num_materials"]
+    for gm, rm in zip(got["materials"], ref["materials"]):
+        assert bool(gm["emit"]) == rm["emit"]
+        assert np.float32(gm["alpha"]) == np.float32(rm["alpha"])
+        for k in ("emission", "diffuse"):
+            if k in rm:
+                np.testing.assert_allclose(np.float32(gm[k]), np.float32(rm[k]), rtol=1e-7)
+        for k in ("n", "roughness"):
+            if k in rm:
+                assert np.float32(gm[k]) == np.float32(rm[k])
+    # geometry: run-length material indices, checksums and the first triangles verbatim
+    mi, rle = got["mat_indices"], []
+    i = 0
+    while i < len(mi):
+        j = i
+        while j < len(mi) and mi[j] == mi[i]:
+            j += 1
+        rle.append([int(mi[i]), j - i])
+        i = j
+    assert rle == ref["mat_indices_rle"]
+    v, n = got["vertices"].reshape(-1).astype(np.float64), got["normals"].reshape(-1).astype(np.float64)
+    assert abs(v.sum() - ref["vertex_sum"]) <= 1e-9 * max(1, abs(ref["vertex_sum"])) + 1e-9
+    assert abs(n.sum() - ref["normal_sum"]) <= 1e-9 * max(1, abs(ref["normal_sum"])) + 1e-9
+    wv = (v * ((np.arange(v.size) % 251) + 1)).sum()
+    assert abs(wv - ref["vertex_wsum"]) <= 1e-9 * max(1, abs(ref["vertex_wsum"])) + 1e-9
+    k = len(ref["first_vertices"])
+    np.testing.assert_array_equal(np.float32(v[:k]), np.float32(ref["first_vertices"]))
+    np.testing.assert_array_equal(np.float32(n[:k]), np.float32(ref["first_normals"]))
+
+
+@pytest.mark.parametrize("case", CASES, ids=[os.path.basename(c)[10:-5] for c in CASES])
+def test_product_parser_matches_reference(case, frontend, capfd):
+    ref = json.load(open(case))
+    path = _scene_path(os.path.basename(case)[10:-5])
+    if "error" in ref:
+        with pytest.raises(frontend.SceneError) as e:
+            frontend.parse_scene(path)
+        assert str(e.value).strip() == ref["error"].strip()
+        assert (e.value.code & 0xff) == ref["exit"]
+    else:
+        _check_against(ref, frontend.parse_scene(path))
+
+
+@pytest.mark.parametrize("case", CASES, ids=[os.path.basename(c)[10:-5] for c in CASES])
+def test_oracle_parser_matches_reference(case):
+    from oracle import scene_py
+    ref = json.load(open(case))
+    path = _scene_path(os.path.basename(case)[10:-5])
+    if "error" in ref:
+        with pytest.raises(scene_py.SceneError) as e:
+            scene_py.parse_scene(path)
+        assert str(e.value).strip() == ref["error"].strip()
+        assert (e.value.code & 0xff) == ref["exit"]
+    else:
+        _check_against(ref, scene_py.parse_scene(path))
+
+
+def test_readme_scene_verbatim(frontend):
+    """The README scene text (README.md:47-131 of the reference), unmodified."""
+    sc = frontend.parse_scene(os.path.join("tests", "golden", "readme_scene.rto"), load_meshes=False)
+    assert (sc["width"], sc["height"], sc["num_samples"], sc["num_bounces"]) == (2000, 2000, 2000, 7)
+    assert sc["output_image"] == "../../images/cornel_box.ppm"
+    assert len(sc["materials"]) == 5 and len(sc["mesh_files"]) == 9
+    assert sc["mesh_files"][6] == ("assets/objs/cornell_box/small_box.obj", 1)
+    assert sc["materials"][1]["n"] == 1.5 and sc["materials"][1]["alpha"] == 0.0
+    assert sc["materials"][4]["emit"] and tuple(sc["materials"][4]["emission"]) == (1.0, 1.0, 1.0)
+
+
+def test_missing_scene_file(frontend):
+    with pytest.raises(frontend.SceneError) as e:
+        frontend.parse_scene("no/such/file.rto")
+    assert "no/such/file.rto not found" in str(e.value) and e.value.code == 1
+
+
+def test_remove_comments_large_input(frontend, tmp_path):
+    """The reference's comment regex recurses per character; the scanner must take megabytes."""
+    p = tmp_path / "big.rto"
+    body = "/*" + "x\n" * 2_000_000 + "*/\n" + open("tests/golden/parser_cases/no_mesh_no_eol.rto").read()
+    p.write_text(body)
+    sc = frontend.parse_scene(str(p))
+    assert sc["num_samples"] == 7 and sc["camera"]["fov"] == 33.25
+
+
+def test_quad_truncated_and_indices(frontend):
+    sc = frontend.parse_scene("tests/golden/parser_cases/color255.rto")
+    v = sc["vertices"].reshape(-1, 3, 3)
+    assert v.shape[0] == 2
+    np.testing.assert_array_equal(v[1], [[0, 0, 0], [1, 0, 0], [1, 1, 0.5]])  # 4th vertex of the quad dropped
+    np.testing.assert_array_equal(sc["normals"].reshape(-1, 3, 3)[0], [[0, 0, 1], [0, 0, 1], [0, 1, 0]])
