@@ -88,7 +88,8 @@ typedef struct lisa_scene_desc {
 
 enum { LISA_SHADOW_CLOSEST = 0, LISA_SHADOW_FIRST_FOUND = 1 };
 enum { LISA_BVH_WIDE8 = 0, LISA_BVH_BINARY = 1 };
-enum { LISA_FLAG_PROFILE_STAGES = 1 };
+enum { LISA_FLAG_PROFILE_STAGES = 1, /* CUDA events around every stage launch */
+       LISA_FLAG_LBVH = 2            /* plain LBVH hierarchy (fastest build) instead of PLOC clustering */ };
 
 typedef struct lisa_options {
   uint32_t struct_size;   /* sizeof(lisa_options) */

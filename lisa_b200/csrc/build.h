@@ -13,6 +13,8 @@ struct BuildInput {
   int                  num_tris;
   int                  num_mats;
   int                  wide;       // 1: compressed 8-wide nodes, 0: binary nodes
+  int                  lbvh;       // 1: plain LBVH hierarchy (fast build), 0: PLOC (default, near-SAH quality)
+  int                  ploc_radius;
 };
 
 struct BuildOutput {
@@ -24,6 +26,7 @@ struct BuildOutput {
   int     root_other, root_emit;
   int     num_emit_tris;
   size_t  node_bytes;
+  float   box_other[6], box_emit[6];  // root bounds (lo.xyz, hi.xyz) of the two partitions
 };
 
 // Returns 0 or a negative lisa_status; on failure err holds a message.  Synchronises the stream.

@@ -5,8 +5,12 @@
 //   2. k_morton            63-bit Morton key per triangle; bit 63 = "triangle emits", so one sort also
 //                          partitions the soup into non-emitters | emitters
 //   3. radix sort          (key, triangle id) pairs                           [cub::DeviceRadixSort]
-//   4. k_karras            LBVH hierarchy per partition (Karras 2012), one thread per internal node
-//   5. k_refit             leaf boxes + bottom-up box refit with arrival counters
+//   4a. PLOC (default)     parallel locally-ordered clustering over the Morton order (Meister & Bittner 2018):
+//                          per round k_ploc_nn (nearest neighbour by merged surface area within +-radius),
+//                          k_ploc_merge (mutual pairs become a node), stream compaction; ~log n rounds.
+//                          Near-SAH quality: large wall triangles stay near the root, small ones cluster first.
+//   4b. LBVH (fast build)  k_karras hierarchy per partition (Karras 2012), one thread per internal node,
+//   5.                     then k_refit: leaf boxes + bottom-up box refit with arrival counters
 //   6a. k_emit_binary      binary traversal nodes (ablation path)          -- or --
 //   6b. k_collapse8        level-by-level collapse into compressed 8-wide nodes (Ylitie et al. 2017):
 //                          greedy largest-area child opening, octant-affinity slot assignment,
@@ -15,6 +19,7 @@
 // Algorithmic bytes per triangle: 72 read soup + 12 key/id + sort 8 passes x 24 +
 // 2 x 80 hierarchy/refit + ~40 collapse + 96 packed write.
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_select.cuh>
 #include <cfloat>
 #include <cstdio>
 
@@ -102,7 +107,7 @@ __device__ __forceinline__ int delta(const unsigned long long* __restrict__ keys
 }
 
 // Node ids inside one partition with n leaves: internal 0..n-2, leaf j -> (n-1)+j.  Arrays are the partition's slices.
-__global__ void k_karras(const unsigned long long* __restrict__ keys, int n, int2* child, int* parent, int2* range) {
+__global__ void k_karras(const unsigned long long* __restrict__ keys, int n, int2* child, int* parent, int* cnt) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n - 1) return;
   int d     = (delta(keys, n, i, i + 1) - delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
@@ -125,7 +130,7 @@ __global__ void k_karras(const unsigned long long* __restrict__ keys, int n, int
   int left  = (lo == gamma) ? (n - 1) + gamma : gamma;
   int right = (hi == gamma + 1) ? (n - 1) + gamma + 1 : gamma + 1;
   child[i]  = make_int2(left, right);
-  range[i]  = make_int2(lo, hi);
+  cnt[i]    = hi - lo + 1;
   parent[left]  = i;
   parent[right] = i;
   if (i == 0) parent[0] = -1;
@@ -155,6 +160,66 @@ __global__ void k_refit(const float* __restrict__ verts, const unsigned int* __r
     cur = parent[cur];
   }
 }
+
+// ---- PLOC ------------------------------------------------------------------------------------------
+__global__ void k_leaf_boxes(const float* __restrict__ verts, const unsigned int* __restrict__ ids, int n, float4* box_lo,
+                             float4* box_hi, int* C) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const float* p = verts + 9ll * ids[j];
+  box_lo[(n - 1) + j] = make_float4(fminf(p[0], fminf(p[3], p[6])), fminf(p[1], fminf(p[4], p[7])), fminf(p[2], fminf(p[5], p[8])), 0.0f);
+  box_hi[(n - 1) + j] = make_float4(fmaxf(p[0], fmaxf(p[3], p[6])), fmaxf(p[1], fmaxf(p[4], p[7])), fmaxf(p[2], fmaxf(p[5], p[8])), 0.0f);
+  C[j] = (n - 1) + j;
+}
+
+__device__ __forceinline__ float merged_half_area(const float4& l0, const float4& h0, const float4& l1, const float4& h1) {
+  float dx = fmaxf(h0.x, h1.x) - fminf(l0.x, l1.x), dy = fmaxf(h0.y, h1.y) - fminf(l0.y, l1.y),
+        dz = fmaxf(h0.z, h1.z) - fminf(l0.z, l1.z);
+  return dx * dy + dy * dz + dz * dx;
+}
+
+// nearest neighbour of cluster i among positions [i-r, i+r]; ties go to the smaller position, which guarantees
+// that at least one mutual pair exists every round
+__global__ void k_ploc_nn(const int* __restrict__ C, int m, const float4* __restrict__ box_lo, const float4* __restrict__ box_hi,
+                          int r, int* nn) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const float4 l = box_lo[C[i]], h = box_hi[C[i]];
+  float best = FLT_MAX;
+  int   bj = -1;
+  const int j0 = max(0, i - r), j1 = min(m - 1, i + r);
+  for (int j = j0; j <= j1; j++) {
+    if (j == i) continue;
+    const int   c = C[j];
+    const float a = merged_half_area(l, h, box_lo[c], box_hi[c]);
+    if (a < best) { best = a; bj = j; }
+  }
+  nn[i] = bj;
+}
+
+__global__ void k_ploc_merge(const int* __restrict__ C, int m, const int* __restrict__ nn, float4* box_lo, float4* box_hi,
+                             int2* child, int* cnt, int n, int* next_internal, int* Cout) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const int j = nn[i];
+  if (j >= 0 && nn[j] == i) {
+    if (i < j) {
+      const int id = atomicAdd(next_internal, 1);
+      const int a = C[i], b = C[j];
+      const float4 l0 = box_lo[a], h0 = box_hi[a], l1 = box_lo[b], h1 = box_hi[b];
+      box_lo[id] = make_float4(fminf(l0.x, l1.x), fminf(l0.y, l1.y), fminf(l0.z, l1.z), 0.0f);
+      box_hi[id] = make_float4(fmaxf(h0.x, h1.x), fmaxf(h0.y, h1.y), fmaxf(h0.z, h1.z), 0.0f);
+      child[id]  = make_int2(a, b);
+      cnt[id]    = (a >= n - 1 ? 1 : cnt[a]) + (b >= n - 1 ? 1 : cnt[b]);
+      Cout[i]    = id;
+    } else {
+      Cout[i] = -1;
+    }
+  } else {
+    Cout[i] = C[i];
+  }
+}
+struct IsValidCluster { __host__ __device__ bool operator()(const int& v) const { return v >= 0; } };
 
 // ---- binary traversal nodes -----------------------------------------------------------------------
 // One node per internal Karras node; tri_base = first final triangle index of the partition.
@@ -189,18 +254,24 @@ __device__ __forceinline__ float half_area(const float4& lo, const float4& hi) {
   float dx = hi.x - lo.x, dy = hi.y - lo.y, dz = hi.z - lo.z;
   return dx * dy + dy * dz + dz * dx;
 }
-__device__ __forceinline__ int node_count(int node, int n, const int2* __restrict__ range) {
-  if (node >= n - 1) return 1;
-  int2 r = range[node];
-  return r.y - r.x + 1;
+__device__ __forceinline__ int node_count(int node, int n, const int* __restrict__ cnt) {
+  return node >= n - 1 ? 1 : cnt[node];
 }
-__device__ __forceinline__ int node_first(int node, int n, const int2* __restrict__ range) {
-  return node >= n - 1 ? node - (n - 1) : range[node].x;
+// leaves (sorted positions) of a subtree with at most LEAF_MAX triangles
+__device__ __forceinline__ int gather_leaves(int node, int n, const int2* __restrict__ child, int* out) {
+  int stack[2 * LEAF_MAX], sp = 0, k = 0;
+  stack[sp++] = node;
+  while (sp) {
+    int c = stack[--sp];
+    if (c >= n - 1) out[k++] = c - (n - 1);
+    else { int2 cc = child[c]; stack[sp++] = cc.y; stack[sp++] = cc.x; }
+  }
+  return k;
 }
 
 // counters: [0] next free wide node, [1] next free final triangle slot, [2] items in the output queue
 __global__ void k_collapse8(const WorkItem* __restrict__ in, int n_in, WorkItem* out_q, int n, const int2* __restrict__ child,
-                            const int2* __restrict__ range, const float4* __restrict__ box_lo,
+                            const int* __restrict__ range, const float4* __restrict__ box_lo,
                             const float4* __restrict__ box_hi, int* counters, float4* nodes,
                             unsigned int* final_to_sorted, int sorted_base) {
   int w = blockIdx.x * blockDim.x + threadIdx.x;
@@ -295,15 +366,17 @@ __global__ void k_collapse8(const WorkItem* __restrict__ in, int n_in, WorkItem*
       int   ql = (int)floorf((l3[a] - plo3[a]) * scale[a]);
       int   qh = (int)ceilf((h3[a] - plo3[a]) * scale[a]);
       ql = max(0, min(255, ql)); qh = max(0, min(255, qh));
-      while (ql > 0 && plo3[a] + (float)ql * step > l3[a]) ql--;     // stay conservative under rounding
-      while (qh < 255 && plo3[a] + (float)qh * step < h3[a]) qh++;
+      // conservative against the exact value of p + q*2^e (double holds it exactly)
+      while (ql > 0 && (double)plo3[a] + (double)ql * (double)step > (double)l3[a]) ql--;
+      while (qh < 255 && (double)plo3[a] + (double)qh * (double)step < (double)h3[a]) qh++;
       qlo[a][s] = (unsigned)ql; qhi[a][s] = (unsigned)qh;
     }
     int cnt = node_count(c, n, range);
     if (cnt <= LEAF_MAX) {
       meta[s]   = (((1u << cnt) - 1u) << 5) | (unsigned)tri_off;
-      int first = node_first(c, n, range);
-      for (int k = 0; k < cnt; k++) final_to_sorted[tri_base + tri_off + k] = (unsigned)(sorted_base + first + k);
+      int leaves[LEAF_MAX];
+      gather_leaves(c, n, child, leaves);
+      for (int k = 0; k < cnt; k++) final_to_sorted[tri_base + tri_off + k] = (unsigned)(sorted_base + leaves[k]);
       tri_off += cnt;
     } else {
       meta[s] = (1u << 5) | (24u + (unsigned)s);
@@ -384,27 +457,73 @@ int build_bvh(const BuildInput& in, BuildOutput* out, cudaStream_t st, char* err
   out->num_emit_tris = n_emit;
 
   // hierarchy storage for both partitions: partition p uses node slice [base_p, base_p + 2 n_p - 1)
-  int2 *  d_child, *d_range;
-  int *   d_parent, *d_flags;
+  int2*   d_child;
+  int *   d_range, *d_parent, *d_flags;  // d_range: triangles below each internal node
   float4 *d_lo, *d_hi;
   const size_t NN = 2ull * T + 2;
   CK(cudaMalloc(&d_child, sizeof(int2) * NN));
-  CK(cudaMalloc(&d_range, sizeof(int2) * NN));
+  CK(cudaMalloc(&d_range, sizeof(int) * NN));
   CK(cudaMalloc(&d_parent, sizeof(int) * NN));
   CK(cudaMalloc(&d_flags, sizeof(int) * NN));
   CK(cudaMalloc(&d_lo, sizeof(float4) * NN));
   CK(cudaMalloc(&d_hi, sizeof(float4) * NN));
   CK(cudaMemsetAsync(d_flags, 0, sizeof(int) * NN, st));
 
-  struct Part { int n, sorted_base, slice; } parts[2] = {{n_other, 0, 0}, {n_emit, n_other, 2 * n_other + 1}};
+  struct Part { int n, sorted_base, slice, root; } parts[2] = {{n_other, 0, 0, 0}, {n_emit, n_other, 2 * n_other + 1, 0}};
+  int *d_C[2] = {nullptr, nullptr}, *d_nn = nullptr, *d_sel = nullptr;
+  void*  d_sel_tmp = nullptr;
+  size_t sel_bytes = 0;
+  if (!in.lbvh) {
+    CK(cudaMalloc(&d_C[0], sizeof(int) * (size_t)T));
+    CK(cudaMalloc(&d_C[1], sizeof(int) * (size_t)T));
+    CK(cudaMalloc(&d_nn, sizeof(int) * (size_t)T));
+    CK(cudaMalloc(&d_sel, sizeof(int) * 2));
+    cub::DeviceSelect::If(nullptr, sel_bytes, d_C[0], d_C[1], d_sel, T, IsValidCluster(), st);
+    CK(cudaMalloc(&d_sel_tmp, sel_bytes ? sel_bytes : 16));
+  }
   for (int p = 0; p < 2; p++) {
-    const Part& P = parts[p];
+    Part& P = parts[p];
     if (P.n == 0) continue;
-    if (P.n > 1)
-      k_karras<<<cdiv(P.n - 1, 256), 256, 0, st>>>(d_keys2 + P.sorted_base, P.n, d_child + P.slice, d_parent + P.slice,
-                                                   d_range + P.slice);
-    k_refit<<<cdiv(P.n, 256), 256, 0, st>>>(in.d_verts, d_ids2 + P.sorted_base, P.n, d_child + P.slice,
-                                            d_parent + P.slice, d_lo + P.slice, d_hi + P.slice, d_flags + P.slice);
+    if (in.lbvh) {
+      if (P.n > 1)
+        k_karras<<<cdiv(P.n - 1, 256), 256, 0, st>>>(d_keys2 + P.sorted_base, P.n, d_child + P.slice, d_parent + P.slice,
+                                                     d_range + P.slice);
+      k_refit<<<cdiv(P.n, 256), 256, 0, st>>>(in.d_verts, d_ids2 + P.sorted_base, P.n, d_child + P.slice,
+                                              d_parent + P.slice, d_lo + P.slice, d_hi + P.slice, d_flags + P.slice);
+      P.root = 0;
+    } else {
+      k_leaf_boxes<<<cdiv(P.n, 256), 256, 0, st>>>(in.d_verts, d_ids2 + P.sorted_base, P.n, d_lo + P.slice, d_hi + P.slice, d_C[0]);
+      int m = P.n, cur = 0, h_next = 0;
+      int* d_next = d_sel + 1;
+      CK(cudaMemcpyAsync(d_next, &h_next, sizeof(int), cudaMemcpyHostToDevice, st));
+      while (m > 1) {
+        k_ploc_nn<<<cdiv(m, 128), 128, 0, st>>>(d_C[cur], m, d_lo + P.slice, d_hi + P.slice, in.ploc_radius, d_nn);
+        k_ploc_merge<<<cdiv(m, 256), 256, 0, st>>>(d_C[cur], m, d_nn, d_lo + P.slice, d_hi + P.slice, d_child + P.slice,
+                                                   d_range + P.slice, P.n, d_next, d_C[cur ^ 1]);
+        // compact in place of the old array: valid entries of d_C[cur^1] -> d_C[cur]
+        CK(cub::DeviceSelect::If(d_sel_tmp, sel_bytes, d_C[cur ^ 1], d_C[cur], d_sel, m, IsValidCluster(), st));
+        int m2 = 0;
+        CK(cudaMemcpyAsync(&m2, d_sel, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (m2 >= m || m2 < 1) { snprintf(err, errlen, "PLOC made no progress (%d -> %d clusters)", m, m2); return -5; }
+        m = m2;
+      }
+      int root = 0;
+      CK(cudaMemcpyAsync(&root, d_C[cur], sizeof(int), cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      P.root = P.n > 1 ? root : 0;
+    }
+  }
+
+  for (int p = 0; p < 2; p++) {  // root bounds of each partition (node 0 of its slice)
+    float* dst = p == 0 ? out->box_other : out->box_emit;
+    for (int k = 0; k < 3; k++) { dst[k] = FLT_MAX; dst[3 + k] = -FLT_MAX; }
+    if (parts[p].n == 0) continue;
+    float4 lo, hi;
+    CK(cudaMemcpyAsync(&lo, d_lo + parts[p].slice + parts[p].root, sizeof(float4), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&hi, d_hi + parts[p].slice + parts[p].root, sizeof(float4), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    dst[0] = lo.x; dst[1] = lo.y; dst[2] = lo.z; dst[3] = hi.x; dst[4] = hi.y; dst[5] = hi.z;
   }
 
   float4* d_nodes = nullptr;
@@ -419,7 +538,7 @@ int build_bvh(const BuildInput& in, BuildOutput* out, cudaStream_t st, char* err
       if (P.n == 0) continue;
       k_emit_binary<<<cdiv(nn[p], 256), 256, 0, st>>>(P.n, d_child + P.slice, d_lo + P.slice, d_hi + P.slice, base,
                                                       P.sorted_base, d_nodes);
-      (p == 0 ? out->root_other : out->root_emit) = base;
+      (p == 0 ? out->root_other : out->root_emit) = base + P.root;
       (p == 0 ? out->nodes_other : out->nodes_emit) = nn[p];
       base += nn[p];
     }
@@ -439,7 +558,7 @@ int build_bvh(const BuildInput& in, BuildOutput* out, cudaStream_t st, char* err
       if (P.n == 0) continue;
       const int root = node_next++;
       (p == 0 ? out->root_other : out->root_emit) = root;
-      WorkItem h_item = {0, root};
+      WorkItem h_item = {P.root, root};
       CK(cudaMemcpyAsync(d_q[0], &h_item, sizeof(h_item), cudaMemcpyHostToDevice, st));
       int n_in = 1, cur = 0;
       const int nodes_before = node_next - 1;
@@ -475,6 +594,7 @@ int build_bvh(const BuildInput& in, BuildOutput* out, cudaStream_t st, char* err
   CK(cudaGetLastError());
 
   cudaFree(d_acc); cudaFree(d_keys); cudaFree(d_keys2); cudaFree(d_ids); cudaFree(d_ids2); cudaFree(d_final_to_sorted);
+  cudaFree(d_C[0]); cudaFree(d_C[1]); cudaFree(d_nn); cudaFree(d_sel); cudaFree(d_sel_tmp);
   cudaFree(d_tmp); cudaFree(d_child); cudaFree(d_range); cudaFree(d_parent); cudaFree(d_flags); cudaFree(d_lo); cudaFree(d_hi);
 
   out->d_nodes = d_nodes;

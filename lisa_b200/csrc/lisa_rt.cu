@@ -213,7 +213,10 @@ static int create_impl(const lisa_scene_desc* sd, const lisa_options* opt, lisa_
   CU(cudaEventRecord(t1, c->stream));
 
   // ---- BVH
-  BuildInput bi{d_verts, d_normals, d_mat_idx, d_emit, T, sd->num_materials, o.bvh_kind == LISA_BVH_WIDE8 ? 1 : 0};
+  int lbvh = (o.flags & LISA_FLAG_LBVH) ? 1 : 0, radius = 16;
+  if (const char* e = getenv("LISA_BUILDER")) lbvh = !strcmp(e, "lbvh");
+  if (const char* e = getenv("LISA_PLOC_RADIUS")) radius = std::max(1, atoi(e));
+  BuildInput bi{d_verts, d_normals, d_mat_idx, d_emit, T, sd->num_materials, o.bvh_kind == LISA_BVH_WIDE8 ? 1 : 0, lbvh, radius};
   int rc = build_bvh(bi, &c->bvh, c->stream, g_err, sizeof(g_err));
   CU(cudaEventRecord(t2, c->stream));
   CU(cudaStreamSynchronize(c->stream));
@@ -234,6 +237,13 @@ static int create_impl(const lisa_scene_desc* sd, const lisa_options* opt, lisa_
   c->scene.num_mats = sd->num_materials;
   c->scene.single_light = single_light;
   c->scene.shadow_first_found = o.shadow_mode == LISA_SHADOW_FIRST_FOUND;
+  {  // emitter bounds, padded by a relative + absolute margin so the quick reject is conservative
+    const float* b = c->bvh.box_emit;
+    float pad[3];
+    for (int k = 0; k < 3; k++) pad[k] = 1e-5f * (fabsf(b[k]) + fabsf(b[3 + k])) + 1e-6f * (b[3 + k] - b[k]) + 1e-30f;
+    c->scene.emit_lo = make_float3(b[0] - pad[0], b[1] - pad[1], b[2] - pad[2]);
+    c->scene.emit_hi = make_float3(b[3] + pad[0], b[4] + pad[1], b[5] + pad[2]);
+  }
 
   c->stats.struct_size = sizeof(lisa_stats);
   c->stats.num_triangles = (uint32_t)T;
@@ -256,7 +266,9 @@ static int create_impl(const lisa_scene_desc* sd, const lisa_options* opt, lisa_
   c->cfg.sm_count = prop.multiProcessorCount;
   c->cfg.extend_block = 256;
   c->cfg.shadow_block = 256;
-  c->cfg.shadow_blocks_per_sm = 4;
+  c->cfg.idle_thresh = 8;
+  if (const char* e2 = getenv("LISA_IDLE_THRESH")) c->cfg.idle_thresh = std::max(1, std::min(32, atoi(e2)));
+  c->cfg.shadow_blocks_per_sm = shadow_occupancy(bi.wide != 0, c->cfg.shadow_block);  // persistent grid = what is resident
   if (const char* e2 = getenv("LISA_SHADOW_BLOCKS_PER_SM")) c->cfg.shadow_blocks_per_sm = std::max(1, atoi(e2));
   // default residency: enough chains to fill the machine several times over, bounded so the state stays
   // a small fraction of HBM (112 B per chain)

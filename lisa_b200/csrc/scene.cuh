@@ -31,6 +31,7 @@ struct DScene {
   int              num_mats;
   int              single_light; // 1 when all emitter triangles share one material
   int              shadow_first_found; // LISA_SHADOW_FIRST_FOUND
+  float3           emit_lo, emit_hi;   // bounds of all emitter triangles (padded): cheap reject before the emitter BVH
 };
 
 }  // namespace lisa

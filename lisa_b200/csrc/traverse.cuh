@@ -129,6 +129,11 @@ __device__ __forceinline__ bool bvh2_trace(const float4* __restrict__ nodes, con
   const RayPre pre  = ray_precompute(o, d);
   const float3 idir = safe_rcp_dir(d);
   const float3 ood  = f3(o.x * idir.x, o.y * idir.y, o.z * idir.z);
+  // lo*idir - o*idir cancels: its absolute error is ~2^-23 |o*idir|.  Shift the near planes down and the far
+  // planes up by that bound so the slab test never rejects a box the (watertight) triangle test would hit.
+  const float  kpad = 6e-7f;
+  const float3 oodn = f3(ood.x + kpad * fabsf(ood.x), ood.y + kpad * fabsf(ood.y), ood.z + kpad * fabsf(ood.z));
+  const float3 oodf = f3(ood.x - kpad * fabsf(ood.x), ood.y - kpad * fabsf(ood.y), ood.z - kpad * fabsf(ood.z));
   stack.clear();
   int cur = root;
   while (true) {
@@ -137,17 +142,16 @@ __device__ __forceinline__ bool bvh2_trace(const float4* __restrict__ nodes, con
                    n3 = __ldg(nodes + 4 * cur + 3);
       n_nodes++;
       // slab test, both children
-      const float c0lox = n0.x * idir.x - ood.x, c0hix = n0.y * idir.x - ood.x;
-      const float c0loy = n0.z * idir.y - ood.y, c0hiy = n0.w * idir.y - ood.y;
-      const float c0loz = n2.x * idir.z - ood.z, c0hiz = n2.y * idir.z - ood.z;
-      const float c1lox = n1.x * idir.x - ood.x, c1hix = n1.y * idir.x - ood.x;
-      const float c1loy = n1.z * idir.y - ood.y, c1hiy = n1.w * idir.y - ood.y;
-      const float c1loz = n2.z * idir.z - ood.z, c1hiz = n2.w * idir.z - ood.z;
-      const float t0n = fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), tmin));
-      const float t0f = fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), hit.t));
-      const float t1n = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), tmin));
-      const float t1f = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), hit.t));
-      const bool  h0 = t0n <= t0f * 1.0000004f, h1 = t1n <= t1f * 1.0000004f;
+      // per axis: (near, far) of both planes, each padded outward
+      const float a0x = n0.x * idir.x, b0x = n0.y * idir.x, a0y = n0.z * idir.y, b0y = n0.w * idir.y;
+      const float a0z = n2.x * idir.z, b0z = n2.y * idir.z;
+      const float a1x = n1.x * idir.x, b1x = n1.y * idir.x, a1y = n1.z * idir.y, b1y = n1.w * idir.y;
+      const float a1z = n2.z * idir.z, b1z = n2.w * idir.z;
+      const float t0n = fmaxf(fmaxf(fminf(a0x, b0x) - oodn.x, fminf(a0y, b0y) - oodn.y), fmaxf(fminf(a0z, b0z) - oodn.z, tmin));
+      const float t0f = fminf(fminf(fmaxf(a0x, b0x) - oodf.x, fmaxf(a0y, b0y) - oodf.y), fminf(fmaxf(a0z, b0z) - oodf.z, hit.t));
+      const float t1n = fmaxf(fmaxf(fminf(a1x, b1x) - oodn.x, fminf(a1y, b1y) - oodn.y), fmaxf(fminf(a1z, b1z) - oodn.z, tmin));
+      const float t1f = fminf(fminf(fmaxf(a1x, b1x) - oodf.x, fmaxf(a1y, b1y) - oodf.y), fminf(fmaxf(a1z, b1z) - oodf.z, hit.t));
+      const bool  h0 = t0n * 0.9999995f <= t0f * 1.0000005f, h1 = t1n * 0.9999995f <= t1f * 1.0000005f;
       int         c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
       if (h0 && h1) {
         if (t1n < t0n) { int t = c0; c0 = c1; c1 = t; }
@@ -225,12 +229,19 @@ __device__ __forceinline__ bool bvh8_trace(const float4* __restrict__ nodes, con
                      sz = __uint_as_float(((eimask >> 16) & 0xffu) << 23);
       const float3 adir = f3(sx * idir.x, sy * idir.y, sz * idir.z);
       const float3 org  = f3((w0.x - o.x) * idir.x, (w0.y - o.y) * idir.y, (w0.z - o.z) * idir.z);
+      // q*adir + org cancels when |org| and |q*adir| are large: absolute error <~ 2^-22 (|org| + 255 |adir|).
+      // Near planes are shifted down and far planes up by that bound (conservative, watertight at the node level).
+      const float  kpad = 6e-7f;
+      const float3 pad  = f3(kpad * (fabsf(org.x) + 256.0f * fabsf(adir.x)), kpad * (fabsf(org.y) + 256.0f * fabsf(adir.y)),
+                             kpad * (fabsf(org.z) + 256.0f * fabsf(adir.z)));
+      const float3 orgn = org - pad, orgf = org + pad;
       node_group.x = __float_as_uint(w1.x);
       tri_group.x  = __float_as_uint(w1.y);
       uint32_t hitmask = 0;
 #pragma unroll
       for (int half = 0; half < 2; half++) {
         const uint32_t meta4 = __float_as_uint(half == 0 ? w1.z : w1.w);
+        if (meta4 == 0u) continue;  // four empty slots
         const uint32_t is_inner4   = (meta4 & (meta4 << 1)) & 0x10101010u;
         const uint32_t inner_mask4 = sign_extend_s8x4(is_inner4 << 3);
         const uint32_t bit_index4  = (meta4 ^ (oct_inv4 & inner_mask4)) & 0x1f1f1f1fu;
@@ -244,12 +255,12 @@ __device__ __forceinline__ bool bvh8_trace(const float4* __restrict__ nodes, con
         const uint32_t nz = d.z < 0.0f ? qhiz : qloz, fz = d.z < 0.0f ? qloz : qhiz;
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-          const float tnx = (float)extract_byte(nx, j) * adir.x + org.x, tfx = (float)extract_byte(fx, j) * adir.x + org.x;
-          const float tny = (float)extract_byte(ny, j) * adir.y + org.y, tfy = (float)extract_byte(fy, j) * adir.y + org.y;
-          const float tnz = (float)extract_byte(nz, j) * adir.z + org.z, tfz = (float)extract_byte(fz, j) * adir.z + org.z;
+          const float tnx = (float)extract_byte(nx, j) * adir.x + orgn.x, tfx = (float)extract_byte(fx, j) * adir.x + orgf.x;
+          const float tny = (float)extract_byte(ny, j) * adir.y + orgn.y, tfy = (float)extract_byte(fy, j) * adir.y + orgf.y;
+          const float tnz = (float)extract_byte(nz, j) * adir.z + orgn.z, tfz = (float)extract_byte(fz, j) * adir.z + orgf.z;
           const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
           const float tf = fminf(fminf(tfx, tfy), fminf(tfz, hit.t));
-          if (tn <= tf * 1.0000004f) {
+          if (tn * 0.9999995f <= tf * 1.0000005f) {
             const uint32_t child_bits = extract_byte(child_bits4, j);
             const uint32_t bit_index  = extract_byte(bit_index4, j);
             hitmask |= child_bits << bit_index;
@@ -280,6 +291,149 @@ __device__ __forceinline__ bool bvh8_trace(const float4* __restrict__ nodes, con
     }
   }
   return hit.prim >= 0;
+}
+
+
+// ================================================================================================
+// Step-wise traversal for the persistent shadow kernel (wavefront.cu: k_shadow).
+//
+// A warp's lanes are at different points of different rays, so the kernel runs a state machine whose
+// loop body is ONE work quantum per lane: at most one node visit followed by at most LISA_TRI_PER_STEP
+// triangle tests.  Lanes therefore reconverge after every quantum instead of after every ray, which is
+// what keeps SIMT efficiency up when rays need between 1 and 10 node visits.
+// ================================================================================================
+#define LISA_TRI_PER_STEP 2
+
+struct StepRay {        // per-ray constants kept in registers
+  float3   idir;        // safe reciprocal direction
+  float    Sx, Sy, Sz;  // watertight shear (ray_precompute)
+  int      kz;
+  uint32_t oct_inv4;    // wide BVH: octant byte replicated x4; bit 2/1/0 set = dir.x/y/z >= 0
+};
+
+__device__ __forceinline__ StepRay step_ray(const float3& d) {
+  StepRay r;
+  r.idir = safe_rcp_dir(d);
+  const float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
+  r.kz = (ax > ay) ? (ax > az ? 0 : 2) : (ay > az ? 1 : 2);
+  const float3 p = perm3(d, r.kz);
+  r.Sz = 1.0f / p.z;
+  r.Sx = p.x * r.Sz;
+  r.Sy = p.y * r.Sz;
+  r.oct_inv4 = ((d.x < 0.0f ? 0u : 4u) | (d.y < 0.0f ? 0u : 2u) | (d.z < 0.0f ? 0u : 1u)) * 0x01010101u;
+  return r;
+}
+
+__device__ __forceinline__ bool step_tri(const float3& o, const StepRay& r, const float4* __restrict__ tri_v, int ti, float tmin,
+                                         float tmax, float& t_out) {
+  const float4 a = __ldg(tri_v + 3 * ti), b = __ldg(tri_v + 3 * ti + 1), c = __ldg(tri_v + 3 * ti + 2);
+  RayPre pre;
+  pre.o = o; pre.kz = r.kz; pre.Sx = r.Sx; pre.Sy = r.Sy; pre.Sz = r.Sz;
+  float u, v;
+  return intersect_tri(pre, f3(a), f3(b), f3(c), tmin, tmax, t_out, u, v);
+}
+
+// byte j of q -> float, on the ALU/FMA pipes (PRMT + FADD) instead of the slow conversion pipe
+__device__ __forceinline__ float byte_to_float(uint32_t q, int j) {
+  return __uint_as_float(__byte_perm(q, 0x4B000000u, 0x7650u | (uint32_t)j)) - 8388608.0f;
+}
+
+// ---- compressed 8-wide --------------------------------------------------------------------------
+struct WideState {
+  uint2 ng, tg;  // node group (child base | hit bits + imask), triangle group (tri base | hit bits)
+  __device__ __forceinline__ void begin(int root) { ng = make_uint2((uint32_t)root, root >= 0 ? 0x80000000u : 0u); tg = make_uint2(0u, 0u); }
+  __device__ __forceinline__ bool has_nodes() const { return (ng.y & 0xff000000u) != 0u; }
+  __device__ __forceinline__ bool has_tris() const { return tg.y != 0u; }
+};
+
+// one node visit; precondition st.has_nodes() && !st.has_tris()
+__device__ __forceinline__ void wide_node_step(const float4* __restrict__ nodes, const float3& o, const StepRay& r, float tmin,
+                                               float tlimit, WideState& st, Stack& stack) {
+  const uint32_t hits_imask      = st.ng.y;
+  const uint32_t child_bit_index = 31u - __clz(hits_imask);
+  const uint32_t child_base      = st.ng.x;
+  st.ng.y &= ~(1u << child_bit_index);
+  if (st.ng.y & 0xff000000u) stack.push(st.ng);
+  const uint32_t slot_index     = (child_bit_index - 24u) ^ (r.oct_inv4 & 0xffu);
+  const uint32_t relative_index = __popc(hits_imask & ~(0xffffffffu << slot_index) & 0xffu);
+  const uint32_t ni             = child_base + relative_index;
+  const float4 w0 = __ldg(nodes + 5 * ni), w1 = __ldg(nodes + 5 * ni + 1), w2 = __ldg(nodes + 5 * ni + 2),
+               w3 = __ldg(nodes + 5 * ni + 3), w4 = __ldg(nodes + 5 * ni + 4);
+  const uint32_t eimask = __float_as_uint(w0.w);
+  const float3 adir = f3(__uint_as_float((eimask & 0xffu) << 23) * r.idir.x, __uint_as_float(((eimask >> 8) & 0xffu) << 23) * r.idir.y,
+                         __uint_as_float(((eimask >> 16) & 0xffu) << 23) * r.idir.z);
+  const float3 org  = f3((w0.x - o.x) * r.idir.x, (w0.y - o.y) * r.idir.y, (w0.z - o.z) * r.idir.z);
+  // conservative planes (see bvh8_trace): |t| <= |org| + 255 |adir|, so one absolute pad of 2^-20 of that bound
+  // covers both the cancellation in q*adir + org and the relative rounding of the result
+  const float  kpad = 1.2e-6f;
+  const float3 pad  = f3(kpad * (fabsf(org.x) + 256.0f * fabsf(adir.x)), kpad * (fabsf(org.y) + 256.0f * fabsf(adir.y)),
+                         kpad * (fabsf(org.z) + 256.0f * fabsf(adir.z)));
+  const float3 an = adir, af = adir;
+  const float3 on = org - pad, of = org + pad;
+  st.ng.x = __float_as_uint(w1.x);
+  st.tg.x = __float_as_uint(w1.y);
+  const bool negx = !(r.oct_inv4 & 4u), negy = !(r.oct_inv4 & 2u), negz = !(r.oct_inv4 & 1u);
+  uint32_t hitmask = 0;
+#pragma unroll
+  for (int half = 0; half < 2; half++) {
+    const uint32_t meta4 = __float_as_uint(half == 0 ? w1.z : w1.w);
+    if (meta4 == 0u) continue;  // four empty slots
+    const uint32_t is_inner4   = (meta4 & (meta4 << 1)) & 0x10101010u;
+    const uint32_t inner_mask4 = sign_extend_s8x4(is_inner4 << 3);
+    const uint32_t bit_index4  = (meta4 ^ (r.oct_inv4 & inner_mask4)) & 0x1f1f1f1fu;
+    const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
+    const uint32_t qlox = __float_as_uint(half == 0 ? w2.x : w2.y), qloy = __float_as_uint(half == 0 ? w2.z : w2.w);
+    const uint32_t qloz = __float_as_uint(half == 0 ? w3.x : w3.y), qhix = __float_as_uint(half == 0 ? w3.z : w3.w);
+    const uint32_t qhiy = __float_as_uint(half == 0 ? w4.x : w4.y), qhiz = __float_as_uint(half == 0 ? w4.z : w4.w);
+    const uint32_t nx = negx ? qhix : qlox, fx = negx ? qlox : qhix;
+    const uint32_t ny = negy ? qhiy : qloy, fy = negy ? qloy : qhiy;
+    const uint32_t nz = negz ? qhiz : qloz, fz = negz ? qloz : qhiz;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const float tnx = byte_to_float(nx, j) * an.x + on.x, tfx = byte_to_float(fx, j) * af.x + of.x;
+      const float tny = byte_to_float(ny, j) * an.y + on.y, tfy = byte_to_float(fy, j) * af.y + of.y;
+      const float tnz = byte_to_float(nz, j) * an.z + on.z, tfz = byte_to_float(fz, j) * af.z + of.z;
+      const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
+      const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tlimit));
+      if (tn <= tf) hitmask |= extract_byte(child_bits4, j) << extract_byte(bit_index4, j);
+    }
+  }
+  st.ng.y = (hitmask & 0xff000000u) | (eimask >> 24);
+  st.tg.y = hitmask & 0x00ffffffu;
+}
+
+// ---- binary ---------------------------------------------------------------------------------------
+#define LISA_BIN_NONE 0x7fffffff
+struct BinState {
+  int cur;  // node index >= 0, leaf ~tri < 0, LISA_BIN_NONE when nothing is pending
+  __device__ __forceinline__ void begin(int root) { cur = root >= 0 ? root : LISA_BIN_NONE; }
+  __device__ __forceinline__ bool has_nodes() const { return cur >= 0 && cur != LISA_BIN_NONE; }
+  __device__ __forceinline__ bool has_tris() const { return cur < 0; }
+};
+
+// one node visit; precondition st.has_nodes().  Leaves st.cur = next node / leaf / NONE (after a pop).
+__device__ __forceinline__ void bin_node_step(const float4* __restrict__ nodes, const float3& o, const StepRay& r, float tmin,
+                                              float tlimit, BinState& st, Stack& stack) {
+  const float4 n0 = __ldg(nodes + 4 * st.cur), n1 = __ldg(nodes + 4 * st.cur + 1), n2 = __ldg(nodes + 4 * st.cur + 2),
+               n3 = __ldg(nodes + 4 * st.cur + 3);
+  // (plane - o) * idir: one rounding each, so a relative pad is enough
+  const float a0x = (n0.x - o.x) * r.idir.x, b0x = (n0.y - o.x) * r.idir.x, a0y = (n0.z - o.y) * r.idir.y, b0y = (n0.w - o.y) * r.idir.y;
+  const float a0z = (n2.x - o.z) * r.idir.z, b0z = (n2.y - o.z) * r.idir.z;
+  const float a1x = (n1.x - o.x) * r.idir.x, b1x = (n1.y - o.x) * r.idir.x, a1y = (n1.z - o.y) * r.idir.y, b1y = (n1.w - o.y) * r.idir.y;
+  const float a1z = (n2.z - o.z) * r.idir.z, b1z = (n2.w - o.z) * r.idir.z;
+  const float t0n = fmaxf(fmaxf(fminf(a0x, b0x), fminf(a0y, b0y)), fminf(a0z, b0z)) * 0.999999f;
+  const float t0f = fminf(fminf(fmaxf(a0x, b0x), fmaxf(a0y, b0y)), fmaxf(a0z, b0z)) * 1.000001f;
+  const float t1n = fmaxf(fmaxf(fminf(a1x, b1x), fminf(a1y, b1y)), fminf(a1z, b1z)) * 0.999999f;
+  const float t1f = fminf(fminf(fmaxf(a1x, b1x), fmaxf(a1y, b1y)), fmaxf(a1z, b1z)) * 1.000001f;
+  const bool  h0 = fmaxf(t0n, tmin) <= fminf(t0f, tlimit), h1 = fmaxf(t1n, tmin) <= fminf(t1f, tlimit);
+  int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
+  if (h0 && h1) {
+    if (t1n < t0n) { int t = c0; c0 = c1; c1 = t; }
+    stack.push(make_uint2((uint32_t)c1, 0u));
+    st.cur = c0;
+  } else if (h0) st.cur = c0;
+  else if (h1) st.cur = c1;
+  else st.cur = stack.empty() ? LISA_BIN_NONE : (int)stack.pop().x;
 }
 
 }  // namespace lisa

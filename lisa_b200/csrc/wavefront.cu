@@ -43,6 +43,17 @@ __device__ __forceinline__ void warp_add(unsigned long long* p, uint32_t v) {
   if (lane_id() == 0 && v) atomicAdd(p, (unsigned long long)v);
 }
 
+// slab test of the ray against the (padded) bounds of all emitters
+__device__ __forceinline__ bool hits_emitter_bounds(const DScene& sc, const float3& o, const float3& d, float tmin, float tmax) {
+  const float3 id = safe_rcp_dir(d);
+  const float  ax = (sc.emit_lo.x - o.x) * id.x, bx = (sc.emit_hi.x - o.x) * id.x;
+  const float  ay = (sc.emit_lo.y - o.y) * id.y, by = (sc.emit_hi.y - o.y) * id.y;
+  const float  az = (sc.emit_lo.z - o.z) * id.z, bz = (sc.emit_hi.z - o.z) * id.z;
+  const float  tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), tmin));
+  const float  tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), tmax));
+  return tn * 0.999999f <= tf * 1.000001f;
+}
+
 template <bool WIDE, bool ANY>
 __device__ __forceinline__ bool trace_one(const DScene& sc, int root, const float3& o, const float3& d, float tmin, float tmax,
                                           Hit& h, Stack& stack, uint32_t& nn, uint32_t& nt) {
@@ -55,7 +66,8 @@ template <bool WIDE>
 __device__ __forceinline__ Hit closest_hit(const DScene& sc, const float3& o, const float3& d, float tmin, float tmax,
                                            Stack& stack, uint32_t& nn, uint32_t& nt) {
   Hit he, ho;
-  trace_one<WIDE, false>(sc, sc.root_emit, o, d, tmin, tmax, he, stack, nn, nt);
+  he.prim = -1; he.t = tmax;
+  if (hits_emitter_bounds(sc, o, d, tmin, tmax)) trace_one<WIDE, false>(sc, sc.root_emit, o, d, tmin, tmax, he, stack, nn, nt);
   trace_one<WIDE, false>(sc, sc.root_other, o, d, tmin, he.t, ho, stack, nn, nt);
   return ho.prim >= 0 ? ho : he;
 }
@@ -66,14 +78,16 @@ template <bool WIDE>
 __device__ __forceinline__ int shadow_query(const DScene& sc, const float3& o, const float3& d, float tmin, float tmax,
                                             int& light, Stack& stack, uint32_t& nn, uint32_t& nt) {
   Hit he, ho;
+  he.prim = -1; he.t = tmax;
+  const bool near_light = hits_emitter_bounds(sc, o, d, tmin, tmax);
   if (sc.shadow_first_found) {
-    if (trace_one<WIDE, true>(sc, sc.root_emit, o, d, tmin, tmax, he, stack, nn, nt)) {
+    if (near_light && trace_one<WIDE, true>(sc, sc.root_emit, o, d, tmin, tmax, he, stack, nn, nt)) {
       light = __float_as_int(__ldg(sc.tri_v + 3 * he.prim).w);
       return 1;
     }
     return trace_one<WIDE, true>(sc, sc.root_other, o, d, tmin, tmax, ho, stack, nn, nt) ? 2 : 0;
   }
-  trace_one<WIDE, false>(sc, sc.root_emit, o, d, tmin, tmax, he, stack, nn, nt);           // closest emitter
+  if (near_light) trace_one<WIDE, false>(sc, sc.root_emit, o, d, tmin, tmax, he, stack, nn, nt);  // closest emitter
   if (trace_one<WIDE, true>(sc, sc.root_other, o, d, tmin, he.t, ho, stack, nn, nt)) return 2;  // any occluder in front
   if (he.prim < 0) return 0;
   light = __float_as_int(__ldg(sc.tri_v + 3 * he.prim).w);
@@ -227,82 +241,182 @@ __global__ void __launch_bounds__(256) k_extend(DScene sc, DState s, DCamera cam
 }
 
 // ------------------------------------------------------------------------------------------------
+// k_shadow: persistent state machine.  Per lane: a JOB (one opaque hit: P, N, RNG state, <=30 tries), the RAY
+// of the current try, and that ray's TRAVERSAL state (phase 0: closest emitter; phase 1: any occluder in
+// front of it).  One loop iteration = one traversal quantum for every lane that has a ray in flight.  Lanes
+// whose ray finished wait until at least `idle_thresh` lanes are idle; then the warp runs the management
+// section once: retire rays (update RayState::hit, Q1), finish jobs (light term + bounce + write-back),
+// fetch new jobs from the queue (warp-local batches, one atomic per SHADOW_BATCH jobs) and start new rays.
 template <bool WIDE>
-__global__ void __launch_bounds__(256) k_shadow(DScene sc, DState s, Tile t, uint32_t iter) {
+struct TravState;
+template <>
+struct TravState<true> : WideState {};
+template <>
+struct TravState<false> : BinState {};
+
+template <bool WIDE>
+__global__ void __launch_bounds__(256) k_shadow(DScene sc, DState s, Tile t, uint32_t iter, uint32_t idle_thresh) {
   extern __shared__ uint2 smem_stack[];
-  Stack               stack(smem_stack);
-  unsigned int*       ring = s.ring + 4 * (iter % 3);
-  const unsigned int  qn   = ring[0];
-  const unsigned      lane = lane_id();
+  Stack              stack(smem_stack);
+  unsigned int*      ring = s.ring + 4 * (iter % 3);
+  const unsigned int qn   = ring[0];
+  const unsigned     lane = lane_id();
+  // job
   int      job = -1;
   float3   P = f3(0, 0, 0), N = f3(0, 0, 0);
   uint32_t seed = 0, flags = 0, tries = 0;
   int      mid = 0;
-  unsigned wnext = 0, wend = 0;  // warp-local slice of the queue
+  // ray of the current try
+  StepRay  ray;
+  ray.idir = f3(0, 0, 0); ray.Sx = ray.Sy = ray.Sz = 0; ray.kz = 0; ray.oct_inv4 = 0;
+  float    ndotl = 0.0f;
+  bool     in_flight = false;  // a ray is being traversed
+  bool     pending = false;    // a finished ray waits to be retired
+  // traversal
+  TravState<WIDE> st;
+  st.begin(-1);
+  int   phase = 0;             // 0: emitter BVH (closest), 1: other BVH (any)
+  float tlimit = LISA_TMAX;    // closest emitter distance found so far
+  int   light_prim = -1;
+  int   outcome = 0;
+  // queue
+  unsigned wnext = 0, wend = 0;
   bool     exhausted = (qn == 0);
   uint32_t n_sh = 0, n_samp = 0, n_done = 0, nn = 0, nt = 0;
+
   while (true) {
-    const bool     need     = job < 0;
-    const unsigned needmask = __ballot_sync(FULL, need);
-    if (needmask) {
-      if (wnext == wend && !exhausted) {
-        unsigned base = 0;
-        if (lane == 0) base = atomicAdd(&ring[1], SHADOW_BATCH);
-        base = __shfl_sync(FULL, base, 0);
-        wnext = min(base, qn);
-        wend  = min(base + SHADOW_BATCH, qn);
-        if (base + SHADOW_BATCH >= qn) exhausted = true;
+    const unsigned idle = __ballot_sync(FULL, !in_flight);
+    if (idle == FULL || (uint32_t)__popc(idle) >= idle_thresh) {
+      // ---- (1) retire finished rays, finish jobs
+      if (pending) {
+        pending = false;
+        tries++;
+        if (outcome == 0) flags &= ~F_STICKY;  // __miss__occlusion
+        else if (outcome == 1) {               // __closesthit__occlusion on an emitter
+          const int light = __float_as_int(__ldg(sc.tri_v + 3 * light_prim).w);
+          flags = (flags & 0x0000ffffu) | F_STICKY | ((uint32_t)light << F_LIGHT_SHIFT);
+        }                                      // outcome 2: RayState::hit keeps its value (Q1)
+        const bool lit = flags & F_STICKY;
+        if (lit || tries == LISA_SHADOW_TRIES) {
+          const float4    a4 = s.a[job], c4 = s.c[job], d4 = s.d[job];
+          const float3    atten = f3(a4);
+          float3          color = f3(c4);
+          const DMaterial m = load_material(sc.mats, mid);
+          if (lit) {
+            const DMaterial lm = load_material(sc.mats, (int)(flags >> F_LIGHT_SHIFT));
+            const float     c = fminf(fmaxf(ndotl, 0.0f), 1.0f);
+            color = color + (lm.emission() * (c * (c * 0.318309886183790672f))) * atten;  // bsdf::BRDF, shader.cu:205,251
+          }
+          const float3 nd = bsdf::bounce(f3(d4), N, seed, m);  // shader.cu:252 (drawn even after the last bounce)
+          const uint32_t bounce = (flags & F_BOUNCE_MASK) + 1;
+          if (bounce >= t.bounces) {
+            const float4   sum4 = s.sum[job];
+            const uint32_t done = __float_as_uint(sum4.w) + 1;
+            s.sum[job] = make_float4(sum4.x + color.x, sum4.y + color.y, sum4.z + color.z, __uint_as_float(done));
+            s.a[job]   = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(seed));
+            s.c[job]   = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(F_NEW));
+            n_samp++;
+            if (done == t.spp) n_done++;
+          } else {
+            flags = (flags & ~F_BOUNCE_MASK) | bounce;
+            s.d[job] = make_float4(nd.x, nd.y, nd.z, 0.0f);
+            s.a[job] = make_float4(atten.x, atten.y, atten.z, __uint_as_float(seed));
+            s.c[job] = make_float4(color.x, color.y, color.z, __uint_as_float(flags));
+          }
+          job = -1;
+        }
       }
-      const unsigned avail = wend - wnext, cnt = __popc(needmask), rank = __popc(needmask & lanemask_lt());
-      if (need && rank < avail) {
-        job = s.shadow_q[wnext + rank];
-        const float4 o4 = s.o[job], n4 = s.n[job], a4 = s.a[job], c4 = s.c[job];
-        P = f3(o4); N = f3(n4);
-        mid   = __float_as_int(n4.w);
-        seed  = __float_as_uint(a4.w);
-        flags = __float_as_uint(c4.w);
-        tries = 0;
+      // ---- (2) fetch jobs
+      const bool     need     = job < 0;
+      const unsigned needmask = __ballot_sync(FULL, need);
+      if (needmask) {
+        if (wnext == wend && !exhausted) {
+          unsigned base = 0;
+          if (lane == 0) base = atomicAdd(&ring[1], SHADOW_BATCH);
+          base = __shfl_sync(FULL, base, 0);
+          wnext = min(base, qn);
+          wend  = min(base + SHADOW_BATCH, qn);
+          if (base + SHADOW_BATCH >= qn) exhausted = true;
+        }
+        const unsigned avail = wend - wnext, cnt = __popc(needmask), rank = __popc(needmask & lanemask_lt());
+        if (need && rank < avail) {
+          job = s.shadow_q[wnext + rank];
+          const float4 o4 = s.o[job], n4 = s.n[job], a4 = s.a[job], c4 = s.c[job];
+          P = f3(o4); N = f3(n4);
+          mid   = __float_as_int(n4.w);
+          seed  = __float_as_uint(a4.w);
+          flags = __float_as_uint(c4.w);
+          tries = 0;
+        }
+        wnext += min(cnt, avail);
       }
-      wnext += min(cnt, avail);
+      // ---- (3) start the next try of every lane that has a job but no ray
+      if (job >= 0 && !in_flight) {
+        const float3 w = shoot_ray_hemisphere(N, seed);  // shader.cu:201
+        ndotl = dot(N, w);
+        ray   = step_ray(w);
+        n_sh++;
+        in_flight  = true;
+        light_prim = -1;
+        tlimit     = LISA_TMAX;
+        stack.clear();
+        if (hits_emitter_bounds(sc, P, w, LISA_TMIN, LISA_TMAX)) { phase = 0; st.begin(sc.root_emit); }
+        else { phase = 1; st.begin(sc.root_other); }
+      }
+      if (__ballot_sync(FULL, in_flight) == 0) break;
     }
-    if (__ballot_sync(FULL, job >= 0) == 0) break;
-    if (job >= 0) {
-      // one try of shoot_ray_to_light (shader.cu:199-207)
-      const float3 w = shoot_ray_hemisphere(N, seed);
-      int          light = (int)(flags >> F_LIGHT_SHIFT);
-      const int    oc = shadow_query<WIDE>(sc, P, w, LISA_TMIN, LISA_TMAX, light, stack, nn, nt);
-      n_sh++;
-      tries++;
-      if (oc == 0) flags &= ~F_STICKY;                                                       // __miss__occlusion
-      else if (oc == 1) flags = (flags & 0x0000ffffu) | F_STICKY | ((uint32_t)light << F_LIGHT_SHIFT);  // emitter
-      // oc == 2: RayState::hit keeps its previous value (Q1)
-      const bool lit = flags & F_STICKY;
-      if (lit || tries == LISA_SHADOW_TRIES) {
-        const float4    a4 = s.a[job], c4 = s.c[job], d4 = s.d[job];
-        const float3    atten = f3(a4);
-        float3          color = f3(c4);
-        const DMaterial m = load_material(sc.mats, mid);
-        if (lit) {
-          const DMaterial lm = load_material(sc.mats, (int)(flags >> F_LIGHT_SHIFT));
-          color = color + (lm.emission() * bsdf::BRDF(N, w, m)) * atten;  // shader.cu:205,251
+    // ---- (4) one traversal quantum
+    if (in_flight) {
+      if (st.has_nodes() && !st.has_tris()) {
+        nn++;
+        if (WIDE) wide_node_step(sc.bvh, P, ray, LISA_TMIN, tlimit, *reinterpret_cast<WideState*>(&st), stack);
+        else bin_node_step(sc.bvh, P, ray, LISA_TMIN, tlimit, *reinterpret_cast<BinState*>(&st), stack);
+      }
+      bool occluded = false;
+      if (WIDE) {
+        WideState& w = *reinterpret_cast<WideState*>(&st);
+#pragma unroll
+        for (int k = 0; k < LISA_TRI_PER_STEP; k++) {
+          if (w.tg.y && !occluded) {
+            const uint32_t b = __ffs(w.tg.y) - 1u;
+            w.tg.y &= w.tg.y - 1u;
+            const int ti = (int)(w.tg.x + b);
+            float tt;
+            nt++;
+            if (step_tri(P, ray, sc.tri_v, ti, LISA_TMIN, tlimit, tt)) {
+              if (phase == 0 && !sc.shadow_first_found) { tlimit = tt; light_prim = ti; }
+              else if (phase == 0) { light_prim = ti; w.tg.y = 0; w.ng.y = 0; stack.clear(); }
+              else occluded = true;
+            }
+          }
         }
-        const float3 nd = bsdf::bounce(f3(d4), N, seed, m);  // shader.cu:252 (drawn even after the last bounce)
-        uint32_t bounce = (flags & F_BOUNCE_MASK) + 1;
-        if (bounce >= t.bounces) {
-          float4   sum4 = s.sum[job];
-          uint32_t done = __float_as_uint(sum4.w) + 1;
-          s.sum[job] = make_float4(sum4.x + color.x, sum4.y + color.y, sum4.z + color.z, __uint_as_float(done));
-          s.a[job]   = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(seed));
-          s.c[job]   = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(F_NEW));
-          n_samp++;
-          if (done == t.spp) n_done++;
+        if (!w.has_tris() && !w.has_nodes() && !stack.empty() && !occluded) w.ng = stack.pop();
+      } else {
+        BinState& b = *reinterpret_cast<BinState*>(&st);
+        if (b.has_tris()) {
+          const int ti = ~b.cur;
+          float tt;
+          nt++;
+          if (step_tri(P, ray, sc.tri_v, ti, LISA_TMIN, tlimit, tt)) {
+            if (phase == 0 && !sc.shadow_first_found) { tlimit = tt; light_prim = ti; }
+            else if (phase == 0) { light_prim = ti; stack.clear(); }
+            else occluded = true;
+          }
+          b.cur = stack.empty() ? LISA_BIN_NONE : (int)stack.pop().x;
+        }
+      }
+      const bool trav_done = occluded || (!st.has_nodes() && !st.has_tris());
+      if (trav_done) {
+        if (phase == 0 && !(sc.shadow_first_found && light_prim >= 0)) {  // emitters done: now any occluder in front
+          phase = 1;
+          stack.clear();
+          st.begin(sc.root_other);
+          if (sc.root_other < 0) { in_flight = false; pending = true; outcome = light_prim >= 0 ? 1 : 0; }
         } else {
-          flags = (flags & ~F_BOUNCE_MASK) | bounce;
-          s.d[job] = make_float4(nd.x, nd.y, nd.z, 0.0f);
-          s.a[job] = make_float4(atten.x, atten.y, atten.z, __uint_as_float(seed));
-          s.c[job] = make_float4(color.x, color.y, color.z, __uint_as_float(flags));
+          in_flight = false;
+          pending   = true;
+          outcome   = occluded ? 2 : (light_prim >= 0 ? 1 : 0);
         }
-        job = -1;
       }
     }
   }
@@ -425,6 +539,13 @@ int configure_kernels(char* err, size_t errlen) {
   return 0;
 }
 
+int shadow_occupancy(bool wide, int block) {
+  int n = 0;
+  cudaError_t e = wide ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_shadow<true>, block, stack_smem(block))
+                       : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_shadow<false>, block, stack_smem(block));
+  return (e == cudaSuccess && n > 0) ? n : 2;
+}
+
 void launch_init_chains(const DState& s, const DCamera& cam, const Tile& t, cudaStream_t st) {
   k_init_chains<<<cdiv(t.n_chains, 256), 256, 0, st>>>(s, cam, t);
 }
@@ -438,8 +559,8 @@ void launch_shadow(const DScene& sc, const DState& s, const Tile& t, uint32_t it
   const int b = cfg.shadow_block;
   unsigned  grid = (unsigned)(cfg.sm_count * cfg.shadow_blocks_per_sm);
   grid = min(grid, max(1u, cdiv(t.n_chains, SHADOW_BATCH * (b / 32)) ));
-  if (sc.wide) k_shadow<true><<<grid, b, stack_smem(b), st>>>(sc, s, t, iter);
-  else k_shadow<false><<<grid, b, stack_smem(b), st>>>(sc, s, t, iter);
+  if (sc.wide) k_shadow<true><<<grid, b, stack_smem(b), st>>>(sc, s, t, iter, (uint32_t)cfg.idle_thresh);
+  else k_shadow<false><<<grid, b, stack_smem(b), st>>>(sc, s, t, iter, (uint32_t)cfg.idle_thresh);
 }
 void launch_finalize(const DState& s, const DCamera&, const Tile& t, float4* accum, cudaStream_t st) {
   k_finalize<<<cdiv(t.npix, 256), 256, 0, st>>>(s, t, accum);

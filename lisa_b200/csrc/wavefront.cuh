@@ -37,6 +37,7 @@ struct LaunchCfg {
   int sm_count;
   int extend_block, shadow_block;
   int shadow_blocks_per_sm;
+  int idle_thresh;  // k_shadow: lanes that must be idle before the warp runs its management section
 };
 
 void launch_init_chains(const DState& s, const DCamera& cam, const Tile& t, cudaStream_t st);
@@ -46,6 +47,7 @@ void launch_shadow(const DScene& sc, const DState& s, const Tile& t, uint32_t it
 void launch_finalize(const DState& s, const DCamera& cam, const Tile& t, float4* accum, cudaStream_t st);
 void launch_resolve(const float4* accum, uint32_t npix, float4* mean_out, uint32_t* rgba8_out, cudaStream_t st);
 int  configure_kernels(char* err, size_t errlen);
+int  shadow_occupancy(bool wide, int block);  // resident CTAs of k_shadow per SM
 
 // diagnostics
 void launch_trace_closest(const DScene& sc, const float* d_org, const float* d_dir, uint32_t n, float tmin, float tmax,

@@ -22,6 +22,7 @@ LISA_OK = 0
 SHADOW_CLOSEST, SHADOW_FIRST_FOUND = 0, 1
 BVH_WIDE8, BVH_BINARY = 0, 1
 FLAG_PROFILE_STAGES = 1
+FLAG_LBVH = 2
 
 
 class Material(ctypes.Structure):

@@ -68,7 +68,7 @@ def test_zero_bounces_and_one_bounce(rt, cornell):
     R = rt.Renderer.from_scene(resized(cornell, 64, bounces=1))
     R.render_subframes(0, 1, 4)
     a = R.read_accum()[..., :3]
-    assert a.max() <= 1.0 + 1 / np.pi + 1e-4 and a[60, 32].min() > 0.99  # the light itself
+    assert a.max() <= 1.0 + 1 / np.pi + 1e-4 and a[53, 32].min() > 0.99  # the light itself
 
 
 def test_rgba8_and_ppm(rt, orc, cornell, tmp_path):
