@@ -211,7 +211,7 @@ def main():
     clk = ClockSampler(local_rank) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     agg = dict(render_ms=0.0, shadow_ms=0.0, extend_ms=0.0, shadow_launches=0, jobs=0, shadow_rays=0, radiance_rays=0, launches=0,
-               nodes=0, tris=0)
+               nodes=0, tris=0, culled=0)
     e0.record()
     t0 = time.perf_counter()
     for i in range(W, W + K):
@@ -226,6 +226,7 @@ def main():
         agg["launches"] += st["last_kernel_launches"] + 2  # + reset memsets are not kernels; finalize/init counted inside
         agg["nodes"] += st["last_nodes_visited"]
         agg["tris"] += st["last_triangles_tested"]
+        agg["culled"] += st["last_shadow_culled"]
     torch.cuda.synchronize()
     e1.record()
     e1.synchronize()
@@ -266,11 +267,14 @@ def main():
 
     if rank == 0:
         peak, peak_src = measured_peaks()
-        rays = agg["shadow_rays"] + agg["radiance_rays"]
+        ref_rays = agg["shadow_rays"] + agg["radiance_rays"]          # rays the reference's programs would trace
+        rays = ref_rays - agg["culled"]                                # rays actually traversed here
+        traced_shadow = agg["shadow_rays"] - agg["culled"]
         nn, nt = agg["nodes"] / max(rays, 1), agg["tris"] / max(rays, 1)
         node_bytes = 80  # compressed 8-wide node
         per_launch = lambda x: x / max(agg["shadow_launches"], 1)
-        alg_bytes = per_launch(agg["jobs"]) * STATE_BYTES_PER_JOB + per_launch(agg["shadow_rays"]) * (node_bytes * nn + 48 * nt)
+        alg_bytes = per_launch(agg["jobs"]) * STATE_BYTES_PER_JOB + per_launch(traced_shadow) * (32 + node_bytes * nn + 48 * nt) \
+            + per_launch(agg["culled"]) * 0
         avg_ms = agg["shadow_ms"] / max(agg["shadow_launches"], 1)
         achieved = alg_bytes / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else None
         traffic = None
@@ -290,6 +294,9 @@ def main():
                        "l2": "inputs larger than L2: %.0f MB of chain state re-read every iteration (L2 is 126 MB)" % (R.stats()["state_bytes"] / 1e6)},
             "mrays_per_s": round(world * rays / T / 1e3, 1),
             "rays_per_sample": round(rays / (npix * S * K), 2),
+            "reference_rays_per_sample": round(ref_rays / (npix * S * K), 2),
+            "reference_equivalent_mrays_per_s": round(world * ref_rays / T / 1e3, 1),
+            "shadow_tries_resolved_without_traversal": round(agg["culled"] / max(agg["shadow_rays"], 1), 4),
             "wall_ms_per_step": round(wall_ms / K, 3), "device_render_ms_per_step": round(agg["render_ms"] / K, 3),
             "gpu_launches": int(agg["launches"]),
             "clocks": clocks,

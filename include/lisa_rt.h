@@ -89,7 +89,11 @@ typedef struct lisa_scene_desc {
 enum { LISA_SHADOW_CLOSEST = 0, LISA_SHADOW_FIRST_FOUND = 1 };
 enum { LISA_BVH_WIDE8 = 0, LISA_BVH_BINARY = 1 };
 enum { LISA_FLAG_PROFILE_STAGES = 1, /* CUDA events around every stage launch */
-       LISA_FLAG_LBVH = 2            /* plain LBVH hierarchy (fastest build) instead of PLOC clustering */ };
+       LISA_FLAG_LBVH = 2,           /* plain LBVH hierarchy (fastest build) instead of PLOC clustering */
+       LISA_FLAG_NO_CULL = 4         /* traverse EVERY shadow try.  By default a try whose outcome provably cannot change
+                                        RayState::hit (hit is false and the ray cannot reach any emitter: outside the cone
+                                        around the emitter bounds) is resolved without traversal; images are bit-identical
+                                        either way and lisa_stats reports how many tries were resolved that way. */ };
 
 typedef struct lisa_options {
   uint32_t struct_size;   /* sizeof(lisa_options) */
@@ -123,6 +127,7 @@ typedef struct lisa_stats {
   uint64_t last_extend_launches, last_shadow_launches, last_shadow_jobs; /* jobs = opaque hits light-sampled */
   uint64_t nodes_visited, triangles_tested;           /* cumulative traversal work (both stages) */
   uint64_t last_nodes_visited, last_triangles_tested;
+  uint64_t shadow_culled, last_shadow_culled;         /* shadow tries resolved without traversal (counted in shadow_rays too) */
 } lisa_stats;
 
 typedef struct lisa_ctx lisa_ctx;
@@ -182,6 +187,7 @@ int lisa_primary_rays(lisa_ctx* ctx, uint32_t subframe, float* dirs, uint32_t* s
  *   6 BRDF(N, L = in_f[6i..])                             -> out_f[i]
  *   7 make_color(rgb = in_f[3i..])                        -> out_u[i] = r | g<<8 | b<<16 | a<<24
  *   8 shading normal(P, n1,n2,n3, v1,v2,v3 = in_f[21i..]) -> out_f[3i..]
+ *   9 rng x3 (conversion-free form) from seed in_u[i]     -> out_f[3i..], out_u[i] = seed after
  * Returns LISA_ERR_ARG for an unknown selector. */
 int lisa_kat_eval(int device, int what, uint32_t n, const float* in_f, const uint32_t* in_u, float* out_f,
                   uint32_t* out_u);

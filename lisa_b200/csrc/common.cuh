@@ -58,9 +58,19 @@ __host__ __device__ __forceinline__ float rnd(uint32_t& prev) { return (float)lc
 // maths.cu:6-8
 __device__ __forceinline__ float rng(uint32_t& seed) { return rnd(seed) * 2.0f - 1.0f; }
 
+// Same value as rng() without the int->float conversion (which issues on the slow conversion pipe):
+// 2*(u/2^24) - 1 = (u - 2^23) * 2^-23 is exactly representable, so building it from the low 23 bits with the
+// 2^23 magic exponent and a constant chosen by bit 23 is bit-identical to the reference's fma(rnd, 2, -1).
+__device__ __forceinline__ float rng_fast(uint32_t& seed) {
+  seed = 1664525u * seed + 1013904223u;
+  const float m = __uint_as_float(0x4B000000u | (seed & 0x007FFFFFu));     // 2^23 + low 23 bits, exact
+  const float c = __uint_as_float(0xC0000000u - (seed & 0x00800000u));     // -2 if bit 23 is clear, -1 if set
+  return fmaf(m, 1.1920928955078125e-07f, c);
+}
+
 // maths.cu:10-15 — draws land in x, y, z in call order (the reference's device code does the same)
 __device__ __forceinline__ float3 shoot_ray_hemisphere(const float3& normal, uint32_t& seed) {
-  float  a = rng(seed), b = rng(seed), c = rng(seed);
+  float  a = rng_fast(seed), b = rng_fast(seed), c = rng_fast(seed);
   float3 d = normalize(f3(a, b, c));
   return d * copysignf(1.0f, dot(d, normal));  // faceforward(d, normal, d), vec_math.h:561
 }

@@ -243,6 +243,17 @@ static int create_impl(const lisa_scene_desc* sd, const lisa_options* opt, lisa_
     for (int k = 0; k < 3; k++) pad[k] = 1e-5f * (fabsf(b[k]) + fabsf(b[3 + k])) + 1e-6f * (b[3 + k] - b[k]) + 1e-30f;
     c->scene.emit_lo = make_float3(b[0] - pad[0], b[1] - pad[1], b[2] - pad[2]);
     c->scene.emit_hi = make_float3(b[3] + pad[0], b[4] + pad[1], b[5] + pad[2]);
+    if (c->bvh.num_emit_tris > 0) {
+      const float3 lo = c->scene.emit_lo, hi = c->scene.emit_hi;
+      c->scene.emit_c = make_float3(0.5f * (lo.x + hi.x), 0.5f * (lo.y + hi.y), 0.5f * (lo.z + hi.z));
+      const float dx = 0.5f * (hi.x - lo.x), dy = 0.5f * (hi.y - lo.y), dz = 0.5f * (hi.z - lo.z);
+      c->scene.emit_r2 = (dx * dx + dy * dy + dz * dz) * 1.0001f;
+    } else {  // no emitter: nothing can ever be lit; an empty sphere culls every non-sticky try
+      c->scene.emit_c = make_float3(0, 0, 0);
+      c->scene.emit_r2 = -1.0f;
+    }
+    c->scene.cull = (o.flags & LISA_FLAG_NO_CULL) ? 0 : 1;
+    if (const char* e = getenv("LISA_CULL")) c->scene.cull = atoi(e) != 0;
   }
 
   c->stats.struct_size = sizeof(lisa_stats);
@@ -258,10 +269,10 @@ static int create_impl(const lisa_scene_desc* sd, const lisa_options* opt, lisa_
   CU(cudaMalloc(&c->d_accum, sizeof(float4) * std::max<size_t>(npix, 1)));
   CU(cudaMemsetAsync(c->d_accum, 0, sizeof(float4) * npix, c->stream));
   CU(cudaMalloc(&c->state.ring, sizeof(unsigned int) * 12));
-  CU(cudaMalloc(&c->state.stats, sizeof(unsigned long long) * 8));
-  CU(cudaMemsetAsync(c->state.stats, 0, sizeof(unsigned long long) * 8, c->stream));
-  CU(cudaMallocHost(&c->h_stats, sizeof(unsigned long long) * 8));
-  memset(c->h_stats, 0, sizeof(unsigned long long) * 8);
+  CU(cudaMalloc(&c->state.stats, sizeof(unsigned long long) * 16));
+  CU(cudaMemsetAsync(c->state.stats, 0, sizeof(unsigned long long) * 16, c->stream));
+  CU(cudaMallocHost(&c->h_stats, sizeof(unsigned long long) * 16));
+  memset(c->h_stats, 0, sizeof(unsigned long long) * 16);
 
   c->cfg.sm_count = prop.multiProcessorCount;
   c->cfg.extend_block = 256;
@@ -306,7 +317,7 @@ extern "C" int lisa_reset_accum(lisa_ctx* c) {
   if (!c) return fail(LISA_ERR_ARG, "null ctx");
   CU(cudaSetDevice(c->device));
   CU(cudaMemsetAsync(c->d_accum, 0, sizeof(float4) * (size_t)c->width * c->height, c->stream));
-  CU(cudaMemsetAsync(c->state.stats, 0, sizeof(unsigned long long) * 8, c->stream));
+  CU(cudaMemsetAsync(c->state.stats, 0, sizeof(unsigned long long) * 16, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   lisa_stats keep = c->stats;
   c->stats.samples = c->stats.radiance_rays = c->stats.shadow_rays = c->stats.null_directions = 0;
@@ -337,7 +348,7 @@ static int run_tile(lisa_ctx* c, const Tile& t, uint64_t* launches, uint64_t* it
       if (c->profile_stages) cudaEventRecord(next_event(c), c->stream);
       *launches += 2;
     }
-    CU(cudaMemcpyAsync(c->h_stats, c->state.stats, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(c->h_stats, c->state.stats, sizeof(unsigned long long) * 16, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     if (c->profile_stages) drain_stage_events(c);
     if (c->h_stats[4] >= t.n_chains) break;
@@ -357,7 +368,7 @@ extern "C" int lisa_render_subframes(lisa_ctx* c, uint32_t first, uint32_t count
   if (!count || !spp) return fail(LISA_ERR_ARG, "count and spp must be positive");
   CU(cudaSetDevice(c->device));
   const uint64_t npix = (uint64_t)c->width * c->height;
-  unsigned long long before[8];
+  unsigned long long before[16];
   CU(cudaMemcpyAsync(c->h_stats, c->state.stats, sizeof(before), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   memcpy(before, c->h_stats, sizeof(before));
@@ -406,6 +417,8 @@ extern "C" int lisa_render_subframes(lisa_ctx* c, uint32_t first, uint32_t count
   s.last_extend_launches = c->profile_stages ? c->stage_launches[0] : iterations;
   s.last_shadow_launches = c->profile_stages ? c->stage_launches[1] : iterations;
   s.last_shadow_jobs = c->h_stats[7] - before[7];
+  s.last_shadow_culled = c->h_stats[8] - before[8];
+  s.shadow_culled = c->h_stats[8];
   s.last_nodes_visited = c->h_stats[5] - before[5];
   s.last_triangles_tested = c->h_stats[6] - before[6];
   s.nodes_visited = c->h_stats[5];
@@ -551,9 +564,9 @@ extern "C" int lisa_primary_rays(lisa_ctx* c, uint32_t subframe, float* dirs, ui
 
 extern "C" int lisa_kat_eval(int device, int what, uint32_t n, const float* in_f, const uint32_t* in_u, float* out_f,
                              uint32_t* out_u) {
-  static const int fin[9] = {0, 0, 3, 2, 8, 7, 6, 3, 21}, uin[9] = {2, 1, 1, 0, 0, 1, 0, 0, 0};
-  static const int fout[9] = {0, 3, 3, 1, 3, 3, 1, 0, 3}, uout[9] = {1, 1, 1, 0, 0, 1, 0, 1, 0};
-  if (what < 0 || what > 8) return fail(LISA_ERR_ARG, "unknown KAT selector %d", what);
+  static const int fin[10] = {0, 0, 3, 2, 8, 7, 6, 3, 21, 0}, uin[10] = {2, 1, 1, 0, 0, 1, 0, 0, 0, 1};
+  static const int fout[10] = {0, 3, 3, 1, 3, 3, 1, 0, 3, 3}, uout[10] = {1, 1, 1, 0, 0, 1, 0, 1, 0, 1};
+  if (what < 0 || what > 9) return fail(LISA_ERR_ARG, "unknown KAT selector %d", what);
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(LISA_ERR_CUDA, "no CUDA device: lisa_rt has no CPU fallback");
   if (device >= 0) CU(cudaSetDevice(device));

@@ -32,6 +32,9 @@ struct DScene {
   int              single_light; // 1 when all emitter triangles share one material
   int              shadow_first_found; // LISA_SHADOW_FIRST_FOUND
   float3           emit_lo, emit_hi;   // bounds of all emitter triangles (padded): cheap reject before the emitter BVH
+  float3           emit_c;             // centre and squared radius of the sphere around those bounds:
+  float            emit_r2;            //   a shadow ray outside the cone (P, sphere) cannot reach an emitter
+  int              cull;               // 1: resolve shadow tries that provably cannot change RayState::hit without traversal
 };
 
 }  // namespace lisa

@@ -36,7 +36,7 @@ namespace lisa {
 #define FULL 0xffffffffu
 #define SHADOW_BATCH 32
 
-enum { ST_RADIANCE = 0, ST_SHADOW = 1, ST_SAMPLES = 2, ST_NULLDIR = 3, ST_CHAINS_DONE = 4, ST_NODES = 5, ST_TRIS = 6, ST_JOBS = 7 };
+enum { ST_RADIANCE = 0, ST_SHADOW = 1, ST_SAMPLES = 2, ST_NULLDIR = 3, ST_CHAINS_DONE = 4, ST_NODES = 5, ST_TRIS = 6, ST_JOBS = 7, ST_CULLED = 8 };
 
 __device__ __forceinline__ void warp_add(unsigned long long* p, uint32_t v) {
   for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
@@ -284,20 +284,54 @@ __global__ void __launch_bounds__(256) k_shadow(DScene sc, DState s, Tile t, uin
   bool     exhausted = (qn == 0);
   uint32_t n_sh = 0, n_samp = 0, n_done = 0, nn = 0, nt = 0;
 
+  // cone (axis, cos of the half angle) around the emitter bounds as seen from P: a direction outside it cannot hit an emitter
+  float3 cone_axis = f3(0, 0, 0);
+  float  cone_cos = -2.0f;
+  uint32_t n_cull = 0;
   while (true) {
     const unsigned idle = __ballot_sync(FULL, !in_flight);
     if (idle == FULL || (uint32_t)__popc(idle) >= idle_thresh) {
-      // ---- (1) retire finished rays, finish jobs
-      if (pending) {
-        pending = false;
-        tries++;
-        if (outcome == 0) flags &= ~F_STICKY;  // __miss__occlusion
-        else if (outcome == 1) {               // __closesthit__occlusion on an emitter
-          const int light = __float_as_int(__ldg(sc.tri_v + 3 * light_prim).w);
-          flags = (flags & 0x0000ffffu) | F_STICKY | ((uint32_t)light << F_LIGHT_SHIFT);
-        }                                      // outcome 2: RayState::hit keeps its value (Q1)
-        const bool lit = flags & F_STICKY;
-        if (lit || tries == LISA_SHADOW_TRIES) {
+      while (true) {
+        // ---- (1) retire the finished ray
+        bool finish = false;
+        if (pending) {
+          pending = false;
+          tries++;
+          if (outcome == 0) flags &= ~F_STICKY;  // __miss__occlusion
+          else if (outcome == 1) {               // __closesthit__occlusion on an emitter
+            const int light = __float_as_int(__ldg(sc.tri_v + 3 * light_prim).w);
+            flags = (flags & 0x0000ffffu) | F_STICKY | ((uint32_t)light << F_LIGHT_SHIFT);
+          }                                      // outcome 2: RayState::hit keeps its value (Q1)
+          finish = (flags & F_STICKY) || tries == LISA_SHADOW_TRIES;
+        }
+        // ---- (2) next tries of shoot_ray_to_light (shader.cu:199-207).  A try can only matter if it may set
+        // RayState::hit (ray can reach an emitter) or clear it (hit currently true): everything else is resolved here.
+        if (job >= 0 && !in_flight && !finish) {
+          while (true) {
+            const float3 w = shoot_ray_hemisphere(N, seed);
+            n_sh++;
+            const bool sticky = flags & F_STICKY;
+            bool       cand = sticky || !sc.cull || dot(w, cone_axis) >= cone_cos;
+            if (cand && !sticky && sc.cull) cand = hits_emitter_bounds(sc, P, w, LISA_TMIN, LISA_TMAX);
+            if (cand) {
+              ndotl = dot(N, w);
+              ray   = step_ray(w);
+              in_flight  = true;
+              light_prim = -1;
+              tlimit     = LISA_TMAX;
+              stack.clear();
+              if ((sticky || !sc.cull) ? hits_emitter_bounds(sc, P, w, LISA_TMIN, LISA_TMAX) : true) { phase = 0; st.begin(sc.root_emit); }
+              else { phase = 1; st.begin(sc.root_other); }
+              break;
+            }
+            n_cull++;
+            tries++;
+            if (tries == LISA_SHADOW_TRIES) { finish = true; break; }
+          }
+        }
+        // ---- (3) finish the job: light term, BSDF bounce, write-back
+        if (finish) {
+          const bool      lit = flags & F_STICKY;
           const float4    a4 = s.a[job], c4 = s.c[job], d4 = s.d[job];
           const float3    atten = f3(a4);
           float3          color = f3(c4);
@@ -325,43 +359,42 @@ __global__ void __launch_bounds__(256) k_shadow(DScene sc, DState s, Tile t, uin
           }
           job = -1;
         }
-      }
-      // ---- (2) fetch jobs
-      const bool     need     = job < 0;
-      const unsigned needmask = __ballot_sync(FULL, need);
-      if (needmask) {
-        if (wnext == wend && !exhausted) {
-          unsigned base = 0;
-          if (lane == 0) base = atomicAdd(&ring[1], SHADOW_BATCH);
-          base = __shfl_sync(FULL, base, 0);
-          wnext = min(base, qn);
-          wend  = min(base + SHADOW_BATCH, qn);
-          if (base + SHADOW_BATCH >= qn) exhausted = true;
+        // ---- (4) fetch jobs
+        const bool     need     = job < 0;
+        const unsigned needmask = __ballot_sync(FULL, need);
+        bool           got = false;
+        if (needmask) {
+          if (wnext == wend && !exhausted) {
+            unsigned base = 0;
+            if (lane == 0) base = atomicAdd(&ring[1], SHADOW_BATCH);
+            base = __shfl_sync(FULL, base, 0);
+            wnext = min(base, qn);
+            wend  = min(base + SHADOW_BATCH, qn);
+            if (base + SHADOW_BATCH >= qn) exhausted = true;
+          }
+          const unsigned avail = wend - wnext, cnt = __popc(needmask), rank = __popc(needmask & lanemask_lt());
+          if (need && rank < avail) {
+            job = s.shadow_q[wnext + rank];
+            const float4 o4 = s.o[job], n4 = s.n[job], a4 = s.a[job], c4 = s.c[job];
+            P = f3(o4); N = f3(n4);
+            mid   = __float_as_int(n4.w);
+            seed  = __float_as_uint(a4.w);
+            flags = __float_as_uint(c4.w);
+            tries = 0;
+            got   = true;
+            // cone around the emitter bounds
+            const float3 v  = sc.emit_c - P;
+            const float  d2 = dot(v, v);
+            if (sc.emit_r2 < 0.0f) { cone_axis = f3(0, 0, 0); cone_cos = 2.0f; }            // no emitters: nothing passes
+            else if (d2 <= sc.emit_r2 * 1.01f) { cone_axis = f3(0, 0, 0); cone_cos = -2.0f; }  // inside the sphere: everything passes
+            else {
+              cone_axis = v * rsqrtf(d2);
+              cone_cos  = sqrtf(fmaxf(1.0f - sc.emit_r2 / d2, 0.0f)) - 1e-4f;
+            }
+          }
+          wnext += min(cnt, avail);
         }
-        const unsigned avail = wend - wnext, cnt = __popc(needmask), rank = __popc(needmask & lanemask_lt());
-        if (need && rank < avail) {
-          job = s.shadow_q[wnext + rank];
-          const float4 o4 = s.o[job], n4 = s.n[job], a4 = s.a[job], c4 = s.c[job];
-          P = f3(o4); N = f3(n4);
-          mid   = __float_as_int(n4.w);
-          seed  = __float_as_uint(a4.w);
-          flags = __float_as_uint(c4.w);
-          tries = 0;
-        }
-        wnext += min(cnt, avail);
-      }
-      // ---- (3) start the next try of every lane that has a job but no ray
-      if (job >= 0 && !in_flight) {
-        const float3 w = shoot_ray_hemisphere(N, seed);  // shader.cu:201
-        ndotl = dot(N, w);
-        ray   = step_ray(w);
-        n_sh++;
-        in_flight  = true;
-        light_prim = -1;
-        tlimit     = LISA_TMAX;
-        stack.clear();
-        if (hits_emitter_bounds(sc, P, w, LISA_TMIN, LISA_TMAX)) { phase = 0; st.begin(sc.root_emit); }
-        else { phase = 1; st.begin(sc.root_other); }
+        if (__ballot_sync(FULL, got) == 0) break;  // new jobs go round again for their first tries
       }
       if (__ballot_sync(FULL, in_flight) == 0) break;
     }
@@ -421,6 +454,7 @@ __global__ void __launch_bounds__(256) k_shadow(DScene sc, DState s, Tile t, uin
     }
   }
   warp_add(&s.stats[ST_SHADOW], n_sh);
+  warp_add(&s.stats[ST_CULLED], n_cull);
   warp_add(&s.stats[ST_SAMPLES], n_samp);
   warp_add(&s.stats[ST_CHAINS_DONE], n_done);
   warp_add(&s.stats[ST_NODES], nn);
@@ -509,6 +543,7 @@ __global__ void k_kat(int what, uint32_t n, const float* __restrict__ in_f, cons
               out_f[3 * i] = r.x; out_f[3 * i + 1] = r.y; out_f[3 * i + 2] = r.z; out_u[i] = s; } break;
     case 6: { const float* p = in_f + 6 * i; out_f[i] = bsdf::BRDF(f3(p[0], p[1], p[2]), f3(p[3], p[4], p[5]), m); } break;
     case 7: out_u[i] = make_color(f3(in_f[3 * i], in_f[3 * i + 1], in_f[3 * i + 2])); break;
+    case 9: { uint32_t sd = in_u[i]; out_f[3 * i] = rng_fast(sd); out_f[3 * i + 1] = rng_fast(sd); out_f[3 * i + 2] = rng_fast(sd); out_u[i] = sd; } break;
     case 8: {  // shading normal at P: watertight-test barycentrics of a ray through P, then interpolation
       const float* p = in_f + 21 * i;
       float3 P = f3(p[0], p[1], p[2]);
@@ -584,7 +619,7 @@ void launch_primary_rays(const DCamera& cam, uint32_t subframe, float* d_dirs, u
   k_primary_rays<<<cdiv(cam.width * cam.height, 256), 256, 0, st>>>(cam, subframe, d_dirs, d_seeds);
 }
 int launch_kat(int what, uint32_t n, const float* in_f, const uint32_t* in_u, float* out_f, uint32_t* out_u, cudaStream_t st) {
-  if (what < 0 || what > 8) return -1;
+  if (what < 0 || what > 9) return -1;
   if (n) k_kat<<<cdiv(n, 128), 128, 0, st>>>(what, n, in_f, in_u, out_f, out_u);
   return 0;
 }

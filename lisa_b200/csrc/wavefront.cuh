@@ -21,7 +21,7 @@ struct DState {
   // ring of 3 per-iteration counter blocks {shadow queue length, shadow queue fetch cursor, -, -}
   unsigned int* ring;
   // cumulative: [0] radiance rays [1] shadow rays [2] samples [3] null directions [4] finished chains
-  // [5] BVH nodes visited [6] triangles tested [7] shadow jobs (opaque hits queued)
+  // [5] BVH nodes visited [6] triangles tested [7] shadow jobs (opaque hits queued) [8] shadow tries resolved without traversal
   unsigned long long* stats;
 };
 

@@ -23,6 +23,7 @@ SHADOW_CLOSEST, SHADOW_FIRST_FOUND = 0, 1
 BVH_WIDE8, BVH_BINARY = 0, 1
 FLAG_PROFILE_STAGES = 1
 FLAG_LBVH = 2
+FLAG_NO_CULL = 4
 
 
 class Material(ctypes.Structure):
@@ -62,7 +63,8 @@ class Stats(ctypes.Structure):
                 ("last_extend_launches", ctypes.c_uint64), ("last_shadow_launches", ctypes.c_uint64),
                 ("last_shadow_jobs", ctypes.c_uint64), ("nodes_visited", ctypes.c_uint64),
                 ("triangles_tested", ctypes.c_uint64), ("last_nodes_visited", ctypes.c_uint64),
-                ("last_triangles_tested", ctypes.c_uint64)]
+                ("last_triangles_tested", ctypes.c_uint64), ("shadow_culled", ctypes.c_uint64),
+                ("last_shadow_culled", ctypes.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if not k.startswith("_")}
@@ -252,7 +254,7 @@ class Renderer:
 
 
 _KAT_SHAPES = {0: (0, 2, 0, 1), 1: (0, 1, 3, 1), 2: (3, 1, 3, 1), 3: (2, 0, 1, 0), 4: (8, 0, 3, 0), 5: (7, 1, 3, 1),
-               6: (6, 0, 1, 0), 7: (3, 0, 0, 1), 8: (21, 0, 3, 0)}
+               6: (6, 0, 1, 0), 7: (3, 0, 0, 1), 8: (21, 0, 3, 0), 9: (0, 1, 3, 1)}
 
 
 def kat_eval(what, in_f=None, in_u=None, device=-1):

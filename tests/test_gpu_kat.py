@@ -37,6 +37,17 @@ def test_tea_matches_oracle_on_random_inputs(rt, orc):
     assert s[:, 0].tolist() == exp
 
 
+def test_conversion_free_rng_is_bit_identical(rt):
+    """rng_fast (common.cuh) == 2*rnd-1 of maths.cu:6-8 for every seed tried, including both halves of bit 23."""
+    rng = np.random.default_rng(9)
+    seeds = rng.integers(0, 2**32, size=(200000, 1), dtype=np.uint64).astype(np.uint32)
+    a, sa = rt.kat_eval(1, in_u=seeds)
+    b, sb = rt.kat_eval(9, in_u=seeds)
+    np.testing.assert_array_equal(sa, sb)
+    np.testing.assert_array_equal(a * np.float32(2) - np.float32(1), b)
+    assert b.min() >= -1.0 and b.max() < 1.0
+
+
 def test_hemisphere(rt, kat):
     c = kat["hemisphere"]
     out, after = rt.kat_eval(2, in_f=[x["N"] for x in c], in_u=[[x["seed"]] for x in c])

@@ -23,6 +23,25 @@ def test_deterministic_and_tiling_invariant(rt, cornell):
         np.testing.assert_array_equal(imgs[0], im)
 
 
+def test_culling_is_exact(rt, cornell):
+    """Shadow tries that cannot change RayState::hit are resolved without traversal (LISA_FLAG_NO_CULL turns
+    that off): same RNG consumption, same counts of reference-semantic rays, bit-identical image."""
+    sc = resized(cornell, 128)
+    out = []
+    for flags in (0, rt.FLAG_NO_CULL):
+        for bvh in (0, 1):
+            R = rt.Renderer.from_scene(sc, flags=flags, bvh_kind=bvh)
+            R.render_subframes(0, 2, 6)
+            out.append((R.read_accum(), R.stats()))
+    base_img, base_st = out[0]
+    for img, st in out[1:]:
+        np.testing.assert_array_equal(base_img, img)
+        assert st["last_shadow_rays"] == base_st["last_shadow_rays"]
+        assert st["last_radiance_rays"] == base_st["last_radiance_rays"]
+    assert out[0][1]["last_shadow_culled"] > 0.8 * out[0][1]["last_shadow_rays"]
+    assert out[2][1]["last_shadow_culled"] == 0
+
+
 def test_subframe_additivity(rt, cornell):
     """render(0..3) == equal-weight merge of render(0..1) and render(2..3): the identity the multi-GPU
     partition relies on (lisa_b200/dist.py)."""
