@@ -245,19 +245,31 @@ def main():
     if not args.no_e2e:
         h2d = sc["vertices"].nbytes + sc["normals"].nbytes + sc["mat_indices"].nbytes + len(sc["materials_packed"])
         d2h = npix * 16
+        # pinned host memory for the step's inputs and for the image that comes back
+        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+        sc_pinned = dict(sc, vertices=pin(sc["vertices"]), normals=pin(sc["normals"]), mat_indices=pin(sc["mat_indices"]))
+        img_pinned = torch.empty((h, w, 4), dtype=torch.float32).pin_memory().numpy()
         barrier()
         t0 = time.perf_counter()
         for i in range(K):
-            R2 = rt.Renderer.from_scene(sc, device=local_rank)            # H2D + BVH build
+            ts = [time.perf_counter()]
+            R2 = rt.Renderer.from_scene(sc_pinned, device=local_rank)     # H2D + BVH build
+            ts.append(time.perf_counter())
             R2.render_subframes((W + K + i) * world + rank, 1, S)
+            ts.append(time.perf_counter())
             if world > 1:
                 t2 = ldist.accum_tensor(R2)
                 dist.reduce(t2, dst=0, op=dist.ReduceOp.SUM)
                 torch.cuda.synchronize()
             if rank == 0:
-                img = R2.read_accum()                                     # D2H
+                img = R2.read_accum(out=img_pinned)                       # D2H
                 assert np.isfinite(img[0, 0, 0])
+            ts.append(time.perf_counter())
             R2.close()
+            ts.append(time.perf_counter())
+            if os.environ.get("BENCH_VERBOSE"):
+                sys.stderr.write("e2e step %d: create %.1f render %.1f read %.1f destroy %.1f ms\n" % (
+                    i, *[(ts[k + 1] - ts[k]) * 1e3 for k in range(4)]))
         barrier()
         te = torch.tensor([(time.perf_counter() - t0) * 1e3], device="cuda", dtype=torch.float64)
         if world > 1:

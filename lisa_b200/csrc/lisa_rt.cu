@@ -38,6 +38,55 @@ static int fail(int code, const char* fmt, ...) {
     if (e_ != cudaSuccess) return fail(LISA_ERR_CUDA, "%s: %s", #x, cudaGetErrorString(e_));    \
   } while (0)
 
+// ---- process-wide cache of large device blocks -----------------------------------------------------------
+// Chain state and accumulators are hundreds of MB; cudaMalloc/cudaFree of such blocks costs milliseconds to
+// >100 ms (and cudaFree synchronises the device), which would dominate a create -> render -> read -> destroy
+// cycle.  Freed blocks are parked here (exact-size reuse, bounded) and handed to the next context.
+#include <mutex>
+namespace {
+struct Block { void* p; size_t bytes; int device; };
+std::mutex         g_cache_mu;
+std::vector<Block> g_cache;
+size_t             g_cache_bytes = 0;
+const size_t       kCacheMinBlock = 1u << 20, kCacheMaxBytes = 8ull << 30;
+
+cudaError_t big_alloc(void** out, size_t bytes, int device) {
+  if (bytes >= kCacheMinBlock) {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    for (size_t i = 0; i < g_cache.size(); i++)
+      if (g_cache[i].bytes == bytes && g_cache[i].device == device) {
+        *out = g_cache[i].p;
+        g_cache_bytes -= bytes;
+        g_cache.erase(g_cache.begin() + i);
+        return cudaSuccess;
+      }
+  }
+  cudaError_t e = cudaMalloc(out, bytes);
+  if (e != cudaSuccess) {  // out of memory: drop the cache and retry once
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    for (Block& b : g_cache) if (b.device == device) cudaFree(b.p);
+    g_cache.erase(std::remove_if(g_cache.begin(), g_cache.end(), [&](const Block& b) { return b.device == device; }), g_cache.end());
+    g_cache_bytes = 0;
+    for (Block& b : g_cache) g_cache_bytes += b.bytes;
+    cudaGetLastError();
+    e = cudaMalloc(out, bytes);
+  }
+  return e;
+}
+void big_free(void* p, size_t bytes, int device) {
+  if (!p) return;
+  if (bytes >= kCacheMinBlock) {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    if (g_cache_bytes + bytes <= kCacheMaxBytes && g_cache.size() < 64) {
+      g_cache.push_back(Block{p, bytes, device});
+      g_cache_bytes += bytes;
+      return;
+    }
+  }
+  cudaFree(p);
+}
+}  // namespace
+
 struct lisa_ctx {
   int          device = 0;
   cudaStream_t stream = nullptr;
@@ -113,25 +162,30 @@ static void camera_frame(const lisa_camera& c, uint32_t w, uint32_t h, DCamera* 
 }
 
 static void free_state(lisa_ctx* c) {
-  cudaFree(c->state.o); cudaFree(c->state.d); cudaFree(c->state.a); cudaFree(c->state.c); cudaFree(c->state.n);
-  cudaFree(c->state.sum); cudaFree(c->state.shadow_q);
+  const size_t n = c->state_chains;
+  big_free(c->state.o, sizeof(float4) * n, c->device); big_free(c->state.d, sizeof(float4) * n, c->device);
+  big_free(c->state.a, sizeof(float4) * n, c->device); big_free(c->state.c, sizeof(float4) * n, c->device);
+  big_free(c->state.n, sizeof(float4) * n, c->device); big_free(c->state.sum, sizeof(float4) * n, c->device);
+  big_free(c->state.shadow_q, sizeof(int) * n, c->device);
+  big_free(c->state.cand_q, sizeof(int) * n, c->device);
   c->state.o = c->state.d = c->state.a = c->state.c = c->state.n = c->state.sum = nullptr;
-  c->state.shadow_q = nullptr;
+  c->state.shadow_q = c->state.cand_q = nullptr;
   c->state_chains = 0;
 }
 
 static int ensure_state(lisa_ctx* c, size_t chains) {
   if (chains <= c->state_chains) return LISA_OK;
   free_state(c);
-  CU(cudaMalloc(&c->state.o, sizeof(float4) * chains));
-  CU(cudaMalloc(&c->state.d, sizeof(float4) * chains));
-  CU(cudaMalloc(&c->state.a, sizeof(float4) * chains));
-  CU(cudaMalloc(&c->state.c, sizeof(float4) * chains));
-  CU(cudaMalloc(&c->state.n, sizeof(float4) * chains));
-  CU(cudaMalloc(&c->state.sum, sizeof(float4) * chains));
-  CU(cudaMalloc(&c->state.shadow_q, sizeof(int) * chains));
+  CU(big_alloc((void**)&c->state.o, sizeof(float4) * chains, c->device));
+  CU(big_alloc((void**)&c->state.d, sizeof(float4) * chains, c->device));
+  CU(big_alloc((void**)&c->state.a, sizeof(float4) * chains, c->device));
+  CU(big_alloc((void**)&c->state.c, sizeof(float4) * chains, c->device));
+  CU(big_alloc((void**)&c->state.n, sizeof(float4) * chains, c->device));
+  CU(big_alloc((void**)&c->state.sum, sizeof(float4) * chains, c->device));
+  CU(big_alloc((void**)&c->state.shadow_q, sizeof(int) * chains, c->device));
+  CU(big_alloc((void**)&c->state.cand_q, sizeof(int) * chains, c->device));
   c->state_chains = chains;
-  c->stats.state_bytes = chains * (6 * sizeof(float4) + sizeof(int));
+  c->stats.state_bytes = chains * (6 * sizeof(float4) + 2 * sizeof(int));
   return LISA_OK;
 }
 
@@ -142,7 +196,13 @@ extern "C" void lisa_destroy(lisa_ctx* c) {
   free_state(c);
   cudaFree(c->state.ring); cudaFree(c->state.stats);
   cudaFree(c->bvh.d_nodes); cudaFree(c->bvh.d_tri_v); cudaFree(c->bvh.d_tri_n); cudaFree(c->bvh.d_final_to_orig);
-  cudaFree(c->d_mats); cudaFree(c->d_accum); cudaFree(c->d_mean); cudaFree(c->d_rgba8);
+  cudaFree(c->d_mats);
+  {
+    const size_t npix = (size_t)c->width * c->height;
+    big_free(c->d_accum, sizeof(float4) * std::max<size_t>(npix, 1), c->device);
+    big_free(c->d_mean, sizeof(float4) * npix, c->device);
+    big_free(c->d_rgba8, sizeof(uint32_t) * npix, c->device);
+  }
   if (c->h_stats) cudaFreeHost(c->h_stats);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
@@ -266,9 +326,9 @@ static int create_impl(const lisa_scene_desc* sd, const lisa_options* opt, lisa_
 
   // ---- accumulators, counters
   const size_t npix = (size_t)c->width * c->height;
-  CU(cudaMalloc(&c->d_accum, sizeof(float4) * std::max<size_t>(npix, 1)));
+  CU(big_alloc((void**)&c->d_accum, sizeof(float4) * std::max<size_t>(npix, 1), c->device));
   CU(cudaMemsetAsync(c->d_accum, 0, sizeof(float4) * npix, c->stream));
-  CU(cudaMalloc(&c->state.ring, sizeof(unsigned int) * 12));
+  CU(cudaMalloc(&c->state.ring, sizeof(unsigned int) * 48));
   CU(cudaMalloc(&c->state.stats, sizeof(unsigned long long) * 16));
   CU(cudaMemsetAsync(c->state.stats, 0, sizeof(unsigned long long) * 16, c->stream));
   CU(cudaMallocHost(&c->h_stats, sizeof(unsigned long long) * 16));
@@ -279,6 +339,7 @@ static int create_impl(const lisa_scene_desc* sd, const lisa_options* opt, lisa_
   c->cfg.shadow_block = 256;
   c->cfg.idle_thresh = 8;
   if (const char* e2 = getenv("LISA_IDLE_THRESH")) c->cfg.idle_thresh = std::max(1, std::min(32, atoi(e2)));
+  c->cfg.tries_blocks_per_sm = tries_occupancy(256);
   c->cfg.shadow_blocks_per_sm = shadow_occupancy(bi.wide != 0, c->cfg.shadow_block);  // persistent grid = what is resident
   if (const char* e2 = getenv("LISA_SHADOW_BLOCKS_PER_SM")) c->cfg.shadow_blocks_per_sm = std::max(1, atoi(e2));
   // default residency: enough chains to fill the machine several times over, bounded so the state stays
@@ -344,9 +405,9 @@ static int run_tile(lisa_ctx* c, const Tile& t, uint64_t* launches, uint64_t* it
       if (c->profile_stages) cudaEventRecord(next_event(c), c->stream);
       launch_extend(c->scene, c->state, c->cam, t, iter, c->cfg, c->stream);
       if (c->profile_stages) cudaEventRecord(next_event(c), c->stream);
-      launch_shadow(c->scene, c->state, t, iter, c->cfg, c->stream);
+      const int nl = launch_shadow(c->scene, c->state, t, iter, c->cfg, c->stream);
       if (c->profile_stages) cudaEventRecord(next_event(c), c->stream);
-      *launches += 2;
+      *launches += 1 + nl;
     }
     CU(cudaMemcpyAsync(c->h_stats, c->state.stats, sizeof(unsigned long long) * 16, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
@@ -435,8 +496,8 @@ extern "C" int lisa_render_subframes(lisa_ctx* c, uint32_t first, uint32_t count
 
 static int resolve(lisa_ctx* c, bool want_mean, bool want_rgba) {
   const size_t npix = (size_t)c->width * c->height;
-  if (want_mean && !c->d_mean) CU(cudaMalloc(&c->d_mean, sizeof(float4) * npix));
-  if (want_rgba && !c->d_rgba8) CU(cudaMalloc(&c->d_rgba8, sizeof(uint32_t) * npix));
+  if (want_mean && !c->d_mean) CU(big_alloc((void**)&c->d_mean, sizeof(float4) * npix, c->device));
+  if (want_rgba && !c->d_rgba8) CU(big_alloc((void**)&c->d_rgba8, sizeof(uint32_t) * npix, c->device));
   launch_resolve(c->d_accum, (uint32_t)npix, want_mean ? c->d_mean : nullptr, want_rgba ? c->d_rgba8 : nullptr, c->stream);
   return LISA_OK;
 }

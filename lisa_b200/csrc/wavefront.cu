@@ -35,12 +35,32 @@ namespace lisa {
 
 #define FULL 0xffffffffu
 #define SHADOW_BATCH 32
+#define RING_STRIDE 16
+#define R_CNTJ 0   // [p] length of the job queue of pass p
+#define R_CURJ 4   // [p] fetch cursor
+#define R_CNTC 8   // [p] length of the candidate queue of pass p
+#define R_CURC 12  // [p] fetch cursor
+#define F_TRIES_SHIFT 10
+#define F_TRIES_MASK (0x1fu << F_TRIES_SHIFT)
+
 
 enum { ST_RADIANCE = 0, ST_SHADOW = 1, ST_SAMPLES = 2, ST_NULLDIR = 3, ST_CHAINS_DONE = 4, ST_NODES = 5, ST_TRIS = 6, ST_JOBS = 7, ST_CULLED = 8 };
 
 __device__ __forceinline__ void warp_add(unsigned long long* p, uint32_t v) {
   for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
   if (lane_id() == 0 && v) atomicAdd(p, (unsigned long long)v);
+}
+
+// warp-aggregated append of `id` for the lanes of the CURRENT convergent group that have push == true
+__device__ __forceinline__ void queue_push(bool push, int id, int* q, unsigned int* count) {
+  const unsigned am = __activemask();
+  const unsigned m  = __ballot_sync(am, push);
+  if (!m) return;
+  const int leader = __ffs(m) - 1;
+  unsigned  base = 0;
+  if ((int)lane_id() == leader) base = atomicAdd(count, __popc(m));
+  base = __shfl_sync(am, base, leader);
+  if (push) q[base + __popc(m & lanemask_lt())] = id;
 }
 
 // slab test of the ray against the (padded) bounds of all emitters
@@ -120,7 +140,7 @@ __device__ __forceinline__ uint32_t chain_seed(const DCamera& cam, uint32_t p, u
 __global__ void k_init_chains(DState s, DCamera cam, Tile t) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i == 0) {
-    for (int k = 0; k < 12; k++) s.ring[k] = 0;
+    for (int k = 0; k < 3 * RING_STRIDE; k++) s.ring[k] = 0;
     s.stats[ST_CHAINS_DONE] = 0;
   }
   if (i >= t.n_chains) return;
@@ -136,13 +156,12 @@ __global__ void __launch_bounds__(256) k_extend(DScene sc, DState s, DCamera cam
   extern __shared__ uint2 smem_stack[];
   Stack          stack(smem_stack);
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  unsigned int*  ring = s.ring + 4 * (iter % 3);
-  if (i == 0) {  // reset the counter block of the NEXT iteration (its last user finished two iterations ago)
-    unsigned int* nxt = s.ring + 4 * ((iter + 1) % 3);
-    nxt[0] = 0; nxt[1] = 0;
+  unsigned int*  ring = s.ring + RING_STRIDE * (iter % 3);
+  if (i < RING_STRIDE) {  // reset the counter block of the NEXT iteration (its last user finished two iterations ago)
+    s.ring[RING_STRIDE * ((iter + 1) % 3) + i] = 0;
   }
   uint32_t n_rad = 0, n_null = 0, n_samp = 0, n_done = 0, nn = 0, nt = 0;
-  bool     push = false;
+  bool     push = false, push_sticky = false;
   if (i < t.n_chains) {
     float4   sum4 = s.sum[i];
     uint32_t done = __float_as_uint(sum4.w);
@@ -204,8 +223,10 @@ __global__ void __launch_bounds__(256) k_extend(DScene sc, DState s, DCamera cam
               if (fresh) s.d[i] = make_float4(d.x, d.y, d.z, 0.0f);
               s.n[i] = make_float4(N.x, N.y, N.z, __int_as_float(mid));
               s.a[i] = make_float4(atten.x, atten.y, atten.z, __uint_as_float(seed));
-              s.c[i] = make_float4(color.x, color.y, color.z, __uint_as_float(flags));
-              push = true;
+              s.c[i] = make_float4(color.x, color.y, color.z, __uint_as_float(flags & ~F_TRIES_MASK));
+              // RayState::hit already true (Q1): the first try is a real ray (it can clear hit) -> candidate queue
+              push_sticky = (flags & F_STICKY) != 0;
+              push = !push_sticky;
             }
           }
         }
@@ -220,18 +241,10 @@ __global__ void __launch_bounds__(256) k_extend(DScene sc, DState s, DCamera cam
       }
     }
   }
-  // stream compaction into the shadow queue: ballot + prefix popcount, one atomic per warp
-  const unsigned m = __ballot_sync(FULL, push);
-  if (m) {
-    unsigned base = 0;
-    const int leader = __ffs(m) - 1;
-    if ((int)lane_id() == leader) {
-      base = atomicAdd(&ring[0], __popc(m));
-      atomicAdd(&s.stats[ST_JOBS], (unsigned long long)__popc(m));
-    }
-    base = __shfl_sync(FULL, base, leader);
-    if (push) s.shadow_q[base + __popc(m & lanemask_lt())] = (int)i;
-  }
+  // stream compaction into the queues: ballot + prefix popcount, one atomic per warp and queue
+  queue_push(push, (int)i, s.shadow_q, &ring[R_CNTJ + 0]);
+  queue_push(push_sticky, (int)i, s.cand_q, &ring[R_CNTC + 0]);
+  warp_add(&s.stats[ST_JOBS], (push || push_sticky) ? 1u : 0u);
   warp_add(&s.stats[ST_RADIANCE], n_rad);
   warp_add(&s.stats[ST_SAMPLES], n_samp);
   warp_add(&s.stats[ST_NULLDIR], n_null);
@@ -241,12 +254,21 @@ __global__ void __launch_bounds__(256) k_extend(DScene sc, DState s, DCamera cam
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_shadow: persistent state machine.  Per lane: a JOB (one opaque hit: P, N, RNG state, <=30 tries), the RAY
-// of the current try, and that ray's TRAVERSAL state (phase 0: closest emitter; phase 1: any occluder in
-// front of it).  One loop iteration = one traversal quantum for every lane that has a ray in flight.  Lanes
-// whose ray finished wait until at least `idle_thresh` lanes are idle; then the warp runs the management
-// section once: retire rays (update RayState::hit, Q1), finish jobs (light term + bounce + write-back),
-// fetch new jobs from the queue (warp-local batches, one atomic per SHADOW_BATCH jobs) and start new rays.
+// Light sampling (shoot_ray_to_light, shader.cu:196-209) in two kernels per pass.
+//
+// A shadow try can only matter if it may SET RayState::hit (the ray can reach an emitter) or CLEAR it (hit is
+// currently true, Q1).  While hit is false, a try whose direction lies outside the cone around the emitter
+// bounds cannot hit an emitter, so its outcome (miss or non-emitter) leaves hit false: it is resolved by
+// consuming its three LCG draws, without traversal, bit-identically (LISA_FLAG_NO_CULL disables this).
+//
+//   k_tries  one WARP per job, one LANE per try: lane i jumps the job's LCG ahead by 3i draws (A^k, C_k per
+//            lane), builds try i's direction and tests it against the cone; a ballot gives the first
+//            candidate try.  Jobs without a candidate are finished here (BSDF bounce, write-back) by the lane
+//            that owns them; jobs with one go to the candidate queue with the RNG state of that try.
+//   k_rays   persistent state machine (one traversal quantum per iteration, dynamic job fetch): traces the
+//            candidate try — phase 0 closest emitter, phase 1 any occluder in front of it — retires it into
+//            RayState::hit, finishes lit jobs, and sends jobs that need more tries back to k_tries (next pass).
+// Passes shrink geometrically; the last pass finishes its leftovers inline.
 template <bool WIDE>
 struct TravState;
 template <>
@@ -254,12 +276,138 @@ struct TravState<true> : WideState {};
 template <>
 struct TravState<false> : BinState {};
 
+struct JobCounters { uint32_t samples, done; };
+
+// End of the opaque branch of __closesthit__radiance for one job (shader.cu:251-252): add the light term,
+// draw the BSDF bounce (also after the last bounce: it consumes RNG), end the sample or store the next ray.
+__device__ __forceinline__ void finish_job(const DScene& sc, const DState& s, const Tile& t, int job, const float3& N, int mid,
+                                           uint32_t seed, uint32_t flags, float ndotl, JobCounters& jc) {
+  const bool      lit = flags & F_STICKY;
+  const float4    a4 = s.a[job], c4 = s.c[job], d4 = s.d[job];
+  const float3    atten = f3(a4);
+  float3          color = f3(c4);
+  const DMaterial m = load_material(sc.mats, mid);
+  if (lit) {
+    const DMaterial lm = load_material(sc.mats, (int)(flags >> F_LIGHT_SHIFT));
+    const float     c = fminf(fmaxf(ndotl, 0.0f), 1.0f);
+    color = color + (lm.emission() * (c * (c * 0.318309886183790672f))) * atten;  // emission * bsdf::BRDF(N, w)
+  }
+  const float3   nd = bsdf::bounce(f3(d4), N, seed, m);
+  const uint32_t bounce = (flags & F_BOUNCE_MASK) + 1;
+  if (bounce >= t.bounces) {
+    const float4   sum4 = s.sum[job];
+    const uint32_t done = __float_as_uint(sum4.w) + 1;
+    s.sum[job] = make_float4(sum4.x + color.x, sum4.y + color.y, sum4.z + color.z, __uint_as_float(done));
+    s.a[job]   = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(seed));
+    s.c[job]   = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(F_NEW));
+    jc.samples++;
+    if (done == t.spp) jc.done++;
+  } else {
+    flags = (flags & ~(F_BOUNCE_MASK | F_TRIES_MASK)) | bounce;
+    s.d[job] = make_float4(nd.x, nd.y, nd.z, 0.0f);
+    s.a[job] = make_float4(atten.x, atten.y, atten.z, __uint_as_float(seed));
+    s.c[job] = make_float4(color.x, color.y, color.z, __uint_as_float(flags));
+  }
+}
+
+// cone (axis, cos half-angle) around the sphere that bounds all emitters, seen from P
+__device__ __forceinline__ void emitter_cone(const DScene& sc, const float3& P, float3& axis, float& cosa) {
+  const float3 v  = sc.emit_c - P;
+  const float  d2 = dot(v, v);
+  if (sc.emit_r2 < 0.0f) { axis = f3(0, 0, 0); cosa = 2.0f; }                 // no emitters: nothing passes
+  else if (!sc.cull || d2 <= sc.emit_r2 * 1.01f) { axis = f3(0, 0, 0); cosa = -2.0f; }  // inside the sphere / culling off
+  else {
+    axis = v * rsqrtf(d2);
+    cosa = sqrtf(fmaxf(1.0f - sc.emit_r2 / d2, 0.0f)) - 1e-4f;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_tries(DScene sc, DState s, Tile t, uint32_t iter, uint32_t pass) {
+  __shared__ uint32_t lcg_a[32], lcg_c[32];  // x -> A^(3k) x + C_(3k): jump ahead by k tries
+  __shared__ float    sP[8][32][3];          // hit points of the warp's batch (read by the rare cone-passing lanes)
+  unsigned int*       ring = s.ring + RING_STRIDE * (iter % 3);
+  const unsigned int  qn   = ring[R_CNTJ + pass];
+  const unsigned      lane = lane_id();
+  uint32_t my_a = 1u, my_c = 0u;
+  for (unsigned k = 0; k < 3 * lane; k++) { my_c = 1664525u * my_c + 1013904223u; my_a *= 1664525u; }
+  if (threadIdx.x < 32) { lcg_a[lane] = my_a; lcg_c[lane] = my_c; }
+  __syncthreads();
+  JobCounters jc = {0, 0};
+  uint32_t    n_sh = 0, n_cull = 0;
+  while (true) {
+    unsigned base = 0;
+    if (lane == 0) base = atomicAdd(&ring[R_CURJ + pass], 32u);
+    base = __shfl_sync(FULL, base, 0);
+    if (base >= qn) break;
+    // lane j owns job j of the batch
+    int      job = base + lane < qn ? s.shadow_q[base + lane] : -1;
+    float3   P = f3(0, 0, 0), N = f3(0, 1, 0), axis = f3(0, 0, 0);
+    float    cosa = 2.0f;
+    uint32_t seed = 0, flags = 0, start = LISA_SHADOW_TRIES;
+    int      mid = 0;
+    if (job >= 0) {
+      const float4 o4 = s.o[job], n4 = s.n[job], a4 = s.a[job], c4 = s.c[job];
+      P = f3(o4); N = f3(n4);
+      mid   = __float_as_int(n4.w);
+      seed  = __float_as_uint(a4.w);
+      flags = __float_as_uint(c4.w);
+      start = (flags & F_TRIES_MASK) >> F_TRIES_SHIFT;
+      emitter_cone(sc, P, axis, cosa);
+    }
+    float* myP = sP[threadIdx.x >> 5][lane];
+    myP[0] = P.x; myP[1] = P.y; myP[2] = P.z;
+    __syncwarp();
+    int      first = -1;  // index (relative to start) of the first candidate try of MY job
+    unsigned valid = __ballot_sync(FULL, job >= 0);
+    while (valid) {
+      const int j = __ffs(valid) - 1;
+      valid &= valid - 1;
+      const float3   Nj = f3(__shfl_sync(FULL, N.x, j), __shfl_sync(FULL, N.y, j), __shfl_sync(FULL, N.z, j));
+      const float3   Aj = f3(__shfl_sync(FULL, axis.x, j), __shfl_sync(FULL, axis.y, j), __shfl_sync(FULL, axis.z, j));
+      const float    cj = __shfl_sync(FULL, cosa, j);
+      const uint32_t sj = __shfl_sync(FULL, seed, j), stj = __shfl_sync(FULL, start, j);
+      uint32_t       sd = my_a * sj + my_c;  // LCG state before try (start + lane)
+      const float3   w  = shoot_ray_hemisphere(Nj, sd);
+      bool           cand = (stj + lane < LISA_SHADOW_TRIES) && dot(w, Aj) >= cj;
+      if (cand && sc.cull) {  // rare: confirm against the box itself
+        const float* pj = sP[threadIdx.x >> 5][j];
+        cand = hits_emitter_bounds(sc, f3(pj[0], pj[1], pj[2]), w, LISA_TMIN, LISA_TMAX);
+      }
+      const unsigned m = __ballot_sync(FULL, cand);
+      if ((int)lane == j) first = m ? __ffs(m) - 1 : -1;
+    }
+    // every lane settles its own job
+    bool push = false;
+    if (job >= 0) {
+      const uint32_t consumed = first >= 0 ? (uint32_t)first : LISA_SHADOW_TRIES - start;  // tries resolved here
+      n_sh += consumed;
+      n_cull += consumed;
+      seed = lcg_a[consumed] * seed + lcg_c[consumed];
+      if (first >= 0) {  // candidate: k_rays regenerates the direction from this state
+        flags = (flags & ~F_TRIES_MASK) | ((start + consumed) << F_TRIES_SHIFT);
+        s.a[job].w = __uint_as_float(seed);
+        s.c[job].w = __uint_as_float(flags);
+        push = true;
+      } else {
+        finish_job(sc, s, t, job, N, mid, seed, flags, 0.0f, jc);  // 30 tries, no light (hit is false)
+      }
+    }
+    queue_push(push, job, s.cand_q, &ring[R_CNTC + pass]);
+    __syncwarp();  // sP is rewritten by the next batch
+  }
+  warp_add(&s.stats[ST_SHADOW], n_sh);
+  warp_add(&s.stats[ST_CULLED], n_cull);
+  warp_add(&s.stats[ST_SAMPLES], jc.samples);
+  warp_add(&s.stats[ST_CHAINS_DONE], jc.done);
+}
+
 template <bool WIDE>
-__global__ void __launch_bounds__(256) k_shadow(DScene sc, DState s, Tile t, uint32_t iter, uint32_t idle_thresh) {
+__global__ void __launch_bounds__(256) k_rays(DScene sc, DState s, Tile t, uint32_t iter, uint32_t pass, uint32_t last,
+                                              uint32_t idle_thresh) {
   extern __shared__ uint2 smem_stack[];
   Stack              stack(smem_stack);
-  unsigned int*      ring = s.ring + 4 * (iter % 3);
-  const unsigned int qn   = ring[0];
+  unsigned int*      ring = s.ring + RING_STRIDE * (iter % 3);
+  const unsigned int qn   = ring[R_CNTC + pass];
   const unsigned     lane = lane_id();
   // job
   int      job = -1;
@@ -267,33 +415,31 @@ __global__ void __launch_bounds__(256) k_shadow(DScene sc, DState s, Tile t, uin
   uint32_t seed = 0, flags = 0, tries = 0;
   int      mid = 0;
   // ray of the current try
-  StepRay  ray;
+  StepRay ray;
   ray.idir = f3(0, 0, 0); ray.Sx = ray.Sy = ray.Sz = 0; ray.kz = 0; ray.oct_inv4 = 0;
-  float    ndotl = 0.0f;
-  bool     in_flight = false;  // a ray is being traversed
-  bool     pending = false;    // a finished ray waits to be retired
+  float ndotl = 0.0f;
+  bool  in_flight = false, pending = false;
   // traversal
   TravState<WIDE> st;
   st.begin(-1);
-  int   phase = 0;             // 0: emitter BVH (closest), 1: other BVH (any)
-  float tlimit = LISA_TMAX;    // closest emitter distance found so far
-  int   light_prim = -1;
-  int   outcome = 0;
-  // queue
-  unsigned wnext = 0, wend = 0;
-  bool     exhausted = (qn == 0);
-  uint32_t n_sh = 0, n_samp = 0, n_done = 0, nn = 0, nt = 0;
-
-  // cone (axis, cos of the half angle) around the emitter bounds as seen from P: a direction outside it cannot hit an emitter
+  int   phase = 0;           // 0: emitter BVH (closest), 1: other BVH (any)
+  float tlimit = LISA_TMAX;  // closest emitter distance found so far
+  int   light_prim = -1, outcome = 0;
+  // inline tries of the last pass
   float3 cone_axis = f3(0, 0, 0);
   float  cone_cos = -2.0f;
-  uint32_t n_cull = 0;
+  // queue
+  unsigned    wnext = 0, wend = 0;
+  bool        exhausted = (qn == 0);
+  JobCounters jc = {0, 0};
+  uint32_t    n_sh = 0, n_cull = 0, nn = 0, nt = 0;
+
   while (true) {
     const unsigned idle = __ballot_sync(FULL, !in_flight);
     if (idle == FULL || (uint32_t)__popc(idle) >= idle_thresh) {
-      while (true) {
-        // ---- (1) retire the finished ray
-        bool finish = false;
+      {
+        // ---- (1) retire the finished ray into RayState::hit
+        bool finish = false, requeue = false;
         if (pending) {
           pending = false;
           tries++;
@@ -303,70 +449,38 @@ __global__ void __launch_bounds__(256) k_shadow(DScene sc, DState s, Tile t, uin
             flags = (flags & 0x0000ffffu) | F_STICKY | ((uint32_t)light << F_LIGHT_SHIFT);
           }                                      // outcome 2: RayState::hit keeps its value (Q1)
           finish = (flags & F_STICKY) || tries == LISA_SHADOW_TRIES;
+          requeue = !finish && !last;
         }
-        // ---- (2) next tries of shoot_ray_to_light (shader.cu:199-207).  A try can only matter if it may set
-        // RayState::hit (ray can reach an emitter) or clear it (hit currently true): everything else is resolved here.
-        if (job >= 0 && !in_flight && !finish) {
+        // ---- (2) last pass only: the remaining tries run here, one lane per job
+        if (last && job >= 0 && !in_flight && !finish) {
           while (true) {
-            const float3 w = shoot_ray_hemisphere(N, seed);
-            n_sh++;
-            const bool sticky = flags & F_STICKY;
-            bool       cand = sticky || !sc.cull || dot(w, cone_axis) >= cone_cos;
+            const uint32_t before = seed;
+            const float3   w = shoot_ray_hemisphere(N, seed);
+            const bool     sticky = flags & F_STICKY;
+            bool           cand = sticky || dot(w, cone_axis) >= cone_cos;
             if (cand && !sticky && sc.cull) cand = hits_emitter_bounds(sc, P, w, LISA_TMIN, LISA_TMAX);
-            if (cand) {
-              ndotl = dot(N, w);
-              ray   = step_ray(w);
-              in_flight  = true;
-              light_prim = -1;
-              tlimit     = LISA_TMAX;
-              stack.clear();
-              if ((sticky || !sc.cull) ? hits_emitter_bounds(sc, P, w, LISA_TMIN, LISA_TMAX) : true) { phase = 0; st.begin(sc.root_emit); }
-              else { phase = 1; st.begin(sc.root_other); }
-              break;
-            }
-            n_cull++;
+            if (cand) { seed = before; break; }  // the ray is started below from `before`
+            n_sh++; n_cull++;
             tries++;
             if (tries == LISA_SHADOW_TRIES) { finish = true; break; }
           }
         }
-        // ---- (3) finish the job: light term, BSDF bounce, write-back
-        if (finish) {
-          const bool      lit = flags & F_STICKY;
-          const float4    a4 = s.a[job], c4 = s.c[job], d4 = s.d[job];
-          const float3    atten = f3(a4);
-          float3          color = f3(c4);
-          const DMaterial m = load_material(sc.mats, mid);
-          if (lit) {
-            const DMaterial lm = load_material(sc.mats, (int)(flags >> F_LIGHT_SHIFT));
-            const float     c = fminf(fmaxf(ndotl, 0.0f), 1.0f);
-            color = color + (lm.emission() * (c * (c * 0.318309886183790672f))) * atten;  // bsdf::BRDF, shader.cu:205,251
-          }
-          const float3 nd = bsdf::bounce(f3(d4), N, seed, m);  // shader.cu:252 (drawn even after the last bounce)
-          const uint32_t bounce = (flags & F_BOUNCE_MASK) + 1;
-          if (bounce >= t.bounces) {
-            const float4   sum4 = s.sum[job];
-            const uint32_t done = __float_as_uint(sum4.w) + 1;
-            s.sum[job] = make_float4(sum4.x + color.x, sum4.y + color.y, sum4.z + color.z, __uint_as_float(done));
-            s.a[job]   = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(seed));
-            s.c[job]   = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(F_NEW));
-            n_samp++;
-            if (done == t.spp) n_done++;
-          } else {
-            flags = (flags & ~F_BOUNCE_MASK) | bounce;
-            s.d[job] = make_float4(nd.x, nd.y, nd.z, 0.0f);
-            s.a[job] = make_float4(atten.x, atten.y, atten.z, __uint_as_float(seed));
-            s.c[job] = make_float4(color.x, color.y, color.z, __uint_as_float(flags));
-          }
-          job = -1;
+        // ---- (3) finish / hand back
+        if (finish) { finish_job(sc, s, t, job, N, mid, seed, flags, ndotl, jc); job = -1; }
+        if (requeue) {
+          flags = (flags & ~F_TRIES_MASK) | (tries << F_TRIES_SHIFT);
+          s.a[job].w = __uint_as_float(seed);
+          s.c[job].w = __uint_as_float(flags);
         }
+        queue_push(requeue, job, s.shadow_q, &ring[R_CNTJ + pass + 1]);
+        if (requeue) job = -1;
         // ---- (4) fetch jobs
         const bool     need     = job < 0;
         const unsigned needmask = __ballot_sync(FULL, need);
-        bool           got = false;
         if (needmask) {
           if (wnext == wend && !exhausted) {
             unsigned base = 0;
-            if (lane == 0) base = atomicAdd(&ring[1], SHADOW_BATCH);
+            if (lane == 0) base = atomicAdd(&ring[R_CURC + pass], SHADOW_BATCH);
             base = __shfl_sync(FULL, base, 0);
             wnext = min(base, qn);
             wend  = min(base + SHADOW_BATCH, qn);
@@ -374,31 +488,38 @@ __global__ void __launch_bounds__(256) k_shadow(DScene sc, DState s, Tile t, uin
           }
           const unsigned avail = wend - wnext, cnt = __popc(needmask), rank = __popc(needmask & lanemask_lt());
           if (need && rank < avail) {
-            job = s.shadow_q[wnext + rank];
+            job = s.cand_q[wnext + rank];
             const float4 o4 = s.o[job], n4 = s.n[job], a4 = s.a[job], c4 = s.c[job];
             P = f3(o4); N = f3(n4);
             mid   = __float_as_int(n4.w);
             seed  = __float_as_uint(a4.w);
             flags = __float_as_uint(c4.w);
-            tries = 0;
-            got   = true;
-            // cone around the emitter bounds
-            const float3 v  = sc.emit_c - P;
-            const float  d2 = dot(v, v);
-            if (sc.emit_r2 < 0.0f) { cone_axis = f3(0, 0, 0); cone_cos = 2.0f; }            // no emitters: nothing passes
-            else if (d2 <= sc.emit_r2 * 1.01f) { cone_axis = f3(0, 0, 0); cone_cos = -2.0f; }  // inside the sphere: everything passes
-            else {
-              cone_axis = v * rsqrtf(d2);
-              cone_cos  = sqrtf(fmaxf(1.0f - sc.emit_r2 / d2, 0.0f)) - 1e-4f;
-            }
+            tries = (flags & F_TRIES_MASK) >> F_TRIES_SHIFT;
+            if (last) emitter_cone(sc, P, cone_axis, cone_cos);
           }
           wnext += min(cnt, avail);
         }
-        if (__ballot_sync(FULL, got) == 0) break;  // new jobs go round again for their first tries
+        // ---- (5) start the ray of the current try (its direction is regenerated from the stored LCG state)
+        if (job >= 0 && !in_flight) {
+          const float3 w = shoot_ray_hemisphere(N, seed);
+          n_sh++;
+          ndotl = dot(N, w);
+          ray   = step_ray(w);
+          in_flight  = true;
+          light_prim = -1;
+          tlimit     = LISA_TMAX;
+          stack.clear();
+          if (hits_emitter_bounds(sc, P, w, LISA_TMIN, LISA_TMAX)) { phase = 0; st.begin(sc.root_emit); }
+          else { phase = 1; st.begin(sc.root_other); }
+        }
       }
-      if (__ballot_sync(FULL, in_flight) == 0) break;
+      // after the management section a lane has a ray in flight exactly when it has a job
+      if (__ballot_sync(FULL, in_flight) == 0) {
+        if (exhausted && wnext == wend) break;  // queue drained
+        continue;                               // the warp's batch ran dry mid-fetch: fetch again
+      }
     }
-    // ---- (4) one traversal quantum
+    // ---- one traversal quantum
     if (in_flight) {
       if (st.has_nodes() && !st.has_tris()) {
         nn++;
@@ -455,8 +576,8 @@ __global__ void __launch_bounds__(256) k_shadow(DScene sc, DState s, Tile t, uin
   }
   warp_add(&s.stats[ST_SHADOW], n_sh);
   warp_add(&s.stats[ST_CULLED], n_cull);
-  warp_add(&s.stats[ST_SAMPLES], n_samp);
-  warp_add(&s.stats[ST_CHAINS_DONE], n_done);
+  warp_add(&s.stats[ST_SAMPLES], jc.samples);
+  warp_add(&s.stats[ST_CHAINS_DONE], jc.done);
   warp_add(&s.stats[ST_NODES], nn);
   warp_add(&s.stats[ST_TRIS], nt);
 }
@@ -568,16 +689,21 @@ int configure_kernels(char* err, size_t errlen) {
   const int   smem = (int)stack_smem(256);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_extend<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_extend<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_shadow<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_shadow<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_rays<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_rays<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) { snprintf(err, errlen, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -2; }
   return 0;
 }
 
 int shadow_occupancy(bool wide, int block) {
   int n = 0;
-  cudaError_t e = wide ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_shadow<true>, block, stack_smem(block))
-                       : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_shadow<false>, block, stack_smem(block));
+  cudaError_t e = wide ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_rays<true>, block, stack_smem(block))
+                       : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_rays<false>, block, stack_smem(block));
+  return (e == cudaSuccess && n > 0) ? n : 2;
+}
+int tries_occupancy(int block) {
+  int n = 0;
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_tries, block, 0);
   return (e == cudaSuccess && n > 0) ? n : 2;
 }
 
@@ -590,12 +716,22 @@ void launch_extend(const DScene& sc, const DState& s, const DCamera& cam, const 
   if (sc.wide) k_extend<true><<<cdiv(t.n_chains, b), b, stack_smem(b), st>>>(sc, s, cam, t, iter);
   else k_extend<false><<<cdiv(t.n_chains, b), b, stack_smem(b), st>>>(sc, s, cam, t, iter);
 }
-void launch_shadow(const DScene& sc, const DState& s, const Tile& t, uint32_t iter, const LaunchCfg& cfg, cudaStream_t st) {
+int launch_shadow(const DScene& sc, const DState& s, const Tile& t, uint32_t iter, const LaunchCfg& cfg, cudaStream_t st) {
   const int b = cfg.shadow_block;
-  unsigned  grid = (unsigned)(cfg.sm_count * cfg.shadow_blocks_per_sm);
-  grid = min(grid, max(1u, cdiv(t.n_chains, SHADOW_BATCH * (b / 32)) ));
-  if (sc.wide) k_shadow<true><<<grid, b, stack_smem(b), st>>>(sc, s, t, iter, (uint32_t)cfg.idle_thresh);
-  else k_shadow<false><<<grid, b, stack_smem(b), st>>>(sc, s, t, iter, (uint32_t)cfg.idle_thresh);
+  int launches = 0;
+  for (int p = 0; p < LISA_SHADOW_PASSES; p++) {
+    const unsigned last = p == LISA_SHADOW_PASSES - 1;
+    // work shrinks roughly 4x per pass: later passes get smaller persistent grids
+    unsigned gt = (unsigned)(cfg.sm_count * cfg.tries_blocks_per_sm), gr = (unsigned)(cfg.sm_count * cfg.shadow_blocks_per_sm);
+    gt = min(gt, max(1u, cdiv(t.n_chains >> (2 * p), 32u * (256 / 32))));
+    gr = min(gr, max(1u, cdiv(t.n_chains >> (2 * p), SHADOW_BATCH * (b / 32))));
+    k_tries<<<gt, 256, 0, st>>>(sc, s, t, iter, (uint32_t)p);
+    launches++;
+    if (sc.wide) k_rays<true><<<gr, b, stack_smem(b), st>>>(sc, s, t, iter, (uint32_t)p, last, (uint32_t)cfg.idle_thresh);
+    else k_rays<false><<<gr, b, stack_smem(b), st>>>(sc, s, t, iter, (uint32_t)p, last, (uint32_t)cfg.idle_thresh);
+    launches++;
+  }
+  return launches;
 }
 void launch_finalize(const DState& s, const DCamera&, const Tile& t, float4* accum, cudaStream_t st) {
   k_finalize<<<cdiv(t.npix, 256), 256, 0, st>>>(s, t, accum);

@@ -17,8 +17,9 @@ struct DState {
   float4* c;    // radiance of the sample in flight .xyz | flags in .w (see F_* in wavefront.cu)
   float4* n;    // shading normal .xyz | material id in .w   (extend -> shadow stage hand-off)
   float4* sum;  // sum of finished samples .xyz | number of finished samples in .w
-  int*    shadow_q;  // chain ids with an opaque hit waiting for light sampling
-  // ring of 3 per-iteration counter blocks {shadow queue length, shadow queue fetch cursor, -, -}
+  int*    shadow_q;  // job queue: chain ids with an opaque hit whose next light-sampling tries are still to be drawn
+  int*    cand_q;    // candidate queue: chain ids whose current try must be traced
+  // ring of 3 per-iteration blocks of 16 counters: queue lengths and fetch cursors of every pass (wavefront.cu R_*)
   unsigned int* ring;
   // cumulative: [0] radiance rays [1] shadow rays [2] samples [3] null directions [4] finished chains
   // [5] BVH nodes visited [6] triangles tested [7] shadow jobs (opaque hits queued) [8] shadow tries resolved without traversal
@@ -37,17 +38,21 @@ struct LaunchCfg {
   int sm_count;
   int extend_block, shadow_block;
   int shadow_blocks_per_sm;
+  int tries_blocks_per_sm;
   int idle_thresh;  // k_shadow: lanes that must be idle before the warp runs its management section
 };
 
 void launch_init_chains(const DState& s, const DCamera& cam, const Tile& t, cudaStream_t st);
 void launch_extend(const DScene& sc, const DState& s, const DCamera& cam, const Tile& t, uint32_t iter, const LaunchCfg& cfg,
                    cudaStream_t st);
-void launch_shadow(const DScene& sc, const DState& s, const Tile& t, uint32_t iter, const LaunchCfg& cfg, cudaStream_t st);
+// all light-sampling passes of one iteration; returns the number of kernels launched
+int  launch_shadow(const DScene& sc, const DState& s, const Tile& t, uint32_t iter, const LaunchCfg& cfg, cudaStream_t st);
+#define LISA_SHADOW_PASSES 4
 void launch_finalize(const DState& s, const DCamera& cam, const Tile& t, float4* accum, cudaStream_t st);
 void launch_resolve(const float4* accum, uint32_t npix, float4* mean_out, uint32_t* rgba8_out, cudaStream_t st);
 int  configure_kernels(char* err, size_t errlen);
-int  shadow_occupancy(bool wide, int block);  // resident CTAs of k_shadow per SM
+int  shadow_occupancy(bool wide, int block);  // resident CTAs of k_rays per SM
+int  tries_occupancy(int block);               // resident CTAs of k_tries per SM
 
 // diagnostics
 void launch_trace_closest(const DScene& sc, const float* d_org, const float* d_dir, uint32_t n, float tmin, float tmax,

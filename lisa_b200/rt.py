@@ -197,8 +197,10 @@ class Renderer:
     def reset(self):
         _check(_L.lisa_reset_accum(self._h))
 
-    def read_accum(self):
-        out = np.empty((self.height, self.width, 4), dtype=np.float32)
+    def read_accum(self, out=None):
+        if out is None:
+            out = np.empty((self.height, self.width, 4), dtype=np.float32)
+        assert out.dtype == np.float32 and out.size == self.height * self.width * 4 and out.flags["C_CONTIGUOUS"]
         _check(_L.lisa_read_accum(self._h, out.ctypes.data))
         return out
 
