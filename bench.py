@@ -35,7 +35,6 @@ os.chdir(ROOT)
 
 SCENE = "scenes/cornell_c2.rto"
 METRIC = "Msamples/s (Cornell 2000x2000, 7 bounces)"
-STATE_BYTES_PER_JOB = 4 + 64 + 48 + 48  # queue entry; o,n,a,c read; a,c,d read at the end; d,a,c written
 
 
 def measured_peaks():
@@ -210,8 +209,8 @@ def main():
     barrier()
     clk = ClockSampler(local_rank) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    agg = dict(render_ms=0.0, shadow_ms=0.0, extend_ms=0.0, shadow_launches=0, jobs=0, shadow_rays=0, radiance_rays=0, launches=0,
-               nodes=0, tris=0, culled=0)
+    agg = dict(render_ms=0.0, shadow_ms=0.0, extend_ms=0.0, shadow_launches=0, extend_launches=0, jobs=0, shadow_rays=0,
+               radiance_rays=0, launches=0, nodes=0, tris=0, culled=0)
     e0.record()
     t0 = time.perf_counter()
     for i in range(W, W + K):
@@ -220,6 +219,7 @@ def main():
         agg["shadow_ms"] += st["last_shadow_ms"]
         agg["extend_ms"] += st["last_extend_ms"]
         agg["shadow_launches"] += st["last_shadow_launches"]
+        agg["extend_launches"] += st["last_extend_launches"]
         agg["jobs"] += st["last_shadow_jobs"]
         agg["shadow_rays"] += st["last_shadow_rays"]
         agg["radiance_rays"] += st["last_radiance_rays"]
@@ -281,21 +281,28 @@ def main():
         peak, peak_src = measured_peaks()
         ref_rays = agg["shadow_rays"] + agg["radiance_rays"]          # rays the reference's programs would trace
         rays = ref_rays - agg["culled"]                                # rays actually traversed here
-        traced_shadow = agg["shadow_rays"] - agg["culled"]
         nn, nt = agg["nodes"] / max(rays, 1), agg["tris"] / max(rays, 1)
-        node_bytes = 80  # compressed 8-wide node
-        per_launch = lambda x: x / max(agg["shadow_launches"], 1)
-        alg_bytes = per_launch(agg["jobs"]) * STATE_BYTES_PER_JOB + per_launch(traced_shadow) * (32 + node_bytes * nn + 48 * nt) \
-            + per_launch(agg["culled"]) * 0
-        avg_ms = agg["shadow_ms"] / max(agg["shadow_launches"], 1)
+        # dominant kernel: k_extend (one radiance ray + material dispatch per live chain and iteration).
+        # Algorithmic bytes per chain (DESIGN.md "Kernels"): chain state 16 (sum) + 32 (a, c) + 32 (o, d) read, 64 written
+        # (o/n/a/c for an opaque hit, o/d/a/c for a dielectric, sum/a/c for a finished sample), hit shading 96
+        # (3 normals + material), ray 32, BVH 80 B per node visited and 48 B per triangle tested.
+        ext_launches = max(agg["extend_launches"], 1)
+        chains_per_launch = agg["radiance_rays"] / ext_launches
+        bytes_per_chain = 144 + 96 + 32 + 80 * nn + 48 * nt
+        alg_bytes = chains_per_launch * bytes_per_chain
+        avg_ms = agg["extend_ms"] / ext_launches
         achieved = alg_bytes / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else None
-        traffic = None
-        prof = os.path.join(ROOT, "profiles", "k_shadow_traffic.json")
+        traffic, issue = None, None
+        prof = os.path.join(ROOT, "profiles", "r01_k_extend.json")
         if os.path.exists(prof):
             try:
-                traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+                pj = json.load(open(prof))["launches"][0]
+                traffic = pj.get("dram_bytes_per_launch")
+                issue = {"issue_slot_utilisation_pct": pj.get("issue_slot_utilisation_pct"),
+                         "avg_active_lanes_per_instruction": pj.get("avg_active_lanes_per_instruction"),
+                         "frac_of_issue_roofline": pj.get("issue_roofline_frac"), "source": "profiles/r01_k_extend.json (ncu --set full)"}
             except Exception:
-                traffic = None
+                pass
         out = {
             "metric": METRIC, "value": round(value, 4), "unit": "Msamples/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": round(T / K, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -313,13 +320,16 @@ def main():
             "gpu_launches": int(agg["launches"]),
             "clocks": clocks,
             "e2e": e2e,
-            "roofline": {"bound": "hbm", "kernel": "k_shadow<wide8>", "achieved": round(achieved, 1) if achieved else None, "peak": peak,
-                         "unit": "GB/s", "frac": round(achieved / peak, 4) if achieved else None, "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": int(alg_bytes), "avg_launch_ms": round(avg_ms, 4),
-                         "launches": int(agg["shadow_launches"]), "share_of_step": round(agg["shadow_ms"] / max(agg["render_ms"], 1e-9), 4),
-                         "nodes_per_ray": round(nn, 2), "tris_per_ray": round(nt, 2),
-                         "note": "scene (11 KB of nodes + 96 KB of triangles) is L1/L2 resident: the kernel is issue/latency bound, "
-                                 "not HBM bound; see profiles/ for issue-slot utilisation"},
+            "roofline": {"bound": "hbm", "kernel": "k_extend<wide8>", "achieved": round(achieved, 1) if achieved else None, "peak": peak,
+                         "unit": "GB/s", "frac": round(achieved / peak, 4) if achieved else None, "traffic": traffic,
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": int(alg_bytes),
+                         "algorithmic_bytes_per_chain": round(bytes_per_chain, 1), "avg_launch_ms": round(avg_ms, 4),
+                         "launches": int(ext_launches), "share_of_step": round(agg["extend_ms"] / max(agg["render_ms"], 1e-9), 4),
+                         "light_sampling_share_of_step": round(agg["shadow_ms"] / max(agg["render_ms"], 1e-9), 4),
+                         "nodes_per_ray": round(nn, 2), "tris_per_ray": round(nt, 2), "issue": issue,
+                         "note": "BVH (11 KB) + triangles (96 KB) are L1/L2 resident: the path is issue/latency bound, not "
+                                 "HBM bound; HBM traffic is the chain state only. `issue` is the north_star's roofline "
+                                 "(issue-slot utilisation x warp execution efficiency) from the committed ncu capture."},
         }
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(sc, S)

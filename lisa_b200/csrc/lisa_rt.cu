@@ -328,18 +328,21 @@ static int create_impl(const lisa_scene_desc* sd, const lisa_options* opt, lisa_
   const size_t npix = (size_t)c->width * c->height;
   CU(big_alloc((void**)&c->d_accum, sizeof(float4) * std::max<size_t>(npix, 1), c->device));
   CU(cudaMemsetAsync(c->d_accum, 0, sizeof(float4) * npix, c->stream));
-  CU(cudaMalloc(&c->state.ring, sizeof(unsigned int) * 48));
+  CU(cudaMalloc(&c->state.ring, sizeof(unsigned int) * 64));
   CU(cudaMalloc(&c->state.stats, sizeof(unsigned long long) * 16));
   CU(cudaMemsetAsync(c->state.stats, 0, sizeof(unsigned long long) * 16, c->stream));
   CU(cudaMallocHost(&c->h_stats, sizeof(unsigned long long) * 16));
   memset(c->h_stats, 0, sizeof(unsigned long long) * 16);
 
   c->cfg.sm_count = prop.multiProcessorCount;
-  c->cfg.extend_block = 256;
-  c->cfg.shadow_block = 256;
-  c->cfg.idle_thresh = 8;
+  c->cfg.extend_block = 128;  // 94 registers/thread: 128-thread CTAs pack 5 per SM (20 warps) where 256 pack 2 (16 warps)
+  c->cfg.shadow_block = 128;
+  if (const char* e2 = getenv("LISA_EXTEND_BLOCK")) c->cfg.extend_block = std::max(32, std::min(256, atoi(e2) / 32 * 32));
+  if (const char* e2 = getenv("LISA_SHADOW_BLOCK")) c->cfg.shadow_block = std::max(32, std::min(256, atoi(e2) / 32 * 32));
+  c->cfg.idle_thresh = 16;  // measured on B200 (Cornell 2000x2000): 1 -> 651, 8 -> 660, 16 -> 674, 20 -> 677 Msamples/s
   if (const char* e2 = getenv("LISA_IDLE_THRESH")) c->cfg.idle_thresh = std::max(1, std::min(32, atoi(e2)));
   c->cfg.tries_blocks_per_sm = tries_occupancy(256);
+  c->cfg.extend_blocks_per_sm = extend_occupancy(bi.wide != 0, c->cfg.extend_block);
   c->cfg.shadow_blocks_per_sm = shadow_occupancy(bi.wide != 0, c->cfg.shadow_block);  // persistent grid = what is resident
   if (const char* e2 = getenv("LISA_SHADOW_BLOCKS_PER_SM")) c->cfg.shadow_blocks_per_sm = std::max(1, atoi(e2));
   // default residency: enough chains to fill the machine several times over, bounded so the state stays

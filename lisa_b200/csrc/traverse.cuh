@@ -333,6 +333,14 @@ __device__ __forceinline__ bool step_tri(const float3& o, const StepRay& r, cons
   return intersect_tri(pre, f3(a), f3(b), f3(c), tmin, tmax, t_out, u, v);
 }
 
+__device__ __forceinline__ bool step_tri_uv(const float3& o, const StepRay& r, const float4* __restrict__ tri_v, int ti, float tmin,
+                                            float tmax, float& t_out, float& u_out, float& v_out) {
+  const float4 a = __ldg(tri_v + 3 * ti), b = __ldg(tri_v + 3 * ti + 1), c = __ldg(tri_v + 3 * ti + 2);
+  RayPre pre;
+  pre.o = o; pre.kz = r.kz; pre.Sx = r.Sx; pre.Sy = r.Sy; pre.Sz = r.Sz;
+  return intersect_tri(pre, f3(a), f3(b), f3(c), tmin, tmax, t_out, u_out, v_out);
+}
+
 // byte j of q -> float, on the ALU/FMA pipes (PRMT + FADD) instead of the slow conversion pipe
 __device__ __forceinline__ float byte_to_float(uint32_t q, int j) {
   return __uint_as_float(__byte_perm(q, 0x4B000000u, 0x7650u | (uint32_t)j)) - 8388608.0f;

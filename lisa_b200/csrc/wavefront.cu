@@ -140,7 +140,7 @@ __device__ __forceinline__ uint32_t chain_seed(const DCamera& cam, uint32_t p, u
 __global__ void k_init_chains(DState s, DCamera cam, Tile t) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i == 0) {
-    for (int k = 0; k < 3 * RING_STRIDE; k++) s.ring[k] = 0;
+    for (int k = 0; k < 3 * RING_STRIDE + 4; k++) s.ring[k] = 0;
     s.stats[ST_CHAINS_DONE] = 0;
   }
   if (i >= t.n_chains) return;
@@ -150,53 +150,70 @@ __global__ void k_init_chains(DState s, DCamera cam, Tile t) {
   s.sum[i] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(0u));
 }
 
-// ------------------------------------------------------------------------------------------------
 template <bool WIDE>
-__global__ void __launch_bounds__(256) k_extend(DScene sc, DState s, DCamera cam, Tile t, uint32_t iter) {
+struct TravState;
+template <>
+struct TravState<true> : WideState {};
+template <>
+struct TravState<false> : BinState {};
+
+// ------------------------------------------------------------------------------------------------
+// k_extend: persistent state machine over ALL chains of the tile.  A lane fetches a chain (warp batches of
+// consecutive ids, so the state loads coalesce), regenerates a camera ray if the previous sample ended,
+// traverses it one quantum per loop iteration (phase 0 closest emitter, phase 1 closest other triangle in
+// front of it), and when enough lanes have finished the warp runs the material dispatch of
+// __closesthit__radiance / __miss__radiance for them together and fetches new chains.
+template <bool WIDE>
+__global__ void __launch_bounds__(256) k_extend(DScene sc, DState s, DCamera cam, Tile t, uint32_t iter, uint32_t idle_thresh) {
   extern __shared__ uint2 smem_stack[];
   Stack          stack(smem_stack);
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   unsigned int*  ring = s.ring + RING_STRIDE * (iter % 3);
-  if (i < RING_STRIDE) {  // reset the counter block of the NEXT iteration (its last user finished two iterations ago)
-    s.ring[RING_STRIDE * ((iter + 1) % 3) + i] = 0;
-  }
-  uint32_t n_rad = 0, n_null = 0, n_samp = 0, n_done = 0, nn = 0, nt = 0;
-  bool     push = false, push_sticky = false;
-  if (i < t.n_chains) {
-    float4   sum4 = s.sum[i];
-    uint32_t done = __float_as_uint(sum4.w);
-    if (done < t.spp) {
-      float4   a4 = s.a[i], c4 = s.c[i];
-      uint32_t flags = __float_as_uint(c4.w), seed = __float_as_uint(a4.w);
-      float3   o, d, atten, color;
-      const bool fresh = flags & F_NEW;
-      if (fresh) {
-        d = camera_ray(cam, t.pix0 + i % t.npix, seed);
-        o = cam.eye;
-        atten = f3(1.0f, 1.0f, 1.0f);
-        color = f3(0.0f, 0.0f, 0.0f);
-        flags = 0;
-      } else {
-        o = f3(s.o[i]); d = f3(s.d[i]);
-        atten = f3(a4); color = f3(c4);
-      }
-      bool finished = false;
-      if (d.x == 0.0f && d.y == 0.0f && d.z == 0.0f) {  // Q7: refract() returned the null vector: treated as a miss
-        n_null++;
-        finished = true;
-      } else {
-        n_rad++;
-        const Hit h = closest_hit<WIDE>(sc, o, d, LISA_TMIN, LISA_TMAX, stack, nn, nt);
-        if (h.prim < 0) {
-          finished = true;  // __miss__radiance: background is 0 (optix_wrapper.cc:354)
+  const unsigned lane = lane_id();
+  if (blockIdx.x == 0 && threadIdx.x < RING_STRIDE)  // reset the NEXT iteration's counters (last used two iterations ago)
+    s.ring[RING_STRIDE * ((iter + 1) % 3) + threadIdx.x] = 0;
+  unsigned int* cursor = &s.ring[3 * RING_STRIDE + (iter % 3)];  // chain fetch cursor of this iteration
+  if (blockIdx.x == 0 && threadIdx.x == 0) s.ring[3 * RING_STRIDE + ((iter + 1) % 3)] = 0;
+
+  int      chain = -1;
+  float3   o = f3(0, 0, 0), d = f3(0, 0, 1);
+  uint32_t seed = 0, flags = 0;
+  bool     fresh = false, nullray = false;
+  StepRay  ray;
+  ray.idir = f3(0, 0, 0); ray.Sx = ray.Sy = ray.Sz = 0; ray.kz = 0; ray.oct_inv4 = 0;
+  bool in_flight = false, pending = false;
+  TravState<WIDE> st;
+  st.begin(-1);
+  int   phase = 0;
+  float best_t = LISA_TMAX, best_u = 0, best_v = 0;
+  int   best_prim = -1;
+  unsigned wnext = 0, wend = 0;
+  bool     exhausted = false;
+  uint32_t n_rad = 0, n_null = 0, n_samp = 0, n_done = 0, n_jobs = 0, nn = 0, nt = 0;
+
+  while (true) {
+    const unsigned idle = __ballot_sync(FULL, !in_flight);
+    if (idle == FULL || (uint32_t)__popc(idle) >= idle_thresh) {
+      // ---- (1) shade the finished rays
+      bool push = false, push_sticky = false;
+      const int shaded = chain;
+      if (pending) {
+        pending = false;
+        const int i = chain;
+        float3 atten = f3(1.0f, 1.0f, 1.0f), color = f3(0.0f, 0.0f, 0.0f);
+        if (!fresh) { atten = f3(s.a[i]); color = f3(s.c[i]); }
+        bool finished = false;
+        if (best_prim < 0) {
+          finished = true;  // __miss__radiance (background 0, optix_wrapper.cc:354) or a null direction (Q7)
         } else {
-          const int       mid = __float_as_int(__ldg(sc.tri_v + 3 * h.prim).w);
+          const int       mid = __float_as_int(__ldg(sc.tri_v + 3 * best_prim).w);
           const DMaterial m   = load_material(sc.mats, mid);
           if (m.emit()) {  // shader.cu:216-218
             color = color + m.emission() * atten;
             finished = true;
           } else {
-            const float3 P = o + h.t * d;  // shader.cu:221
+            const float3 P = o + best_t * d;  // shader.cu:221
+            Hit h;
+            h.t = best_t; h.u = best_u; h.v = best_v; h.prim = best_prim;
             const float3 N = shading_normal(sc, h);
             uint32_t bounce = (flags & F_BOUNCE_MASK);
             if (m.alpha() < 1.0f) {  // dielectric, shader.cu:226-246
@@ -217,7 +234,7 @@ __global__ void __launch_bounds__(256) k_extend(DScene sc, DState s, DCamera cam
                 s.a[i] = make_float4(atten.x, atten.y, atten.z, __uint_as_float(seed));
                 s.c[i] = make_float4(color.x, color.y, color.z, __uint_as_float(flags));
               }
-            } else {  // opaque, shader.cu:248-253: light sampling + bounce happen in k_shadow
+            } else {  // opaque, shader.cu:248-253: light sampling + bounce happen in k_tries / k_rays
               atten = atten * m.diffuse();
               s.o[i] = make_float4(P.x, P.y, P.z, 0.0f);
               if (fresh) s.d[i] = make_float4(d.x, d.y, d.z, 0.0f);
@@ -227,28 +244,125 @@ __global__ void __launch_bounds__(256) k_extend(DScene sc, DState s, DCamera cam
               // RayState::hit already true (Q1): the first try is a real ray (it can clear hit) -> candidate queue
               push_sticky = (flags & F_STICKY) != 0;
               push = !push_sticky;
+              n_jobs++;
             }
           }
         }
+        if (finished) {
+          const float4   sum4 = s.sum[i];
+          const uint32_t done = __float_as_uint(sum4.w) + 1;
+          n_samp++;
+          s.sum[i] = make_float4(sum4.x + color.x, sum4.y + color.y, sum4.z + color.z, __uint_as_float(done));
+          s.a[i]   = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(seed));
+          s.c[i]   = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(F_NEW));
+          if (done == t.spp) n_done++;
+        }
+        chain = -1;
       }
-      if (finished) {
-        done++;
-        n_samp++;
-        s.sum[i] = make_float4(sum4.x + color.x, sum4.y + color.y, sum4.z + color.z, __uint_as_float(done));
-        s.a[i]   = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(seed));
-        s.c[i]   = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(F_NEW));
-        if (done == t.spp) n_done++;
+      // stream compaction into the queues: ballot + prefix popcount, one atomic per warp and queue
+      queue_push(push, shaded, s.shadow_q, &ring[R_CNTJ + 0]);
+      queue_push(push_sticky, shaded, s.cand_q, &ring[R_CNTC + 0]);
+      // ---- (2) fetch chains
+      const bool     need     = chain < 0;
+      const unsigned needmask = __ballot_sync(FULL, need);
+      if (needmask) {
+        if (wnext == wend && !exhausted) {
+          unsigned base = 0;
+          if (lane == 0) base = atomicAdd(cursor, 64u);
+          base = __shfl_sync(FULL, base, 0);
+          wnext = min(base, t.n_chains);
+          wend  = min(base + 64u, t.n_chains);
+          if (base + 64u >= t.n_chains) exhausted = true;
+        }
+        const unsigned avail = wend - wnext, cnt = __popc(needmask), rank = __popc(needmask & lanemask_lt());
+        if (need && rank < avail) {
+          const int    i = (int)(wnext + rank);
+          const float4 sum4 = s.sum[i];
+          if (__float_as_uint(sum4.w) < t.spp) {  // chains that have all their samples are skipped
+            chain = i;
+            const float4 a4 = s.a[i], c4 = s.c[i];
+            flags = __float_as_uint(c4.w);
+            seed  = __float_as_uint(a4.w);
+            fresh = flags & F_NEW;
+            if (fresh) {
+              d = camera_ray(cam, t.pix0 + i % t.npix, seed);
+              o = cam.eye;
+              flags = 0;
+            } else {
+              o = f3(s.o[i]); d = f3(s.d[i]);
+            }
+            // ---- (3) start the radiance ray (trace_radiance, shader.cu:77-98)
+            best_prim = -1; best_t = LISA_TMAX;
+            nullray = (d.x == 0.0f && d.y == 0.0f && d.z == 0.0f);  // Q7: refract() returned the null vector
+            if (nullray) { n_null++; pending = true; }
+            else {
+              n_rad++;
+              ray = step_ray(d);
+              in_flight = true;
+              stack.clear();
+              if (hits_emitter_bounds(sc, o, d, LISA_TMIN, LISA_TMAX)) { phase = 0; st.begin(sc.root_emit); }
+              else { phase = 1; st.begin(sc.root_other); }
+              if (phase == 1 && sc.root_other < 0) { in_flight = false; pending = true; }
+            }
+          }
+        }
+        wnext += min(cnt, avail);
+      }
+      if (__ballot_sync(FULL, in_flight) == 0) {
+        if (__ballot_sync(FULL, pending) != 0) continue;  // null rays / empty scene: shade them
+        if (exhausted && wnext == wend) break;
+        continue;
+      }
+    }
+    // ---- one traversal quantum (closest hit)
+    if (in_flight) {
+      if (st.has_nodes() && !st.has_tris()) {
+        nn++;
+        if (WIDE) wide_node_step(sc.bvh, o, ray, LISA_TMIN, best_t, *reinterpret_cast<WideState*>(&st), stack);
+        else bin_node_step(sc.bvh, o, ray, LISA_TMIN, best_t, *reinterpret_cast<BinState*>(&st), stack);
+      }
+      if (WIDE) {
+        WideState& w = *reinterpret_cast<WideState*>(&st);
+#pragma unroll
+        for (int k = 0; k < LISA_TRI_PER_STEP; k++) {
+          if (w.tg.y) {
+            const uint32_t b = __ffs(w.tg.y) - 1u;
+            w.tg.y &= w.tg.y - 1u;
+            const int ti = (int)(w.tg.x + b);
+            float tt, uu, vv;
+            nt++;
+            if (step_tri_uv(o, ray, sc.tri_v, ti, LISA_TMIN, best_t, tt, uu, vv)) { best_t = tt; best_u = uu; best_v = vv; best_prim = ti; }
+          }
+        }
+        if (!w.has_tris() && !w.has_nodes() && !stack.empty()) w.ng = stack.pop();
+      } else {
+        BinState& b = *reinterpret_cast<BinState*>(&st);
+        if (b.has_tris()) {
+          const int ti = ~b.cur;
+          float tt, uu, vv;
+          nt++;
+          if (step_tri_uv(o, ray, sc.tri_v, ti, LISA_TMIN, best_t, tt, uu, vv)) { best_t = tt; best_u = uu; best_v = vv; best_prim = ti; }
+          b.cur = stack.empty() ? LISA_BIN_NONE : (int)stack.pop().x;
+        }
+      }
+      if (!st.has_nodes() && !st.has_tris()) {
+        if (phase == 0) {  // emitters done: now the closest other triangle in front of the closest emitter
+          phase = 1;
+          stack.clear();
+          st.begin(sc.root_other);
+          if (sc.root_other < 0) { in_flight = false; pending = true; }
+        } else {
+          in_flight = false;
+          pending   = true;
+        }
       }
     }
   }
-  // stream compaction into the queues: ballot + prefix popcount, one atomic per warp and queue
-  queue_push(push, (int)i, s.shadow_q, &ring[R_CNTJ + 0]);
-  queue_push(push_sticky, (int)i, s.cand_q, &ring[R_CNTC + 0]);
-  warp_add(&s.stats[ST_JOBS], (push || push_sticky) ? 1u : 0u);
   warp_add(&s.stats[ST_RADIANCE], n_rad);
   warp_add(&s.stats[ST_SAMPLES], n_samp);
   warp_add(&s.stats[ST_NULLDIR], n_null);
   warp_add(&s.stats[ST_CHAINS_DONE], n_done);
+  warp_add(&s.stats[ST_JOBS], n_jobs);
   warp_add(&s.stats[ST_NODES], nn);
   warp_add(&s.stats[ST_TRIS], nt);
 }
@@ -269,13 +383,6 @@ __global__ void __launch_bounds__(256) k_extend(DScene sc, DState s, DCamera cam
 //            candidate try — phase 0 closest emitter, phase 1 any occluder in front of it — retires it into
 //            RayState::hit, finishes lit jobs, and sends jobs that need more tries back to k_tries (next pass).
 // Passes shrink geometrically; the last pass finishes its leftovers inline.
-template <bool WIDE>
-struct TravState;
-template <>
-struct TravState<true> : WideState {};
-template <>
-struct TravState<false> : BinState {};
-
 struct JobCounters { uint32_t samples, done; };
 
 // End of the opaque branch of __closesthit__radiance for one job (shader.cu:251-252): add the light term,
@@ -701,6 +808,12 @@ int shadow_occupancy(bool wide, int block) {
                        : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_rays<false>, block, stack_smem(block));
   return (e == cudaSuccess && n > 0) ? n : 2;
 }
+int extend_occupancy(bool wide, int block) {
+  int n = 0;
+  cudaError_t e = wide ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_extend<true>, block, stack_smem(block))
+                       : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_extend<false>, block, stack_smem(block));
+  return (e == cudaSuccess && n > 0) ? n : 2;
+}
 int tries_occupancy(int block) {
   int n = 0;
   cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_tries, block, 0);
@@ -713,8 +826,10 @@ void launch_init_chains(const DState& s, const DCamera& cam, const Tile& t, cuda
 void launch_extend(const DScene& sc, const DState& s, const DCamera& cam, const Tile& t, uint32_t iter, const LaunchCfg& cfg,
                    cudaStream_t st) {
   const int b = cfg.extend_block;
-  if (sc.wide) k_extend<true><<<cdiv(t.n_chains, b), b, stack_smem(b), st>>>(sc, s, cam, t, iter);
-  else k_extend<false><<<cdiv(t.n_chains, b), b, stack_smem(b), st>>>(sc, s, cam, t, iter);
+  unsigned grid = (unsigned)(cfg.sm_count * cfg.extend_blocks_per_sm);
+  grid = min(grid, max(1u, cdiv(t.n_chains, 64u * (b / 32))));
+  if (sc.wide) k_extend<true><<<grid, b, stack_smem(b), st>>>(sc, s, cam, t, iter, (uint32_t)cfg.idle_thresh);
+  else k_extend<false><<<grid, b, stack_smem(b), st>>>(sc, s, cam, t, iter, (uint32_t)cfg.idle_thresh);
 }
 int launch_shadow(const DScene& sc, const DState& s, const Tile& t, uint32_t iter, const LaunchCfg& cfg, cudaStream_t st) {
   const int b = cfg.shadow_block;

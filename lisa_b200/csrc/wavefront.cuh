@@ -39,6 +39,7 @@ struct LaunchCfg {
   int extend_block, shadow_block;
   int shadow_blocks_per_sm;
   int tries_blocks_per_sm;
+  int extend_blocks_per_sm;
   int idle_thresh;  // k_shadow: lanes that must be idle before the warp runs its management section
 };
 
@@ -52,6 +53,7 @@ void launch_finalize(const DState& s, const DCamera& cam, const Tile& t, float4*
 void launch_resolve(const float4* accum, uint32_t npix, float4* mean_out, uint32_t* rgba8_out, cudaStream_t st);
 int  configure_kernels(char* err, size_t errlen);
 int  shadow_occupancy(bool wide, int block);  // resident CTAs of k_rays per SM
+int  extend_occupancy(bool wide, int block);
 int  tries_occupancy(int block);               // resident CTAs of k_tries per SM
 
 // diagnostics

@@ -11,6 +11,8 @@ w = int(sys.argv[2]) if len(sys.argv) > 2 else 2000
 sc = fe.parse_scene("scenes/cornell_c2.rto")
 sc["width"] = sc["height"] = w
 R = rt.Renderer.from_scene(sc, bvh_kind=int(os.environ.get("PROF_BVH", "0")))
+if os.environ.get('PROF_WARM', '1') == '1' and 'NCU' not in os.environ:
+    R.render_subframes(99, 1, 2); R.reset()
 R.render_subframes(0, 1, spp)
 st = R.stats()
 print("render %.1f ms, %.2f Msamples/s, %.1f Mrays/s, launches %d" % (st["last_render_ms"], st["last_samples"] / st["last_render_ms"] / 1e3,
