@@ -118,3 +118,65 @@ def test_shadow_policy_sensitivity(rt, cornell):
     shift = b.reshape(-1, 3).mean(0) / a.reshape(-1, 3).mean(0)
     assert (shift >= 0.999).all()      # ignoring occluders in front of the light can only brighten
     assert (shift < 1.5).all()
+
+
+def _knot_scene(cornell, nu, nv):
+    """BASELINE configs[2] in small: Cornell walls + light, plus a closed torus-knot tube in glass (n = 1.5)."""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "assets"))
+    import gen_knot
+    kv, kn = gen_knot.soup_arrays(nu, nv)
+    T = len(cornell["mat_indices"])
+    keep = np.isin(np.arange(T), np.r_[0:10, T - 2:T])
+    v = np.concatenate([cornell["vertices"].reshape(-1, 3, 3)[keep].reshape(-1, 3), kv])
+    n = np.concatenate([cornell["normals"].reshape(-1, 3, 3)[keep].reshape(-1, 3), kn])
+    m = np.concatenate([cornell["mat_indices"][keep], np.full(len(kv) // 3, 1, np.int32)])
+    return v, n, m
+
+
+def test_glass_knot_scene_matches_oracle(rt, orc, cornell):
+    """Dielectric-heavy scene (Fresnel reflection/refraction, TIR null directions, tint on exit), 12 bounces."""
+    v, n, m = _knot_scene(cornell, 96, 24)   # 4608 knot triangles
+    cam = cornell["camera"]
+    S = orc.Scene(v, n, m, cornell["materials_packed"])
+    w, h, spp, bounces = 96, 54, 4, 12
+    ref, cnt = S.render(cam["eye"], cam["look_at"], cam["fov"], w, h, bounces, spp)
+    for bvh in (0, 1):
+        R = rt.Renderer(v, n, m, cornell["materials_packed"], w, h, cam["eye"], cam["look_at"], cam["fov"], spp, bounces, bvh_kind=bvh)
+        R.render_subframes(0, 1, spp)
+        acc, st = R.read_accum(), R.stats()
+        assert (np.abs(acc[..., :3] - ref[..., :3]).max(axis=2) < 1e-4).mean() >= 0.93
+        np.testing.assert_allclose(acc[..., :3].mean(), ref[..., :3].mean(), rtol=0.02)
+        assert cnt["null_dirs"] > 0 and abs(st["null_directions"] - cnt["null_dirs"]) <= 0.1 * cnt["null_dirs"] + 8
+        assert abs(st["last_radiance_rays"] - cnt["radiance_rays"]) <= 0.01 * cnt["radiance_rays"]
+
+
+def test_two_lights_and_rough_materials(rt, orc, cornell):
+    """Several emitter materials (RayState::material of the LAST light found is used, Q1), roughness 0 / 0.25 (non-unit
+    bounce directions, Q5) and a scene open on every side (most shadow rays escape: hit is cleared)."""
+    rng = np.random.default_rng(4)
+    def quad(c, ex, ey, nrm):
+        c, ex, ey = np.float32(c), np.float32(ex), np.float32(ey)
+        p = [c - ex - ey, c + ex - ey, c + ex + ey, c - ex + ey]
+        return np.float32([p[0], p[1], p[2], p[0], p[2], p[3]]), np.tile(np.float32([nrm]), (6, 1))
+    parts = [quad((0, 0, 0), (1, 0, 0), (0, 0, 1), (0, 1, 0)), quad((0, 1.2, 0), (0.3, 0, 0), (0, 0, 0.3), (0, -1, 0)),
+             quad((-0.8, 0.5, 0), (0, 0.2, 0), (0, 0, 0.2), (1, 0, 0)), quad((0.3, 0.3, 0.2), (0.25, 0, 0), (0, 0, 0.25), (0, 1, 0)),
+             quad((0, 0.5, -0.9), (0.9, 0, 0), (0, 0.5, 0), (0, 0, 1))]
+    v = np.concatenate([p[0] for p in parts]); n = np.concatenate([p[1] for p in parts])
+    m = np.repeat(np.int32([0, 1, 2, 3, 4]), 2)
+    mats = [dict(emit=False, alpha=1.0, diffuse=(0.8, 0.7, 0.6), roughness=1.0), dict(emit=True, alpha=1.0, emission=(1.0, 0.9, 0.8)),
+            dict(emit=True, alpha=1.0, emission=(0.1, 0.2, 0.9)), dict(emit=False, alpha=1.0, diffuse=(0.9, 0.9, 0.9), roughness=0.25),
+            dict(emit=False, alpha=1.0, diffuse=(0.5, 0.9, 0.5), roughness=0.0)]
+    from oracle.scene_py import pack_material
+    mp = b"".join(pack_material(roughness=x.get("roughness", 0), alpha=x["alpha"], diffuse=x.get("diffuse", (0, 0, 0)), emit=x["emit"],
+                                emission=x.get("emission", (0, 0, 0))) for x in mats)
+    S = orc.Scene(v, n, m, mp)
+    eye, look, fov, w, h = (0.2, 0.9, 2.6), (0, 0.4, 0), 40.0, 80, 60
+    ref, cnt = S.render(eye, look, fov, w, h, 6, 6)
+    R = rt.Renderer(v, n, m, mats, w, h, eye, look, fov, 6, 6)
+    R.render_subframes(0, 1, 6)
+    acc, st = R.read_accum(), R.stats()
+    assert st["num_emitter_triangles"] == 4
+    assert (np.abs(acc[..., :3] - ref[..., :3]).max(axis=2) < 1e-4).mean() >= 0.97
+    np.testing.assert_allclose(acc[..., :3].reshape(-1, 3).mean(0), ref[..., :3].reshape(-1, 3).mean(0), rtol=0.02)
+    assert abs(st["last_shadow_rays"] - cnt["shadow_rays"]) <= 0.02 * cnt["shadow_rays"]
