@@ -24,6 +24,7 @@
 #include <cstdio>
 
 #include "build.h"
+#include "devmem.h"
 #include "common.cuh"
 
 namespace lisa {
@@ -434,12 +435,12 @@ int build_bvh(const BuildInput& in, BuildOutput* out, cudaStream_t st, char* err
   BoundsAcc*          d_acc;
   unsigned long long *d_keys, *d_keys2;
   unsigned int *      d_ids, *d_ids2, *d_final_to_sorted;
-  CK(cudaMalloc(&d_acc, sizeof(BoundsAcc)));
-  CK(cudaMalloc(&d_keys, sizeof(unsigned long long) * T));
-  CK(cudaMalloc(&d_keys2, sizeof(unsigned long long) * T));
-  CK(cudaMalloc(&d_ids, sizeof(unsigned int) * T));
-  CK(cudaMalloc(&d_ids2, sizeof(unsigned int) * T));
-  CK(cudaMalloc(&d_final_to_sorted, sizeof(unsigned int) * T));
+  CK(dev_alloc((void**)&d_acc, sizeof(BoundsAcc)));
+  CK(dev_alloc((void**)&d_keys, sizeof(unsigned long long) * T));
+  CK(dev_alloc((void**)&d_keys2, sizeof(unsigned long long) * T));
+  CK(dev_alloc((void**)&d_ids, sizeof(unsigned int) * T));
+  CK(dev_alloc((void**)&d_ids2, sizeof(unsigned int) * T));
+  CK(dev_alloc((void**)&d_final_to_sorted, sizeof(unsigned int) * T));
 
   k_init_bounds<<<1, 1, 0, st>>>(d_acc);
   k_centroid_bounds<<<min(cdiv(T, 256), 148 * 8), 256, 0, st>>>(in.d_verts, T, d_acc);
@@ -448,7 +449,7 @@ int build_bvh(const BuildInput& in, BuildOutput* out, cudaStream_t st, char* err
   size_t tmp_bytes = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_keys, d_keys2, d_ids, d_ids2, T, 0, 64, st);
   void* d_tmp;
-  CK(cudaMalloc(&d_tmp, tmp_bytes ? tmp_bytes : 16));
+  CK(dev_alloc((void**)&d_tmp, tmp_bytes ? tmp_bytes : 16));
   CK(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_keys, d_keys2, d_ids, d_ids2, T, 0, 64, st));
   BoundsAcc h_acc;
   CK(cudaMemcpyAsync(&h_acc, d_acc, sizeof(h_acc), cudaMemcpyDeviceToHost, st));
@@ -461,12 +462,12 @@ int build_bvh(const BuildInput& in, BuildOutput* out, cudaStream_t st, char* err
   int *   d_range, *d_parent, *d_flags;  // d_range: triangles below each internal node
   float4 *d_lo, *d_hi;
   const size_t NN = 2ull * T + 2;
-  CK(cudaMalloc(&d_child, sizeof(int2) * NN));
-  CK(cudaMalloc(&d_range, sizeof(int) * NN));
-  CK(cudaMalloc(&d_parent, sizeof(int) * NN));
-  CK(cudaMalloc(&d_flags, sizeof(int) * NN));
-  CK(cudaMalloc(&d_lo, sizeof(float4) * NN));
-  CK(cudaMalloc(&d_hi, sizeof(float4) * NN));
+  CK(dev_alloc((void**)&d_child, sizeof(int2) * NN));
+  CK(dev_alloc((void**)&d_range, sizeof(int) * NN));
+  CK(dev_alloc((void**)&d_parent, sizeof(int) * NN));
+  CK(dev_alloc((void**)&d_flags, sizeof(int) * NN));
+  CK(dev_alloc((void**)&d_lo, sizeof(float4) * NN));
+  CK(dev_alloc((void**)&d_hi, sizeof(float4) * NN));
   CK(cudaMemsetAsync(d_flags, 0, sizeof(int) * NN, st));
 
   struct Part { int n, sorted_base, slice, root; } parts[2] = {{n_other, 0, 0, 0}, {n_emit, n_other, 2 * n_other + 1, 0}};
@@ -474,12 +475,12 @@ int build_bvh(const BuildInput& in, BuildOutput* out, cudaStream_t st, char* err
   void*  d_sel_tmp = nullptr;
   size_t sel_bytes = 0;
   if (!in.lbvh) {
-    CK(cudaMalloc(&d_C[0], sizeof(int) * (size_t)T));
-    CK(cudaMalloc(&d_C[1], sizeof(int) * (size_t)T));
-    CK(cudaMalloc(&d_nn, sizeof(int) * (size_t)T));
-    CK(cudaMalloc(&d_sel, sizeof(int) * 2));
+    CK(dev_alloc((void**)&d_C[0], sizeof(int) * (size_t)T));
+    CK(dev_alloc((void**)&d_C[1], sizeof(int) * (size_t)T));
+    CK(dev_alloc((void**)&d_nn, sizeof(int) * (size_t)T));
+    CK(dev_alloc((void**)&d_sel, sizeof(int) * 2));
     cub::DeviceSelect::If(nullptr, sel_bytes, d_C[0], d_C[1], d_sel, T, IsValidCluster(), st);
-    CK(cudaMalloc(&d_sel_tmp, sel_bytes ? sel_bytes : 16));
+    CK(dev_alloc((void**)&d_sel_tmp, sel_bytes ? sel_bytes : 16));
   }
   for (int p = 0; p < 2; p++) {
     Part& P = parts[p];
@@ -531,7 +532,7 @@ int build_bvh(const BuildInput& in, BuildOutput* out, cudaStream_t st, char* err
   if (!in.wide) {
     int nn[2] = {n_other ? max(n_other - 1, 1) : 0, n_emit ? max(n_emit - 1, 1) : 0};
     total_nodes = nn[0] + nn[1];
-    CK(cudaMalloc(&d_nodes, sizeof(float4) * 4 * (size_t)max(total_nodes, 1)));
+    CK(dev_alloc((void**)&d_nodes, sizeof(float4) * 4 * (size_t)max(total_nodes, 1)));
     int base = 0;
     for (int p = 0; p < 2; p++) {
       const Part& P = parts[p];
@@ -546,12 +547,12 @@ int build_bvh(const BuildInput& in, BuildOutput* out, cudaStream_t st, char* err
   } else {
     // every wide node has >= 2 children except degenerate roots, so #wide nodes <= #binary internal nodes + 2
     const size_t max_nodes = (size_t)T + 4;
-    CK(cudaMalloc(&d_nodes, sizeof(float4) * 5 * max_nodes));
+    CK(dev_alloc((void**)&d_nodes, sizeof(float4) * 5 * max_nodes));
     WorkItem *d_q[2];
     int*      d_counters;
-    CK(cudaMalloc(&d_q[0], sizeof(WorkItem) * max_nodes));
-    CK(cudaMalloc(&d_q[1], sizeof(WorkItem) * max_nodes));
-    CK(cudaMalloc(&d_counters, sizeof(int) * 4));
+    CK(dev_alloc((void**)&d_q[0], sizeof(WorkItem) * max_nodes));
+    CK(dev_alloc((void**)&d_q[1], sizeof(WorkItem) * max_nodes));
+    CK(dev_alloc((void**)&d_counters, sizeof(int) * 4));
     int node_next = 0, tri_next = 0;
     for (int p = 0; p < 2; p++) {
       const Part& P = parts[p];
@@ -580,22 +581,22 @@ int build_bvh(const BuildInput& in, BuildOutput* out, cudaStream_t st, char* err
       }
     }
     total_nodes = node_next;
-    cudaFree(d_q[0]); cudaFree(d_q[1]); cudaFree(d_counters);
+    dev_free(d_q[0]); dev_free(d_q[1]); dev_free(d_counters);
   }
 
   float4 *d_tri_v, *d_tri_n;
   int*    d_final_to_orig;
-  CK(cudaMalloc(&d_tri_v, sizeof(float4) * 3 * (size_t)T));
-  CK(cudaMalloc(&d_tri_n, sizeof(float4) * 3 * (size_t)T));
-  CK(cudaMalloc(&d_final_to_orig, sizeof(int) * (size_t)T));
+  CK(dev_alloc((void**)&d_tri_v, sizeof(float4) * 3 * (size_t)T));
+  CK(dev_alloc((void**)&d_tri_n, sizeof(float4) * 3 * (size_t)T));
+  CK(dev_alloc((void**)&d_final_to_orig, sizeof(int) * (size_t)T));
   k_pack_triangles<<<cdiv(T, 256), 256, 0, st>>>(in.d_verts, in.d_normals, in.d_mat_idx, d_ids2, d_final_to_sorted, T,
                                                  d_tri_v, d_tri_n, d_final_to_orig);
   CK(cudaStreamSynchronize(st));
   CK(cudaGetLastError());
 
-  cudaFree(d_acc); cudaFree(d_keys); cudaFree(d_keys2); cudaFree(d_ids); cudaFree(d_ids2); cudaFree(d_final_to_sorted);
-  cudaFree(d_C[0]); cudaFree(d_C[1]); cudaFree(d_nn); cudaFree(d_sel); cudaFree(d_sel_tmp);
-  cudaFree(d_tmp); cudaFree(d_child); cudaFree(d_range); cudaFree(d_parent); cudaFree(d_flags); cudaFree(d_lo); cudaFree(d_hi);
+  dev_free(d_acc); dev_free(d_keys); dev_free(d_keys2); dev_free(d_ids); dev_free(d_ids2); dev_free(d_final_to_sorted);
+  dev_free(d_C[0]); dev_free(d_C[1]); dev_free(d_nn); dev_free(d_sel); dev_free(d_sel_tmp);
+  dev_free(d_tmp); dev_free(d_child); dev_free(d_range); dev_free(d_parent); dev_free(d_flags); dev_free(d_lo); dev_free(d_hi);
 
   out->d_nodes = d_nodes;
   out->num_nodes = total_nodes;

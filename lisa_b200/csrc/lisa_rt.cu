@@ -11,12 +11,14 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <string>
 #include <vector>
 
 #include "../../include/lisa_rt.h"
 #include "build.h"
+#include "devmem.h"
 #include "scene.cuh"
 #include "wavefront.cuh"
 
@@ -37,55 +39,6 @@ static int fail(int code, const char* fmt, ...) {
     cudaError_t e_ = (x);                                                                       \
     if (e_ != cudaSuccess) return fail(LISA_ERR_CUDA, "%s: %s", #x, cudaGetErrorString(e_));    \
   } while (0)
-
-// ---- process-wide cache of large device blocks -----------------------------------------------------------
-// Chain state and accumulators are hundreds of MB; cudaMalloc/cudaFree of such blocks costs milliseconds to
-// >100 ms (and cudaFree synchronises the device), which would dominate a create -> render -> read -> destroy
-// cycle.  Freed blocks are parked here (exact-size reuse, bounded) and handed to the next context.
-#include <mutex>
-namespace {
-struct Block { void* p; size_t bytes; int device; };
-std::mutex         g_cache_mu;
-std::vector<Block> g_cache;
-size_t             g_cache_bytes = 0;
-const size_t       kCacheMinBlock = 1u << 20, kCacheMaxBytes = 8ull << 30;
-
-cudaError_t big_alloc(void** out, size_t bytes, int device) {
-  if (bytes >= kCacheMinBlock) {
-    std::lock_guard<std::mutex> lk(g_cache_mu);
-    for (size_t i = 0; i < g_cache.size(); i++)
-      if (g_cache[i].bytes == bytes && g_cache[i].device == device) {
-        *out = g_cache[i].p;
-        g_cache_bytes -= bytes;
-        g_cache.erase(g_cache.begin() + i);
-        return cudaSuccess;
-      }
-  }
-  cudaError_t e = cudaMalloc(out, bytes);
-  if (e != cudaSuccess) {  // out of memory: drop the cache and retry once
-    std::lock_guard<std::mutex> lk(g_cache_mu);
-    for (Block& b : g_cache) if (b.device == device) cudaFree(b.p);
-    g_cache.erase(std::remove_if(g_cache.begin(), g_cache.end(), [&](const Block& b) { return b.device == device; }), g_cache.end());
-    g_cache_bytes = 0;
-    for (Block& b : g_cache) g_cache_bytes += b.bytes;
-    cudaGetLastError();
-    e = cudaMalloc(out, bytes);
-  }
-  return e;
-}
-void big_free(void* p, size_t bytes, int device) {
-  if (!p) return;
-  if (bytes >= kCacheMinBlock) {
-    std::lock_guard<std::mutex> lk(g_cache_mu);
-    if (g_cache_bytes + bytes <= kCacheMaxBytes && g_cache.size() < 64) {
-      g_cache.push_back(Block{p, bytes, device});
-      g_cache_bytes += bytes;
-      return;
-    }
-  }
-  cudaFree(p);
-}
-}  // namespace
 
 struct lisa_ctx {
   int          device = 0;
@@ -163,11 +116,11 @@ static void camera_frame(const lisa_camera& c, uint32_t w, uint32_t h, DCamera* 
 
 static void free_state(lisa_ctx* c) {
   const size_t n = c->state_chains;
-  big_free(c->state.o, sizeof(float4) * n, c->device); big_free(c->state.d, sizeof(float4) * n, c->device);
-  big_free(c->state.a, sizeof(float4) * n, c->device); big_free(c->state.c, sizeof(float4) * n, c->device);
-  big_free(c->state.n, sizeof(float4) * n, c->device); big_free(c->state.sum, sizeof(float4) * n, c->device);
-  big_free(c->state.shadow_q, sizeof(int) * n, c->device);
-  big_free(c->state.cand_q, sizeof(int) * n, c->device);
+  dev_free(c->state.o); dev_free(c->state.d);
+  dev_free(c->state.a); dev_free(c->state.c);
+  dev_free(c->state.n); dev_free(c->state.sum);
+  dev_free(c->state.shadow_q);
+  dev_free(c->state.cand_q);
   c->state.o = c->state.d = c->state.a = c->state.c = c->state.n = c->state.sum = nullptr;
   c->state.shadow_q = c->state.cand_q = nullptr;
   c->state_chains = 0;
@@ -176,14 +129,14 @@ static void free_state(lisa_ctx* c) {
 static int ensure_state(lisa_ctx* c, size_t chains) {
   if (chains <= c->state_chains) return LISA_OK;
   free_state(c);
-  CU(big_alloc((void**)&c->state.o, sizeof(float4) * chains, c->device));
-  CU(big_alloc((void**)&c->state.d, sizeof(float4) * chains, c->device));
-  CU(big_alloc((void**)&c->state.a, sizeof(float4) * chains, c->device));
-  CU(big_alloc((void**)&c->state.c, sizeof(float4) * chains, c->device));
-  CU(big_alloc((void**)&c->state.n, sizeof(float4) * chains, c->device));
-  CU(big_alloc((void**)&c->state.sum, sizeof(float4) * chains, c->device));
-  CU(big_alloc((void**)&c->state.shadow_q, sizeof(int) * chains, c->device));
-  CU(big_alloc((void**)&c->state.cand_q, sizeof(int) * chains, c->device));
+  CU(dev_alloc((void**)&c->state.o, sizeof(float4) * chains));
+  CU(dev_alloc((void**)&c->state.d, sizeof(float4) * chains));
+  CU(dev_alloc((void**)&c->state.a, sizeof(float4) * chains));
+  CU(dev_alloc((void**)&c->state.c, sizeof(float4) * chains));
+  CU(dev_alloc((void**)&c->state.n, sizeof(float4) * chains));
+  CU(dev_alloc((void**)&c->state.sum, sizeof(float4) * chains));
+  CU(dev_alloc((void**)&c->state.shadow_q, sizeof(int) * chains));
+  CU(dev_alloc((void**)&c->state.cand_q, sizeof(int) * chains));
   c->state_chains = chains;
   c->stats.state_bytes = chains * (6 * sizeof(float4) + 2 * sizeof(int));
   return LISA_OK;
@@ -191,23 +144,37 @@ static int ensure_state(lisa_ctx* c, size_t chains) {
 
 extern "C" void lisa_destroy(lisa_ctx* c) {
   if (!c) return;
+  const bool dbg = getenv("LISA_DEBUG_TIMING") != nullptr;
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+    return std::chrono::duration<double, std::milli>(b - a).count();
+  };
+  auto t0 = now();
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
+  auto t1 = now();
   free_state(c);
-  cudaFree(c->state.ring); cudaFree(c->state.stats);
-  cudaFree(c->bvh.d_nodes); cudaFree(c->bvh.d_tri_v); cudaFree(c->bvh.d_tri_n); cudaFree(c->bvh.d_final_to_orig);
-  cudaFree(c->d_mats);
   {
     const size_t npix = (size_t)c->width * c->height;
-    big_free(c->d_accum, sizeof(float4) * std::max<size_t>(npix, 1), c->device);
-    big_free(c->d_mean, sizeof(float4) * npix, c->device);
-    big_free(c->d_rgba8, sizeof(uint32_t) * npix, c->device);
+    dev_free(c->d_accum);
+    dev_free(c->d_mean);
+    dev_free(c->d_rgba8);
   }
-  if (c->h_stats) cudaFreeHost(c->h_stats);
+  auto t2 = now();
+  dev_free(c->state.ring); dev_free(c->state.stats);
+  dev_free(c->bvh.d_nodes); dev_free(c->bvh.d_tri_v); dev_free(c->bvh.d_tri_n); dev_free(c->bvh.d_final_to_orig);
+  dev_free(c->d_mats);
+  auto t3 = now();
+  pinned_slot_free(c->h_stats);
+  auto t4 = now();
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
   if (c->stream) cudaStreamDestroy(c->stream);
+  auto t5 = now();
+  if (dbg)
+    fprintf(stderr, "lisa_destroy: sync %.2f  cache %.2f  cudaFree %.2f  freeHost %.2f  events+stream %.2f ms\n", ms(t0, t1), ms(t1, t2),
+            ms(t2, t3), ms(t3, t4), ms(t4, t5));
   delete c;
 }
 
@@ -227,12 +194,17 @@ static int create_impl(const lisa_scene_desc* sd, const lisa_options* opt, lisa_
     return fail(LISA_ERR_CUDA, "no CUDA device (%s): lisa_rt has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
   if (o.device >= 0) { CU(cudaSetDevice(o.device)); }
   CU(cudaGetDevice(&c->device));
-  cudaDeviceProp prop;
-  CU(cudaGetDeviceProperties(&prop, c->device));
+  // per-device constants are queried once per process (cudaGetDeviceProperties alone can take ~100 ms)
+  struct DevInfo { bool ok = false; int sms = 0, occ_rays[2] = {0, 0}, occ_ext[2] = {0, 0}, occ_tries = 0; };
+  static DevInfo dev_info[64];
+  DevInfo& di = dev_info[c->device & 63];
+  if (!di.ok) {
+    CU(cudaDeviceGetAttribute(&di.sms, cudaDevAttrMultiProcessorCount, c->device));
+    if (configure_kernels(g_err, sizeof(g_err))) return LISA_ERR_CUDA;
+  }
   CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CU(cudaEventCreate(&c->ev0));
   CU(cudaEventCreate(&c->ev1));
-  if (configure_kernels(g_err, sizeof(g_err))) return LISA_ERR_CUDA;
 
   const int T = sd->num_vertices / 3;
   c->width = sd->width; c->height = sd->height;
@@ -259,10 +231,10 @@ static int create_impl(const lisa_scene_desc* sd, const lisa_options* opt, lisa_
   }
   CU(cudaEventRecord(t0, c->stream));
   const size_t vb = sizeof(float) * 9 * (size_t)std::max(T, 1);
-  CU(cudaMalloc(&d_verts, vb)); CU(cudaMalloc(&d_normals, vb));
-  CU(cudaMalloc(&d_mat_idx, sizeof(int) * (size_t)std::max(T, 1)));
-  CU(cudaMalloc(&d_emit, emit.size()));
-  CU(cudaMalloc(&c->d_mats, sizeof(DMaterial) * mats.size()));
+  CU(dev_alloc((void**)&d_verts, vb)); CU(dev_alloc((void**)&d_normals, vb));
+  CU(dev_alloc((void**)&d_mat_idx, sizeof(int) * (size_t)std::max(T, 1)));
+  CU(dev_alloc((void**)&d_emit, emit.size()));
+  CU(dev_alloc((void**)&c->d_mats, sizeof(DMaterial) * mats.size()));
   if (T) {
     CU(cudaMemcpyAsync(d_verts, sd->vertices, sizeof(float) * 9 * (size_t)T, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(d_normals, sd->normals, sizeof(float) * 9 * (size_t)T, cudaMemcpyHostToDevice, c->stream));
@@ -280,7 +252,7 @@ static int create_impl(const lisa_scene_desc* sd, const lisa_options* opt, lisa_
   int rc = build_bvh(bi, &c->bvh, c->stream, g_err, sizeof(g_err));
   CU(cudaEventRecord(t2, c->stream));
   CU(cudaStreamSynchronize(c->stream));
-  cudaFree(d_verts); cudaFree(d_normals); cudaFree(d_mat_idx); cudaFree(d_emit);
+  dev_free(d_verts); dev_free(d_normals); dev_free(d_mat_idx); dev_free(d_emit);
   if (rc) return rc;
   cudaEventElapsedTime(&c->stats.upload_ms, t0, t1);
   cudaEventElapsedTime(&c->stats.bvh_build_ms, t1, t2);
@@ -326,24 +298,37 @@ static int create_impl(const lisa_scene_desc* sd, const lisa_options* opt, lisa_
 
   // ---- accumulators, counters
   const size_t npix = (size_t)c->width * c->height;
-  CU(big_alloc((void**)&c->d_accum, sizeof(float4) * std::max<size_t>(npix, 1), c->device));
+  CU(dev_alloc((void**)&c->d_accum, sizeof(float4) * std::max<size_t>(npix, 1)));
   CU(cudaMemsetAsync(c->d_accum, 0, sizeof(float4) * npix, c->stream));
-  CU(cudaMalloc(&c->state.ring, sizeof(unsigned int) * 64));
-  CU(cudaMalloc(&c->state.stats, sizeof(unsigned long long) * 16));
+  CU(dev_alloc((void**)&c->state.ring, sizeof(unsigned int) * 64));
+  CU(dev_alloc((void**)&c->state.stats, sizeof(unsigned long long) * 16));
   CU(cudaMemsetAsync(c->state.stats, 0, sizeof(unsigned long long) * 16, c->stream));
-  CU(cudaMallocHost(&c->h_stats, sizeof(unsigned long long) * 16));
+  c->h_stats = (unsigned long long*)pinned_slot_alloc();
+  if (!c->h_stats) return fail(LISA_ERR_NOMEM, "pinned host allocation failed");
   memset(c->h_stats, 0, sizeof(unsigned long long) * 16);
 
-  c->cfg.sm_count = prop.multiProcessorCount;
+  c->cfg.sm_count = di.sms;
   c->cfg.extend_block = 128;  // 94 registers/thread: 128-thread CTAs pack 5 per SM (20 warps) where 256 pack 2 (16 warps)
   c->cfg.shadow_block = 128;
   if (const char* e2 = getenv("LISA_EXTEND_BLOCK")) c->cfg.extend_block = std::max(32, std::min(256, atoi(e2) / 32 * 32));
   if (const char* e2 = getenv("LISA_SHADOW_BLOCK")) c->cfg.shadow_block = std::max(32, std::min(256, atoi(e2) / 32 * 32));
   c->cfg.idle_thresh = 16;  // measured on B200 (Cornell 2000x2000): 1 -> 651, 8 -> 660, 16 -> 674, 20 -> 677 Msamples/s
   if (const char* e2 = getenv("LISA_IDLE_THRESH")) c->cfg.idle_thresh = std::max(1, std::min(32, atoi(e2)));
-  c->cfg.tries_blocks_per_sm = tries_occupancy(256);
-  c->cfg.extend_blocks_per_sm = extend_occupancy(bi.wide != 0, c->cfg.extend_block);
-  c->cfg.shadow_blocks_per_sm = shadow_occupancy(bi.wide != 0, c->cfg.shadow_block);  // persistent grid = what is resident
+  // measured on B200 (Cornell 2000x2000): 4 passes 668, 3: 683, 2: 718, 1: 744 Msamples/s — the fill/drain of every extra
+  // persistent launch (~14 us) costs more than finishing the few re-tries inline in k_rays
+  c->cfg.shadow_passes = 1;
+  if (const char* e2 = getenv("LISA_SHADOW_PASSES")) c->cfg.shadow_passes = atoi(e2);
+  {
+    const int w = bi.wide != 0;
+    if (!di.ok || getenv("LISA_EXTEND_BLOCK") || getenv("LISA_SHADOW_BLOCK")) {
+      di.occ_tries = tries_occupancy(256);
+      for (int k = 0; k < 2; k++) { di.occ_ext[k] = extend_occupancy(k != 0, c->cfg.extend_block); di.occ_rays[k] = shadow_occupancy(k != 0, c->cfg.shadow_block); }
+      di.ok = true;
+    }
+    c->cfg.tries_blocks_per_sm = di.occ_tries;
+    c->cfg.extend_blocks_per_sm = di.occ_ext[w];
+    c->cfg.shadow_blocks_per_sm = di.occ_rays[w];
+  }
   if (const char* e2 = getenv("LISA_SHADOW_BLOCKS_PER_SM")) c->cfg.shadow_blocks_per_sm = std::max(1, atoi(e2));
   // default residency: enough chains to fill the machine several times over, bounded so the state stays
   // a small fraction of HBM (112 B per chain)
@@ -499,8 +484,8 @@ extern "C" int lisa_render_subframes(lisa_ctx* c, uint32_t first, uint32_t count
 
 static int resolve(lisa_ctx* c, bool want_mean, bool want_rgba) {
   const size_t npix = (size_t)c->width * c->height;
-  if (want_mean && !c->d_mean) CU(big_alloc((void**)&c->d_mean, sizeof(float4) * npix, c->device));
-  if (want_rgba && !c->d_rgba8) CU(big_alloc((void**)&c->d_rgba8, sizeof(uint32_t) * npix, c->device));
+  if (want_mean && !c->d_mean) CU(dev_alloc((void**)&c->d_mean, sizeof(float4) * npix));
+  if (want_rgba && !c->d_rgba8) CU(dev_alloc((void**)&c->d_rgba8, sizeof(uint32_t) * npix));
   launch_resolve(c->d_accum, (uint32_t)npix, want_mean ? c->d_mean : nullptr, want_rgba ? c->d_rgba8 : nullptr, c->stream);
   return LISA_OK;
 }
@@ -568,8 +553,8 @@ extern "C" int    lisa_sync(lisa_ctx* c) {
 template <typename T>
 struct DevBuf {
   T* p = nullptr;
-  ~DevBuf() { cudaFree(p); }
-  cudaError_t alloc(size_t n) { return cudaMalloc(&p, sizeof(T) * std::max<size_t>(n, 1)); }
+  ~DevBuf() { dev_free(p); }
+  cudaError_t alloc(size_t n) { return dev_alloc((void**)&p, sizeof(T) * std::max<size_t>(n, 1)); }
 };
 
 extern "C" int lisa_trace_closest(lisa_ctx* c, const float* org, const float* dir, uint32_t n, float tmin, float tmax,

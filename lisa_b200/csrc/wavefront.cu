@@ -44,6 +44,13 @@ namespace lisa {
 #define F_TRIES_MASK (0x1fu << F_TRIES_SHIFT)
 
 
+// Chain state is streamed (read once and written once per stage): evict-first loads/stores keep it from displacing
+// the BVH and the triangles in L1/L2.
+__device__ __forceinline__ float4 ld_state(const float4* p) { return __ldcs(p); }
+__device__ __forceinline__ void   st_state(float4* p, const float4& v) { __stcs(p, v); }
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 enum { ST_RADIANCE = 0, ST_SHADOW = 1, ST_SAMPLES = 2, ST_NULLDIR = 3, ST_CHAINS_DONE = 4, ST_NODES = 5, ST_TRIS = 6, ST_JOBS = 7, ST_CULLED = 8 };
 
 __device__ __forceinline__ void warp_add(unsigned long long* p, uint32_t v) {
@@ -145,9 +152,9 @@ __global__ void k_init_chains(DState s, DCamera cam, Tile t) {
   }
   if (i >= t.n_chains) return;
   const uint32_t p = t.pix0 + i % t.npix, f = t.f0 + i / t.npix;
-  s.a[i]   = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(chain_seed(cam, p, f)));
-  s.c[i]   = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(F_NEW));
-  s.sum[i] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(0u));
+  st_state(&s.a[i], make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(chain_seed(cam, p, f))));
+  st_state(&s.c[i], make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(F_NEW)));
+  st_state(&s.sum[i], make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(0u)));
 }
 
 template <bool WIDE>
@@ -200,7 +207,7 @@ __global__ void __launch_bounds__(256) k_extend(DScene sc, DState s, DCamera cam
         pending = false;
         const int i = chain;
         float3 atten = f3(1.0f, 1.0f, 1.0f), color = f3(0.0f, 0.0f, 0.0f);
-        if (!fresh) { atten = f3(s.a[i]); color = f3(s.c[i]); }
+        if (!fresh) { atten = f3(ld_state(&s.a[i])); color = f3(ld_state(&s.c[i])); }
         bool finished = false;
         if (best_prim < 0) {
           finished = true;  // __miss__radiance (background 0, optix_wrapper.cc:354) or a null direction (Q7)
@@ -229,18 +236,18 @@ __global__ void __launch_bounds__(256) k_extend(DScene sc, DState s, DCamera cam
               if (bounce >= t.bounces) finished = true;
               else {
                 flags = (flags & ~F_BOUNCE_MASK) | bounce;
-                s.o[i] = make_float4(P.x, P.y, P.z, 0.0f);
-                s.d[i] = make_float4(nd.x, nd.y, nd.z, 0.0f);
-                s.a[i] = make_float4(atten.x, atten.y, atten.z, __uint_as_float(seed));
-                s.c[i] = make_float4(color.x, color.y, color.z, __uint_as_float(flags));
+                st_state(&s.o[i], make_float4(P.x, P.y, P.z, 0.0f));
+                st_state(&s.d[i], make_float4(nd.x, nd.y, nd.z, 0.0f));
+                st_state(&s.a[i], make_float4(atten.x, atten.y, atten.z, __uint_as_float(seed)));
+                st_state(&s.c[i], make_float4(color.x, color.y, color.z, __uint_as_float(flags)));
               }
             } else {  // opaque, shader.cu:248-253: light sampling + bounce happen in k_tries / k_rays
               atten = atten * m.diffuse();
-              s.o[i] = make_float4(P.x, P.y, P.z, 0.0f);
-              if (fresh) s.d[i] = make_float4(d.x, d.y, d.z, 0.0f);
-              s.n[i] = make_float4(N.x, N.y, N.z, __int_as_float(mid));
-              s.a[i] = make_float4(atten.x, atten.y, atten.z, __uint_as_float(seed));
-              s.c[i] = make_float4(color.x, color.y, color.z, __uint_as_float(flags & ~F_TRIES_MASK));
+              st_state(&s.o[i], make_float4(P.x, P.y, P.z, 0.0f));
+              if (fresh) st_state(&s.d[i], make_float4(d.x, d.y, d.z, 0.0f));
+              st_state(&s.n[i], make_float4(N.x, N.y, N.z, __int_as_float(mid)));
+              st_state(&s.a[i], make_float4(atten.x, atten.y, atten.z, __uint_as_float(seed)));
+              st_state(&s.c[i], make_float4(color.x, color.y, color.z, __uint_as_float(flags & ~F_TRIES_MASK)));
               // RayState::hit already true (Q1): the first try is a real ray (it can clear hit) -> candidate queue
               push_sticky = (flags & F_STICKY) != 0;
               push = !push_sticky;
@@ -249,12 +256,12 @@ __global__ void __launch_bounds__(256) k_extend(DScene sc, DState s, DCamera cam
           }
         }
         if (finished) {
-          const float4   sum4 = s.sum[i];
+          const float4   sum4 = ld_state(&s.sum[i]);
           const uint32_t done = __float_as_uint(sum4.w) + 1;
           n_samp++;
-          s.sum[i] = make_float4(sum4.x + color.x, sum4.y + color.y, sum4.z + color.z, __uint_as_float(done));
-          s.a[i]   = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(seed));
-          s.c[i]   = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(F_NEW));
+          st_state(&s.sum[i], make_float4(sum4.x + color.x, sum4.y + color.y, sum4.z + color.z, __uint_as_float(done)));
+          st_state(&s.a[i], make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(seed)));
+          st_state(&s.c[i], make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(F_NEW)));
           if (done == t.spp) n_done++;
         }
         chain = -1;
@@ -273,14 +280,24 @@ __global__ void __launch_bounds__(256) k_extend(DScene sc, DState s, DCamera cam
           wnext = min(base, t.n_chains);
           wend  = min(base + 64u, t.n_chains);
           if (base + 64u >= t.n_chains) exhausted = true;
+          // the batch's state (5 arrays x 64 chains x 16 B = 40 lines) is pulled into L2 now; the lanes that take
+          // chains from it in later rounds then see L2 latency instead of HBM latency
+          if (wnext < wend) {
+            for (unsigned k = lane; k < 40u; k += 32u) {
+              const float4* arr = k < 8u ? s.sum : k < 16u ? s.a : k < 24u ? s.c : k < 32u ? s.o : s.d;
+              const unsigned idx = min(wnext + (k & 7u) * 8u, wend - 1u);
+              prefetch_l2(arr + idx);
+            }
+          }
         }
         const unsigned avail = wend - wnext, cnt = __popc(needmask), rank = __popc(needmask & lanemask_lt());
         if (need && rank < avail) {
           const int    i = (int)(wnext + rank);
-          const float4 sum4 = s.sum[i];
+          // five independent loads in flight (o, d are wasted on a fresh chain; HBM is not the limit here)
+          const float4 sum4 = ld_state(&s.sum[i]), a4 = ld_state(&s.a[i]), c4 = ld_state(&s.c[i]), o4 = ld_state(&s.o[i]),
+                       d4 = ld_state(&s.d[i]);
           if (__float_as_uint(sum4.w) < t.spp) {  // chains that have all their samples are skipped
             chain = i;
-            const float4 a4 = s.a[i], c4 = s.c[i];
             flags = __float_as_uint(c4.w);
             seed  = __float_as_uint(a4.w);
             fresh = flags & F_NEW;
@@ -289,7 +306,7 @@ __global__ void __launch_bounds__(256) k_extend(DScene sc, DState s, DCamera cam
               o = cam.eye;
               flags = 0;
             } else {
-              o = f3(s.o[i]); d = f3(s.d[i]);
+              o = f3(o4); d = f3(d4);
             }
             // ---- (3) start the radiance ray (trace_radiance, shader.cu:77-98)
             best_prim = -1; best_t = LISA_TMAX;
@@ -382,7 +399,7 @@ __global__ void __launch_bounds__(256) k_extend(DScene sc, DState s, DCamera cam
 //   k_rays   persistent state machine (one traversal quantum per iteration, dynamic job fetch): traces the
 //            candidate try — phase 0 closest emitter, phase 1 any occluder in front of it — retires it into
 //            RayState::hit, finishes lit jobs, and sends jobs that need more tries back to k_tries (next pass).
-// Passes shrink geometrically; the last pass finishes its leftovers inline.
+// Passes shrink geometrically; the last pass finishes its leftovers inline (default: a single pass, see lisa_rt.cu).
 struct JobCounters { uint32_t samples, done; };
 
 // End of the opaque branch of __closesthit__radiance for one job (shader.cu:251-252): add the light term,
@@ -390,7 +407,7 @@ struct JobCounters { uint32_t samples, done; };
 __device__ __forceinline__ void finish_job(const DScene& sc, const DState& s, const Tile& t, int job, const float3& N, int mid,
                                            uint32_t seed, uint32_t flags, float ndotl, JobCounters& jc) {
   const bool      lit = flags & F_STICKY;
-  const float4    a4 = s.a[job], c4 = s.c[job], d4 = s.d[job];
+  const float4    a4 = ld_state(&s.a[job]), c4 = ld_state(&s.c[job]), d4 = ld_state(&s.d[job]);
   const float3    atten = f3(a4);
   float3          color = f3(c4);
   const DMaterial m = load_material(sc.mats, mid);
@@ -402,18 +419,18 @@ __device__ __forceinline__ void finish_job(const DScene& sc, const DState& s, co
   const float3   nd = bsdf::bounce(f3(d4), N, seed, m);
   const uint32_t bounce = (flags & F_BOUNCE_MASK) + 1;
   if (bounce >= t.bounces) {
-    const float4   sum4 = s.sum[job];
+    const float4   sum4 = ld_state(&s.sum[job]);
     const uint32_t done = __float_as_uint(sum4.w) + 1;
-    s.sum[job] = make_float4(sum4.x + color.x, sum4.y + color.y, sum4.z + color.z, __uint_as_float(done));
-    s.a[job]   = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(seed));
-    s.c[job]   = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(F_NEW));
+    st_state(&s.sum[job], make_float4(sum4.x + color.x, sum4.y + color.y, sum4.z + color.z, __uint_as_float(done)));
+    st_state(&s.a[job], make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(seed)));
+    st_state(&s.c[job], make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(F_NEW)));
     jc.samples++;
     if (done == t.spp) jc.done++;
   } else {
     flags = (flags & ~(F_BOUNCE_MASK | F_TRIES_MASK)) | bounce;
-    s.d[job] = make_float4(nd.x, nd.y, nd.z, 0.0f);
-    s.a[job] = make_float4(atten.x, atten.y, atten.z, __uint_as_float(seed));
-    s.c[job] = make_float4(color.x, color.y, color.z, __uint_as_float(flags));
+    st_state(&s.d[job], make_float4(nd.x, nd.y, nd.z, 0.0f));
+    st_state(&s.a[job], make_float4(atten.x, atten.y, atten.z, __uint_as_float(seed)));
+    st_state(&s.c[job], make_float4(color.x, color.y, color.z, __uint_as_float(flags)));
   }
 }
 
@@ -453,19 +470,21 @@ __global__ void __launch_bounds__(256) k_tries(DScene sc, DState s, Tile t, uint
     uint32_t seed = 0, flags = 0, start = LISA_SHADOW_TRIES;
     int      mid = 0;
     if (job >= 0) {
-      const float4 o4 = s.o[job], n4 = s.n[job], a4 = s.a[job], c4 = s.c[job];
+      const float4 o4 = ld_state(&s.o[job]), n4 = ld_state(&s.n[job]), a4 = ld_state(&s.a[job]), c4 = ld_state(&s.c[job]);
       P = f3(o4); N = f3(n4);
       mid   = __float_as_int(n4.w);
       seed  = __float_as_uint(a4.w);
       flags = __float_as_uint(c4.w);
       start = (flags & F_TRIES_MASK) >> F_TRIES_SHIFT;
       emitter_cone(sc, P, axis, cosa);
+      // every try lies in the hemisphere of N: if the whole cone is below that horizon no try can be a candidate
+      if (cosa > -1.0f && cosa <= 1.0f && dot(N, axis) < -sqrtf(fmaxf(1.0f - cosa * cosa, 0.0f)) - 1e-3f) cosa = 2.0f;
     }
     float* myP = sP[threadIdx.x >> 5][lane];
     myP[0] = P.x; myP[1] = P.y; myP[2] = P.z;
     __syncwarp();
     int      first = -1;  // index (relative to start) of the first candidate try of MY job
-    unsigned valid = __ballot_sync(FULL, job >= 0);
+    unsigned valid = __ballot_sync(FULL, job >= 0 && cosa <= 1.0f);  // cosa == 2: nothing can pass (no emitter in reach)
     while (valid) {
       const int j = __ffs(valid) - 1;
       valid &= valid - 1;
@@ -592,11 +611,15 @@ __global__ void __launch_bounds__(256) k_rays(DScene sc, DState s, Tile t, uint3
             wnext = min(base, qn);
             wend  = min(base + SHADOW_BATCH, qn);
             if (base + SHADOW_BATCH >= qn) exhausted = true;
+            if (wnext + lane < wend) {  // pull the state of the whole batch into L2 while the first lanes consume it
+              const int pj = s.cand_q[wnext + lane];
+              prefetch_l2(s.o + pj); prefetch_l2(s.n + pj); prefetch_l2(s.a + pj); prefetch_l2(s.c + pj); prefetch_l2(s.d + pj);
+            }
           }
           const unsigned avail = wend - wnext, cnt = __popc(needmask), rank = __popc(needmask & lanemask_lt());
           if (need && rank < avail) {
             job = s.cand_q[wnext + rank];
-            const float4 o4 = s.o[job], n4 = s.n[job], a4 = s.a[job], c4 = s.c[job];
+            const float4 o4 = ld_state(&s.o[job]), n4 = ld_state(&s.n[job]), a4 = ld_state(&s.a[job]), c4 = ld_state(&s.c[job]);
             P = f3(o4); N = f3(n4);
             mid   = __float_as_int(n4.w);
             seed  = __float_as_uint(a4.w);
@@ -834,8 +857,9 @@ void launch_extend(const DScene& sc, const DState& s, const DCamera& cam, const 
 int launch_shadow(const DScene& sc, const DState& s, const Tile& t, uint32_t iter, const LaunchCfg& cfg, cudaStream_t st) {
   const int b = cfg.shadow_block;
   int launches = 0;
-  for (int p = 0; p < LISA_SHADOW_PASSES; p++) {
-    const unsigned last = p == LISA_SHADOW_PASSES - 1;
+  const int passes = max(1, min(cfg.shadow_passes, LISA_SHADOW_PASSES));
+  for (int p = 0; p < passes; p++) {
+    const unsigned last = p == passes - 1;
     // work shrinks roughly 4x per pass: later passes get smaller persistent grids
     unsigned gt = (unsigned)(cfg.sm_count * cfg.tries_blocks_per_sm), gr = (unsigned)(cfg.sm_count * cfg.shadow_blocks_per_sm);
     gt = min(gt, max(1u, cdiv(t.n_chains >> (2 * p), 32u * (256 / 32))));

@@ -3,7 +3,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 os.chdir(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import lisa_b200.frontend as fe, lisa_b200.rt as rt
 sc = fe.parse_scene("scenes/cornell_c2.rto")
-for i in range(3):
+for i in range(8):
     t0 = time.perf_counter(); R = rt.Renderer.from_scene(sc); t1 = time.perf_counter()
     R.render_subframes(i, 1, 50); t2 = time.perf_counter()
     img = R.read_accum(); t3 = time.perf_counter()
