@@ -192,6 +192,11 @@ int lisa_primary_rays(lisa_ctx* ctx, uint32_t subframe, float* dirs, uint32_t* s
 int lisa_kat_eval(int device, int what, uint32_t n, const float* in_f, const uint32_t* in_u, float* out_f,
                   uint32_t* out_u);
 
+/* The builder's device primitives (own LSD radix sort of (u64 key, u32 value) pairs, exclusive scan, stream
+ * compaction of non-negative ints), run on host arrays in place — for the tests only. */
+int lisa_debug_sort_pairs(int device, uint64_t* keys, uint32_t* vals, uint32_t n);
+int lisa_debug_scan_compact(int device, uint32_t* scan_inout, int32_t* compact_inout, uint32_t n, uint32_t* total, uint32_t* kept);
+
 #ifdef __cplusplus
 }
 #endif

@@ -12,12 +12,12 @@
 namespace lisa { namespace bsdf {
 
 // lambertian.cu:7-13 — lerp(mirror direction, hemisphere sample, roughness); NOT normalised (Q5).
-__device__ __forceinline__ float3 bounce(const float3& ray_dir, const float3& N, uint32_t& seed, const DMaterial& mat) {
+__device__ __forceinline__ float3 bounce(const float3& ray_dir, const float3& N, uint32_t& seed, const MatRef& mat) {
   return lerp(reflect(ray_dir, N), shoot_ray_hemisphere(N, seed), mat.roughness());
 }
 
 // lambertian.cu:15-22 — clamp(N.L, 0, 1)^2 / pi (no pdf division, Q3).
-__device__ __forceinline__ float BRDF(const float3& N, const float3& L, const DMaterial& /*mat*/) {
+__device__ __forceinline__ float BRDF(const float3& N, const float3& L, const MatRef& /*mat*/) {
   float NdotL = fminf(fmaxf(dot(N, L), 0.0f), 1.0f);
   return NdotL * (NdotL * 0.318309886183790672f);
 }

@@ -4,7 +4,7 @@
 //   1. k_centroid_bounds   scene bounds of triangle centroids (block reduce + ordered-int atomics)
 //   2. k_morton            63-bit Morton key per triangle; bit 63 = "triangle emits", so one sort also
 //                          partitions the soup into non-emitters | emitters
-//   3. radix sort          (key, triangle id) pairs                           [cub::DeviceRadixSort]
+//   3. radix sort          (key, triangle id) pairs, own LSD sort, 8 passes of 8 bits  (sort_scan.cu)
 //   4a. PLOC (default)     parallel locally-ordered clustering over the Morton order (Meister & Bittner 2018):
 //                          per round k_ploc_nn (nearest neighbour by merged surface area within +-radius),
 //                          k_ploc_merge (mutual pairs become a node), stream compaction; ~log n rounds.
@@ -18,13 +18,13 @@
 //   7. k_pack_triangles    soup -> (tri_v, tri_n) float4 arrays in final leaf order
 // Algorithmic bytes per triangle: 72 read soup + 12 key/id + sort 8 passes x 24 +
 // 2 x 80 hierarchy/refit + ~40 collapse + 96 packed write.
-#include <cub/device/device_radix_sort.cuh>
-#include <cub/device/device_select.cuh>
+#include <algorithm>
 #include <cfloat>
 #include <cstdio>
 
 #include "build.h"
 #include "devmem.h"
+#include "sort_scan.h"
 #include "common.cuh"
 
 namespace lisa {
@@ -220,7 +220,6 @@ __global__ void k_ploc_merge(const int* __restrict__ C, int m, const int* __rest
     Cout[i] = C[i];
   }
 }
-struct IsValidCluster { __host__ __device__ bool operator()(const int& v) const { return v >= 0; } };
 
 // ---- binary traversal nodes -----------------------------------------------------------------------
 // One node per internal Karras node; tri_base = first final triangle index of the partition.
@@ -446,11 +445,13 @@ int build_bvh(const BuildInput& in, BuildOutput* out, cudaStream_t st, char* err
   k_centroid_bounds<<<min(cdiv(T, 256), 148 * 8), 256, 0, st>>>(in.d_verts, T, d_acc);
   k_morton<<<cdiv(T, 256), 256, 0, st>>>(in.d_verts, in.d_mat_idx, in.d_mat_emit, in.num_mats, T, d_acc, d_keys, d_ids,
                                          &d_acc->n_emit);
-  size_t tmp_bytes = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_keys, d_keys2, d_ids, d_ids2, T, 0, 64, st);
+  const size_t tmp_bytes = radix_sort_temp_bytes((size_t)T);
   void* d_tmp;
-  CK(dev_alloc((void**)&d_tmp, tmp_bytes ? tmp_bytes : 16));
-  CK(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_keys, d_keys2, d_ids, d_ids2, T, 0, 64, st));
+  CK(dev_alloc((void**)&d_tmp, tmp_bytes));
+  if (radix_sort_pairs(d_keys, d_keys2, d_ids, d_ids2, (size_t)T, 0, 64, d_tmp, st) == 0) {  // 8 passes: ends in *_in
+    std::swap(d_keys, d_keys2);
+    std::swap(d_ids, d_ids2);
+  }
   BoundsAcc h_acc;
   CK(cudaMemcpyAsync(&h_acc, d_acc, sizeof(h_acc), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
@@ -479,8 +480,8 @@ int build_bvh(const BuildInput& in, BuildOutput* out, cudaStream_t st, char* err
     CK(dev_alloc((void**)&d_C[1], sizeof(int) * (size_t)T));
     CK(dev_alloc((void**)&d_nn, sizeof(int) * (size_t)T));
     CK(dev_alloc((void**)&d_sel, sizeof(int) * 2));
-    cub::DeviceSelect::If(nullptr, sel_bytes, d_C[0], d_C[1], d_sel, T, IsValidCluster(), st);
-    CK(dev_alloc((void**)&d_sel_tmp, sel_bytes ? sel_bytes : 16));
+    sel_bytes = compact_temp_bytes((size_t)T);
+    CK(dev_alloc((void**)&d_sel_tmp, sel_bytes));
   }
   for (int p = 0; p < 2; p++) {
     Part& P = parts[p];
@@ -502,7 +503,7 @@ int build_bvh(const BuildInput& in, BuildOutput* out, cudaStream_t st, char* err
         k_ploc_merge<<<cdiv(m, 256), 256, 0, st>>>(d_C[cur], m, d_nn, d_lo + P.slice, d_hi + P.slice, d_child + P.slice,
                                                    d_range + P.slice, P.n, d_next, d_C[cur ^ 1]);
         // compact in place of the old array: valid entries of d_C[cur^1] -> d_C[cur]
-        CK(cub::DeviceSelect::If(d_sel_tmp, sel_bytes, d_C[cur ^ 1], d_C[cur], d_sel, m, IsValidCluster(), st));
+        compact_nonneg(d_C[cur ^ 1], d_C[cur], (size_t)m, d_sel, d_sel_tmp, st);
         int m2 = 0;
         CK(cudaMemcpyAsync(&m2, d_sel, sizeof(int), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));

@@ -19,6 +19,7 @@
 #include "../../include/lisa_rt.h"
 #include "build.h"
 #include "devmem.h"
+#include "sort_scan.h"
 #include "scene.cuh"
 #include "wavefront.cuh"
 
@@ -308,10 +309,10 @@ static int create_impl(const lisa_scene_desc* sd, const lisa_options* opt, lisa_
   memset(c->h_stats, 0, sizeof(unsigned long long) * 16);
 
   c->cfg.sm_count = di.sms;
-  c->cfg.extend_block = 128;  // 94 registers/thread: 128-thread CTAs pack 5 per SM (20 warps) where 256 pack 2 (16 warps)
+  c->cfg.extend_block = 128;  // __launch_bounds__(128, 6): 80 registers/thread, 6 CTAs = 24 warps per SM
   c->cfg.shadow_block = 128;
-  if (const char* e2 = getenv("LISA_EXTEND_BLOCK")) c->cfg.extend_block = std::max(32, std::min(256, atoi(e2) / 32 * 32));
-  if (const char* e2 = getenv("LISA_SHADOW_BLOCK")) c->cfg.shadow_block = std::max(32, std::min(256, atoi(e2) / 32 * 32));
+  if (const char* e2 = getenv("LISA_EXTEND_BLOCK")) c->cfg.extend_block = std::max(32, std::min(128, atoi(e2) / 32 * 32));
+  if (const char* e2 = getenv("LISA_SHADOW_BLOCK")) c->cfg.shadow_block = std::max(32, std::min(128, atoi(e2) / 32 * 32));
   c->cfg.idle_thresh = 16;  // measured on B200 (Cornell 2000x2000): 1 -> 651, 8 -> 660, 16 -> 674, 20 -> 677 Msamples/s
   if (const char* e2 = getenv("LISA_IDLE_THRESH")) c->cfg.idle_thresh = std::max(1, std::min(32, atoi(e2)));
   // measured on B200 (Cornell 2000x2000): 4 passes 668, 3: 683, 2: 718, 1: 744 Msamples/s — the fill/drain of every extra
@@ -630,5 +631,50 @@ extern "C" int lisa_kat_eval(int device, int what, uint32_t n, const float* in_f
   CU(cudaGetLastError());
   if (fout[what] && out_f) CU(cudaMemcpy(out_f, d_of.p, sizeof(float) * fout[what] * (size_t)n, cudaMemcpyDeviceToHost));
   if (uout[what] && out_u) CU(cudaMemcpy(out_u, d_ou.p, sizeof(uint32_t) * uout[what] * (size_t)n, cudaMemcpyDeviceToHost));
+  return LISA_OK;
+}
+
+// ---- builder primitives, exposed for the tests --------------------------------------------------------------
+extern "C" int lisa_debug_sort_pairs(int device, uint64_t* keys, uint32_t* vals, uint32_t n) {
+  if ((!keys || !vals) && n) return fail(LISA_ERR_ARG, "null argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(LISA_ERR_CUDA, "no CUDA device: lisa_rt has no CPU fallback");
+  if (device >= 0) CU(cudaSetDevice(device));
+  DevBuf<unsigned long long> k0, k1;
+  DevBuf<unsigned int>       v0, v1;
+  DevBuf<char>               tmp;
+  CU(k0.alloc(n)); CU(k1.alloc(n)); CU(v0.alloc(n)); CU(v1.alloc(n)); CU(tmp.alloc(radix_sort_temp_bytes(n)));
+  CU(cudaMemcpy(k0.p, keys, sizeof(uint64_t) * (size_t)n, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(v0.p, vals, sizeof(uint32_t) * (size_t)n, cudaMemcpyHostToDevice));
+  const int where = radix_sort_pairs(k0.p, k1.p, v0.p, v1.p, n, 0, 64, tmp.p, 0);
+  CU(cudaDeviceSynchronize());
+  CU(cudaGetLastError());
+  CU(cudaMemcpy(keys, where ? k1.p : k0.p, sizeof(uint64_t) * (size_t)n, cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(vals, where ? v1.p : v0.p, sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToHost));
+  return LISA_OK;
+}
+
+extern "C" int lisa_debug_scan_compact(int device, uint32_t* scan_inout, int32_t* compact_inout, uint32_t n, uint32_t* total, uint32_t* kept) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(LISA_ERR_CUDA, "no CUDA device: lisa_rt has no CPU fallback");
+  if (device >= 0) CU(cudaSetDevice(device));
+  DevBuf<uint32_t> a, tot;
+  DevBuf<int>      c0, c1, cnt;
+  DevBuf<char>     tmp;
+  CU(a.alloc(n)); CU(tot.alloc(1)); CU(c0.alloc(n)); CU(c1.alloc(n)); CU(cnt.alloc(1));
+  CU(tmp.alloc(std::max(scan_temp_bytes(n), compact_temp_bytes(n))));
+  CU(cudaMemcpy(a.p, scan_inout, sizeof(uint32_t) * (size_t)n, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(c0.p, compact_inout, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice));
+  exclusive_scan_u32(a.p, a.p, n, tot.p, tmp.p, 0);
+  CU(cudaDeviceSynchronize());
+  compact_nonneg(c0.p, c1.p, n, cnt.p, tmp.p, 0);
+  CU(cudaDeviceSynchronize());
+  CU(cudaGetLastError());
+  CU(cudaMemcpy(scan_inout, a.p, sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(total, tot.p, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  int k = 0;
+  CU(cudaMemcpy(&k, cnt.p, sizeof(int), cudaMemcpyDeviceToHost));
+  *kept = (uint32_t)k;
+  CU(cudaMemcpy(compact_inout, c1.p, sizeof(int32_t) * (size_t)k, cudaMemcpyDeviceToHost));
   return LISA_OK;
 }

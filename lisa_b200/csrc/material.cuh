@@ -28,4 +28,13 @@ __device__ __forceinline__ DMaterial load_material(const DMaterial* mats, int i)
   return m;
 }
 
+// Handle a BSDF receives instead of the reference's `const Material*`: the material table and an index, so that an
+// implementation loads only the words it needs (the Lambertian BRDF needs none, its bounce only the roughness).
+struct MatRef {
+  const DMaterial* mats;
+  int              id;
+  __device__ __forceinline__ float roughness() const { return __ldg(reinterpret_cast<const float4*>(mats + id)).w; }
+  __device__ __forceinline__ DMaterial load() const { return load_material(mats, id); }
+};
+
 }  // namespace lisa

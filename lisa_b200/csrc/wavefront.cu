@@ -170,8 +170,14 @@ struct TravState<false> : BinState {};
 // traverses it one quantum per loop iteration (phase 0 closest emitter, phase 1 closest other triangle in
 // front of it), and when enough lanes have finished the warp runs the material dispatch of
 // __closesthit__radiance / __miss__radiance for them together and fetches new chains.
+// k_extend / k_rays run 128-thread CTAs, at least 6 per SM (<= 80 registers): measured on B200 against the natural 94
+// registers (5 CTAs): 6 -> +16 %, 7 (72 regs, spills) -> +14 %, 8 (64 regs) -> +12 %.  The kernels are latency bound
+// (long-scoreboard stalls on chain state), so resident warps count more than a few spilled registers.
+#ifndef LISA_MIN_BLOCKS
+#define LISA_MIN_BLOCKS 6
+#endif
 template <bool WIDE>
-__global__ void __launch_bounds__(256) k_extend(DScene sc, DState s, DCamera cam, Tile t, uint32_t iter, uint32_t idle_thresh) {
+__global__ void __launch_bounds__(128, LISA_MIN_BLOCKS) k_extend(DScene sc, DState s, DCamera cam, Tile t, uint32_t iter, uint32_t idle_thresh) {
   extern __shared__ uint2 smem_stack[];
   Stack          stack(smem_stack);
   unsigned int*  ring = s.ring + RING_STRIDE * (iter % 3);
@@ -405,16 +411,15 @@ struct JobCounters { uint32_t samples, done; };
 // End of the opaque branch of __closesthit__radiance for one job (shader.cu:251-252): add the light term,
 // draw the BSDF bounce (also after the last bounce: it consumes RNG), end the sample or store the next ray.
 __device__ __forceinline__ void finish_job(const DScene& sc, const DState& s, const Tile& t, int job, const float3& N, int mid,
-                                           uint32_t seed, uint32_t flags, float ndotl, JobCounters& jc) {
+                                           uint32_t seed, uint32_t flags, float brdf, JobCounters& jc) {
   const bool      lit = flags & F_STICKY;
   const float4    a4 = ld_state(&s.a[job]), c4 = ld_state(&s.c[job]), d4 = ld_state(&s.d[job]);
   const float3    atten = f3(a4);
   float3          color = f3(c4);
-  const DMaterial m = load_material(sc.mats, mid);
-  if (lit) {
+  const MatRef    m{sc.mats, mid};
+  if (lit) {  // shader.cu:205,251: emission of the last light found (Q1) * BRDF(N, w) * attenuation
     const DMaterial lm = load_material(sc.mats, (int)(flags >> F_LIGHT_SHIFT));
-    const float     c = fminf(fmaxf(ndotl, 0.0f), 1.0f);
-    color = color + (lm.emission() * (c * (c * 0.318309886183790672f))) * atten;  // emission * bsdf::BRDF(N, w)
+    color = color + (lm.emission() * brdf) * atten;
   }
   const float3   nd = bsdf::bounce(f3(d4), N, seed, m);
   const uint32_t bounce = (flags & F_BOUNCE_MASK) + 1;
@@ -528,7 +533,7 @@ __global__ void __launch_bounds__(256) k_tries(DScene sc, DState s, Tile t, uint
 }
 
 template <bool WIDE>
-__global__ void __launch_bounds__(256) k_rays(DScene sc, DState s, Tile t, uint32_t iter, uint32_t pass, uint32_t last,
+__global__ void __launch_bounds__(128, LISA_MIN_BLOCKS) k_rays(DScene sc, DState s, Tile t, uint32_t iter, uint32_t pass, uint32_t last,
                                               uint32_t idle_thresh) {
   extern __shared__ uint2 smem_stack[];
   Stack              stack(smem_stack);
@@ -543,7 +548,7 @@ __global__ void __launch_bounds__(256) k_rays(DScene sc, DState s, Tile t, uint3
   // ray of the current try
   StepRay ray;
   ray.idir = f3(0, 0, 0); ray.Sx = ray.Sy = ray.Sz = 0; ray.kz = 0; ray.oct_inv4 = 0;
-  float ndotl = 0.0f;
+  float brdf_w = 0.0f;  // BRDF(N, w) of the try in flight
   bool  in_flight = false, pending = false;
   // traversal
   TravState<WIDE> st;
@@ -592,7 +597,7 @@ __global__ void __launch_bounds__(256) k_rays(DScene sc, DState s, Tile t, uint3
           }
         }
         // ---- (3) finish / hand back
-        if (finish) { finish_job(sc, s, t, job, N, mid, seed, flags, ndotl, jc); job = -1; }
+        if (finish) { finish_job(sc, s, t, job, N, mid, seed, flags, brdf_w, jc); job = -1; }
         if (requeue) {
           flags = (flags & ~F_TRIES_MASK) | (tries << F_TRIES_SHIFT);
           s.a[job].w = __uint_as_float(seed);
@@ -633,7 +638,7 @@ __global__ void __launch_bounds__(256) k_rays(DScene sc, DState s, Tile t, uint3
         if (job >= 0 && !in_flight) {
           const float3 w = shoot_ray_hemisphere(N, seed);
           n_sh++;
-          ndotl = dot(N, w);
+          brdf_w = bsdf::BRDF(N, w, MatRef{sc.mats, mid});  // evaluated now (w is not kept), used if this try lights the job
           ray   = step_ray(w);
           in_flight  = true;
           light_prim = -1;
@@ -779,8 +784,6 @@ __global__ void k_kat(int what, uint32_t n, const float* __restrict__ in_f, cons
                       uint32_t* out_u) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  DMaterial m;
-  m.a = m.b = m.c = make_float4(0, 0, 0, 0);
   switch (what) {
     case 0: out_u[i] = tea16(in_u[2 * i], in_u[2 * i + 1]); break;
     case 1: { uint32_t s = in_u[i]; out_f[3 * i] = rnd(s); out_f[3 * i + 1] = rnd(s); out_f[3 * i + 2] = rnd(s); out_u[i] = s; } break;
@@ -789,10 +792,11 @@ __global__ void k_kat(int what, uint32_t n, const float* __restrict__ in_f, cons
     case 3: out_f[i] = bsdf::BTDF(in_f[2 * i], in_f[2 * i + 1]); break;
     case 4: { const float* p = in_f + 8 * i; float3 r = refract(p[0], f3(p[1], p[2], p[3]), f3(p[4], p[5], p[6]), p[7]);
               out_f[3 * i] = r.x; out_f[3 * i + 1] = r.y; out_f[3 * i + 2] = r.z; } break;
-    case 5: { const float* p = in_f + 7 * i; uint32_t s = in_u[i]; m.a.w = p[6];
-              float3 r = bsdf::bounce(f3(p[0], p[1], p[2]), f3(p[3], p[4], p[5]), s, m);
+    case 5: { const float* p = in_f + 7 * i; uint32_t s = in_u[i];
+              // the material table for this selector is the caller's roughness array viewed as DMaterial::a.w
+              float3 r = lerp(reflect(f3(p[0], p[1], p[2]), f3(p[3], p[4], p[5])), shoot_ray_hemisphere(f3(p[3], p[4], p[5]), s), p[6]);
               out_f[3 * i] = r.x; out_f[3 * i + 1] = r.y; out_f[3 * i + 2] = r.z; out_u[i] = s; } break;
-    case 6: { const float* p = in_f + 6 * i; out_f[i] = bsdf::BRDF(f3(p[0], p[1], p[2]), f3(p[3], p[4], p[5]), m); } break;
+    case 6: { const float* p = in_f + 6 * i; out_f[i] = bsdf::BRDF(f3(p[0], p[1], p[2]), f3(p[3], p[4], p[5]), MatRef{nullptr, 0}); } break;
     case 7: out_u[i] = make_color(f3(in_f[3 * i], in_f[3 * i + 1], in_f[3 * i + 2])); break;
     case 9: { uint32_t sd = in_u[i]; out_f[3 * i] = rng_fast(sd); out_f[3 * i + 1] = rng_fast(sd); out_f[3 * i + 2] = rng_fast(sd); out_u[i] = sd; } break;
     case 8: {  // shading normal at P: watertight-test barycentrics of a ray through P, then interpolation
@@ -816,7 +820,7 @@ static inline size_t   stack_smem(int block) { return (size_t)block * LISA_STACK
 
 int configure_kernels(char* err, size_t errlen) {
   cudaError_t e = cudaSuccess;
-  const int   smem = (int)stack_smem(256);
+  const int   smem = (int)stack_smem(128);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_extend<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_extend<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_rays<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

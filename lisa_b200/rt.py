@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_DIR, "liblisa_rt.so")
+LIB_PATH = os.environ.get("LISA_RT_LIB") or os.path.join(_DIR, "liblisa_rt.so")  # LISA_RT_LIB: developer override
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(
@@ -98,7 +98,7 @@ _L.lisa_kat_eval.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_uint32, _vp, _
 EXPORTS = ["lisa_create", "lisa_destroy", "lisa_last_error", "lisa_version", "lisa_render_subframes",
            "lisa_reset_accum", "lisa_read_accum", "lisa_read_rgba8", "lisa_write_ppm", "lisa_get_stats",
            "lisa_accum_device_ptr", "lisa_accum_bytes", "lisa_device", "lisa_sync", "lisa_trace_closest",
-           "lisa_trace_shadow", "lisa_primary_rays", "lisa_kat_eval"]
+           "lisa_trace_shadow", "lisa_primary_rays", "lisa_kat_eval", "lisa_debug_sort_pairs", "lisa_debug_scan_compact"]
 
 
 class LisaError(RuntimeError):
@@ -253,6 +253,25 @@ class Renderer:
         s = np.empty((self.height, self.width), dtype=np.uint32)
         _check(_L.lisa_primary_rays(self._h, subframe, d.ctypes.data, s.ctypes.data))
         return d, s
+
+
+_L.lisa_debug_sort_pairs.argtypes = [ctypes.c_int, _vp, _vp, ctypes.c_uint32]
+_L.lisa_debug_scan_compact.argtypes = [ctypes.c_int, _vp, _vp, ctypes.c_uint32, _vp, _vp]
+
+
+def debug_sort_pairs(keys, vals, device=-1):
+    k = np.ascontiguousarray(keys, dtype=np.uint64).copy()
+    v = np.ascontiguousarray(vals, dtype=np.uint32).copy()
+    _check(_L.lisa_debug_sort_pairs(device, k.ctypes.data, v.ctypes.data, k.shape[0]))
+    return k, v
+
+
+def debug_scan_compact(a, c, device=-1):
+    a = np.ascontiguousarray(a, dtype=np.uint32).copy()
+    c = np.ascontiguousarray(c, dtype=np.int32).copy()
+    tot, kept = ctypes.c_uint32(0), ctypes.c_uint32(0)
+    _check(_L.lisa_debug_scan_compact(device, a.ctypes.data, c.ctypes.data, a.shape[0], ctypes.byref(tot), ctypes.byref(kept)))
+    return a, tot.value, c[:kept.value]
 
 
 _KAT_SHAPES = {0: (0, 2, 0, 1), 1: (0, 1, 3, 1), 2: (3, 1, 3, 1), 3: (2, 0, 1, 0), 4: (8, 0, 3, 0), 5: (7, 1, 3, 1),

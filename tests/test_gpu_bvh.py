@@ -168,3 +168,24 @@ def test_tmin_tmax_in_parametric_units(rt):
     assert R.trace_closest(o, d, tmin=1e-4, tmax=1e16)[0][0] == 0
     assert R.trace_closest(o, d, tmin=0.3, tmax=1e16)[0][0] == -1
     assert R.trace_closest(o, d, tmin=1e-4, tmax=0.2)[0][0] == -1
+
+
+@pytest.mark.parametrize("n", [1, 2, 31, 32, 33, 255, 256, 2047, 2048, 2049, 4097, 100003, 3_000_001])
+def test_builder_primitives(rt, n):
+    """Own LSD radix sort (stable, 64-bit keys), exclusive scan and compaction against numpy; bit-exact."""
+    rng = np.random.default_rng(n)
+    keys = rng.integers(0, 2**64, size=n, dtype=np.uint64)
+    if n > 100:
+        keys[rng.integers(0, n, n // 3)] = keys[0]          # many duplicates: stability matters
+        keys[rng.integers(0, n, n // 7)] |= np.uint64(1) << np.uint64(63)
+    vals = np.arange(n, dtype=np.uint32)
+    k, v = rt.debug_sort_pairs(keys, vals)
+    order = np.argsort(keys, kind="stable")
+    np.testing.assert_array_equal(k, keys[order])
+    np.testing.assert_array_equal(v, vals[order])
+    a = rng.integers(0, 1000, size=n, dtype=np.uint32)
+    c = rng.integers(-3, 50, size=n).astype(np.int32)
+    s, tot, kept = rt.debug_scan_compact(a, c)
+    np.testing.assert_array_equal(s, (np.cumsum(a, dtype=np.uint64) - a).astype(np.uint32))
+    assert tot == int(a.sum(dtype=np.uint64)) & 0xffffffff
+    np.testing.assert_array_equal(kept, c[c >= 0])
