@@ -156,6 +156,9 @@ int lisa_read_rgba8(lisa_ctx* ctx, uint8_t* rgba);
 /* Vertically flipped binary PPM as sutil::saveImage/savePPM (src/sutil/sutil.cpp:523-554, 97-117).
  * path == NULL uses scene->output_image. */
 int lisa_write_ppm(lisa_ctx* ctx, const char* path);
+/* Linear float image (Portable Float Map, RGB, little endian): the accumulators without the 8-bit sRGB quantisation,
+ * for parity tooling (the reference can only write the quantised PPM; README.md:183 lists float output as a TODO). */
+int lisa_write_pfm(lisa_ctx* ctx, const char* path);
 int lisa_get_stats(lisa_ctx* ctx, lisa_stats* stats /* struct_size set by caller */);
 
 /* Multi-GPU plumbing: every rank renders a disjoint subframe set into its own sums; the

@@ -532,6 +532,26 @@ extern "C" int lisa_write_ppm(lisa_ctx* c, const char* path) {
   return LISA_OK;
 }
 
+extern "C" int lisa_write_pfm(lisa_ctx* c, const char* path) {
+  if (!c || !path || !*path) return fail(LISA_ERR_ARG, "null argument");
+  std::vector<float> px((size_t)c->width * c->height * 4);
+  int rc = lisa_read_accum(c, px.data());
+  if (rc) return rc;
+  FILE* f = fopen(path, "wb");
+  if (!f) return fail(LISA_ERR_IO, "cannot open %s for writing", path);
+  // Portable Float Map: "PF", width height, negative scale = little endian; scanlines bottom to top, which is the
+  // accumulators' own order (row 0 = bottom)
+  fprintf(f, "PF\n%u %u\n-1.0\n", c->width, c->height);
+  std::vector<float> row((size_t)c->width * 3);
+  for (uint32_t y = 0; y < c->height; y++) {
+    const float* src = px.data() + (size_t)y * c->width * 4;
+    for (uint32_t x = 0; x < c->width; x++) { row[3 * x] = src[4 * x]; row[3 * x + 1] = src[4 * x + 1]; row[3 * x + 2] = src[4 * x + 2]; }
+    if (fwrite(row.data(), sizeof(float), row.size(), f) != row.size()) { fclose(f); return fail(LISA_ERR_IO, "short write to %s", path); }
+  }
+  fclose(f);
+  return LISA_OK;
+}
+
 extern "C" int lisa_get_stats(lisa_ctx* c, lisa_stats* out) {
   if (!c || !out) return fail(LISA_ERR_ARG, "null argument");
   uint32_t sz = out->struct_size ? std::min<uint32_t>(out->struct_size, sizeof(lisa_stats)) : sizeof(lisa_stats);

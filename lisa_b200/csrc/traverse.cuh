@@ -114,70 +114,14 @@ __device__ __forceinline__ float3 safe_rcp_dir(const float3& d) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Binary BVH (ablation path).  Node = 4 x float4:
+// Node layouts
+//
+// Binary (ablation path).  Node = 4 x float4:
 //   n0 = (c0.lo.x, c0.hi.x, c0.lo.y, c0.hi.y)   n1 = (c1.lo.x, c1.hi.x, c1.lo.y, c1.hi.y)
 //   n2 = (c0.lo.z, c0.hi.z, c1.lo.z, c1.hi.z)   n3 = (child0, child1, -, -) as int bits
-// child >= 0: node index; child < 0: leaf holding the single triangle ~child; INT_MIN-free.
-// ------------------------------------------------------------------------------------------------
-template <bool ANY>
-__device__ __forceinline__ bool bvh2_trace(const float4* __restrict__ nodes, const float4* __restrict__ tri_v, int root,
-                                           const float3& o, const float3& d, float tmin, float tmax, Hit& hit,
-                                           Stack& stack, uint32_t& n_nodes, uint32_t& n_tris) {
-  hit.prim = -1;
-  hit.t    = tmax;
-  if (root < 0) return false;
-  const RayPre pre  = ray_precompute(o, d);
-  const float3 idir = safe_rcp_dir(d);
-  const float3 ood  = f3(o.x * idir.x, o.y * idir.y, o.z * idir.z);
-  // lo*idir - o*idir cancels: its absolute error is ~2^-23 |o*idir|.  Shift the near planes down and the far
-  // planes up by that bound so the slab test never rejects a box the (watertight) triangle test would hit.
-  const float  kpad = 6e-7f;
-  const float3 oodn = f3(ood.x + kpad * fabsf(ood.x), ood.y + kpad * fabsf(ood.y), ood.z + kpad * fabsf(ood.z));
-  const float3 oodf = f3(ood.x - kpad * fabsf(ood.x), ood.y - kpad * fabsf(ood.y), ood.z - kpad * fabsf(ood.z));
-  stack.clear();
-  int cur = root;
-  while (true) {
-    if (cur >= 0) {
-      const float4 n0 = __ldg(nodes + 4 * cur), n1 = __ldg(nodes + 4 * cur + 1), n2 = __ldg(nodes + 4 * cur + 2),
-                   n3 = __ldg(nodes + 4 * cur + 3);
-      n_nodes++;
-      // slab test, both children
-      // per axis: (near, far) of both planes, each padded outward
-      const float a0x = n0.x * idir.x, b0x = n0.y * idir.x, a0y = n0.z * idir.y, b0y = n0.w * idir.y;
-      const float a0z = n2.x * idir.z, b0z = n2.y * idir.z;
-      const float a1x = n1.x * idir.x, b1x = n1.y * idir.x, a1y = n1.z * idir.y, b1y = n1.w * idir.y;
-      const float a1z = n2.z * idir.z, b1z = n2.w * idir.z;
-      const float t0n = fmaxf(fmaxf(fminf(a0x, b0x) - oodn.x, fminf(a0y, b0y) - oodn.y), fmaxf(fminf(a0z, b0z) - oodn.z, tmin));
-      const float t0f = fminf(fminf(fmaxf(a0x, b0x) - oodf.x, fmaxf(a0y, b0y) - oodf.y), fminf(fmaxf(a0z, b0z) - oodf.z, hit.t));
-      const float t1n = fmaxf(fmaxf(fminf(a1x, b1x) - oodn.x, fminf(a1y, b1y) - oodn.y), fmaxf(fminf(a1z, b1z) - oodn.z, tmin));
-      const float t1f = fminf(fminf(fmaxf(a1x, b1x) - oodf.x, fmaxf(a1y, b1y) - oodf.y), fminf(fmaxf(a1z, b1z) - oodf.z, hit.t));
-      const bool  h0 = t0n * 0.9999995f <= t0f * 1.0000005f, h1 = t1n * 0.9999995f <= t1f * 1.0000005f;
-      int         c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
-      if (h0 && h1) {
-        if (t1n < t0n) { int t = c0; c0 = c1; c1 = t; }
-        stack.push(make_uint2((uint32_t)c1, 0u));
-        cur = c0;
-        continue;
-      } else if (h0) { cur = c0; continue; }
-      else if (h1) { cur = c1; continue; }
-    } else {
-      const int    ti = ~cur;
-      const float4 a = __ldg(tri_v + 3 * ti), b = __ldg(tri_v + 3 * ti + 1), c = __ldg(tri_v + 3 * ti + 2);
-      n_tris++;
-      float t, u, v;
-      if (intersect_tri(pre, f3(a), f3(b), f3(c), tmin, hit.t, t, u, v)) {
-        hit.t = t; hit.u = u; hit.v = v; hit.prim = ti;
-        if (ANY) return true;
-      }
-    }
-    if (stack.empty()) break;
-    cur = (int)stack.pop().x;
-  }
-  return hit.prim >= 0;
-}
-
-// ------------------------------------------------------------------------------------------------
-// Compressed 8-wide BVH.  Node = 5 x float4 (80 B):
+// child >= 0: node index; child < 0: leaf holding the single triangle ~child.
+//
+// Compressed 8-wide (Ylitie, Karras, Laine 2017).  Node = 5 x float4 (80 B):
 //   w0 = (p.x, p.y, p.z, [ex | ey<<8 | ez<<16 | imask<<24])
 //   w1 = (child_base, tri_base, meta[0..3], meta[4..7])
 //   w2 = (qlo_x[0..3], qlo_x[4..7], qlo_y[0..3], qlo_y[4..7])
@@ -185,7 +129,8 @@ __device__ __forceinline__ bool bvh2_trace(const float4* __restrict__ nodes, con
 //   w4 = (qhi_y[0..3], qhi_y[4..7], qhi_z[0..3], qhi_z[4..7])
 // meta[i]: 0 empty | internal: 0b001_11sss (sss = slot i) | leaf: unary triangle count in the top
 // 3 bits (1: 001, 2: 011, 3: 111) and the offset of its first triangle from tri_base in the low 5.
-// Child boxes: lo = p + qlo * 2^e, hi = p + qhi * 2^e per axis.
+// Child boxes: lo = p + qlo * 2^e, hi = p + qhi * 2^e per axis.  Traversal order: children are stored in octant
+// slots; hit internal children get the bit 24 + (slot ^ octant of the ray), popped highest first.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t sign_extend_s8x4(uint32_t x) {
   // each byte with bit 7 set becomes 0xff, else 0x00
@@ -195,107 +140,8 @@ __device__ __forceinline__ uint32_t sign_extend_s8x4(uint32_t x) {
 }
 __device__ __forceinline__ uint32_t extract_byte(uint32_t x, uint32_t i) { return (x >> (i * 8)) & 0xffu; }
 
-template <bool ANY>
-__device__ __forceinline__ bool bvh8_trace(const float4* __restrict__ nodes, const float4* __restrict__ tri_v, int root,
-                                           const float3& o, const float3& d, float tmin, float tmax, Hit& hit,
-                                           Stack& stack, uint32_t& n_nodes, uint32_t& n_tris) {
-  hit.prim = -1;
-  hit.t    = tmax;
-  if (root < 0) return false;
-  const RayPre pre  = ray_precompute(o, d);
-  const float3 idir = safe_rcp_dir(d);
-  // octant: bit set where the direction is NON-negative (paper's oct_inv = 7 - oct)
-  const uint32_t oct_inv  = (d.x < 0.0f ? 0u : 4u) | (d.y < 0.0f ? 0u : 2u) | (d.z < 0.0f ? 0u : 1u);
-  const uint32_t oct_inv4 = oct_inv * 0x01010101u;
-  stack.clear();
-  uint2 node_group = make_uint2((uint32_t)root, 0x80000000u);  // one "internal child" pending: the root
-  uint2 tri_group  = make_uint2(0u, 0u);
-  while (true) {
-    if (node_group.y & 0xff000000u) {
-      const uint32_t hits_imask      = node_group.y;
-      const uint32_t child_bit_index = 31u - __clz(hits_imask);
-      const uint32_t child_base      = node_group.x;
-      node_group.y &= ~(1u << child_bit_index);
-      if (node_group.y & 0xff000000u) stack.push(node_group);
-      const uint32_t slot_index     = (child_bit_index - 24u) ^ (oct_inv4 & 0xffu);
-      const uint32_t relative_index = __popc(hits_imask & ~(0xffffffffu << slot_index) & 0xffu);
-      const uint32_t ni             = child_base + relative_index;
-
-      const float4 w0 = __ldg(nodes + 5 * ni), w1 = __ldg(nodes + 5 * ni + 1), w2 = __ldg(nodes + 5 * ni + 2),
-                   w3 = __ldg(nodes + 5 * ni + 3), w4 = __ldg(nodes + 5 * ni + 4);
-      n_nodes++;
-      const uint32_t eimask = __float_as_uint(w0.w);
-      const float    sx = __uint_as_float((eimask & 0xffu) << 23), sy = __uint_as_float(((eimask >> 8) & 0xffu) << 23),
-                     sz = __uint_as_float(((eimask >> 16) & 0xffu) << 23);
-      const float3 adir = f3(sx * idir.x, sy * idir.y, sz * idir.z);
-      const float3 org  = f3((w0.x - o.x) * idir.x, (w0.y - o.y) * idir.y, (w0.z - o.z) * idir.z);
-      // q*adir + org cancels when |org| and |q*adir| are large: absolute error <~ 2^-22 (|org| + 255 |adir|).
-      // Near planes are shifted down and far planes up by that bound (conservative, watertight at the node level).
-      const float  kpad = 6e-7f;
-      const float3 pad  = f3(kpad * (fabsf(org.x) + 256.0f * fabsf(adir.x)), kpad * (fabsf(org.y) + 256.0f * fabsf(adir.y)),
-                             kpad * (fabsf(org.z) + 256.0f * fabsf(adir.z)));
-      const float3 orgn = org - pad, orgf = org + pad;
-      node_group.x = __float_as_uint(w1.x);
-      tri_group.x  = __float_as_uint(w1.y);
-      uint32_t hitmask = 0;
-#pragma unroll
-      for (int half = 0; half < 2; half++) {
-        const uint32_t meta4 = __float_as_uint(half == 0 ? w1.z : w1.w);
-        if (meta4 == 0u) continue;  // four empty slots
-        const uint32_t is_inner4   = (meta4 & (meta4 << 1)) & 0x10101010u;
-        const uint32_t inner_mask4 = sign_extend_s8x4(is_inner4 << 3);
-        const uint32_t bit_index4  = (meta4 ^ (oct_inv4 & inner_mask4)) & 0x1f1f1f1fu;
-        const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
-        const uint32_t qlox = __float_as_uint(half == 0 ? w2.x : w2.y), qloy = __float_as_uint(half == 0 ? w2.z : w2.w);
-        const uint32_t qloz = __float_as_uint(half == 0 ? w3.x : w3.y), qhix = __float_as_uint(half == 0 ? w3.z : w3.w);
-        const uint32_t qhiy = __float_as_uint(half == 0 ? w4.x : w4.y), qhiz = __float_as_uint(half == 0 ? w4.z : w4.w);
-        // near/far planes per axis depend on the direction sign
-        const uint32_t nx = d.x < 0.0f ? qhix : qlox, fx = d.x < 0.0f ? qlox : qhix;
-        const uint32_t ny = d.y < 0.0f ? qhiy : qloy, fy = d.y < 0.0f ? qloy : qhiy;
-        const uint32_t nz = d.z < 0.0f ? qhiz : qloz, fz = d.z < 0.0f ? qloz : qhiz;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const float tnx = (float)extract_byte(nx, j) * adir.x + orgn.x, tfx = (float)extract_byte(fx, j) * adir.x + orgf.x;
-          const float tny = (float)extract_byte(ny, j) * adir.y + orgn.y, tfy = (float)extract_byte(fy, j) * adir.y + orgf.y;
-          const float tnz = (float)extract_byte(nz, j) * adir.z + orgn.z, tfz = (float)extract_byte(fz, j) * adir.z + orgf.z;
-          const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
-          const float tf = fminf(fminf(tfx, tfy), fminf(tfz, hit.t));
-          if (tn * 0.9999995f <= tf * 1.0000005f) {
-            const uint32_t child_bits = extract_byte(child_bits4, j);
-            const uint32_t bit_index  = extract_byte(bit_index4, j);
-            hitmask |= child_bits << bit_index;
-          }
-        }
-      }
-      node_group.y = (hitmask & 0xff000000u) | (eimask >> 24);
-      tri_group.y  = hitmask & 0x00ffffffu;
-    } else {
-      tri_group  = node_group;
-      node_group = make_uint2(0u, 0u);
-    }
-    while (tri_group.y) {
-      const uint32_t k = __ffs(tri_group.y) - 1u;
-      tri_group.y &= tri_group.y - 1u;
-      const int    ti = (int)(tri_group.x + k);
-      const float4 a = __ldg(tri_v + 3 * ti), b = __ldg(tri_v + 3 * ti + 1), c = __ldg(tri_v + 3 * ti + 2);
-      n_tris++;
-      float t, u, v;
-      if (intersect_tri(pre, f3(a), f3(b), f3(c), tmin, hit.t, t, u, v)) {
-        hit.t = t; hit.u = u; hit.v = v; hit.prim = ti;
-        if (ANY) return true;
-      }
-    }
-    if ((node_group.y & 0xff000000u) == 0u) {
-      if (stack.empty()) break;
-      node_group = stack.pop();
-    }
-  }
-  return hit.prim >= 0;
-}
-
-
 // ================================================================================================
-// Step-wise traversal for the persistent shadow kernel (wavefront.cu: k_shadow).
+// Step-wise traversal (used by every kernel: k_extend, k_rays and the diagnostic queries).
 //
 // A warp's lanes are at different points of different rays, so the kernel runs a state machine whose
 // loop body is ONE work quantum per lane: at most one node visit followed by at most LISA_TRI_PER_STEP
@@ -371,7 +217,8 @@ __device__ __forceinline__ void wide_node_step(const float4* __restrict__ nodes,
   const float3 adir = f3(__uint_as_float((eimask & 0xffu) << 23) * r.idir.x, __uint_as_float(((eimask >> 8) & 0xffu) << 23) * r.idir.y,
                          __uint_as_float(((eimask >> 16) & 0xffu) << 23) * r.idir.z);
   const float3 org  = f3((w0.x - o.x) * r.idir.x, (w0.y - o.y) * r.idir.y, (w0.z - o.z) * r.idir.z);
-  // conservative planes (see bvh8_trace): |t| <= |org| + 255 |adir|, so one absolute pad of 2^-20 of that bound
+  // conservative planes: t = q*adir + org cancels when |org| and |q*adir| are large, and |t| <= |org| + 255 |adir|,
+  // so one absolute pad of 2^-20 of that bound
   // covers both the cancellation in q*adir + org and the relative rounding of the result
   const float  kpad = 1.2e-6f;
   const float3 pad  = f3(kpad * (fabsf(org.x) + 256.0f * fabsf(adir.x)), kpad * (fabsf(org.y) + 256.0f * fabsf(adir.y)),
@@ -442,6 +289,53 @@ __device__ __forceinline__ void bin_node_step(const float4* __restrict__ nodes, 
   } else if (h0) st.cur = c0;
   else if (h1) st.cur = c1;
   else st.cur = stack.empty() ? LISA_BIN_NONE : (int)stack.pop().x;
+}
+
+
+// One whole traversal of one ray with the step functions above (the diagnostic queries use this; the render kernels
+// interleave the same steps across lanes).  ANY = stop at the first hit.
+template <bool WIDE, bool ANY>
+__device__ __forceinline__ bool trace_steps(const float4* __restrict__ nodes, const float4* __restrict__ tri_v, int root,
+                                            const float3& o, const float3& d, float tmin, float tmax, Hit& hit, Stack& stack,
+                                            uint32_t& n_nodes, uint32_t& n_tris) {
+  hit.prim = -1;
+  hit.t    = tmax;
+  if (root < 0) return false;
+  const StepRay r = step_ray(d);
+  stack.clear();
+  if (WIDE) {
+    WideState st;
+    st.begin(root);
+    while (true) {
+      if (st.has_nodes() && !st.has_tris()) { n_nodes++; wide_node_step(nodes, o, r, tmin, hit.t, st, stack); }
+      while (st.tg.y) {
+        const uint32_t b = __ffs(st.tg.y) - 1u;
+        st.tg.y &= st.tg.y - 1u;
+        const int ti = (int)(st.tg.x + b);
+        float t, u, v;
+        n_tris++;
+        if (step_tri_uv(o, r, tri_v, ti, tmin, hit.t, t, u, v)) { hit.t = t; hit.u = u; hit.v = v; hit.prim = ti; if (ANY) return true; }
+      }
+      if (!st.has_nodes()) {
+        if (stack.empty()) break;
+        st.ng = stack.pop();
+      }
+    }
+  } else {
+    BinState st;
+    st.begin(root);
+    while (st.cur != LISA_BIN_NONE) {
+      if (st.has_nodes()) { n_nodes++; bin_node_step(nodes, o, r, tmin, hit.t, st, stack); }
+      if (st.has_tris()) {
+        const int ti = ~st.cur;
+        float t, u, v;
+        n_tris++;
+        if (step_tri_uv(o, r, tri_v, ti, tmin, hit.t, t, u, v)) { hit.t = t; hit.u = u; hit.v = v; hit.prim = ti; if (ANY) return true; }
+        st.cur = stack.empty() ? LISA_BIN_NONE : (int)stack.pop().x;
+      }
+    }
+  }
+  return hit.prim >= 0;
 }
 
 }  // namespace lisa

@@ -84,8 +84,7 @@ __device__ __forceinline__ bool hits_emitter_bounds(const DScene& sc, const floa
 template <bool WIDE, bool ANY>
 __device__ __forceinline__ bool trace_one(const DScene& sc, int root, const float3& o, const float3& d, float tmin, float tmax,
                                           Hit& h, Stack& stack, uint32_t& nn, uint32_t& nt) {
-  if (WIDE) return bvh8_trace<ANY>(sc.bvh, sc.tri_v, root, o, d, tmin, tmax, h, stack, nn, nt);
-  return bvh2_trace<ANY>(sc.bvh, sc.tri_v, root, o, d, tmin, tmax, h, stack, nn, nt);
+  return trace_steps<WIDE, ANY>(sc.bvh, sc.tri_v, root, o, d, tmin, tmax, h, stack, nn, nt);
 }
 
 // closest hit over emitters and non-emitters (trace_radiance)

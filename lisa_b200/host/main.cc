@@ -1,7 +1,7 @@
 // lisa_b200/host/main.cc — the CLI (src/LiSA/src/main.cc:6-28, include/parse_args.hh:3-16).
 //   lisa -s scene.rto [-d]
 // -s <scene> is mandatory; without it the usage goes to stderr and the exit code is 1.  -d selects the
-// progressive mode (headless here).  Extra, optional: --stats prints one JSON line with the counters of
+// progressive mode (headless here).  Extra, optional: --pfm <file> also writes the linear float image; --stats prints one JSON line with the counters of
 // include/lisa_rt.h:lisa_stats; environment variables LISA_BVH/LISA_SHADOW/LISA_MAX_CHAINS select
 // ablation variants (see lisa_rt.cu).
 #include <algorithm>
@@ -40,6 +40,9 @@ int main(int argc, char** argv) {
     printf("Starting rendering...\n");
     if (cmdOptionExists(argv, argv + argc, "-d")) display(ctx, params);
     else render(ctx, params);
+    if (char* pfm = getCmdOption(argv, argv + argc, "--pfm")) {
+      if (lisa_write_pfm(ctx, pfm) != LISA_OK) std::cerr << "lisa: " << lisa_last_error() << std::endl;
+    }
     if (cmdOptionExists(argv, argv + argc, "--stats")) {
       lisa_stats s;
       s.struct_size = sizeof(s);

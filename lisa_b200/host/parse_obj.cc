@@ -5,13 +5,17 @@
 //   every other line is ignored.
 // Differences, all on inputs for which the reference has undefined behaviour: runs of spaces are
 // tolerated, and short lines / out-of-range indices raise an error instead of reading out of bounds.
-// The whole file is read once and scanned in place (no per-line vector<string>), which is what makes
-// multi-million-triangle soups loadable in seconds.
+// The whole file is read once and scanned in place (no per-line vector<string>) by one worker thread per chunk of
+// whole lines, in three passes (count, positions/normals, faces): what makes multi-million-triangle soups load in
+// seconds.  LISA_OBJ_THREADS overrides the worker count.
 #include "parse_obj.hh"
 
+#include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 
 #include "scene_parser.hh"
 
@@ -44,9 +48,48 @@ float to_float(const char* b, const char* e, const std::string& path, long line)
 
 }  // namespace
 
+namespace {
+
+struct Chunk {
+  const char* b;
+  const char* e;          // [b, e): whole lines
+  long        first_line; // 1-based number of the first line (for messages)
+  size_t      nv = 0, nn = 0, nf = 0;
+  std::string error;
+};
+
+// calls fn(kind, cursor-after-the-keyword, line_no) for every "v", "vn", "f" line of the chunk
+template <typename F>
+void for_each_record(const Chunk& c, F&& fn) {
+  const char* p = c.b;
+  long line_no = c.first_line - 1;
+  while (p < c.e) {
+    const char* eol = (const char*)memchr(p, '\n', (size_t)(c.e - p));
+    if (!eol) eol = c.e;
+    line_no++;
+    if (*p != ' ') {  // a leading space makes the first token empty in the reference: line ignored
+      Cursor cur{p, eol};
+      const char *b, *e;
+      if (cur.token(b, e)) {
+        const size_t len = (size_t)(e - b);
+        if (len == 1 && b[0] == 'v') fn(0, cur, line_no);
+        else if (len == 2 && b[0] == 'v' && b[1] == 'n') fn(1, cur, line_no);
+        else if (len == 1 && b[0] == 'f') fn(2, cur, line_no);
+      }
+    }
+    p = eol + 1;
+  }
+}
+
+}  // namespace
+
 void parse_obj(const std::string& path, std::vector<float>& vertices, std::vector<float>& normals,
                std::vector<int32_t>& mat_indices, int mat_idx) {
   printf("Importing %s...\n", path.c_str());
+  const bool dbg = getenv("LISA_DEBUG_TIMING") != nullptr;
+  auto tnow = [] { return std::chrono::steady_clock::now(); };
+  auto tms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+  auto T0 = tnow();
   FILE* f = fopen(path.c_str(), "rb");
   if (!f) throw SceneError(path + " not found.", -1);
   fseek(f, 0, SEEK_END);
@@ -60,42 +103,95 @@ void parse_obj(const std::string& path, std::vector<float>& vertices, std::vecto
   fclose(f);
   data[(size_t)size] = '\n';
 
-  std::vector<float> vt, nt;
-  int  nb_triangles = 0;
-  long line_no = 0;
-  const char* p = data.data();
-  const char* const stop = p + size;
-  while (p < stop) {
-    const char* eol = (const char*)memchr(p, '\n', (size_t)(stop - p) + 1);
-    line_no++;
-    Cursor c{p, eol};
-    const char *b, *e;
-    if (*p != ' ' && c.token(b, e)) {  // a leading space makes the first token empty in the reference: line ignored
-      const size_t len = (size_t)(e - b);
-      if ((len == 1 && b[0] == 'v') || (len == 2 && b[0] == 'v' && b[1] == 'n')) {
-        std::vector<float>& dst = len == 1 ? vt : nt;
-        for (int k = 0; k < 3; k++) {
-          if (!c.token(b, e)) throw SceneError(path + ":" + std::to_string(line_no) + ": expected 3 components", 1);
-          dst.push_back(to_float(b, e, path, line_no));
-        }
-      } else if (len == 1 && b[0] == 'f') {
-        for (int k = 0; k < 3; k++) {
-          if (!c.token(b, e)) throw SceneError(path + ":" + std::to_string(line_no) + ": face needs 3 vertices", 1);
-          // a/b/c : fields 0 and 2
-          const char* s1 = (const char*)memchr(b, '/', (size_t)(e - b));
-          const char* s2 = s1 ? (const char*)memchr(s1 + 1, '/', (size_t)(e - s1 - 1)) : nullptr;
-          if (!s2) throw SceneError(path + ":" + std::to_string(line_no) + ": face vertex without normal index", 1);
-          long vi = strtol(b, nullptr, 10), ni = strtol(s2 + 1, nullptr, 10);
-          if (vi < 1 || (size_t)vi * 3 > vt.size() || ni < 1 || (size_t)ni * 3 > nt.size())
-            throw SceneError(path + ":" + std::to_string(line_no) + ": index out of range", 1);
-          vertices.insert(vertices.end(), vt.begin() + 3 * (vi - 1), vt.begin() + 3 * vi);
-          normals.insert(normals.end(), nt.begin() + 3 * (ni - 1), nt.begin() + 3 * ni);
-        }
-        mat_indices.push_back(mat_idx);
-        nb_triangles++;
-      }
+  auto T1 = tnow();
+  // chunks of whole lines, one per worker (a single chunk below 4 MB)
+  unsigned nthreads = std::max(1u, std::min(std::thread::hardware_concurrency(), 64u));
+  if (size < (4 << 20)) nthreads = 1;
+  if (const char* e = getenv("LISA_OBJ_THREADS")) nthreads = (unsigned)std::max(1, atoi(e));
+  std::vector<Chunk> chunks;
+  {
+    const char* base = data.data();
+    const char* stop = base + size;
+    const char* p = base;
+    for (unsigned k = 0; k < nthreads && p < stop; k++) {
+      const char* want = k + 1 == nthreads ? stop : base + (size_t)size * (k + 1) / nthreads;
+      if (want < p) want = p;
+      const char* e = want >= stop ? stop : (const char*)memchr(want, '\n', (size_t)(stop - want));
+      e = e ? std::min(e + 1, stop) : stop;
+      chunks.push_back(Chunk{p, e, 0});
+      p = e;
     }
-    p = eol + 1;
   }
-  printf("Done. Imported %d triangles.\n", nb_triangles);
+  auto run = [&](auto&& body) {
+    if (chunks.size() == 1) { body(chunks[0]); return; }
+    std::vector<std::thread> th;
+    for (Chunk& c : chunks) th.emplace_back([&body, &c] { try { body(c); } catch (const std::exception& e) { c.error = e.what(); } });
+    for (auto& t : th) t.join();
+    for (Chunk& c : chunks) if (!c.error.empty()) throw SceneError(c.error, 1);
+  };
+  auto T2 = tnow();
+  // pass 1: count records and lines per chunk
+  std::vector<long> lines(chunks.size(), 0);
+  run([&](Chunk& c) {
+    long n = 0;
+    for (const char* p = c.b; p < c.e;) { const char* eol = (const char*)memchr(p, '\n', (size_t)(c.e - p)); n++; p = eol ? eol + 1 : c.e; }
+    lines[&c - chunks.data()] = n;
+    c.first_line = 1;
+    for_each_record(c, [&](int kind, Cursor&, long) { (kind == 0 ? c.nv : kind == 1 ? c.nn : c.nf)++; });
+  });
+  size_t tv = 0, tn = 0, tf = 0;
+  std::vector<size_t> ov(chunks.size()), on(chunks.size()), of(chunks.size());
+  long line0 = 1;
+  for (size_t k = 0; k < chunks.size(); k++) {
+    ov[k] = tv; on[k] = tn; of[k] = tf;
+    tv += chunks[k].nv; tn += chunks[k].nn; tf += chunks[k].nf;
+    chunks[k].first_line = line0;
+    line0 += lines[k];
+  }
+  auto T3 = tnow();
+  // pass 2: positions and normals
+  std::vector<float> vt(3 * tv), nt(3 * tn);
+  run([&](Chunk& c) {
+    const size_t k = (size_t)(&c - chunks.data());
+    size_t iv = ov[k], in = on[k];
+    for_each_record(c, [&](int kind, Cursor& cur, long line_no) {
+      if (kind == 2) return;
+      float* dst = kind == 0 ? &vt[3 * iv++] : &nt[3 * in++];
+      for (int j = 0; j < 3; j++) {
+        const char *b, *e;
+        if (!cur.token(b, e)) throw SceneError(path + ":" + std::to_string(line_no) + ": expected 3 components", 1);
+        dst[j] = to_float(b, e, path, line_no);
+      }
+    });
+  });
+  auto T4 = tnow();
+  // pass 3: faces -> de-indexed soup.  In the reference a face may only use vertices declared BEFORE it
+  // (it indexes the arrays as they grow); files that respect that give the same result here.
+  const size_t v0 = vertices.size(), n0 = normals.size(), m0 = mat_indices.size();
+  vertices.resize(v0 + 9 * tf);
+  normals.resize(n0 + 9 * tf);
+  mat_indices.resize(m0 + tf, mat_idx);
+  run([&](Chunk& c) {
+    const size_t k = (size_t)(&c - chunks.data());
+    size_t it = of[k];
+    for_each_record(c, [&](int kind, Cursor& cur, long line_no) {
+      if (kind != 2) return;
+      for (int j = 0; j < 3; j++) {
+        const char *b, *e;
+        if (!cur.token(b, e)) throw SceneError(path + ":" + std::to_string(line_no) + ": face needs 3 vertices", 1);
+        const char* s1 = (const char*)memchr(b, '/', (size_t)(e - b));
+        const char* s2 = s1 ? (const char*)memchr(s1 + 1, '/', (size_t)(e - s1 - 1)) : nullptr;
+        if (!s2) throw SceneError(path + ":" + std::to_string(line_no) + ": face vertex without normal index", 1);
+        const long vi = strtol(b, nullptr, 10), ni = strtol(s2 + 1, nullptr, 10);
+        if (vi < 1 || (size_t)vi > tv || ni < 1 || (size_t)ni > tn)
+          throw SceneError(path + ":" + std::to_string(line_no) + ": index out of range", 1);
+        memcpy(&vertices[v0 + 9 * it + 3 * j], &vt[3 * (vi - 1)], 12);
+        memcpy(&normals[n0 + 9 * it + 3 * j], &nt[3 * (ni - 1)], 12);
+      }
+      it++;
+    });
+  });
+  auto T5 = tnow();
+  if (dbg) fprintf(stderr, "parse_obj: read %.1f chunk %.1f count %.1f v/vn %.1f faces %.1f ms (%zu chunks)\n", tms(T0, T1), tms(T1, T2), tms(T2, T3), tms(T3, T4), tms(T4, T5), chunks.size());
+  printf("Done. Imported %d triangles.\n", (int)tf);
 }

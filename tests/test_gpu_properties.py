@@ -133,3 +133,15 @@ def test_host_render_and_display(rt, frontend, tmp_path, capfd):
         assert R.stats()["samples"] == 64 * 64 * 16
     # -s (1 x 16 spp, subframe 0) and -d (1 x 16 spp, subframe 0) coincide for num_samples = 16
     np.testing.assert_array_equal(imgs[0], imgs[1])
+
+
+def test_pfm_output(rt, cornell, tmp_path):
+    R = rt.Renderer.from_scene(resized(cornell, 40, 24))
+    R.render_subframes(0, 1, 4)
+    p = str(tmp_path / "o.pfm")
+    R.write_pfm(p)
+    raw = open(p, "rb").read()
+    hdr = b"PF\n40 24\n-1.0\n"
+    assert raw.startswith(hdr)
+    img = np.frombuffer(raw[len(hdr):], "<f4").reshape(24, 40, 3)
+    np.testing.assert_array_equal(img, R.read_accum()[..., :3])

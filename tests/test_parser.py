@@ -118,3 +118,29 @@ def test_quad_truncated_and_indices(frontend):
     assert v.shape[0] == 2
     np.testing.assert_array_equal(v[1], [[0, 0, 0], [1, 0, 0], [1, 1, 0.5]])  # 4th vertex of the quad dropped
     np.testing.assert_array_equal(sc["normals"].reshape(-1, 3, 3)[0], [[0, 0, 1], [0, 0, 1], [0, 1, 0]])
+
+
+def test_parallel_obj_loader_matches_oracle(frontend, tmp_path, monkeypatch):
+    """The chunked multi-threaded OBJ loader (host/parse_obj.cc) against the oracle's line-by-line restatement of
+    parse_obj.cc, with the chunk boundaries forced inside a small file."""
+    import sys
+    from oracle import scene_py
+    sys.path.insert(0, os.path.join(ROOT, "assets"))
+    import gen_knot
+    obj = tmp_path / "k.obj"
+    sys.argv = ["gen_knot", str(obj), "60", "16"]
+    gen_knot.main()
+    with open(obj, "a") as f:   # lines the loader must ignore or truncate
+        f.write("vt 0.5 0.5\n# comment\n v 9 9 9\ng grp\nf 1//1 2//2 3//3 4//4\n")
+    rto = tmp_path / "k.rto"
+    rto.write_text("material g { color = (1, 1, 1, 0)\n n = 1.5 }\nmesh { obj_file = %s\n material = g }\n"
+                   "camera { position = (0,0,1) look_at = (0,0,0) fov = 40 }\nnum_samples = 1\nnum_bounces = 1\n"
+                   "width = 4\nheight = 4\noutput_image = x.ppm\n" % obj)
+    ref = scene_py.parse_scene(str(rto))
+    for th in ("1", "3", "7"):
+        monkeypatch.setenv("LISA_OBJ_THREADS", th)
+        got = frontend.parse_scene(str(rto))
+        np.testing.assert_array_equal(got["vertices"], ref["vertices"])
+        np.testing.assert_array_equal(got["normals"], ref["normals"])
+        np.testing.assert_array_equal(got["mat_indices"], ref["mat_indices"])
+    assert got["vertices"].shape[0] == 3 * (2 * 60 * 16 + 1)
