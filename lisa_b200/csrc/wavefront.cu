@@ -25,6 +25,10 @@
 #include "traverse.cuh"
 #include "wavefront.cuh"
 
+#ifndef LISA_STATE_NO_L1
+#define LISA_STATE_NO_L1 0
+#endif
+
 namespace lisa {
 
 // flags word (DState::c .w)
@@ -46,7 +50,15 @@ namespace lisa {
 
 // Chain state is streamed (read once and written once per stage): evict-first loads/stores keep it from displacing
 // the BVH and the triangles in L1/L2.
-__device__ __forceinline__ float4 ld_state(const float4* p) { return __ldcs(p); }
+__device__ __forceinline__ float4 ld_state(const float4* p) {
+#if LISA_STATE_NO_L1
+  float4 v;  // do not allocate the line in L1 at all: the L1 is for BVH nodes and triangles
+  asm volatile("ld.global.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+#else
+  return __ldcs(p);
+#endif
+}
 __device__ __forceinline__ void   st_state(float4* p, const float4& v) { __stcs(p, v); }
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
@@ -172,6 +184,15 @@ struct TravState<false> : BinState {};
 // k_extend / k_rays run 128-thread CTAs, at least 6 per SM (<= 80 registers): measured on B200 against the natural 94
 // registers (5 CTAs): 6 -> +16 %, 7 (72 regs, spills) -> +14 %, 8 (64 regs) -> +12 %.  The kernels are latency bound
 // (long-scoreboard stalls on chain state), so resident warps count more than a few spilled registers.
+#ifndef LISA_VOTE_SECTIONS
+#define LISA_VOTE_SECTIONS 0
+#endif
+#ifndef LISA_VOTE_WN
+#define LISA_VOTE_WN 1
+#endif
+#ifndef LISA_VOTE_WT
+#define LISA_VOTE_WT 1
+#endif
 #ifndef LISA_MIN_BLOCKS
 #define LISA_MIN_BLOCKS 6
 #endif
@@ -337,13 +358,22 @@ __global__ void __launch_bounds__(128, LISA_MIN_BLOCKS) k_extend(DScene sc, DSta
       }
     }
     // ---- one traversal quantum (closest hit)
+#if LISA_VOTE_SECTIONS
+    // the warp runs only the section (node visit / triangle tests) that more of its lanes are waiting for
+    const unsigned vN = __ballot_sync(FULL, in_flight && st.has_nodes() && !st.has_tris());
+    const unsigned vT = __ballot_sync(FULL, in_flight && st.has_tris());
+    const bool     runN = __popc(vN) * LISA_VOTE_WN >= __popc(vT) * LISA_VOTE_WT, runT = !runN || vT == 0u;
+#else
+    const bool runN = true, runT = true;
+#endif
     if (in_flight) {
-      if (st.has_nodes() && !st.has_tris()) {
+      if (runN && st.has_nodes() && !st.has_tris()) {
         nn++;
         if (WIDE) wide_node_step(sc.bvh, o, ray, LISA_TMIN, best_t, *reinterpret_cast<WideState*>(&st), stack);
         else bin_node_step(sc.bvh, o, ray, LISA_TMIN, best_t, *reinterpret_cast<BinState*>(&st), stack);
       }
-      if (WIDE) {
+      if (!runT) {
+      } else if (WIDE) {
         WideState& w = *reinterpret_cast<WideState*>(&st);
 #pragma unroll
         for (int k = 0; k < LISA_TRI_PER_STEP; k++) {
@@ -452,7 +482,6 @@ __device__ __forceinline__ void emitter_cone(const DScene& sc, const float3& P, 
 
 __global__ void __launch_bounds__(256) k_tries(DScene sc, DState s, Tile t, uint32_t iter, uint32_t pass) {
   __shared__ uint32_t lcg_a[32], lcg_c[32];  // x -> A^(3k) x + C_(3k): jump ahead by k tries
-  __shared__ float    sP[8][32][3];          // hit points of the warp's batch (read by the rare cone-passing lanes)
   unsigned int*       ring = s.ring + RING_STRIDE * (iter % 3);
   const unsigned int  qn   = ring[R_CNTJ + pass];
   const unsigned      lane = lane_id();
@@ -484,10 +513,9 @@ __global__ void __launch_bounds__(256) k_tries(DScene sc, DState s, Tile t, uint
       // every try lies in the hemisphere of N: if the whole cone is below that horizon no try can be a candidate
       if (cosa > -1.0f && cosa <= 1.0f && dot(N, axis) < -sqrtf(fmaxf(1.0f - cosa * cosa, 0.0f)) - 1e-3f) cosa = 2.0f;
     }
-    float* myP = sP[threadIdx.x >> 5][lane];
-    myP[0] = P.x; myP[1] = P.y; myP[2] = P.z;
-    __syncwarp();
-    int      first = -1;  // index (relative to start) of the first candidate try of MY job
+    // Pass A: the warp walks the jobs; lane i evaluates try (start + i) of job j against the cone.  Lane j keeps the
+    // ballot: bit i set = try start+i of MY job points into the cone.
+    unsigned cone_mask = 0;
     unsigned valid = __ballot_sync(FULL, job >= 0 && cosa <= 1.0f);  // cosa == 2: nothing can pass (no emitter in reach)
     while (valid) {
       const int j = __ffs(valid) - 1;
@@ -498,13 +526,23 @@ __global__ void __launch_bounds__(256) k_tries(DScene sc, DState s, Tile t, uint
       const uint32_t sj = __shfl_sync(FULL, seed, j), stj = __shfl_sync(FULL, start, j);
       uint32_t       sd = my_a * sj + my_c;  // LCG state before try (start + lane)
       const float3   w  = shoot_ray_hemisphere(Nj, sd);
-      bool           cand = (stj + lane < LISA_SHADOW_TRIES) && dot(w, Aj) >= cj;
-      if (cand && sc.cull) {  // rare: confirm against the box itself
-        const float* pj = sP[threadIdx.x >> 5][j];
-        cand = hits_emitter_bounds(sc, f3(pj[0], pj[1], pj[2]), w, LISA_TMIN, LISA_TMAX);
+      const unsigned m  = __ballot_sync(FULL, (stj + lane < LISA_SHADOW_TRIES) && dot(w, Aj) >= cj);
+      if ((int)lane == j) cone_mask = m;
+    }
+    // Pass B: every lane confirms the (few) cone hits of its own job against the emitter box itself, in try order
+    int first = -1;  // index (relative to start) of the first candidate try of MY job
+    while (__any_sync(FULL, cone_mask != 0u && first < 0)) {
+      if (cone_mask != 0u && first < 0) {
+        const int b = __ffs(cone_mask) - 1;
+        cone_mask &= cone_mask - 1;
+        bool ok = true;
+        if (sc.cull) {
+          uint32_t     sd = lcg_a[b] * seed + lcg_c[b];
+          const float3 w  = shoot_ray_hemisphere(N, sd);
+          ok = hits_emitter_bounds(sc, P, w, LISA_TMIN, LISA_TMAX);
+        }
+        if (ok) first = b;
       }
-      const unsigned m = __ballot_sync(FULL, cand);
-      if ((int)lane == j) first = m ? __ffs(m) - 1 : -1;
     }
     // every lane settles its own job
     bool push = false;
@@ -523,7 +561,6 @@ __global__ void __launch_bounds__(256) k_tries(DScene sc, DState s, Tile t, uint
       }
     }
     queue_push(push, job, s.cand_q, &ring[R_CNTC + pass]);
-    __syncwarp();  // sP is rewritten by the next batch
   }
   warp_add(&s.stats[ST_SHADOW], n_sh);
   warp_add(&s.stats[ST_CULLED], n_cull);
@@ -654,14 +691,22 @@ __global__ void __launch_bounds__(128, LISA_MIN_BLOCKS) k_rays(DScene sc, DState
       }
     }
     // ---- one traversal quantum
+#if LISA_VOTE_SECTIONS
+    const unsigned vN = __ballot_sync(FULL, in_flight && st.has_nodes() && !st.has_tris());
+    const unsigned vT = __ballot_sync(FULL, in_flight && st.has_tris());
+    const bool     runN = __popc(vN) * LISA_VOTE_WN >= __popc(vT) * LISA_VOTE_WT, runT = !runN || vT == 0u;
+#else
+    const bool runN = true, runT = true;
+#endif
     if (in_flight) {
-      if (st.has_nodes() && !st.has_tris()) {
+      if (runN && st.has_nodes() && !st.has_tris()) {
         nn++;
         if (WIDE) wide_node_step(sc.bvh, P, ray, LISA_TMIN, tlimit, *reinterpret_cast<WideState*>(&st), stack);
         else bin_node_step(sc.bvh, P, ray, LISA_TMIN, tlimit, *reinterpret_cast<BinState*>(&st), stack);
       }
       bool occluded = false;
-      if (WIDE) {
+      if (!runT) {
+      } else if (WIDE) {
         WideState& w = *reinterpret_cast<WideState*>(&st);
 #pragma unroll
         for (int k = 0; k < LISA_TRI_PER_STEP; k++) {
