@@ -318,6 +318,8 @@ static int create_impl(const lisa_scene_desc* sd, const lisa_options* opt, lisa_
   // measured on B200 (Cornell 2000x2000): 4 passes 668, 3: 683, 2: 718, 1: 744 Msamples/s — the fill/drain of every extra
   // persistent launch (~14 us) costs more than finishing the few re-tries inline in k_rays
   c->cfg.shadow_passes = 1;
+  c->cfg.defer_retries = 0;  // measured: no gain (813 vs 811 Msamples/s) for 16 % more iterations
+  if (const char* e2 = getenv("LISA_DEFER")) c->cfg.defer_retries = atoi(e2) != 0;
   if (const char* e2 = getenv("LISA_SHADOW_PASSES")) c->cfg.shadow_passes = atoi(e2);
   {
     const int w = bi.wide != 0;
@@ -384,9 +386,10 @@ static int run_tile(lisa_ctx* c, const Tile& t, uint64_t* launches, uint64_t* it
   if (rc) return rc;
   launch_init_chains(c->state, c->cam, t, c->stream);
   (*launches)++;
-  // Every chain needs between spp and spp*bounces iterations; poll the finished-chain counter in bursts.
+  // Every chain needs at least spp iterations (typically ~4.5 per sample); poll the finished-chain counter in bursts.
   uint32_t iter = 0;
-  const uint64_t max_iter = (uint64_t)t.spp * std::max(t.bounces, 1u) + 2;
+  // a bounce takes 1 iteration, plus one for every failed light-sampling candidate when retries are deferred (<= 30)
+  const uint64_t max_iter = (uint64_t)t.spp * std::max(t.bounces, 1u) * (LISA_SHADOW_TRIES + 1) + 8;
   // a sample takes at least one iteration, so nothing can finish before spp iterations
   uint32_t burst = std::max<uint32_t>(1, t.spp);
   while (true) {

@@ -35,6 +35,7 @@ namespace lisa {
 #define F_BOUNCE_MASK 0x000000ffu
 #define F_STICKY 0x00000100u  // RayState::hit carried across bounces of one sample (Q1)
 #define F_NEW 0x00000200u     // previous sample ended: regenerate a camera ray
+#define F_DEFER 0x00008000u   // light sampling of this bounce continues in the NEXT iteration: k_extend skips the chain
 #define F_LIGHT_SHIFT 16      // material id of the last light found (RayState::material)
 
 #define FULL 0xffffffffu
@@ -322,7 +323,8 @@ __global__ void __launch_bounds__(128, LISA_MIN_BLOCKS) k_extend(DScene sc, DSta
           // five independent loads in flight (o, d are wasted on a fresh chain; HBM is not the limit here)
           const float4 sum4 = ld_state(&s.sum[i]), a4 = ld_state(&s.a[i]), c4 = ld_state(&s.c[i]), o4 = ld_state(&s.o[i]),
                        d4 = ld_state(&s.d[i]);
-          if (__float_as_uint(sum4.w) < t.spp) {  // chains that have all their samples are skipped
+          // chains that have all their samples, and chains whose light sampling is still running, are skipped
+          if (__float_as_uint(sum4.w) < t.spp && !(__float_as_uint(c4.w) & F_DEFER)) {
             chain = i;
             flags = __float_as_uint(c4.w);
             seed  = __float_as_uint(a4.w);
@@ -461,7 +463,7 @@ __device__ __forceinline__ void finish_job(const DScene& sc, const DState& s, co
     jc.samples++;
     if (done == t.spp) jc.done++;
   } else {
-    flags = (flags & ~(F_BOUNCE_MASK | F_TRIES_MASK)) | bounce;
+    flags = (flags & ~(F_BOUNCE_MASK | F_TRIES_MASK | F_DEFER)) | bounce;
     st_state(&s.d[job], make_float4(nd.x, nd.y, nd.z, 0.0f));
     st_state(&s.a[job], make_float4(atten.x, atten.y, atten.z, __uint_as_float(seed)));
     st_state(&s.c[job], make_float4(color.x, color.y, color.z, __uint_as_float(flags)));
@@ -616,10 +618,10 @@ __global__ void __launch_bounds__(128, LISA_MIN_BLOCKS) k_rays(DScene sc, DState
             flags = (flags & 0x0000ffffu) | F_STICKY | ((uint32_t)light << F_LIGHT_SHIFT);
           }                                      // outcome 2: RayState::hit keeps its value (Q1)
           finish = (flags & F_STICKY) || tries == LISA_SHADOW_TRIES;
-          requeue = !finish && !last;
+          requeue = !finish && last != 1u;  // last: 0 = next pass of this iteration, 1 = finish inline, 2 = next iteration
         }
         // ---- (2) last pass only: the remaining tries run here, one lane per job
-        if (last && job >= 0 && !in_flight && !finish) {
+        if (last == 1u && job >= 0 && !in_flight && !finish) {
           while (true) {
             const uint32_t before = seed;
             const float3   w = shoot_ray_hemisphere(N, seed);
@@ -635,11 +637,14 @@ __global__ void __launch_bounds__(128, LISA_MIN_BLOCKS) k_rays(DScene sc, DState
         // ---- (3) finish / hand back
         if (finish) { finish_job(sc, s, t, job, N, mid, seed, flags, brdf_w, jc); job = -1; }
         if (requeue) {
-          flags = (flags & ~F_TRIES_MASK) | (tries << F_TRIES_SHIFT);
+          flags = (flags & ~F_TRIES_MASK) | (tries << F_TRIES_SHIFT) | (last == 2u ? F_DEFER : 0u);
           s.a[job].w = __uint_as_float(seed);
           s.c[job].w = __uint_as_float(flags);
         }
-        queue_push(requeue, job, s.shadow_q, &ring[R_CNTJ + pass + 1]);
+        // next pass of this iteration, or (last == 2) the job queue of the NEXT iteration: chains are independent, so a
+        // bounce may take more than one iteration; its k_tries then runs at full width together with the new jobs
+        queue_push(requeue, job, s.shadow_q,
+                   last == 2u ? &s.ring[RING_STRIDE * ((iter + 1) % 3) + R_CNTJ + 0] : &ring[R_CNTJ + pass + 1]);
         if (requeue) job = -1;
         // ---- (4) fetch jobs
         const bool     need     = job < 0;
@@ -666,7 +671,7 @@ __global__ void __launch_bounds__(128, LISA_MIN_BLOCKS) k_rays(DScene sc, DState
             seed  = __float_as_uint(a4.w);
             flags = __float_as_uint(c4.w);
             tries = (flags & F_TRIES_MASK) >> F_TRIES_SHIFT;
-            if (last) emitter_cone(sc, P, cone_axis, cone_cos);
+            if (last == 1u) emitter_cone(sc, P, cone_axis, cone_cos);
           }
           wnext += min(cnt, avail);
         }
@@ -907,7 +912,7 @@ int launch_shadow(const DScene& sc, const DState& s, const Tile& t, uint32_t ite
   int launches = 0;
   const int passes = max(1, min(cfg.shadow_passes, LISA_SHADOW_PASSES));
   for (int p = 0; p < passes; p++) {
-    const unsigned last = p == passes - 1;
+    const unsigned last = p == passes - 1 ? (cfg.defer_retries ? 2u : 1u) : 0u;
     // work shrinks roughly 4x per pass: later passes get smaller persistent grids
     unsigned gt = (unsigned)(cfg.sm_count * cfg.tries_blocks_per_sm), gr = (unsigned)(cfg.sm_count * cfg.shadow_blocks_per_sm);
     gt = min(gt, max(1u, cdiv(t.n_chains >> (2 * p), 32u * (256 / 32))));

@@ -39,6 +39,7 @@ struct LaunchCfg {
   int extend_block, shadow_block;
   int shadow_blocks_per_sm;
   int tries_blocks_per_sm;
+  int defer_retries;  // 1: jobs that need more tries after a failed candidate wait for the next iteration's k_tries
   int shadow_passes;  // k_tries/k_rays rounds per iteration (<= LISA_SHADOW_PASSES); the last one finishes leftovers inline
   int extend_blocks_per_sm;
   int idle_thresh;  // k_shadow: lanes that must be idle before the warp runs its management section
