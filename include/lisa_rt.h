@@ -164,6 +164,9 @@ int lisa_get_stats(lisa_ctx* ctx, lisa_stats* stats /* struct_size set by caller
 /* Multi-GPU plumbing: every rank renders a disjoint subframe set into its own sums; the
  * caller reduces the sum buffers (one NCCL reduce) and the root reads the image.  The buffer holds W*H
  * float4 = (sum of subframe means .xyz, number of subframes .w) and lives on the context's device. */
+/* Same-process alternative to the NCCL reduce: dst's accumulators += src's, as ONE kernel on dst's device that reads
+ * src's buffer over NVLink through the peer mapping (falls back to a peer copy where P2P is unavailable). */
+int    lisa_accum_add_peer(lisa_ctx* dst, lisa_ctx* src);
 void*  lisa_accum_device_ptr(lisa_ctx* ctx);
 size_t lisa_accum_bytes(lisa_ctx* ctx);
 int    lisa_device(lisa_ctx* ctx);

@@ -20,6 +20,8 @@
 // 2 x 80 hierarchy/refit + ~40 collapse + 96 packed write.
 #include <algorithm>
 #include <cfloat>
+#include <chrono>
+#include <cstdlib>
 #include <cstdio>
 
 #include "build.h"
@@ -427,6 +429,16 @@ static inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
 
 int build_bvh(const BuildInput& in, BuildOutput* out, cudaStream_t st, char* err, size_t errlen) {
   const int T = in.num_tris;
+  const bool dbg = getenv("LISA_DEBUG_TIMING") != nullptr;
+  auto tick = [&](const char* what) {
+    static std::chrono::steady_clock::time_point last;
+    if (!dbg) return;
+    cudaStreamSynchronize(st);
+    auto now = std::chrono::steady_clock::now();
+    if (what) fprintf(stderr, "  build %-10s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(now - last).count());
+    last = now;
+  };
+  tick(nullptr);
   memset(out, 0, sizeof(*out));
   out->root_other = out->root_emit = -1;
   if (T == 0) return 0;
@@ -452,6 +464,7 @@ int build_bvh(const BuildInput& in, BuildOutput* out, cudaStream_t st, char* err
     std::swap(d_keys, d_keys2);
     std::swap(d_ids, d_ids2);
   }
+  tick("morton+sort");
   BoundsAcc h_acc;
   CK(cudaMemcpyAsync(&h_acc, d_acc, sizeof(h_acc), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
@@ -495,7 +508,7 @@ int build_bvh(const BuildInput& in, BuildOutput* out, cudaStream_t st, char* err
       P.root = 0;
     } else {
       k_leaf_boxes<<<cdiv(P.n, 256), 256, 0, st>>>(in.d_verts, d_ids2 + P.sorted_base, P.n, d_lo + P.slice, d_hi + P.slice, d_C[0]);
-      int m = P.n, cur = 0, h_next = 0;
+      int m = P.n, cur = 0, h_next = 0, rounds = 0;
       int* d_next = d_sel + 1;
       CK(cudaMemcpyAsync(d_next, &h_next, sizeof(int), cudaMemcpyHostToDevice, st));
       while (m > 1) {
@@ -509,7 +522,9 @@ int build_bvh(const BuildInput& in, BuildOutput* out, cudaStream_t st, char* err
         CK(cudaStreamSynchronize(st));
         if (m2 >= m || m2 < 1) { snprintf(err, errlen, "PLOC made no progress (%d -> %d clusters)", m, m2); return -5; }
         m = m2;
+        rounds++;
       }
+      if (dbg) fprintf(stderr, "  ploc partition %d: %d leaves, %d rounds\n", p, P.n, rounds);
       int root = 0;
       CK(cudaMemcpyAsync(&root, d_C[cur], sizeof(int), cudaMemcpyDeviceToHost, st));
       CK(cudaStreamSynchronize(st));
@@ -517,6 +532,7 @@ int build_bvh(const BuildInput& in, BuildOutput* out, cudaStream_t st, char* err
     }
   }
 
+  tick(in.lbvh ? "lbvh" : "ploc");
   for (int p = 0; p < 2; p++) {  // root bounds of each partition (node 0 of its slice)
     float* dst = p == 0 ? out->box_other : out->box_emit;
     for (int k = 0; k < 3; k++) { dst[k] = FLT_MAX; dst[3 + k] = -FLT_MAX; }
@@ -585,6 +601,7 @@ int build_bvh(const BuildInput& in, BuildOutput* out, cudaStream_t st, char* err
     dev_free(d_q[0]); dev_free(d_q[1]); dev_free(d_counters);
   }
 
+  tick("collapse");
   float4 *d_tri_v, *d_tri_n;
   int*    d_final_to_orig;
   CK(dev_alloc((void**)&d_tri_v, sizeof(float4) * 3 * (size_t)T));
@@ -594,6 +611,7 @@ int build_bvh(const BuildInput& in, BuildOutput* out, cudaStream_t st, char* err
                                                  d_tri_v, d_tri_n, d_final_to_orig);
   CK(cudaStreamSynchronize(st));
   CK(cudaGetLastError());
+  tick("pack");
 
   dev_free(d_acc); dev_free(d_keys); dev_free(d_keys2); dev_free(d_ids); dev_free(d_ids2); dev_free(d_final_to_sorted);
   dev_free(d_C[0]); dev_free(d_C[1]); dev_free(d_nn); dev_free(d_sel); dev_free(d_sel_tmp);

@@ -563,6 +563,37 @@ extern "C" int lisa_get_stats(lisa_ctx* c, lisa_stats* out) {
   return LISA_OK;
 }
 
+extern "C" int lisa_accum_add_peer(lisa_ctx* dst, lisa_ctx* src) {
+  if (!dst || !src) return fail(LISA_ERR_ARG, "null ctx");
+  if (dst->width != src->width || dst->height != src->height) return fail(LISA_ERR_ARG, "accumulators differ in size");
+  CU(cudaSetDevice(src->device));
+  CU(cudaStreamSynchronize(src->stream));
+  CU(cudaSetDevice(dst->device));
+  const uint32_t npix = dst->width * dst->height;
+  const float4*  from = src->d_accum;
+  float4*        staged = nullptr;
+  if (src->device != dst->device) {
+    int can = 0;
+    CU(cudaDeviceCanAccessPeer(&can, dst->device, src->device));
+    if (can) {
+      cudaError_t e = cudaDeviceEnablePeerAccess(src->device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(LISA_ERR_CUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
+      cudaGetLastError();
+    } else {  // no peer mapping (different PCIe roots without NVLink): stage through a copy, still on the GPU
+      CU(dev_alloc((void**)&staged, sizeof(float4) * (size_t)npix));
+      CU(cudaMemcpyPeerAsync(staged, dst->device, src->d_accum, src->device, sizeof(float4) * (size_t)npix, dst->stream));
+      from = staged;
+    }
+  }
+  launch_accum_add(dst->d_accum, from, npix, dst->cfg.sm_count, dst->stream);
+  CU(cudaStreamSynchronize(dst->stream));
+  CU(cudaGetLastError());
+  dev_free(staged);
+  dst->stats.subframes_accumulated += src->stats.subframes_accumulated;
+  dst->stats.samples += src->stats.samples;
+  return LISA_OK;
+}
+
 extern "C" void*  lisa_accum_device_ptr(lisa_ctx* c) { return c ? (void*)c->d_accum : nullptr; }
 extern "C" size_t lisa_accum_bytes(lisa_ctx* c) { return c ? sizeof(float4) * (size_t)c->width * c->height : 0; }
 extern "C" int    lisa_device(lisa_ctx* c) { return c ? c->device : -1; }

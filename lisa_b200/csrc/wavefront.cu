@@ -781,6 +781,17 @@ __global__ void k_finalize(DState s, Tile t, float4* accum) {
   accum[t.pix0 + k] = acc;
 }
 
+// dst += src where src may live on ANOTHER GPU: the loads go over NVLink through the peer mapping (P2P), so the
+// reduce of the sample-space partition is one kernel on the root device, no staging copy
+__global__ void k_accum_add(float4* dst, const float4* __restrict__ src, uint32_t npix) {
+  for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += gridDim.x * blockDim.x) {
+    const float4 b = src[p];
+    float4       a = dst[p];
+    a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    dst[p] = a;
+  }
+}
+
 // accumulators -> mean image (float4, alpha 1) and/or sRGB8 (shader.cu:165-166)
 __global__ void k_resolve(const float4* __restrict__ accum, uint32_t npix, float4* mean_out, uint32_t* rgba8_out) {
   uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -930,6 +941,9 @@ void launch_finalize(const DState& s, const DCamera&, const Tile& t, float4* acc
 }
 void launch_resolve(const float4* accum, uint32_t npix, float4* mean_out, uint32_t* rgba8_out, cudaStream_t st) {
   k_resolve<<<cdiv(npix, 256), 256, 0, st>>>(accum, npix, mean_out, rgba8_out);
+}
+void launch_accum_add(float4* dst, const float4* src, uint32_t npix, int sm_count, cudaStream_t st) {
+  k_accum_add<<<min(cdiv(npix, 256u), (unsigned)sm_count * 8u), 256, 0, st>>>(dst, src, npix);
 }
 void launch_trace_closest(const DScene& sc, const float* d_org, const float* d_dir, uint32_t n, float tmin, float tmax,
                           int* d_prim, float* d_t, cudaStream_t st) {

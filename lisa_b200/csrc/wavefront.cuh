@@ -53,6 +53,7 @@ int  launch_shadow(const DScene& sc, const DState& s, const Tile& t, uint32_t it
 #define LISA_SHADOW_PASSES 4
 void launch_finalize(const DState& s, const DCamera& cam, const Tile& t, float4* accum, cudaStream_t st);
 void launch_resolve(const float4* accum, uint32_t npix, float4* mean_out, uint32_t* rgba8_out, cudaStream_t st);
+void launch_accum_add(float4* dst, const float4* src, uint32_t npix, int sm_count, cudaStream_t st);
 int  configure_kernels(char* err, size_t errlen);
 int  shadow_occupancy(bool wide, int block);  // resident CTAs of k_rays per SM
 int  extend_occupancy(bool wide, int block);

@@ -1,7 +1,8 @@
 // lisa_b200/host/main.cc — the CLI (src/LiSA/src/main.cc:6-28, include/parse_args.hh:3-16).
 //   lisa -s scene.rto [-d]
 // -s <scene> is mandatory; without it the usage goes to stderr and the exit code is 1.  -d selects the
-// progressive mode (headless here).  Extra, optional: --pfm <file> also writes the linear float image; --stats prints one JSON line with the counters of
+// progressive mode (headless here).  Extra, optional: --gpus N renders N subframes of num_samples/N spp on N GPUs of
+// this box and reduces them over NVLink peer memory; --pfm <file> also writes the linear float image; --stats prints one JSON line with the counters of
 // include/lisa_rt.h:lisa_stats; environment variables LISA_BVH/LISA_SHADOW/LISA_MAX_CHAINS select
 // ablation variants (see lisa_rt.cu).
 #include <algorithm>
@@ -31,6 +32,13 @@ int main(int argc, char** argv) {
   try {
     SceneParser     parser(scene_path);
     lisa_scene_desc params = parser.get_params();
+    if (char* g = getCmdOption(argv, argv + argc, "--gpus")) {  // sample-space partition over the GPUs of this box
+      if (atoi(g) > 1) {
+        printf("Starting rendering...\n");
+        render_multi(params, atoi(g));
+        return 0;
+      }
+    }
     lisa_ctx*       ctx = nullptr;
     if (lisa_create(&params, nullptr, &ctx) != LISA_OK) {
       // the reference throws sutil::Exception out of OptixWrapper's constructor and aborts

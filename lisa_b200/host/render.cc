@@ -6,6 +6,8 @@
 #include <cstdio>
 #include <stdexcept>
 #include <string>
+#include <thread>
+#include <vector>
 
 static void check(int rc, const char* what) {
   if (rc != LISA_OK) throw std::runtime_error(std::string(what) + ": " + lisa_last_error());
@@ -43,4 +45,33 @@ void display(lisa_ctx* ctx, const lisa_scene_desc& params) {
   save_image(ctx, params);
   std::chrono::duration<float> total = std::chrono::system_clock::now() - start;
   printf("Rendering finished in %.2f mn.\n", total.count() / 60.0f);
+}
+
+double render_multi(const lisa_scene_desc& params, int ngpus) {
+  if (ngpus < 1) ngpus = 1;
+  const unsigned spp = (params.num_samples + ngpus - 1) / ngpus;
+  std::vector<lisa_ctx*>   ctx(ngpus, nullptr);
+  std::vector<std::string> err(ngpus);
+  auto start = std::chrono::system_clock::now();
+  std::vector<std::thread> th;
+  for (int g = 0; g < ngpus; g++)
+    th.emplace_back([&, g] {
+      lisa_options o{};
+      o.struct_size = sizeof(o);
+      o.device = g;
+      if (lisa_create(&params, &o, &ctx[g]) != LISA_OK) { err[g] = lisa_last_error(); return; }
+      if (lisa_render_subframes(ctx[g], (uint32_t)g, 1, spp) != LISA_OK) err[g] = lisa_last_error();
+    });
+  for (auto& t : th) t.join();
+  for (int g = 0; g < ngpus; g++)
+    if (!err[g].empty()) {
+      for (lisa_ctx* c : ctx) lisa_destroy(c);
+      throw std::runtime_error("GPU " + std::to_string(g) + ": " + err[g]);
+    }
+  for (int g = 1; g < ngpus; g++) check(lisa_accum_add_peer(ctx[0], ctx[g]), "reduce");
+  save_image(ctx[0], params);
+  std::chrono::duration<double> total = std::chrono::system_clock::now() - start;
+  for (lisa_ctx* c : ctx) lisa_destroy(c);
+  printf("Rendering finished in %.2f mn.\n", total.count() / 60.0);
+  return total.count();
 }

@@ -10,3 +10,9 @@ void render(lisa_ctx* ctx, const lisa_scene_desc& params);
 // (optix_wrapper.cc:430) until subframe_index * spp >= num_samples, one stats line per subframe in place
 // of the ImGui overlay (sutil.cpp:735-743, render.cc:110-115), then the PPM.
 void display(lisa_ctx* ctx, const lisa_scene_desc& params);
+
+// Sample-space partition over `ngpus` GPUs of this box, single process: the num_samples are split into
+// `ngpus` subframes of ceil(num_samples / ngpus) spp; GPU g (own context: full scene, own BVH) renders subframe g on
+// its own host thread; the sums are added onto GPU 0 by lisa_accum_add_peer (one kernel reading peer memory over
+// NVLink) and GPU 0 writes the PPM.  Returns the render wall time in seconds.
+double render_multi(const lisa_scene_desc& params, int ngpus);

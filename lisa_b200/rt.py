@@ -85,6 +85,7 @@ _L.lisa_read_rgba8.argtypes = [_vp, _vp]
 _L.lisa_write_ppm.argtypes = [_vp, ctypes.c_char_p]
 _L.lisa_write_pfm.argtypes = [_vp, ctypes.c_char_p]
 _L.lisa_get_stats.argtypes = [_vp, ctypes.POINTER(Stats)]
+_L.lisa_accum_add_peer.argtypes = [_vp, _vp]
 _L.lisa_accum_device_ptr.argtypes = [_vp]
 _L.lisa_accum_device_ptr.restype = _vp
 _L.lisa_accum_bytes.argtypes = [_vp]
@@ -98,7 +99,7 @@ _L.lisa_kat_eval.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_uint32, _vp, _
 
 EXPORTS = ["lisa_create", "lisa_destroy", "lisa_last_error", "lisa_version", "lisa_render_subframes",
            "lisa_reset_accum", "lisa_read_accum", "lisa_read_rgba8", "lisa_write_ppm", "lisa_write_pfm", "lisa_get_stats",
-           "lisa_accum_device_ptr", "lisa_accum_bytes", "lisa_device", "lisa_sync", "lisa_trace_closest",
+           "lisa_accum_add_peer", "lisa_accum_device_ptr", "lisa_accum_bytes", "lisa_device", "lisa_sync", "lisa_trace_closest",
            "lisa_trace_shadow", "lisa_primary_rays", "lisa_kat_eval", "lisa_debug_sort_pairs", "lisa_debug_scan_compact"]
 
 
@@ -221,6 +222,10 @@ class Renderer:
         s.struct_size = ctypes.sizeof(Stats)
         _check(_L.lisa_get_stats(self._h, ctypes.byref(s)))
         return s.as_dict()
+
+    def accum_add_peer(self, other):
+        """self += other (another Renderer, possibly on another GPU of this process)."""
+        _check(_L.lisa_accum_add_peer(self._h, other._h))
 
     def accum_device_ptr(self):
         return _L.lisa_accum_device_ptr(self._h)
