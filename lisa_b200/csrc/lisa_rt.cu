@@ -116,7 +116,6 @@ static void camera_frame(const lisa_camera& c, uint32_t w, uint32_t h, DCamera* 
 }
 
 static void free_state(lisa_ctx* c) {
-  const size_t n = c->state_chains;
   dev_free(c->state.o); dev_free(c->state.d);
   dev_free(c->state.a); dev_free(c->state.c);
   dev_free(c->state.n); dev_free(c->state.sum);
@@ -156,7 +155,6 @@ extern "C" void lisa_destroy(lisa_ctx* c) {
   auto t1 = now();
   free_state(c);
   {
-    const size_t npix = (size_t)c->width * c->height;
     dev_free(c->d_accum);
     dev_free(c->d_mean);
     dev_free(c->d_rgba8);
@@ -371,12 +369,10 @@ extern "C" int lisa_reset_accum(lisa_ctx* c) {
   CU(cudaMemsetAsync(c->d_accum, 0, sizeof(float4) * (size_t)c->width * c->height, c->stream));
   CU(cudaMemsetAsync(c->state.stats, 0, sizeof(unsigned long long) * 16, c->stream));
   CU(cudaStreamSynchronize(c->stream));
-  lisa_stats keep = c->stats;
   c->stats.samples = c->stats.radiance_rays = c->stats.shadow_rays = c->stats.null_directions = 0;
   c->stats.kernel_launches = c->stats.iterations = 0;
   c->stats.render_ms = 0;
   c->stats.subframes_accumulated = 0;
-  (void)keep;
   return LISA_OK;
 }
 
