@@ -21,7 +21,11 @@
 // images are bit-reproducible run to run and independent of queue order.
 #include <cstdio>
 
-#include "bsdf/lambertian.cuh"
+// The interchangeable BSDF (seam B4): chosen at compile time, like `#include "bsdfs/lambertian.cu"` in shader.cu:4
+#ifndef LISA_BSDF_HEADER
+#define LISA_BSDF_HEADER "bsdf/lambertian.cuh"
+#endif
+#include LISA_BSDF_HEADER
 #include "traverse.cuh"
 #include "wavefront.cuh"
 

@@ -96,3 +96,13 @@ def test_product_never_imports_oracle():
                     if re.search(r"(from|import)\s+oracle|oracle/|liboracle|cpu_ref", txt):
                         bad.append(os.path.join(dp, f))
     assert not bad, bad
+
+
+def test_second_bsdf_variant_builds_and_exports(built):
+    """The BSDF seam is real: the same kernels compile against bsdf/ggx.cuh (make BSDF=ggx) into a library with the
+    same C ABI."""
+    import subprocess
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "lisa_b200"), "BSDF=ggx", "variant"])
+    lib = ctypes.CDLL(os.path.join(ROOT, "lisa_b200", "liblisa_rt_ggx.so"))
+    for n in _declared("lisa_rt.h"):
+        assert hasattr(lib, n), n
