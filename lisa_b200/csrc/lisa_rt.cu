@@ -311,8 +311,10 @@ static int create_impl(const lisa_scene_desc* sd, const lisa_options* opt, lisa_
   c->cfg.shadow_block = 128;
   if (const char* e2 = getenv("LISA_EXTEND_BLOCK")) c->cfg.extend_block = std::max(32, std::min(128, atoi(e2) / 32 * 32));
   if (const char* e2 = getenv("LISA_SHADOW_BLOCK")) c->cfg.shadow_block = std::max(32, std::min(128, atoi(e2) / 32 * 32));
-  c->cfg.idle_thresh = 16;  // measured on B200 (Cornell 2000x2000): 1 -> 651, 8 -> 660, 16 -> 674, 20 -> 677 Msamples/s
+  c->cfg.idle_thresh = 20;  // measured on B200 (Cornell 2000x2000): 4 -> 784, 8 -> 790, 12 -> 799, 16 -> 808, 20 -> 811, 24 -> 789 Msamples/s
   if (const char* e2 = getenv("LISA_IDLE_THRESH")) c->cfg.idle_thresh = std::max(1, std::min(32, atoi(e2)));
+  c->cfg.idle_thresh_rays = c->cfg.idle_thresh;
+  if (const char* e2 = getenv("LISA_IDLE_THRESH_RAYS")) c->cfg.idle_thresh_rays = std::max(1, std::min(32, atoi(e2)));
   // measured on B200 (Cornell 2000x2000): 4 passes 668, 3: 683, 2: 718, 1: 744 Msamples/s — the fill/drain of every extra
   // persistent launch (~14 us) costs more than finishing the few re-tries inline in k_rays
   c->cfg.shadow_passes = 1;

@@ -934,8 +934,8 @@ int launch_shadow(const DScene& sc, const DState& s, const Tile& t, uint32_t ite
     gr = min(gr, max(1u, cdiv(t.n_chains >> (2 * p), SHADOW_BATCH * (b / 32))));
     k_tries<<<gt, 256, 0, st>>>(sc, s, t, iter, (uint32_t)p);
     launches++;
-    if (sc.wide) k_rays<true><<<gr, b, stack_smem(b), st>>>(sc, s, t, iter, (uint32_t)p, last, (uint32_t)cfg.idle_thresh);
-    else k_rays<false><<<gr, b, stack_smem(b), st>>>(sc, s, t, iter, (uint32_t)p, last, (uint32_t)cfg.idle_thresh);
+    if (sc.wide) k_rays<true><<<gr, b, stack_smem(b), st>>>(sc, s, t, iter, (uint32_t)p, last, (uint32_t)cfg.idle_thresh_rays);
+    else k_rays<false><<<gr, b, stack_smem(b), st>>>(sc, s, t, iter, (uint32_t)p, last, (uint32_t)cfg.idle_thresh_rays);
     launches++;
   }
   return launches;

@@ -42,7 +42,8 @@ struct LaunchCfg {
   int defer_retries;  // 1: jobs that need more tries after a failed candidate wait for the next iteration's k_tries
   int shadow_passes;  // k_tries/k_rays rounds per iteration (<= LISA_SHADOW_PASSES); the last one finishes leftovers inline
   int extend_blocks_per_sm;
-  int idle_thresh;  // k_shadow: lanes that must be idle before the warp runs its management section
+  int idle_thresh;       // k_extend: lanes that must be idle before the warp runs its management section
+  int idle_thresh_rays;  // same for k_rays
 };
 
 void launch_init_chains(const DState& s, const DCamera& cam, const Tile& t, cudaStream_t st);
