@@ -212,8 +212,12 @@ static int create_impl(const lisa_scene_desc* sd, const lisa_options* opt, lisa_
   camera_frame(sd->camera, sd->width, sd->height, &c->cam);
 
   // ---- upload (Q11: one material index per triangle; Q12: the caller zero-fills unused material fields)
-  cudaEvent_t t0, t1, t2;
-  CU(cudaEventCreate(&t0)); CU(cudaEventCreate(&t1)); CU(cudaEventCreate(&t2));
+  struct Ev3 {  // destroyed on every exit path
+    cudaEvent_t e[3] = {nullptr, nullptr, nullptr};
+    ~Ev3() { for (cudaEvent_t x : e) if (x) cudaEventDestroy(x); }
+  } ev3;
+  for (cudaEvent_t& x : ev3.e) CU(cudaEventCreate(&x));
+  cudaEvent_t t0 = ev3.e[0], t1 = ev3.e[1], t2 = ev3.e[2];
   float *d_verts = nullptr, *d_normals = nullptr;
   int*   d_mat_idx = nullptr;
   unsigned char* d_emit = nullptr;
@@ -255,7 +259,6 @@ static int create_impl(const lisa_scene_desc* sd, const lisa_options* opt, lisa_
   if (rc) return rc;
   cudaEventElapsedTime(&c->stats.upload_ms, t0, t1);
   cudaEventElapsedTime(&c->stats.bvh_build_ms, t1, t2);
-  cudaEventDestroy(t0); cudaEventDestroy(t1); cudaEventDestroy(t2);
 
   c->scene.tri_v = c->bvh.d_tri_v;
   c->scene.tri_n = c->bvh.d_tri_n;
