@@ -1,24 +1,26 @@
 // lisa_b200/csrc/wavefront.cu — wavefront path tracing kernels (sm_100a).
 //
-// Replaces the reference's single OptiX megakernel launch (src/LiSA/src/shader.cu, 5 programs,
-// one thread per pixel looping samples x bounces x <=30 shadow tries) by two stages that run once per
-// "iteration" over SoA chain state in HBM (DState, wavefront.cuh):
+// Replaces the reference's single OptiX megakernel launch (src/LiSA/src/shader.cu, 5 programs, one thread per pixel
+// looping samples x bounces x <=30 shadow tries) by three stages that run once per "iteration" (= one radiance bounce
+// of every live chain) over SoA chain state in HBM (DState, wavefront.cuh).  A chain is one (pixel, subframe)
+// sample sequence with its own LCG stream.
 //
-//   k_extend  one thread per chain.  Regenerates a camera ray when the previous sample ended
-//             (__raygen__rg, shader.cu:141-152), traces the radiance ray (closest hit,
-//             trace_radiance shader.cu:77-98), and runs the material dispatch of
-//             __closesthit__radiance / __miss__radiance (shader.cu:189-194, 211-246): miss and emitter
-//             end the sample, a dielectric produces the next direction in place, an opaque hit
-//             stores P, N, attenuation and is appended to the shadow queue by warp-ballot +
-//             prefix-popcount compaction (one atomicAdd per warp).
-//   k_shadow  persistent CTAs; every LANE pulls opaque hits from the shadow queue and runs
-//             shoot_ray_to_light (shader.cu:196-209): up to 30 hemisphere tries, each a shadow query;
-//             a lane that finishes its job (light found or 30 failures) does the BSDF bounce
-//             (lambertian.cu:7-13), writes the chain back and immediately fetches another job, so the
-//             1..30-try spread does not idle lanes (dynamic fetch, warp-local batches of the queue).
+//   k_extend  persistent CTAs; a LANE fetches a chain, regenerates a camera ray when the previous sample ended
+//             (__raygen__rg, shader.cu:141-152), traverses the radiance ray (closest hit, trace_radiance
+//             shader.cu:77-98) one work quantum per loop iteration, and the warp runs the material dispatch of
+//             __closesthit__radiance / __miss__radiance (shader.cu:189-194, 211-246) for its finished lanes together:
+//             miss and emitter end the sample, a dielectric produces the next direction in place, an opaque hit
+//             stores P, N, attenuation and is appended to the job queue (or, when RayState::hit is already true, to
+//             the candidate queue) by warp-ballot + prefix-popcount compaction (one atomicAdd per warp and queue).
+//   k_tries   shoot_ray_to_light (shader.cu:196-209) without traversal: one WARP per job, one LANE per try (LCG
+//             jump-ahead); tries that provably cannot change RayState::hit are resolved here; jobs whose 30 tries are
+//             all of that kind get their BSDF bounce (lambertian.cu:7-13) and are written back; the others go to the
+//             candidate queue at their first try that can reach an emitter.
+//   k_rays    persistent CTAs over the candidate queue: traces that try (closest emitter, then any occluder in front
+//             of it), retires it into RayState::hit, finishes lit jobs, continues the remaining tries of the others.
 //
-// Every chain owns its LCG stream, so the order in which chains are processed never changes a result:
-// images are bit-reproducible run to run and independent of queue order.
+// Every chain owns its LCG stream, so the order in which chains are processed never changes a result: images are
+// bit-reproducible run to run and independent of queue order, tile size and launch configuration.
 #include <cstdio>
 
 // The interchangeable BSDF (seam B4): chosen at compile time, like `#include "bsdfs/lambertian.cu"` in shader.cu:4
