@@ -191,6 +191,11 @@ struct TravState<false> : BinState {};
 // k_extend / k_rays run 128-thread CTAs, at least 6 per SM (<= 80 registers): measured on B200 against the natural 94
 // registers (5 CTAs): 6 -> +16 %, 7 (72 regs, spills) -> +14 %, 8 (64 regs) -> +12 %.  The kernels are latency bound
 // (long-scoreboard stalls on chain state), so resident warps count more than a few spilled registers.
+// k_rays (last pass): tries a lane may run per management section while the lanes in flight wait.  Measured on B200:
+// 30 (run to completion) 826, 8 -> 836, 4 -> 831 Msamples/s.
+#ifndef LISA_INLINE_TRIES
+#define LISA_INLINE_TRIES 8
+#endif
 #ifndef LISA_VOTE_SECTIONS
 #define LISA_VOTE_SECTIONS 0
 #endif
@@ -627,17 +632,19 @@ __global__ void __launch_bounds__(128, LISA_MIN_BLOCKS) k_rays(DScene sc, DState
           requeue = !finish && last != 1u;  // last: 0 = next pass of this iteration, 1 = finish inline, 2 = next iteration
         }
         // ---- (2) last pass only: the remaining tries run here, one lane per job
+        bool still_trying = false;
         if (last == 1u && job >= 0 && !in_flight && !finish) {
-          while (true) {
+          still_trying = true;
+          for (int k = 0; k < LISA_INLINE_TRIES; k++) {  // bounded: the lanes in flight are waiting for this section
             const uint32_t before = seed;
             const float3   w = shoot_ray_hemisphere(N, seed);
             const bool     sticky = flags & F_STICKY;
             bool           cand = sticky || dot(w, cone_axis) >= cone_cos;
             if (cand && !sticky && sc.cull) cand = hits_emitter_bounds(sc, P, w, LISA_TMIN, LISA_TMAX);
-            if (cand) { seed = before; break; }  // the ray is started below from `before`
+            if (cand) { seed = before; still_trying = false; break; }  // the ray is started below from `before`
             n_sh++; n_cull++;
             tries++;
-            if (tries == LISA_SHADOW_TRIES) { finish = true; break; }
+            if (tries == LISA_SHADOW_TRIES) { finish = true; still_trying = false; break; }
           }
         }
         // ---- (3) finish / hand back
@@ -682,7 +689,7 @@ __global__ void __launch_bounds__(128, LISA_MIN_BLOCKS) k_rays(DScene sc, DState
           wnext += min(cnt, avail);
         }
         // ---- (5) start the ray of the current try (its direction is regenerated from the stored LCG state)
-        if (job >= 0 && !in_flight) {
+        if (job >= 0 && !in_flight && !still_trying) {
           const float3 w = shoot_ray_hemisphere(N, seed);
           n_sh++;
           brdf_w = bsdf::BRDF(N, w, MatRef{sc.mats, mid});  // evaluated now (w is not kept), used if this try lights the job
@@ -695,10 +702,10 @@ __global__ void __launch_bounds__(128, LISA_MIN_BLOCKS) k_rays(DScene sc, DState
           else { phase = 1; st.begin(sc.root_other); }
         }
       }
-      // after the management section a lane has a ray in flight exactly when it has a job
+      // after the management section a lane with a job has a ray in flight (or is between two slices of its tries)
       if (__ballot_sync(FULL, in_flight) == 0) {
-        if (exhausted && wnext == wend) break;  // queue drained
-        continue;                               // the warp's batch ran dry mid-fetch: fetch again
+        if (exhausted && wnext == wend && __ballot_sync(FULL, job >= 0) == 0) break;  // queue drained, nothing pending
+        continue;  // the warp's batch ran dry mid-fetch, or tries are still running: go round again
       }
     }
     // ---- one traversal quantum
