@@ -129,14 +129,25 @@ def main():
     W = lambda name, geo, what: write_obj(os.path.join(out, name), *geo, comment=what)
 
     W("bot.obj", quad((X0, Y0, Z1), (X1, Y0, Z1), (X1, Y0, Z0), (X0, Y0, Z0), (0, 1, 0)), "floor, normal +y")
-    W("top.obj", quad((X0, Y1, Z0), (X1, Y1, Z0), (X1, Y1, Z1), (X0, Y1, Z1), (0, -1, 0)), "ceiling, normal -y")
+    # The ceiling is a frame around a hole of the light's footprint.  The reference asks OptiX for the first-FOUND hit
+    # of a shadow ray (shader.cu:69); with a ceiling 1 mm behind the light that is, depending on the BVH OptiX
+    # happens to build, sometimes the ceiling, and the light sample is lost (measured: 4 % of the image mean on the
+    # 871k-triangle scene, none on this one).  With nothing behind the emitter the reference's image is well defined.
+    lh = 0.05
+    strips = [((X0, Z0), (CX - lh, Z1)), ((CX + lh, Z0), (X1, Z1)), ((CX - lh, Z0), (CX + lh, CZ - lh)), ((CX - lh, CZ + lh), (CX + lh, Z1))]
+    tv, tf = [], []
+    for (xa, za), (xb, zb) in strips:
+        b = len(tv)
+        tv += [(xa, Y1, za), (xb, Y1, za), (xb, Y1, zb), (xa, Y1, zb)]
+        tf += [((b, 0), (b + 1, 0), (b + 2, 0)), ((b, 0), (b + 2, 0), (b + 3, 0))]
+    W("top.obj", (tv, [(0, -1, 0)], tf), "ceiling (frame around the light's footprint), normal -y")
     W("back.obj", quad((X0, Y0, Z0), (X1, Y0, Z0), (X1, Y1, Z0), (X0, Y1, Z0), (0, 0, 1)), "back wall, normal +z")
     W("right.obj", quad((X1, Y0, Z0), (X1, Y0, Z1), (X1, Y1, Z1), (X1, Y1, Z0), (-1, 0, 0)), "right wall, normal -x")
     W("left.obj", quad((X0, Y0, Z1), (X0, Y0, Z0), (X0, Y1, Z0), (X0, Y1, Z1), (1, 0, 0)), "left wall, normal +x")
     W("large_box.obj", box(-0.08, -0.27, 0.12, 0.24, 0.12, Y0 + LIFT, 17.0), "tall block")
     W("small_box.obj", box(0.07, -0.13, 0.12, 0.12, 0.12, Y0 + LIFT, -17.0), "short block (glass in the README scene)")
     W("sphere.obj", uv_sphere((-0.10, Y0 + 0.05 + LIFT, -0.09), 0.05), "uv sphere 32x16, smooth normals")
-    ly, lh = Y1 - 1e-3, 0.05
+    ly = Y1 - 1e-3
     W("light.obj", quad((CX - lh, ly, CZ - lh), (CX + lh, ly, CZ - lh), (CX + lh, ly, CZ + lh), (CX - lh, ly, CZ + lh),
                         (0, -1, 0)), "area light 0.1 x 0.1 just below the ceiling, normal -y")
 

@@ -4,7 +4,7 @@
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--spp-per-step S]
 
 Workload (config.workload): BASELINE.json configs[1] — the README Cornell box (scenes/cornell_c2.rto:
-2000x2000, 7 bounces, 996 authored triangles).  A STEP is one subframe of S samples per pixel over the
+2000x2000, 7 bounces, 1002 authored triangles).  A STEP is one subframe of S samples per pixel over the
 full image (S = 50 by default: the 2000-spp render is 40 such steps; subframes are the reference's own
 unit of independently seeded samples, shader.cu:140-141, render.cc:75-131).  Every step renders a NEW
 subframe index, so no step can reuse an earlier result.
@@ -307,7 +307,7 @@ def main():
             "metric": METRIC, "value": round(value, 4), "unit": "Msamples/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": round(T / K, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": "BASELINE configs[1]: README Cornell box 2000x2000, 7 bounces, 996 authored triangles; "
+            "config": {"workload": "BASELINE configs[1]: README Cornell box 2000x2000, 7 bounces, 1002 authored triangles; "
                                    "step = one subframe of %d spp per GPU (2000 spp = %d steps)" % (S, max(1, 2000 // S)),
                        "width": w, "height": h, "bounces": sc["num_bounces"], "spp_per_step": S, "parallelism": "sample-space x%d" % world,
                        "l2": "inputs larger than L2: %.0f MB of chain state re-read every iteration (L2 is 126 MB)" % (R.stats()["state_bytes"] / 1e6)},

@@ -48,7 +48,7 @@ def main():
         sc = fe.parse_scene("scenes/cornell_c1.rto")
         kv, kn = gen_knot.soup_arrays()
         # Cornell walls + light (drop the two blocks and the sphere), plus the knot in glass (material 1: n = 1.5)
-        keep = np.isin(np.arange(len(sc["mat_indices"])), np.r_[0:10, len(sc["mat_indices"]) - 2:len(sc["mat_indices"])])
+        keep = np.isin(np.arange(len(sc["mat_indices"])), np.r_[0:16, len(sc["mat_indices"]) - 2:len(sc["mat_indices"])])
         v = np.concatenate([sc["vertices"].reshape(-1, 3, 3)[keep].reshape(-1, 3), kv])
         n = np.concatenate([sc["normals"].reshape(-1, 3, 3)[keep].reshape(-1, 3), kn])
         m = np.concatenate([sc["mat_indices"][keep], np.full(len(kv) // 3, 1, np.int32)])

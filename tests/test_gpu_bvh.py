@@ -51,7 +51,7 @@ def _compare_with_oracle(R, S, o, d, m=3000):
 def test_cornell_closest_and_shadow(rt, orc, cornell, bvh):
     R = rt.Renderer.from_scene(resized(cornell, 16), bvh_kind=bvh)
     st = R.stats()
-    assert st["num_triangles"] == 996 and st["num_emitter_triangles"] == 2
+    assert st["num_triangles"] == 1002 and st["num_emitter_triangles"] == 2
     S = orc.Scene(cornell["vertices"], cornell["normals"], cornell["mat_indices"], cornell["materials_packed"])
     rng = np.random.default_rng(3)
     o, d = _rays(rng, cornell["vertices"].min(0), cornell["vertices"].max(0), 100000)

@@ -127,7 +127,7 @@ def _knot_scene(cornell, nu, nv):
     import gen_knot
     kv, kn = gen_knot.soup_arrays(nu, nv)
     T = len(cornell["mat_indices"])
-    keep = np.isin(np.arange(T), np.r_[0:10, T - 2:T])
+    keep = np.isin(np.arange(T), np.r_[0:16, T - 2:T])  # the five walls (floor 2, ceiling frame 8, back 2, right 2, left 2) + light
     v = np.concatenate([cornell["vertices"].reshape(-1, 3, 3)[keep].reshape(-1, 3), kv])
     n = np.concatenate([cornell["normals"].reshape(-1, 3, 3)[keep].reshape(-1, 3), kn])
     m = np.concatenate([cornell["mat_indices"][keep], np.full(len(kv) // 3, 1, np.int32)])
