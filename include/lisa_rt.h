@@ -90,10 +90,12 @@ enum { LISA_SHADOW_CLOSEST = 0, LISA_SHADOW_FIRST_FOUND = 1 };
 enum { LISA_BVH_WIDE8 = 0, LISA_BVH_BINARY = 1 };
 enum { LISA_FLAG_PROFILE_STAGES = 1, /* CUDA events around every stage launch */
        LISA_FLAG_LBVH = 2,           /* plain LBVH hierarchy (fastest build) instead of PLOC clustering */
-       LISA_FLAG_NO_CULL = 4         /* traverse EVERY shadow try.  By default a try whose outcome provably cannot change
+       LISA_FLAG_NO_CULL = 4,        /* traverse EVERY shadow try.  By default a try whose outcome provably cannot change
                                         RayState::hit (hit is false and the ray cannot reach any emitter: outside the cone
                                         around the emitter bounds) is resolved without traversal; images are bit-identical
-                                        either way and lisa_stats reports how many tries were resolved that way. */ };
+                                        either way and lisa_stats reports how many tries were resolved that way. */
+       LISA_FLAG_WAVEFRONT = 8       /* render with the wavefront pipeline (three kernels per bounce over chain state in HBM)
+                                        instead of the default single persistent kernel per tile; bit-identical images */ };
 
 typedef struct lisa_options {
   uint32_t struct_size;   /* sizeof(lisa_options) */

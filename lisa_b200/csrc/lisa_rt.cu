@@ -61,6 +61,8 @@ struct lisa_ctx {
   uint32_t     width = 0, height = 0, num_samples = 0, num_bounces = 0;
   std::string  output_image;
   bool         profile_stages = false;
+  int          pipeline = 1;        // 1: k_path (one persistent launch per tile), 0: wavefront (k_extend / k_tries / k_rays)
+  bool         state_full = false;  // the wavefront arrays are allocated (k_path needs only state.sum)
   std::vector<cudaEvent_t> ev_pool;  // stage profiling: 3 events per iteration (extend start, shadow start, shadow end)
   size_t       ev_used = 0;
   double       stage_ms[2] = {0, 0};
@@ -124,21 +126,27 @@ static void free_state(lisa_ctx* c) {
   c->state.o = c->state.d = c->state.a = c->state.c = c->state.n = c->state.sum = nullptr;
   c->state.shadow_q = c->state.cand_q = nullptr;
   c->state_chains = 0;
+  c->state_full = false;
 }
 
 static int ensure_state(lisa_ctx* c, size_t chains) {
-  if (chains <= c->state_chains) return LISA_OK;
+  const bool full = c->pipeline == 0;
+  if (chains <= c->state_chains && (c->state_full || !full)) return LISA_OK;
+  chains = std::max(chains, c->state_chains);
   free_state(c);
-  CU(dev_alloc((void**)&c->state.o, sizeof(float4) * chains));
-  CU(dev_alloc((void**)&c->state.d, sizeof(float4) * chains));
-  CU(dev_alloc((void**)&c->state.a, sizeof(float4) * chains));
-  CU(dev_alloc((void**)&c->state.c, sizeof(float4) * chains));
-  CU(dev_alloc((void**)&c->state.n, sizeof(float4) * chains));
   CU(dev_alloc((void**)&c->state.sum, sizeof(float4) * chains));
-  CU(dev_alloc((void**)&c->state.shadow_q, sizeof(int) * chains));
-  CU(dev_alloc((void**)&c->state.cand_q, sizeof(int) * chains));
+  if (full) {
+    CU(dev_alloc((void**)&c->state.o, sizeof(float4) * chains));
+    CU(dev_alloc((void**)&c->state.d, sizeof(float4) * chains));
+    CU(dev_alloc((void**)&c->state.a, sizeof(float4) * chains));
+    CU(dev_alloc((void**)&c->state.c, sizeof(float4) * chains));
+    CU(dev_alloc((void**)&c->state.n, sizeof(float4) * chains));
+    CU(dev_alloc((void**)&c->state.shadow_q, sizeof(int) * chains));
+    CU(dev_alloc((void**)&c->state.cand_q, sizeof(int) * chains));
+  }
   c->state_chains = chains;
-  c->stats.state_bytes = chains * (6 * sizeof(float4) + 2 * sizeof(int));
+  c->state_full = full;
+  c->stats.state_bytes = full ? chains * (6 * sizeof(float4) + 2 * sizeof(int)) : chains * sizeof(float4);
   return LISA_OK;
 }
 
@@ -194,7 +202,7 @@ static int create_impl(const lisa_scene_desc* sd, const lisa_options* opt, lisa_
   if (o.device >= 0) { CU(cudaSetDevice(o.device)); }
   CU(cudaGetDevice(&c->device));
   // per-device constants are queried once per process (cudaGetDeviceProperties alone can take ~100 ms)
-  struct DevInfo { bool ok = false; int sms = 0, occ_rays[2] = {0, 0}, occ_ext[2] = {0, 0}, occ_tries = 0; };
+  struct DevInfo { bool ok = false; int sms = 0, occ_rays[2] = {0, 0}, occ_ext[2] = {0, 0}, occ_path[2] = {0, 0}, occ_tries = 0; };
   static DevInfo dev_info[64];
   DevInfo& di = dev_info[c->device & 63];
   if (!di.ok) {
@@ -328,13 +336,19 @@ static int create_impl(const lisa_scene_desc* sd, const lisa_options* opt, lisa_
     const int w = bi.wide != 0;
     if (!di.ok || getenv("LISA_EXTEND_BLOCK") || getenv("LISA_SHADOW_BLOCK")) {
       di.occ_tries = tries_occupancy(256);
-      for (int k = 0; k < 2; k++) { di.occ_ext[k] = extend_occupancy(k != 0, c->cfg.extend_block); di.occ_rays[k] = shadow_occupancy(k != 0, c->cfg.shadow_block); }
+      for (int k = 0; k < 2; k++) { di.occ_ext[k] = extend_occupancy(k != 0, c->cfg.extend_block); di.occ_rays[k] = shadow_occupancy(k != 0, c->cfg.shadow_block); di.occ_path[k] = path_occupancy(k != 0, 128); }
       di.ok = true;
     }
     c->cfg.tries_blocks_per_sm = di.occ_tries;
     c->cfg.extend_blocks_per_sm = di.occ_ext[w];
     c->cfg.shadow_blocks_per_sm = di.occ_rays[w];
+    c->cfg.path_blocks_per_sm = di.occ_path[w];
   }
+  c->pipeline = (o.flags & LISA_FLAG_WAVEFRONT) ? 0 : 1;
+  if (const char* e2 = getenv("LISA_PIPELINE")) c->pipeline = strcmp(e2, "wavefront") == 0 ? 0 : 1;
+  c->cfg.path_wait_thresh = 16;  // measured on B200 (Cornell 2000x2000): 8 -> 1057, 12 -> 1090, 16 -> 1115, 20 -> 1107, 24 -> 1073, 28 -> 999 Msamples/s
+  if (const char* e2 = getenv("LISA_WAIT_THRESH")) c->cfg.path_wait_thresh = std::max(1, std::min(32, atoi(e2)));
+  if (const char* e2 = getenv("LISA_PATH_BLOCKS_PER_SM")) c->cfg.path_blocks_per_sm = std::max(1, std::min(c->cfg.path_blocks_per_sm, atoi(e2)));
   if (const char* e2 = getenv("LISA_SHADOW_BLOCKS_PER_SM")) c->cfg.shadow_blocks_per_sm = std::max(1, atoi(e2));
   // default residency: enough chains to fill the machine several times over, bounded so the state stays
   // a small fraction of HBM (112 B per chain)
@@ -385,6 +399,16 @@ extern "C" int lisa_reset_accum(lisa_ctx* c) {
 static int run_tile(lisa_ctx* c, const Tile& t, uint64_t* launches, uint64_t* iterations) {
   int rc = ensure_state(c, t.n_chains);
   if (rc) return rc;
+  if (c->pipeline == 1) {
+    if (c->profile_stages) cudaEventRecord(next_event(c), c->stream);
+    launch_path(c->scene, c->state, c->cam, t, c->cfg, c->stream);
+    if (c->profile_stages) { cudaEvent_t e = next_event(c); cudaEventRecord(e, c->stream); cudaEventRecord(next_event(c), c->stream); }
+    launch_finalize(c->state, c->cam, t, c->d_accum, c->stream);
+    *launches += 2;
+    *iterations += 1;
+    if (c->profile_stages) { CU(cudaStreamSynchronize(c->stream)); drain_stage_events(c); }
+    return LISA_OK;
+  }
   launch_init_chains(c->state, c->cam, t, c->stream);
   (*launches)++;
   // Every chain needs at least spp iterations (typically ~4.5 per sample); poll the finished-chain counter in bursts.

@@ -44,6 +44,8 @@ struct LaunchCfg {
   int extend_blocks_per_sm;
   int idle_thresh;       // k_extend: lanes that must be idle before the warp runs its management section
   int idle_thresh_rays;  // same for k_rays
+  int path_blocks_per_sm;  // k_path: resident CTAs per SM
+  int path_wait_thresh;    // k_path: lanes that must be waiting before the warp runs its management section
 };
 
 void launch_init_chains(const DState& s, const DCamera& cam, const Tile& t, cudaStream_t st);
@@ -59,6 +61,9 @@ int  configure_kernels(char* err, size_t errlen);
 int  shadow_occupancy(bool wide, int block);  // resident CTAs of k_rays per SM
 int  extend_occupancy(bool wide, int block);
 int  tries_occupancy(int block);               // resident CTAs of k_tries per SM
+int  path_occupancy(bool wide, int block);     // resident CTAs of k_path per SM
+// the whole tile in one persistent launch (chains fetched from a cursor in s.ring[0]; only s.sum, s.ring, s.stats are used)
+void launch_path(const DScene& sc, const DState& s, const DCamera& cam, const Tile& t, const LaunchCfg& cfg, cudaStream_t st);
 
 // diagnostics
 void launch_trace_closest(const DScene& sc, const float* d_org, const float* d_dir, uint32_t n, float tmin, float tmax,

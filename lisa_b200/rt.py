@@ -24,6 +24,7 @@ BVH_WIDE8, BVH_BINARY = 0, 1
 FLAG_PROFILE_STAGES = 1
 FLAG_LBVH = 2
 FLAG_NO_CULL = 4
+FLAG_WAVEFRONT = 8
 
 
 class Material(ctypes.Structure):
