@@ -9,11 +9,13 @@ full image (S = 50 by default: the 2000-spp render is 40 such steps; subframes a
 unit of independently seeded samples, shader.cu:140-141, render.cc:75-131).  Every step renders a NEW
 subframe index, so no step can reuse an earlier result.
 
-  value   Msamples/s with the scene, BVH and chain state resident in HBM (device time, CUDA events).
+  value   Msamples/s with the scene and its BVH resident in HBM (device time, CUDA events).
   e2e     the same metric through the C ABI with HOST buffers every step: lisa_create (H2D of the soup +
           device BVH build) + lisa_render_subframes + lisa_read_accum (D2H of the float4 image) + destroy.
-  roofline  dominant kernel k_shadow (>90 % of rays): algorithmic bytes per launch / its mean launch time
-          (CUDA events around every launch, LISA_FLAG_PROFILE_STAGES) against the measured HBM peak.
+  roofline  dominant kernel k_path (the whole estimator, one persistent launch per step): algorithmic bytes per
+          launch / its launch time (CUDA events around the launch, LISA_FLAG_PROFILE_STAGES) against the
+          measured HBM peak, plus the issue-slot figures of the committed ncu capture (the kernel is issue bound).
+  --pipeline wavefront  times the three-kernel wavefront pipeline instead (ablation; same images).
   cpu_baseline  the oracle (oracle/cpu_ref.c, OpenMP) on a bounded pixel sample of the same workload.
   --impl reference  the UNMODIFIED reference (gaetanserre/LiSA OptiX renderer built headless from its own
           sources, oracle/_ref/lisa_optix_ref) on the same config; falls back to the oracle port if OptiX
@@ -35,6 +37,22 @@ os.chdir(ROOT)
 
 SCENE = "scenes/cornell_c2.rto"
 METRIC = "Msamples/s (Cornell 2000x2000, 7 bounces)"
+
+
+def parse_quiet(fe, path):
+    """fe.parse_scene with the loader's `Importing ...` lines (the reference prints them on stdout, parse_obj.cc) sent to
+    stderr, so that this script's stdout is the ONE JSON line."""
+    sys.stdout.flush()
+    keep = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        return fe.parse_scene(path)
+    finally:
+        sys.stdout.flush()
+        import ctypes
+        ctypes.CDLL(None).fflush(None)  # the loader writes through C stdio: flush its buffer while fd 1 still points at stderr
+        os.dup2(keep, 1)
+        os.close(keep)
 
 
 def measured_peaks():
@@ -142,7 +160,7 @@ def run_reference(args, rank):
             sys.stderr.write("reference OptiX harness failed: %r\n" % (e,))
     if out is None:
         # OptiX could not start: time the CPU restatement instead (labelled as a port)
-        sc = fe.parse_scene(SCENE)
+        sc = parse_quiet(fe, SCENE)
         cb = cpu_baseline(sc, S, target_s=20.0)
         out = dict(base, value=cb["value"], ms_per_step=round(w * h * S / (cb["value"] * 1e3), 1), cpu_baseline=cb, gpu_launches=0,
                    clocks={"sm_mhz": None, "sm_max_mhz": None, "reasons": []},
@@ -160,6 +178,7 @@ def main():
     ap.add_argument("--spp-per-step", type=int, default=50)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--pipeline", default="path", choices=["path", "wavefront"])
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -187,16 +206,22 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    sc = fe.parse_scene(SCENE)
+    sc = parse_quiet(fe, SCENE)
     w, h, S, K, W = sc["width"], sc["height"], args.spp_per_step, args.steps, max(args.warmup, 0)
     npix = w * h
-    R = rt.Renderer.from_scene(sc, device=local_rank, flags=rt.FLAG_PROFILE_STAGES)
+    pipe_flag = rt.FLAG_WAVEFRONT if args.pipeline == "wavefront" else 0
+    R = rt.Renderer.from_scene(sc, device=local_rank, flags=rt.FLAG_PROFILE_STAGES | pipe_flag)
+    # L2 is flushed between steps (a buffer twice its size is rewritten): the kernel's own inputs (BVH, triangles:
+    # ~150 KB) are far smaller than L2, so nothing may survive from the previous step
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     acc_t = ldist.accum_tensor(R) if world > 1 else None
     total = torch.zeros_like(acc_t) if (world > 1 and rank == 0) else None
 
     def step(i):
         """One pass of the hot path: this rank's subframe of step i (+ the one reduce when N > 1)."""
         R.reset()
+        flush.fill_(i & 0xff)
+        torch.cuda.current_stream().synchronize()
         R.render_subframes(i * world + rank, 1, S)
         if world > 1:
             dist.reduce(acc_t, dst=0, op=dist.ReduceOp.SUM)
@@ -253,7 +278,7 @@ def main():
         t0 = time.perf_counter()
         for i in range(K):
             ts = [time.perf_counter()]
-            R2 = rt.Renderer.from_scene(sc_pinned, device=local_rank)     # H2D + BVH build
+            R2 = rt.Renderer.from_scene(sc_pinned, device=local_rank, flags=pipe_flag)     # H2D + BVH build
             ts.append(time.perf_counter())
             R2.render_subframes((W + K + i) * world + rank, 1, S)
             ts.append(time.perf_counter())
@@ -282,25 +307,40 @@ def main():
         ref_rays = agg["shadow_rays"] + agg["radiance_rays"]          # rays the reference's programs would trace
         rays = ref_rays - agg["culled"]                                # rays actually traversed here
         nn, nt = agg["nodes"] / max(rays, 1), agg["tris"] / max(rays, 1)
-        # dominant kernel: k_extend (one radiance ray + material dispatch per live chain and iteration).
-        # Algorithmic bytes per chain (DESIGN.md "Kernels"): chain state 16 (sum) + 32 (a, c) + 32 (o, d) read, 64 written
-        # (o/n/a/c for an opaque hit, o/d/a/c for a dielectric, sum/a/c for a finished sample), hit shading 96
-        # (3 normals + material), ray 32, BVH 80 B per node visited and 48 B per triangle tested.
         ext_launches = max(agg["extend_launches"], 1)
-        chains_per_launch = agg["radiance_rays"] / ext_launches
-        bytes_per_chain = 144 + 96 + 32 + 80 * nn + 48 * nt
-        alg_bytes = chains_per_launch * bytes_per_chain
         avg_ms = agg["extend_ms"] / ext_launches
+        if args.pipeline == "path":
+            # dominant kernel: k_path.  Algorithmic bytes (DESIGN.md "Kernels"): per traversed ray 80 B per node visited
+            # and 48 B per triangle tested; per radiance hit 48 B of vertex normals + 48 B of material; per chain one
+            # 16 B sum written.  All of it but the sums is served by L1/L2 (BVH 11 KB + triangles 96 KB).
+            kname, prof_name = "k_path<wide8>", "r01_k_path.json"
+            alg_bytes = (rays * (80 * nn + 48 * nt) + agg["radiance_rays"] * 96 + npix * K * 16) / ext_launches
+            per_unit = alg_bytes / (npix * S)
+            per_unit_name = "algorithmic_bytes_per_sample"
+            note = ("one persistent launch per step; chain state never leaves the SM, BVH (11 KB) + triangles (96 KB) are L1 "
+                    "resident (99.7 % hit rate): the kernel is issue bound, HBM sees only the 16-byte sum per chain. `issue` "
+                    "(issue-slot utilisation x active lanes / 32, committed ncu capture) is the roofline that binds.")
+        else:
+            # k_extend (one radiance ray + material dispatch per live chain and iteration): chain state 16 (sum) + 32 (a, c)
+            # + 32 (o, d) read, 64 written, hit shading 96, ray 32, BVH 80 B per node visited and 48 B per triangle tested
+            kname, prof_name = "k_extend<wide8>", "r01_k_extend.json"
+            chains_per_launch = agg["radiance_rays"] / ext_launches
+            per_unit = 144 + 96 + 32 + 80 * nn + 48 * nt
+            per_unit_name = "algorithmic_bytes_per_chain"
+            alg_bytes = chains_per_launch * per_unit
+            note = ("wavefront pipeline (ablation): BVH + triangles are L1/L2 resident, HBM traffic is the chain state; "
+                    "latency/issue bound.")
         achieved = alg_bytes / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else None
         traffic, issue = None, None
-        prof = os.path.join(ROOT, "profiles", "r01_k_extend.json")
+        prof = os.path.join(ROOT, "profiles", prof_name)
         if os.path.exists(prof):
             try:
                 pj = json.load(open(prof))["launches"][0]
                 traffic = pj.get("dram_bytes_per_launch")
                 issue = {"issue_slot_utilisation_pct": pj.get("issue_slot_utilisation_pct"),
                          "avg_active_lanes_per_instruction": pj.get("avg_active_lanes_per_instruction"),
-                         "frac_of_issue_roofline": pj.get("issue_roofline_frac"), "source": "profiles/r01_k_extend.json (ncu --set full)"}
+                         "frac_of_issue_roofline": pj.get("issue_roofline_frac"),
+                         "capture": pj.get("capture", "profiles/%s (ncu --set full)" % prof_name)}
             except Exception:
                 pass
         out = {
@@ -310,7 +350,7 @@ def main():
             "config": {"workload": "BASELINE configs[1]: README Cornell box 2000x2000, 7 bounces, 1002 authored triangles; "
                                    "step = one subframe of %d spp per GPU (2000 spp = %d steps)" % (S, max(1, 2000 // S)),
                        "width": w, "height": h, "bounces": sc["num_bounces"], "spp_per_step": S, "parallelism": "sample-space x%d" % world,
-                       "l2": "inputs larger than L2: %.0f MB of chain state re-read every iteration (L2 is 126 MB)" % (R.stats()["state_bytes"] / 1e6)},
+                       "pipeline": args.pipeline, "l2": "flushed between steps (256 MB rewritten; L2 is 126 MB)"},
             "mrays_per_s": round(world * rays / T / 1e3, 1),
             "rays_per_sample": round(rays / (npix * S * K), 2),
             "reference_rays_per_sample": round(ref_rays / (npix * S * K), 2),
@@ -320,16 +360,14 @@ def main():
             "gpu_launches": int(agg["launches"]),
             "clocks": clocks,
             "e2e": e2e,
-            "roofline": {"bound": "hbm", "kernel": "k_extend<wide8>", "achieved": round(achieved, 1) if achieved else None, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": kname, "achieved": round(achieved, 1) if achieved else None, "peak": peak,
                          "unit": "GB/s", "frac": round(achieved / peak, 4) if achieved else None, "traffic": traffic,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": int(alg_bytes),
-                         "algorithmic_bytes_per_chain": round(bytes_per_chain, 1), "avg_launch_ms": round(avg_ms, 4),
+                         per_unit_name: round(per_unit, 1), "avg_launch_ms": round(avg_ms, 4),
                          "launches": int(ext_launches), "share_of_step": round(agg["extend_ms"] / max(agg["render_ms"], 1e-9), 4),
                          "light_sampling_share_of_step": round(agg["shadow_ms"] / max(agg["render_ms"], 1e-9), 4),
                          "nodes_per_ray": round(nn, 2), "tris_per_ray": round(nt, 2), "issue": issue,
-                         "note": "BVH (11 KB) + triangles (96 KB) are L1/L2 resident: the path is issue/latency bound, not "
-                                 "HBM bound; HBM traffic is the chain state only. `issue` is the north_star's roofline "
-                                 "(issue-slot utilisation x warp execution efficiency) from the committed ncu capture."},
+                         "note": note},
         }
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(sc, S)

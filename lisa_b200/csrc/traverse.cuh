@@ -153,7 +153,9 @@ __device__ __forceinline__ uint32_t extract_byte(uint32_t x, uint32_t i) { retur
 // triangle tests.  Lanes therefore reconverge after every quantum instead of after every ray, which is
 // what keeps SIMT efficiency up when rays need between 1 and 10 node visits.
 // ================================================================================================
+#ifndef LISA_TRI_PER_STEP
 #define LISA_TRI_PER_STEP 2
+#endif
 
 struct StepRay {        // per-ray constants kept in registers
   float3   idir;        // safe reciprocal direction

@@ -1040,31 +1040,26 @@ __global__ void __launch_bounds__(128, LISA_PATH_MIN_BLOCKS) k_path(DScene sc, D
         color = f3(0.0f, 0.0f, 0.0f);
         start_rad = true;
       }
-      // ---- (8) start the ray
-      if (start_rad) {  // trace_radiance, shader.cu:77-98
-        shadow_ray = false; occluded = false;
+      // ---- (8) start the ray: trace_radiance (shader.cu:77-98) along d, or trace_occlusion (shader.cu:53-74) along w;
+      // one section for both kinds, so that the lanes starting either run it together
+      if (start_rad || start_shd) {
+        const float3 rd = start_rad ? d : w;
+        shadow_ray = !start_rad; occluded = false;
         best_prim = -1; best_t = LISA_TMAX;
-        if (d.x == 0.0f && d.y == 0.0f && d.z == 0.0f) { n_null++; pending = true; }  // Q7: refract() returned the null vector
+        if (start_shd) {
+          n_sh++;
+          brdf_w = bsdf::BRDF(N, w, MatRef{sc.mats, mid});  // evaluated now (w is not kept), used if this try lights the job
+        }
+        if (start_rad && rd.x == 0.0f && rd.y == 0.0f && rd.z == 0.0f) { n_null++; pending = true; }  // Q7: refract() returned the null vector
         else {
-          n_rad++;
-          ray = step_ray(d);
+          if (start_rad) n_rad++;
+          ray = step_ray(rd);
           in_flight = true;
           stack.clear();
-          if (hits_emitter_bounds(sc, o, d, LISA_TMIN, LISA_TMAX)) { phase = 0; st.begin(sc.root_emit); }
+          if (hits_emitter_bounds(sc, o, rd, LISA_TMIN, LISA_TMAX)) { phase = 0; st.begin(sc.root_emit); }
           else { phase = 1; st.begin(sc.root_other); }
           if (phase == 1 && sc.root_other < 0) { in_flight = false; pending = true; }
         }
-      } else if (start_shd) {  // trace_occlusion, shader.cu:53-74
-        n_sh++;
-        brdf_w = bsdf::BRDF(N, w, MatRef{sc.mats, mid});  // evaluated now (w is not kept), used if this try lights the job
-        shadow_ray = true; occluded = false;
-        best_prim = -1; best_t = LISA_TMAX;
-        ray = step_ray(w);
-        in_flight = true;
-        stack.clear();
-        if (hits_emitter_bounds(sc, o, w, LISA_TMIN, LISA_TMAX)) { phase = 0; st.begin(sc.root_emit); }
-        else { phase = 1; st.begin(sc.root_other); }
-        if (phase == 1 && sc.root_other < 0) { in_flight = false; pending = true; }
       }
       continue;
     }
