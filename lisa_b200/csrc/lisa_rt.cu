@@ -346,6 +346,7 @@ static int create_impl(const lisa_scene_desc* sd, const lisa_options* opt, lisa_
   }
   c->pipeline = (o.flags & LISA_FLAG_WAVEFRONT) ? 0 : 1;
   if (const char* e2 = getenv("LISA_PIPELINE")) c->pipeline = strcmp(e2, "wavefront") == 0 ? 0 : 1;
+  if (c->width > 65535u || c->height > 65535u) c->pipeline = 0;  // k_path packs a chain's pixel as x | y << 16
   c->cfg.path_wait_thresh = 16;  // measured on B200 (Cornell 2000x2000): 8 -> 1057, 12 -> 1090, 16 -> 1115, 20 -> 1107, 24 -> 1073, 28 -> 999 Msamples/s
   if (const char* e2 = getenv("LISA_WAIT_THRESH")) c->cfg.path_wait_thresh = std::max(1, std::min(32, atoi(e2)));
   if (const char* e2 = getenv("LISA_PATH_BLOCKS_PER_SM")) c->cfg.path_blocks_per_sm = std::max(1, std::min(c->cfg.path_blocks_per_sm, atoi(e2)));

@@ -159,7 +159,13 @@ __device__ __forceinline__ float3 shading_normal(const DScene& sc, const Hit& h)
   return normalize(w0 * f3(n0) + h.u * f3(n1) + h.v * f3(n2));
 }
 
-// camera ray of pixel p for the chain's next sample (shader.cu:149-152)
+// camera ray of pixel (x, y) for the chain's next sample (shader.cu:149-152)
+__device__ __forceinline__ float3 camera_ray_xy(const DCamera& cam, uint32_t x, uint32_t y, uint32_t& seed) {
+  const float jx = rng(seed), jy = rng(seed);
+  const float dx = (2.0f * (float)x + jx) / (float)cam.width - 1.0f;
+  const float dy = (2.0f * (float)y + jy) / (float)cam.height - 1.0f;
+  return normalize(dx * cam.U + dy * cam.V + cam.W);
+}
 __device__ __forceinline__ float3 camera_ray(const DCamera& cam, uint32_t p, uint32_t& seed) {
   const uint32_t x = p % cam.width, y = p / cam.width;
   const float    jx = rng(seed), jy = rng(seed);
@@ -963,8 +969,10 @@ __global__ void __launch_bounds__(128, LISA_PATH_MIN_BLOCKS) k_path(DScene sc, D
           if ((int)lane == j) cone_mask = m;
         }
         __syncwarp();
+        // the few cone hits are confirmed against the emitter box, in try order, by the job's owner, with the reference's
+        // own expression for the direction (measured: spreading these events over the warp's lanes gains nothing)
+        int first = -1;
         if (trying) {
-          int first = -1;
           while (cone_mask) {
             const int b = __ffs(cone_mask) - 1;
             cone_mask &= cone_mask - 1u;
@@ -1023,8 +1031,9 @@ __global__ void __launch_bounds__(128, LISA_PATH_MIN_BLOCKS) k_path(DScene sc, D
         const unsigned avail = wend - wnext, cnt = __popc(needmask), rank = __popc(needmask & lanemask_lt());
         if (need && rank < avail) {
           chain = (int)(wnext + rank);
-          pixel = t.pix0 + (uint32_t)chain % t.npix;
-          seed  = chain_seed(cam, pixel, t.f0 + (uint32_t)chain / t.npix);
+          const uint32_t p = t.pix0 + (uint32_t)chain % t.npix;
+          seed  = chain_seed(cam, p, t.f0 + (uint32_t)chain / t.npix);
+          pixel = (p % cam.width) | ((p / cam.width) << 16);  // x | y << 16 (images are at most 65535 wide/high here)
           sum   = f3(0, 0, 0);
           done  = 0;
           fresh = true;
@@ -1033,7 +1042,7 @@ __global__ void __launch_bounds__(128, LISA_PATH_MIN_BLOCKS) k_path(DScene sc, D
       }
       // ---- (7) next camera ray (shader.cu:149-152)
       if (fresh) {
-        d = camera_ray(cam, pixel, seed);
+        d = camera_ray_xy(cam, pixel & 0xffffu, pixel >> 16, seed);
         o = cam.eye;
         flags = 0;
         atten = f3(1.0f, 1.0f, 1.0f);
