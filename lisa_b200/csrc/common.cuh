@@ -24,7 +24,11 @@ __host__ __device__ __forceinline__ float3 operator-(float3 a) { return f3(-a.x,
 __host__ __device__ __forceinline__ float3 operator*(float3 a, float3 b) { return f3(a.x * b.x, a.y * b.y, a.z * b.z); }
 __host__ __device__ __forceinline__ float3 operator*(float3 a, float s) { return f3(a.x * s, a.y * s, a.z * s); }
 __host__ __device__ __forceinline__ float3 operator*(float s, float3 a) { return f3(a.x * s, a.y * s, a.z * s); }
-__host__ __device__ __forceinline__ float  dot(float3 a, float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+// Every multiply-add of the estimator is spelled out (fmaf) and the CUDA sources are compiled with -fmad=false, so that
+// no kernel can contract an expression differently from another: the pipelines stay bit-identical by construction.
+__host__ __device__ __forceinline__ float  dot(float3 a, float3 b) { return fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)); }
+// a + s * b
+__host__ __device__ __forceinline__ float3 madd(float3 a, float s, float3 b) { return f3(fmaf(s, b.x, a.x), fmaf(s, b.y, a.y), fmaf(s, b.z, a.z)); }
 __host__ __device__ __forceinline__ float3 cross(float3 a, float3 b) {
   return f3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
 }
@@ -34,9 +38,9 @@ __host__ __device__ __forceinline__ float3 fmax3(float3 a, float3 b) { return f3
 // vec_math.h:539-543
 __device__ __forceinline__ float3 normalize(float3 v) { return v * rsqrtf(dot(v, v)); }
 // vec_math.h:494
-__device__ __forceinline__ float3 lerp(float3 a, float3 b, float t) { return a + (b - a) * t; }
+__device__ __forceinline__ float3 lerp(float3 a, float3 b, float t) { return f3(fmaf(b.x - a.x, t, a.x), fmaf(b.y - a.y, t, a.y), fmaf(b.z - a.z, t, a.z)); }
 // vec_math.h:552
-__device__ __forceinline__ float3 reflect(float3 i, float3 n) { return i - n * (2.0f * dot(n, i)); }
+__device__ __forceinline__ float3 reflect(float3 i, float3 n) { return madd(i, -2.0f * dot(n, i), n); }
 
 // ---- RNG (src/cuda/random.h) ------------------------------------------------------------------
 __host__ __device__ __forceinline__ uint32_t tea16(uint32_t val0, uint32_t val1) {
@@ -56,7 +60,7 @@ __host__ __device__ __forceinline__ uint32_t lcg(uint32_t& prev) {
 // rnd = lcg / 2^24: the multiply by 2^-24 is exact, like the reference's div.approx by a power of two
 __host__ __device__ __forceinline__ float rnd(uint32_t& prev) { return (float)lcg(prev) * (1.0f / 16777216.0f); }
 // maths.cu:6-8
-__device__ __forceinline__ float rng(uint32_t& seed) { return rnd(seed) * 2.0f - 1.0f; }
+__device__ __forceinline__ float rng(uint32_t& seed) { return fmaf(rnd(seed), 2.0f, -1.0f); }
 
 // Same value as rng() without the int->float conversion (which issues on the slow conversion pipe):
 // 2*(u/2^24) - 1 = (u - 2^23) * 2^-23 is exactly representable, so building it from the low 23 bits with the
@@ -81,19 +85,19 @@ __device__ __forceinline__ float fresnel(float cosT, float eta) {
   float r  = (1.0f - eta) / (1.0f + eta);
   float R0 = r * r;
   float m  = 1.0f - cosT, m2 = m * m;
-  return R0 + (1.0f - R0) * (m2 * m2 * m);
+  return fmaf(1.0f - R0, m2 * m2 * m, R0);
 }
 // maths.cu:22-30 — zero vector under total internal reflection (Q7)
 __device__ __forceinline__ float3 refract(float cosI, const float3& d, const float3& N, float eta) {
-  float  cost2 = 1.0f - eta * eta * (1.0f - cosI * cosI);
-  float3 t     = eta * d + (eta * cosI - sqrtf(fabsf(cost2))) * N;
+  float  cost2 = fmaf(-(eta * eta), fmaf(-cosI, cosI, 1.0f), 1.0f);
+  float3 t     = madd(eta * d, fmaf(eta, cosI, -sqrtf(fabsf(cost2))), N);
   return cost2 > 0.0f ? t : f3(0.0f, 0.0f, 0.0f);
 }
 
 // ---- tonemap (src/cuda/helpers.h:107-138) ------------------------------------------------------
 __device__ __forceinline__ float to_srgb(float c) {
   c = fminf(fmaxf(c, 0.0f), 1.0f);
-  return c < 0.0031308f ? 12.92f * c : 1.055f * powf(c, 1.0f / 2.4f) - 0.055f;
+  return c < 0.0031308f ? 12.92f * c : fmaf(1.055f, powf(c, 1.0f / 2.4f), -0.055f);
 }
 __device__ __forceinline__ uint32_t quantize8(float x) {
   x          = fminf(fmaxf(x, 0.0f), 1.0f);

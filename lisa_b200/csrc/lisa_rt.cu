@@ -202,7 +202,7 @@ static int create_impl(const lisa_scene_desc* sd, const lisa_options* opt, lisa_
   if (o.device >= 0) { CU(cudaSetDevice(o.device)); }
   CU(cudaGetDevice(&c->device));
   // per-device constants are queried once per process (cudaGetDeviceProperties alone can take ~100 ms)
-  struct DevInfo { bool ok = false; int sms = 0, occ_rays[2] = {0, 0}, occ_ext[2] = {0, 0}, occ_path[2] = {0, 0}, occ_tries = 0; };
+  struct DevInfo { bool ok = false; int sms = 0, occ_rays[2] = {0, 0}, occ_ext[2] = {0, 0}, occ_path[2] = {0, 0}, occ_pool[2] = {0, 0}, occ_tries = 0; };
   static DevInfo dev_info[64];
   DevInfo& di = dev_info[c->device & 63];
   if (!di.ok) {
@@ -336,17 +336,22 @@ static int create_impl(const lisa_scene_desc* sd, const lisa_options* opt, lisa_
     const int w = bi.wide != 0;
     if (!di.ok || getenv("LISA_EXTEND_BLOCK") || getenv("LISA_SHADOW_BLOCK")) {
       di.occ_tries = tries_occupancy(256);
-      for (int k = 0; k < 2; k++) { di.occ_ext[k] = extend_occupancy(k != 0, c->cfg.extend_block); di.occ_rays[k] = shadow_occupancy(k != 0, c->cfg.shadow_block); di.occ_path[k] = path_occupancy(k != 0, 128); }
+      for (int k = 0; k < 2; k++) { di.occ_ext[k] = extend_occupancy(k != 0, c->cfg.extend_block); di.occ_rays[k] = shadow_occupancy(k != 0, c->cfg.shadow_block); di.occ_path[k] = path_occupancy(k != 0, 128); di.occ_pool[k] = pool_occupancy(k != 0); }
       di.ok = true;
     }
     c->cfg.tries_blocks_per_sm = di.occ_tries;
     c->cfg.extend_blocks_per_sm = di.occ_ext[w];
     c->cfg.shadow_blocks_per_sm = di.occ_rays[w];
     c->cfg.path_blocks_per_sm = di.occ_path[w];
+    c->cfg.pool_blocks_per_sm = di.occ_pool[w];
   }
   c->pipeline = (o.flags & LISA_FLAG_WAVEFRONT) ? 0 : 1;
-  if (const char* e2 = getenv("LISA_PIPELINE")) c->pipeline = strcmp(e2, "wavefront") == 0 ? 0 : 1;
-  if (c->width > 65535u || c->height > 65535u) c->pipeline = 0;  // k_path packs a chain's pixel as x | y << 16
+  if (const char* e2 = getenv("LISA_PIPELINE")) c->pipeline = strcmp(e2, "wavefront") == 0 ? 0 : strcmp(e2, "pool") == 0 ? 2 : 1;
+  c->cfg.pool_dry_thresh = 16;
+  if (const char* e2 = getenv("LISA_DRY_THRESH")) c->cfg.pool_dry_thresh = std::max(1, std::min(32, atoi(e2)));
+  if (const char* e2 = getenv("LISA_POOL_BLOCKS_PER_SM")) c->cfg.pool_blocks_per_sm = std::max(1, std::min(c->cfg.pool_blocks_per_sm, atoi(e2)));
+  if (getenv("LISA_DEBUG_TIMING")) fprintf(stderr, "[lisa] pipeline %d, k_path %d CTAs/SM, k_pool %d CTAs/SM\n", c->pipeline, c->cfg.path_blocks_per_sm, c->cfg.pool_blocks_per_sm);
+  if ((c->width > 65535u || c->height > 65535u) && c->pipeline) c->pipeline = 0;  // k_path packs a chain's pixel as x | y << 16
   c->cfg.path_wait_thresh = 16;  // measured on B200 (Cornell 2000x2000): 8 -> 1057, 12 -> 1090, 16 -> 1115, 20 -> 1107, 24 -> 1073, 28 -> 999 Msamples/s
   if (const char* e2 = getenv("LISA_WAIT_THRESH")) c->cfg.path_wait_thresh = std::max(1, std::min(32, atoi(e2)));
   if (const char* e2 = getenv("LISA_PATH_BLOCKS_PER_SM")) c->cfg.path_blocks_per_sm = std::max(1, std::min(c->cfg.path_blocks_per_sm, atoi(e2)));
@@ -400,9 +405,10 @@ extern "C" int lisa_reset_accum(lisa_ctx* c) {
 static int run_tile(lisa_ctx* c, const Tile& t, uint64_t* launches, uint64_t* iterations) {
   int rc = ensure_state(c, t.n_chains);
   if (rc) return rc;
-  if (c->pipeline == 1) {
+  if (c->pipeline >= 1) {
     if (c->profile_stages) cudaEventRecord(next_event(c), c->stream);
-    launch_path(c->scene, c->state, c->cam, t, c->cfg, c->stream);
+    if (c->pipeline == 2) launch_pool(c->scene, c->state, c->cam, t, c->cfg, c->stream);
+    else launch_path(c->scene, c->state, c->cam, t, c->cfg, c->stream);
     if (c->profile_stages) { cudaEvent_t e = next_event(c); cudaEventRecord(e, c->stream); cudaEventRecord(next_event(c), c->stream); }
     launch_finalize(c->state, c->cam, t, c->d_accum, c->stream);
     *launches += 2;

@@ -53,22 +53,22 @@ __device__ __forceinline__ RayPre ray_precompute(const float3& o, const float3& 
 __device__ __forceinline__ bool intersect_tri(const RayPre& r, const float3& v0, const float3& v1, const float3& v2,
                                               float tmin, float tmax, float& t_out, float& u_out, float& v_out) {
   const float3 A = perm3(v0 - r.o, r.kz), B = perm3(v1 - r.o, r.kz), C = perm3(v2 - r.o, r.kz);
-  const float  Ax = A.x - r.Sx * A.z, Ay = A.y - r.Sy * A.z;
-  const float  Bx = B.x - r.Sx * B.z, By = B.y - r.Sy * B.z;
-  const float  Cx = C.x - r.Sx * C.z, Cy = C.y - r.Sy * C.z;
+  const float  Ax = fmaf(-r.Sx, A.z, A.x), Ay = fmaf(-r.Sy, A.z, A.y);
+  const float  Bx = fmaf(-r.Sx, B.z, B.x), By = fmaf(-r.Sy, B.z, B.y);
+  const float  Cx = fmaf(-r.Sx, C.z, C.x), Cy = fmaf(-r.Sy, C.z, C.y);
   // edge functions: explicit round-to-nearest mul/sub, never contracted to fma
   float U = __fsub_rn(__fmul_rn(Cx, By), __fmul_rn(Cy, Bx));
   float V = __fsub_rn(__fmul_rn(Ax, Cy), __fmul_rn(Ay, Cx));
   float W = __fsub_rn(__fmul_rn(Bx, Ay), __fmul_rn(By, Ax));
   if (U == 0.0f || V == 0.0f || W == 0.0f) {
-    U = (float)((double)Cx * (double)By - (double)Cy * (double)Bx);
-    V = (float)((double)Ax * (double)Cy - (double)Ay * (double)Cx);
-    W = (float)((double)Bx * (double)Ay - (double)By * (double)Ax);
+    U = (float)__dsub_rn(__dmul_rn((double)Cx, (double)By), __dmul_rn((double)Cy, (double)Bx));
+    V = (float)__dsub_rn(__dmul_rn((double)Ax, (double)Cy), __dmul_rn((double)Ay, (double)Cx));
+    W = (float)__dsub_rn(__dmul_rn((double)Bx, (double)Ay), __dmul_rn((double)By, (double)Ax));
   }
   if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) return false;
   const float det = U + V + W;
   if (det == 0.0f) return false;
-  const float T   = U * (r.Sz * A.z) + V * (r.Sz * B.z) + W * (r.Sz * C.z);
+  const float T   = fmaf(W, r.Sz * C.z, fmaf(V, r.Sz * B.z, U * (r.Sz * A.z)));
   const float rcp = 1.0f / det;
   const float t   = T * rcp;
   if (!(t > tmin && t < tmax)) return false;
@@ -228,8 +228,8 @@ __device__ __forceinline__ void wide_node_step(const float4* __restrict__ nodes,
   // so one absolute pad of 2^-20 of that bound
   // covers both the cancellation in q*adir + org and the relative rounding of the result
   const float  kpad = 1.2e-6f;
-  const float3 pad  = f3(kpad * (fabsf(org.x) + 256.0f * fabsf(adir.x)), kpad * (fabsf(org.y) + 256.0f * fabsf(adir.y)),
-                         kpad * (fabsf(org.z) + 256.0f * fabsf(adir.z)));
+  const float3 pad  = f3(kpad * fmaf(256.0f, fabsf(adir.x), fabsf(org.x)), kpad * fmaf(256.0f, fabsf(adir.y), fabsf(org.y)),
+                         kpad * fmaf(256.0f, fabsf(adir.z), fabsf(org.z)));
   const float3 an = adir, af = adir;
   const float3 on = org - pad, of = org + pad;
   st.ng.x = __float_as_uint(w1.x);
@@ -252,9 +252,9 @@ __device__ __forceinline__ void wide_node_step(const float4* __restrict__ nodes,
     const uint32_t nz = negz ? qhiz : qloz, fz = negz ? qloz : qhiz;
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-      const float tnx = byte_to_float(nx, j) * an.x + on.x, tfx = byte_to_float(fx, j) * af.x + of.x;
-      const float tny = byte_to_float(ny, j) * an.y + on.y, tfy = byte_to_float(fy, j) * af.y + of.y;
-      const float tnz = byte_to_float(nz, j) * an.z + on.z, tfz = byte_to_float(fz, j) * af.z + of.z;
+      const float tnx = fmaf(byte_to_float(nx, j), an.x, on.x), tfx = fmaf(byte_to_float(fx, j), af.x, of.x);
+      const float tny = fmaf(byte_to_float(ny, j), an.y, on.y), tfy = fmaf(byte_to_float(fy, j), af.y, of.y);
+      const float tnz = fmaf(byte_to_float(nz, j), an.z, on.z), tfz = fmaf(byte_to_float(fz, j), af.z, of.z);
       const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
       const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tlimit));
       if (tn <= tf) hitmask |= extract_byte(child_bits4, j) << extract_byte(bit_index4, j);

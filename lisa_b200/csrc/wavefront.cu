@@ -156,7 +156,7 @@ __device__ __forceinline__ float3 shading_normal(const DScene& sc, const Hit& h)
   // barycentric_normal (maths.cu:33-57) with the barycentrics of the intersection test
   const float4 n0 = __ldg(sc.tri_n + 3 * h.prim), n1 = __ldg(sc.tri_n + 3 * h.prim + 1), n2 = __ldg(sc.tri_n + 3 * h.prim + 2);
   const float  w0 = 1.0f - h.u - h.v;
-  return normalize(w0 * f3(n0) + h.u * f3(n1) + h.v * f3(n2));
+  return normalize(madd(madd(w0 * f3(n0), h.u, f3(n1)), h.v, f3(n2)));
 }
 
 // camera ray of pixel (x, y) for the chain's next sample (shader.cu:149-152)
@@ -164,14 +164,11 @@ __device__ __forceinline__ float3 camera_ray_xy(const DCamera& cam, uint32_t x, 
   const float jx = rng(seed), jy = rng(seed);
   const float dx = (2.0f * (float)x + jx) / (float)cam.width - 1.0f;
   const float dy = (2.0f * (float)y + jy) / (float)cam.height - 1.0f;
-  return normalize(dx * cam.U + dy * cam.V + cam.W);
+  return normalize(madd(madd(cam.W, dy, cam.V), dx, cam.U));
 }
 __device__ __forceinline__ float3 camera_ray(const DCamera& cam, uint32_t p, uint32_t& seed) {
   const uint32_t x = p % cam.width, y = p / cam.width;
-  const float    jx = rng(seed), jy = rng(seed);
-  const float    dx = (2.0f * (float)x + jx) / (float)cam.width - 1.0f;
-  const float    dy = (2.0f * (float)y + jy) / (float)cam.height - 1.0f;
-  return normalize(dx * cam.U + dy * cam.V + cam.W);
+  return camera_ray_xy(cam, x, y, seed);
 }
 
 __device__ __forceinline__ uint32_t chain_seed(const DCamera& cam, uint32_t p, uint32_t subframe) {
@@ -275,7 +272,7 @@ __global__ void __launch_bounds__(128, LISA_MIN_BLOCKS) k_extend(DScene sc, DSta
             color = add_emission(color, m.emission(), atten);
             finished = true;
           } else {
-            const float3 P = o + best_t * d;  // shader.cu:221
+            const float3 P = madd(o, best_t, d);  // shader.cu:221
             Hit h;
             h.t = best_t; h.u = best_u; h.v = best_v; h.prim = best_prim;
             const float3 N = shading_normal(sc, h);
@@ -882,7 +879,7 @@ __global__ void __launch_bounds__(128, LISA_PATH_MIN_BLOCKS) k_path(DScene sc, D
               color = add_emission(color, m.emission(), atten);
               end_sample = true;
             } else {
-              const float3 P = o + best_t * d;  // shader.cu:221
+              const float3 P = madd(o, best_t, d);  // shader.cu:221
               Hit h;
               h.t = best_t; h.u = best_u; h.v = best_v; h.prim = best_prim;
               N = shading_normal(sc, h);
@@ -960,9 +957,9 @@ __global__ void __launch_bounds__(128, LISA_PATH_MIN_BLOCKS) k_path(DScene sc, D
           const float    a = rng_fast(sd), b = rng_fast(sd), c = rng_fast(sd);
           // w = +-v/|v| with the sign of v.N (shoot_ray_hemisphere); w.A >= cos  <=>  q|q| >= cos|cos| * v.v with
           // q = +-v.A, no normalisation needed.  Where the sign of v.N is within rounding of zero the try is kept.
-          const float    sN = a * r0.x + b * r0.y + c * r0.z;
-          const float    qA = a * r1.x + b * r1.y + c * r1.z;
-          const float    vv = a * a + b * b + c * c;
+          const float    sN = fmaf(c, r0.z, fmaf(b, r0.y, a * r0.x));
+          const float    qA = fmaf(c, r1.z, fmaf(b, r1.y, a * r1.x));
+          const float    vv = fmaf(c, c, fmaf(b, b, a * a));
           const float    q  = __uint_as_float(__float_as_uint(qA) ^ (__float_as_uint(sN) & 0x80000000u));
           const bool     in_cone = q * fabsf(q) >= r0.w * vv || fabsf(sN) < 4e-6f;
           const unsigned m = __ballot_sync(FULL, in_cone && lane < left);
@@ -1139,6 +1136,8 @@ __global__ void __launch_bounds__(128, LISA_PATH_MIN_BLOCKS) k_path(DScene sc, D
   warp_add(&s.stats[ST_CULLED], n_cull);
 }
 
+#include "pool.cuh"
+
 // ------------------------------------------------------------------------------------------------
 // Chain sums -> accumulators.  accum.xyz += mean of every subframe of the tile, accum.w += subframes,
 // in subframe order (fixed order => deterministic sums).
@@ -1149,7 +1148,7 @@ __global__ void k_finalize(DState s, Tile t, float4* accum) {
   for (uint32_t f = 0; f < t.nf; f++) {
     const float4 sm = s.sum[f * t.npix + k];
     const float  inv = 1.0f / (float)t.spp;  // shader.cu:158
-    acc.x += sm.x * inv; acc.y += sm.y * inv; acc.z += sm.z * inv; acc.w += 1.0f;
+    acc.x = fmaf(sm.x, inv, acc.x); acc.y = fmaf(sm.y, inv, acc.y); acc.z = fmaf(sm.z, inv, acc.z); acc.w += 1.0f;
   }
   accum[t.pix0 + k] = acc;
 }
@@ -1260,8 +1259,28 @@ int configure_kernels(char* err, size_t errlen) {
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_rays<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_path<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_path<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  const int psm = smem + 4 * (int)sizeof(PoolWarp);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_pool<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, psm);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_pool<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, psm);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_pool<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_pool<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   if (e != cudaSuccess) { snprintf(err, errlen, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -2; }
   return 0;
+}
+
+static inline size_t pool_smem() { return stack_smem(128) + 4 * sizeof(PoolWarp); }
+int pool_occupancy(bool wide) {
+  int n = 0;
+  cudaError_t e = wide ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_pool<true>, 128, pool_smem())
+                       : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_pool<false>, 128, pool_smem());
+  return (e == cudaSuccess && n > 0) ? n : 1;
+}
+void launch_pool(const DScene& sc, const DState& s, const DCamera& cam, const Tile& t, const LaunchCfg& cfg, cudaStream_t st) {
+  unsigned grid = (unsigned)(cfg.sm_count * cfg.pool_blocks_per_sm);
+  grid = min(grid, max(1u, cdiv(t.n_chains, POOL_SLOTS * 4u)));
+  cudaMemsetAsync(s.ring, 0, sizeof(unsigned int), st);  // chain fetch cursor
+  if (sc.wide) k_pool<true><<<grid, 128, pool_smem(), st>>>(sc, s, cam, t, (uint32_t)cfg.pool_dry_thresh);
+  else k_pool<false><<<grid, 128, pool_smem(), st>>>(sc, s, cam, t, (uint32_t)cfg.pool_dry_thresh);
 }
 
 int path_occupancy(bool wide, int block) {

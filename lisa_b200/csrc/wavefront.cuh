@@ -46,6 +46,8 @@ struct LaunchCfg {
   int idle_thresh_rays;  // same for k_rays
   int path_blocks_per_sm;  // k_path: resident CTAs per SM
   int path_wait_thresh;    // k_path: lanes that must be waiting before the warp runs its management section
+  int pool_blocks_per_sm;  // k_pool: resident CTAs per SM
+  int pool_dry_thresh;     // k_pool: pending slots that trigger a management section once the ready queue is empty
 };
 
 void launch_init_chains(const DState& s, const DCamera& cam, const Tile& t, cudaStream_t st);
@@ -62,6 +64,8 @@ int  shadow_occupancy(bool wide, int block);  // resident CTAs of k_rays per SM
 int  extend_occupancy(bool wide, int block);
 int  tries_occupancy(int block);               // resident CTAs of k_tries per SM
 int  path_occupancy(bool wide, int block);     // resident CTAs of k_path per SM
+int  pool_occupancy(bool wide);                // resident CTAs of k_pool per SM
+void launch_pool(const DScene& sc, const DState& s, const DCamera& cam, const Tile& t, const LaunchCfg& cfg, cudaStream_t st);
 // the whole tile in one persistent launch (chains fetched from a cursor in s.ring[0]; only s.sum, s.ring, s.stats are used)
 void launch_path(const DScene& sc, const DState& s, const DCamera& cam, const Tile& t, const LaunchCfg& cfg, cudaStream_t st);
 
