@@ -12,10 +12,11 @@ subframe index, so no step can reuse an earlier result.
   value   Msamples/s with the scene and its BVH resident in HBM (device time, CUDA events).
   e2e     the same metric through the C ABI with HOST buffers every step: lisa_create (H2D of the soup +
           device BVH build) + lisa_render_subframes + lisa_read_accum (D2H of the float4 image) + destroy.
-  roofline  dominant kernel k_path (the whole estimator, one persistent launch per step): algorithmic bytes per
+  roofline  dominant kernel k_pool (the whole estimator, one persistent launch per step): algorithmic bytes per
           launch / its launch time (CUDA events around the launch, LISA_FLAG_PROFILE_STAGES) against the
           measured HBM peak, plus the issue-slot figures of the committed ncu capture (the kernel is issue bound).
-  --pipeline wavefront  times the three-kernel wavefront pipeline instead (ablation; same images).
+  --pipeline path|pool|wavefront  forces one schedule of the estimator (ablation; same images).  Default: the
+          library's own choice per tile, which is k_pool for this workload.
   cpu_baseline  the oracle (oracle/cpu_ref.c, OpenMP) on a bounded pixel sample of the same workload.
   --impl reference  the UNMODIFIED reference (gaetanserre/LiSA OptiX renderer built headless from its own
           sources, oracle/_ref/lisa_optix_ref) on the same config; falls back to the oracle port if OptiX
@@ -178,7 +179,7 @@ def main():
     ap.add_argument("--spp-per-step", type=int, default=50)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--pipeline", default="path", choices=["path", "wavefront"])
+    ap.add_argument("--pipeline", default="auto", choices=["auto", "pool", "path", "wavefront"])
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -210,6 +211,8 @@ def main():
     w, h, S, K, W = sc["width"], sc["height"], args.spp_per_step, args.steps, max(args.warmup, 0)
     npix = w * h
     pipe_flag = rt.FLAG_WAVEFRONT if args.pipeline == "wavefront" else 0
+    if args.pipeline != "auto":
+        os.environ["LISA_PIPELINE"] = args.pipeline   # read by lisa_create (ablation switch)
     R = rt.Renderer.from_scene(sc, device=local_rank, flags=rt.FLAG_PROFILE_STAGES | pipe_flag)
     # L2 is flushed between steps (a buffer twice its size is rewritten): the kernel's own inputs (BVH, triangles:
     # ~150 KB) are far smaller than L2, so nothing may survive from the previous step
@@ -309,17 +312,18 @@ def main():
         nn, nt = agg["nodes"] / max(rays, 1), agg["tris"] / max(rays, 1)
         ext_launches = max(agg["extend_launches"], 1)
         avg_ms = agg["extend_ms"] / ext_launches
-        if args.pipeline == "path":
-            # dominant kernel: k_path.  Algorithmic bytes (DESIGN.md "Kernels"): per traversed ray 80 B per node visited
+        if args.pipeline != "wavefront":
+            # dominant kernel: k_pool (the default picks it for this workload: 4 M chains per step) or k_path.  Algorithmic bytes (DESIGN.md "Kernels"): per traversed ray 80 B per node visited
             # and 48 B per triangle tested; per radiance hit 48 B of vertex normals + 48 B of material; per chain one
             # 16 B sum written.  All of it but the sums is served by L1/L2 (BVH 11 KB + triangles 96 KB).
-            kname, prof_name = "k_path<wide8>", "r01_k_path.json"
+            kname, prof_name = ("k_path<wide8>", "r01_k_path.json") if args.pipeline == "path" else ("k_pool<wide8>", "r01_k_pool.json")
             alg_bytes = (rays * (80 * nn + 48 * nt) + agg["radiance_rays"] * 96 + npix * K * 16) / ext_launches
             per_unit = alg_bytes / (npix * S)
             per_unit_name = "algorithmic_bytes_per_sample"
-            note = ("one persistent launch per step; chain state never leaves the SM, BVH (11 KB) + triangles (96 KB) are L1 "
-                    "resident (99.7 % hit rate): the kernel is issue bound, HBM sees only the 16-byte sum per chain. `issue` "
-                    "(issue-slot utilisation x active lanes / 32, committed ncu capture) is the roofline that binds.")
+            note = ("one persistent launch per step; chain state never leaves the SM (registers for k_path, shared memory for "
+                    "k_pool), BVH (11 KB) + triangles (96 KB) are L1/L2 resident: the kernel is issue bound, HBM sees only the "
+                    "16-byte sum per chain. `issue` (issue-slot utilisation x active lanes / 32, committed ncu capture) is the "
+                    "roofline that binds.")
         else:
             # k_extend (one radiance ray + material dispatch per live chain and iteration): chain state 16 (sum) + 32 (a, c)
             # + 32 (o, d) read, 64 written, hit shading 96, ray 32, BVH 80 B per node visited and 48 B per triangle tested

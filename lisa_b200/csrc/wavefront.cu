@@ -1269,6 +1269,7 @@ int configure_kernels(char* err, size_t errlen) {
 }
 
 static inline size_t pool_smem() { return stack_smem(128) + 4 * sizeof(PoolWarp); }
+int pool_chains_per_cta() { return POOL_SLOTS * 4; }
 int pool_occupancy(bool wide) {
   int n = 0;
   cudaError_t e = wide ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_pool<true>, 128, pool_smem())

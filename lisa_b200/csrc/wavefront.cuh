@@ -65,6 +65,7 @@ int  extend_occupancy(bool wide, int block);
 int  tries_occupancy(int block);               // resident CTAs of k_tries per SM
 int  path_occupancy(bool wide, int block);     // resident CTAs of k_path per SM
 int  pool_occupancy(bool wide);                // resident CTAs of k_pool per SM
+int  pool_chains_per_cta();                    // chains a k_pool CTA keeps in shared memory
 void launch_pool(const DScene& sc, const DState& s, const DCamera& cam, const Tile& t, const LaunchCfg& cfg, cudaStream_t st);
 // the whole tile in one persistent launch (chains fetched from a cursor in s.ring[0]; only s.sum, s.ring, s.stats are used)
 void launch_path(const DScene& sc, const DState& s, const DCamera& cam, const Tile& t, const LaunchCfg& cfg, cudaStream_t st);

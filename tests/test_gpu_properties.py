@@ -42,25 +42,58 @@ def test_culling_is_exact(rt, cornell):
     assert out[2][1]["last_shadow_culled"] == 0
 
 
-def test_pipelines_are_bit_identical(rt, cornell):
-    """The default pipeline (one persistent kernel per tile, chain state on chip) and the wavefront pipeline
-    (LISA_FLAG_WAVEFRONT: three kernels per bounce over chain state in HBM) run the same per-chain arithmetic in
-    the same order: identical accumulators and identical ray counts, for every BVH kind, shadow policy and with
-    culling on or off."""
+def test_pipelines_are_bit_identical(rt, cornell, monkeypatch):
+    """Three schedules of the same estimator: k_path (a lane owns a chain, state in registers), k_pool (a warp owns 64
+    chains in shared memory, ready/pending queues) and the wavefront pipeline (three kernels per bounce over chain state
+    in HBM).  Every multiply-add is spelled out and the kernels are compiled with -fmad=false, so they run the same
+    per-chain arithmetic in the same order: identical accumulators and identical ray / node / triangle counters, for
+    every BVH kind, shadow policy and with culling on or off."""
     sc = resized(cornell, 128)
+    keys = ("last_radiance_rays", "last_shadow_rays", "last_shadow_culled", "last_shadow_jobs", "null_directions",
+            "last_nodes_visited", "last_triangles_tested")
+    first = None
     for kw in (dict(), dict(bvh_kind=1), dict(shadow_mode=1), dict(flags=rt.FLAG_NO_CULL), dict(bvh_kind=1, shadow_mode=1)):
-        res = []
-        for pipe in (0, rt.FLAG_WAVEFRONT):
-            k = dict(kw)
-            k["flags"] = k.get("flags", 0) | pipe
-            R = rt.Renderer.from_scene(sc, **k)
+        res = {}
+        for pipe in ("path", "pool", "wavefront"):
+            monkeypatch.setenv("LISA_PIPELINE", pipe)
+            R = rt.Renderer.from_scene(sc, **kw)
             R.render_subframes(0, 2, 8)
-            res.append((R.read_accum(), R.stats()))
+            res[pipe] = (R.read_accum(), R.stats())
             R.close()
-        np.testing.assert_array_equal(res[0][0], res[1][0])
-        for key in ("last_radiance_rays", "last_shadow_rays", "last_shadow_culled", "last_shadow_jobs", "null_directions"):
-            assert res[0][1][key] == res[1][1][key], (kw, key)
-        assert res[0][1]["last_kernel_launches"] < res[1][1]["last_kernel_launches"]
+        monkeypatch.delenv("LISA_PIPELINE")
+        for pipe in ("pool", "wavefront"):
+            np.testing.assert_array_equal(res["path"][0], res[pipe][0])
+            for key in keys:
+                assert res["path"][1][key] == res[pipe][1][key], (kw, pipe, key)
+        assert res["path"][1]["last_kernel_launches"] == res["pool"][1]["last_kernel_launches"] < res["wavefront"][1]["last_kernel_launches"]
+        first = first if first is not None else res["path"][0]
+    # the option flag selects the wavefront pipeline too
+    R = rt.Renderer.from_scene(sc, flags=rt.FLAG_WAVEFRONT)
+    R.render_subframes(0, 2, 8)
+    np.testing.assert_array_equal(R.read_accum(), first)
+    assert R.stats()["last_kernel_launches"] > 10
+    R.close()
+
+
+def test_default_pipeline_choice_is_invisible(rt, cornell, monkeypatch):
+    """By default a tile with enough chains to fill k_pool's slots twice runs k_pool, a smaller one k_path: a 640x640
+    subframe (409,600 chains) is on the k_pool side of the switch and must equal k_path's image; so must a ragged
+    image whose chain count is not a multiple of anything."""
+    for w, h in ((640, 640), (333, 17)):
+        sc = resized(cornell, w)
+        sc["height"] = h
+        imgs = []
+        for pipe in (None, "path", "pool"):
+            if pipe:
+                monkeypatch.setenv("LISA_PIPELINE", pipe)
+            R = rt.Renderer.from_scene(sc)
+            R.render_subframes(3, 1, 2)
+            imgs.append(R.read_accum())
+            R.close()
+            if pipe:
+                monkeypatch.delenv("LISA_PIPELINE")
+        np.testing.assert_array_equal(imgs[0], imgs[1])
+        np.testing.assert_array_equal(imgs[0], imgs[2])
 
 
 def test_subframe_additivity(rt, cornell):
