@@ -1,7 +1,7 @@
 // lisa_b200/csrc/bsdf/lambertian.cuh — the interchangeable BSDF (seam B4).
 //
 // Same three functions, same argument meaning as the reference's
-// src/LiSA/src/bsdfs/lambertian.cu:7-27; the integrator (wavefront.cu) only ever calls
+// src/LiSA/src/bsdfs/lambertian.cu:7-27; the integrator (estimator.cuh and the sched_*.cuh kernels) only ever calls
 // bsdf::bounce / bsdf::BRDF / bsdf::BTDF, and the implementation is chosen at compile time by
 // which header LISA_BSDF_HEADER names (default: this file), like the reference's
 // `#include "bsdfs/lambertian.cu"` (shader.cu:4).  All three are pure except for advancing `seed`.

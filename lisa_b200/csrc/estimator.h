@@ -1,4 +1,4 @@
-// lisa_b200/csrc/wavefront.cuh — host-visible declarations of the wavefront path tracer (wavefront.cu).
+// lisa_b200/csrc/estimator.h — host-visible declarations of the render kernels (estimator.cu).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -14,12 +14,12 @@ struct DState {
   float4* o;    // ray origin .xyz (hit point P after the extend stage)
   float4* d;    // ray direction .xyz (not unit, Q5)
   float4* a;    // attenuation .xyz | LCG state in .w
-  float4* c;    // radiance of the sample in flight .xyz | flags in .w (see F_* in wavefront.cu)
+  float4* c;    // radiance of the sample in flight .xyz | flags in .w (see F_* in estimator.cuh)
   float4* n;    // shading normal .xyz | material id in .w   (extend -> shadow stage hand-off)
   float4* sum;  // sum of finished samples .xyz | number of finished samples in .w
   int*    shadow_q;  // job queue: chain ids with an opaque hit whose next light-sampling tries are still to be drawn
   int*    cand_q;    // candidate queue: chain ids whose current try must be traced
-  // ring of 3 per-iteration blocks of 16 counters: queue lengths and fetch cursors of every pass (wavefront.cu R_*)
+  // ring of 3 per-iteration blocks of 16 counters: queue lengths and fetch cursors of every pass (estimator.cuh R_*)
   unsigned int* ring;
   // cumulative: [0] radiance rays [1] shadow rays [2] samples [3] null directions [4] finished chains
   // [5] BVH nodes visited [6] triangles tested [7] shadow jobs (opaque hits queued) [8] shadow tries resolved without traversal

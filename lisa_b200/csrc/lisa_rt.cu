@@ -1,7 +1,7 @@
 // lisa_b200/csrc/lisa_rt.cu — implementation of the C ABI in include/lisa_rt.h.
 //
 // Host-side driver of the render path: scene upload, device BVH build (bvh_build.cu), camera frame,
-// the wavefront iteration loop (wavefront.cu) and read-back.  It stands where the reference has
+// the render drivers (estimator.cu) and read-back.  It stands where the reference has
 // OptixWrapper (src/LiSA/src/optix_wrapper.cc) and launchSubframe/render (src/LiSA/src/render.cc).
 // There is no CPU path: every entry point that computes needs a CUDA device.
 #include <cuda_runtime.h>
@@ -21,7 +21,7 @@
 #include "devmem.h"
 #include "sort_scan.h"
 #include "scene.cuh"
-#include "wavefront.cuh"
+#include "estimator.h"
 
 using namespace lisa;
 

@@ -1,4 +1,4 @@
-// lisa_b200/csrc/pool.cuh — k_pool: the persistent estimator with warp-local chain slots (included by wavefront.cu).
+// lisa_b200/csrc/sched_pool.cuh — k_pool: the persistent estimator with warp-local chain slots (included by estimator.cu).
 //
 // k_path ties a chain to a lane: a lane whose ray has finished waits for the warp's next management section, and that
 // section runs on the waiting lanes only (profiles/r01_k_path_regions.txt: node visits at 21/32 lanes, management at
@@ -22,6 +22,9 @@
 //   H  Sx, Sy, Sz | kz          G  chain id, pixel (x | y<<16), finished samples, -
 // The sum of a chain's finished samples lives in s.sum[chain] (read-modify-write once per sample, L2 resident).
 #pragma once
+#include "estimator.cuh"
+
+namespace lisa {
 
 #ifndef LISA_POOL_MIN_BLOCKS
 #define LISA_POOL_MIN_BLOCKS 5
@@ -420,3 +423,5 @@ __global__ void __launch_bounds__(128, LISA_POOL_MIN_BLOCKS) k_pool(DScene sc, D
   warp_add(&s.stats[ST_JOBS], n_jobs);
   warp_add(&s.stats[ST_CULLED], n_cull);
 }
+
+}  // namespace lisa

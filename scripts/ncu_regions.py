@@ -19,7 +19,7 @@ for r in rows:
     ln=int(r[0]); thr=num(r[ci["Thread Instructions Executed"]]); w=num(r[ci["Instructions Executed"]])
     text=r[1]
     k=cur
-    if cur in ("traverse.cuh","wavefront.cu","common.cuh","pool.cuh"):
+    if cur in ("traverse.cuh","wavefront.cu","common.cuh","pool.cuh","estimator.cuh","estimator.cu","sched_pool.cuh","sched_path.cuh","sched_wavefront.cuh"):
         k="%s:%d-%d"%(cur, (ln//10)*10, (ln//10)*10+9)
     agg[k]+=thr; aggw[k]+=w
 T=sum(agg.values()); W=sum(aggw.values())
