@@ -161,6 +161,14 @@ int lisa_write_ppm(lisa_ctx* ctx, const char* path);
 /* Linear float image (Portable Float Map, RGB, little endian): the accumulators without the 8-bit sRGB quantisation,
  * for parity tooling (the reference can only write the quantised PPM; README.md:183 lists float output as a TODO). */
 int lisa_write_pfm(lisa_ctx* ctx, const char* path);
+/* Checkpoint / resume of a progressive render (the reference keeps its accum_buffer only in device
+ * memory, src/LiSA/src/render.cc:75-131).  lisa_save_accum writes the raw accumulators (W*H float4: sum of subframe
+ * means | subframe count) with a header naming the image size and the number of subframes accumulated;
+ * lisa_load_accum replaces the accumulators of a context of the same size with a saved file and reports through
+ * *subframes how many subframes it holds, so that rendering resumes at that subframe index: the resumed image is
+ * bit-identical to an uninterrupted one. */
+int lisa_save_accum(lisa_ctx* ctx, const char* path);
+int lisa_load_accum(lisa_ctx* ctx, const char* path, uint32_t* subframes);
 int lisa_get_stats(lisa_ctx* ctx, lisa_stats* stats /* struct_size set by caller */);
 
 /* Multi-GPU plumbing: every rank renders a disjoint subframe set into its own sums; the

@@ -593,6 +593,51 @@ extern "C" int lisa_write_pfm(lisa_ctx* c, const char* path) {
   return LISA_OK;
 }
 
+// accumulator checkpoint: "LISAACC1", width, height, subframes (u32 each), then W*H float4
+extern "C" int lisa_save_accum(lisa_ctx* c, const char* path) {
+  if (!c || !path || !*path) return fail(LISA_ERR_ARG, "null argument");
+  CU(cudaSetDevice(c->device));
+  const size_t npix = (size_t)c->width * c->height;
+  std::vector<float4> px(npix);
+  CU(cudaMemcpyAsync(px.data(), c->d_accum, sizeof(float4) * npix, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  const std::string tmp = std::string(path) + ".tmp";  // written aside and renamed: an interrupted save never truncates a good file
+  FILE* f = fopen(tmp.c_str(), "wb");
+  if (!f) return fail(LISA_ERR_IO, "cannot open %s for writing", tmp.c_str());
+  const uint32_t hdr[3] = {c->width, c->height, c->stats.subframes_accumulated};
+  bool ok = fwrite("LISAACC1", 1, 8, f) == 8 && fwrite(hdr, sizeof(uint32_t), 3, f) == 3 && fwrite(px.data(), sizeof(float4), npix, f) == npix;
+  ok = (fclose(f) == 0) && ok;
+  if (!ok || rename(tmp.c_str(), path) != 0) { remove(tmp.c_str()); return fail(LISA_ERR_IO, "short write to %s", path); }
+  return LISA_OK;
+}
+
+extern "C" int lisa_load_accum(lisa_ctx* c, const char* path, uint32_t* subframes) {
+  if (!c || !path || !*path) return fail(LISA_ERR_ARG, "null argument");
+  FILE* f = fopen(path, "rb");
+  if (!f) return fail(LISA_ERR_IO, "cannot open %s", path);
+  char     magic[8];
+  uint32_t hdr[3];
+  if (fread(magic, 1, 8, f) != 8 || memcmp(magic, "LISAACC1", 8) != 0 || fread(hdr, sizeof(uint32_t), 3, f) != 3) {
+    fclose(f);
+    return fail(LISA_ERR_IO, "%s is not an accumulator checkpoint", path);
+  }
+  if (hdr[0] != c->width || hdr[1] != c->height) {
+    fclose(f);
+    return fail(LISA_ERR_ARG, "%s holds a %ux%u image, the context renders %ux%u", path, hdr[0], hdr[1], c->width, c->height);
+  }
+  const size_t npix = (size_t)c->width * c->height;
+  std::vector<float4> px(npix);
+  const bool ok = fread(px.data(), sizeof(float4), npix, f) == npix;
+  fclose(f);
+  if (!ok) return fail(LISA_ERR_IO, "%s is truncated", path);
+  CU(cudaSetDevice(c->device));
+  CU(cudaMemcpyAsync(c->d_accum, px.data(), sizeof(float4) * npix, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  c->stats.subframes_accumulated = hdr[2];
+  if (subframes) *subframes = hdr[2];
+  return LISA_OK;
+}
+
 extern "C" int lisa_get_stats(lisa_ctx* c, lisa_stats* out) {
   if (!c || !out) return fail(LISA_ERR_ARG, "null argument");
   uint32_t sz = out->struct_size ? std::min<uint32_t>(out->struct_size, sizeof(lisa_stats)) : sizeof(lisa_stats);

@@ -2,7 +2,9 @@
 //   lisa -s scene.rto [-d]
 // -s <scene> is mandatory; without it the usage goes to stderr and the exit code is 1.  -d selects the
 // progressive mode (headless here).  Extra, optional: --gpus N renders N subframes of num_samples/N spp on N GPUs of
-// this box and reduces them over NVLink peer memory; --pfm <file> also writes the linear float image; --stats prints one JSON line with the counters of
+// this box and reduces them over NVLink peer memory; --pfm <file> also writes the linear float image; with -d,
+// --snapshot-every K rewrites the PPM every K subframes, --checkpoint <file> saves the accumulators then (and at the
+// end) and --resume <file> continues an interrupted render from such a file; --stats prints one JSON line with the counters of
 // include/lisa_rt.h:lisa_stats; environment variables LISA_BVH/LISA_SHADOW/LISA_MAX_CHAINS select
 // ablation variants (see lisa_rt.cu).
 #include <algorithm>
@@ -46,8 +48,13 @@ int main(int argc, char** argv) {
       return 134;
     }
     printf("Starting rendering...\n");
-    if (cmdOptionExists(argv, argv + argc, "-d")) display(ctx, params);
-    else render(ctx, params);
+    if (cmdOptionExists(argv, argv + argc, "-d")) {
+      DisplayOptions dopt;
+      if (char* e = getCmdOption(argv, argv + argc, "--snapshot-every")) dopt.snapshot_every = (unsigned)std::max(0, atoi(e));
+      dopt.checkpoint = getCmdOption(argv, argv + argc, "--checkpoint");
+      dopt.resume = getCmdOption(argv, argv + argc, "--resume");
+      display(ctx, params, dopt);
+    } else render(ctx, params);
     if (char* pfm = getCmdOption(argv, argv + argc, "--pfm")) {
       if (lisa_write_pfm(ctx, pfm) != LISA_OK) std::cerr << "lisa: " << lisa_last_error() << std::endl;
     }

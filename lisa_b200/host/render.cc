@@ -26,12 +26,23 @@ void render(lisa_ctx* ctx, const lisa_scene_desc& params) {
   printf("Rendering finished in %.2f mn.\n", total.count() / 60.0f);
 }
 
-void display(lisa_ctx* ctx, const lisa_scene_desc& params) {
+void display(lisa_ctx* ctx, const lisa_scene_desc& params) { display(ctx, params, DisplayOptions()); }
+
+void display(lisa_ctx* ctx, const lisa_scene_desc& params, const DisplayOptions& opt) {
   const unsigned spl = params.num_samples > 16 ? 16 : params.num_samples;  // optix_wrapper.cc:430
   auto start = std::chrono::system_clock::now();
   check(lisa_reset_accum(ctx), "reset");
   unsigned subframe = 0;
   double   render_s = 0;
+  if (opt.resume) {
+    check(lisa_load_accum(ctx, opt.resume, &subframe), "resume");
+    printf("resumed %s at subframe %u (%llu samples)\n", opt.resume, subframe, (unsigned long long)subframe * spl);
+    if ((unsigned long long)subframe * spl >= params.num_samples) {  // the checkpoint already holds the whole render
+      save_image(ctx, params);
+      printf("Rendering finished in %.2f mn.\n", 0.0f);
+      return;
+    }
+  }
   do {
     auto t0 = std::chrono::steady_clock::now();
     check(lisa_render_subframes(ctx, subframe, 1, spl), "render");
@@ -41,8 +52,13 @@ void display(lisa_ctx* ctx, const lisa_scene_desc& params) {
     // stands in for sutil::displayStats + the "nb sample" overlay
     printf("render %8.2f ms | nb sample   : %8u\n", dt.count() * 1e3, subframe * spl);
     fflush(stdout);
+    if (opt.snapshot_every && subframe % opt.snapshot_every == 0 && (unsigned long long)subframe * spl < params.num_samples) {
+      save_image(ctx, params);
+      if (opt.checkpoint) check(lisa_save_accum(ctx, opt.checkpoint), "checkpoint");
+    }
   } while ((unsigned long long)subframe * spl < params.num_samples);  // render.cc:121
   save_image(ctx, params);
+  if (opt.checkpoint) check(lisa_save_accum(ctx, opt.checkpoint), "checkpoint");
   std::chrono::duration<float> total = std::chrono::system_clock::now() - start;
   printf("Rendering finished in %.2f mn.\n", total.count() / 60.0f);
 }

@@ -11,6 +11,17 @@ void render(lisa_ctx* ctx, const lisa_scene_desc& params);
 // of the ImGui overlay (sutil.cpp:735-743, render.cc:110-115), then the PPM.
 void display(lisa_ctx* ctx, const lisa_scene_desc& params);
 
+// The same progressive render for a headless box: every `snapshot_every` subframes (0 = never)
+// the PPM is rewritten and, if `checkpoint` is given, the accumulators are saved there (lisa_save_accum); with
+// `resume` the accumulators are loaded from that file first and rendering continues at the subframe it holds, so an
+// interrupted render finishes with the image it would have had.
+struct DisplayOptions {
+  unsigned    snapshot_every = 0;
+  const char* checkpoint = nullptr;
+  const char* resume = nullptr;
+};
+void display(lisa_ctx* ctx, const lisa_scene_desc& params, const DisplayOptions& opt);
+
 // Sample-space partition over `ngpus` GPUs of this box, single process: the num_samples are split into
 // `ngpus` subframes of ceil(num_samples / ngpus) spp; GPU g (own context: full scene, own BVH) renders subframe g on
 // its own host thread; the sums are added onto GPU 0 by lisa_accum_add_peer (one kernel reading peer memory over

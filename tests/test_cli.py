@@ -1,6 +1,7 @@
 """The `lisa` CLI keeps the reference's surface (src/LiSA/src/main.cc:6-28): -s mandatory, usage + exit 1
 without it, parser failures print the reference's message and exit with its code."""
 import os
+import re
 import subprocess
 
 import pytest
@@ -52,3 +53,38 @@ def test_render_end_to_end(built, tmp_path):
         assert raw.startswith(b"P6\n64 64\n255\n") and len(raw) == len(b"P6\n64 64\n255\n") + 64 * 64 * 3
         px = np.frombuffer(raw[13:], dtype=np.uint8).reshape(64, 64, 3)
         assert px[2:12, 20:44].mean() > px[30:, :].mean()  # the light is at the TOP of the file (rows are flipped)
+
+
+@pytest.mark.gpu
+def test_cli_checkpoint_and_resume(built, tmp_path):
+    """`-d --snapshot-every K --checkpoint f` rewrites the PPM and saves the accumulators every K
+    subframes; `--resume f` continues from the subframe the file holds and ends with the uninterrupted render's image."""
+    out_a, out_b, ck = tmp_path / "a.ppm", tmp_path / "b.ppm", tmp_path / "acc.bin"
+
+    def scene(path, out, spp):
+        txt = open(os.path.join(ROOT, "scenes/cornell_tiny.rto")).read()
+        txt = re.sub(r"output_image\s*=.*", "output_image = %s" % out, txt)
+        txt = re.sub(r"num_samples\s*=\s*\d+", "num_samples = %d" % spp, txt)
+        path.write_text(txt)
+        return str(path)
+
+    def run(*args):
+        r = _run(*args)
+        assert r.returncode == 0, r.stderr.decode()
+        return r.stdout.decode()
+
+    run("-s", scene(tmp_path / "full.rto", out_a, 64), "-d")                                   # 4 subframes straight
+    so = run("-s", scene(tmp_path / "half.rto", out_b, 32), "-d", "--snapshot-every", "1", "--checkpoint", str(ck))
+    assert so.count("nb sample") == 2 and ck.exists()
+    assert ck.stat().st_size == 8 + 12 + 64 * 64 * 16 and ck.read_bytes()[:8] == b"LISAACC1"
+    so = run("-s", scene(tmp_path / "rest.rto", out_b, 64), "-d", "--resume", str(ck))         # subframes 2 and 3
+    assert "resumed %s at subframe 2 (32 samples)" % ck in so and so.count("nb sample") == 2 and "nb sample   :       64" in so
+    assert out_a.read_bytes() == out_b.read_bytes()
+    # a checkpoint that already holds every sample: nothing is rendered, the image is written
+    so = run("-s", str(tmp_path / "half.rto"), "-d", "--resume", str(ck))
+    assert so.count("nb sample") == 0 and "Rendering finished" in so
+    # a file that is not a checkpoint is refused
+    bad = tmp_path / "bad.bin"
+    bad.write_bytes(b"P6\n64 64\n255\n" + bytes(100))
+    r = _run("-s", str(tmp_path / "rest.rto"), "-d", "--resume", str(bad))
+    assert r.returncode != 0 and b"is not an accumulator checkpoint" in r.stderr

@@ -189,6 +189,33 @@ def test_host_render_and_display(rt, frontend, tmp_path, capfd):
     np.testing.assert_array_equal(imgs[0], imgs[1])
 
 
+def test_accumulator_checkpoint(rt, cornell, tmp_path):
+    """lisa_save_accum / lisa_load_accum: a render resumed in a NEW context from a checkpoint is bit-identical to the
+    uninterrupted one; a checkpoint of another image size is refused."""
+    sc = resized(cornell, 48, 40)
+    R = rt.Renderer.from_scene(sc)
+    for f in range(4):
+        R.render_subframes(f, 1, 3)
+    full = R.read_accum()
+    R.close()
+    ck = str(tmp_path / "acc.bin")
+    R = rt.Renderer.from_scene(sc)
+    R.render_subframes(0, 2, 3)
+    R.save_accum(ck)
+    R.close()
+    R = rt.Renderer.from_scene(sc)
+    assert R.load_accum(ck) == 2 and R.stats()["subframes_accumulated"] == 2
+    R.render_subframes(2, 1, 3)
+    R.render_subframes(3, 1, 3)
+    np.testing.assert_array_equal(R.read_accum(), full)
+    assert R.stats()["subframes_accumulated"] == 4
+    R.close()
+    R = rt.Renderer.from_scene(resized(cornell, 40, 48))
+    with pytest.raises(rt.LisaError, match="holds a 48x40 image"):
+        R.load_accum(ck)
+    R.close()
+
+
 def test_pfm_output(rt, cornell, tmp_path):
     R = rt.Renderer.from_scene(resized(cornell, 40, 24))
     R.render_subframes(0, 1, 4)
