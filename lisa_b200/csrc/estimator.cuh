@@ -179,4 +179,189 @@ __device__ __forceinline__ void emitter_cone(const DScene& sc, const float3& P, 
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// One event of a chain — the management stages the persistent kernels (sched_path.cuh, sched_pool.cuh) share.
+// Called by ALL 32 lanes of a warp together (it votes); a lane takes part with has_event == true.
+//   in   ev        the chain's finished ray: kind, closest hit (t, u, v, prim; prim < 0 = miss), occluded (shadow rays)
+//   io   c         the chain's registers (origin of the finished ray -> hit point, radiance direction, attenuation,
+//                  radiance, normal, material, LCG, flags, tries, BRDF of the shadow ray that was in flight)
+//   out            what the chain needs next: end of the sample, a radiance ray along c.d from c.o, or a shadow ray
+//                  along w from c.o
+// Stages: (1) material dispatch of a radiance hit (__closesthit__radiance / __miss__radiance, shader.cu:189-194,211-253);
+// (2) retiring a shadow ray into RayState::hit (shader.cu:172-184, Q1); (3) shoot_ray_to_light (shader.cu:196-209):
+// every try the job has left is evaluated at once, warp-cooperatively — the warp walks its jobs, lane i jumps the job's
+// LCG ahead by 3i draws (lcg_a / lcg_c: x -> A^(3k) x + C_(3k)), draws try i's direction and tests it against the cone
+// around the emitter bounds; the job's owner confirms the few cone hits against the emitter box in try order with the
+// reference's own expression; tries that cannot change RayState::hit are thereby resolved without traversal, exactly;
+// (4) the light term and the BSDF bounce (shader.cu:251-252).
+struct ChainRegs {
+  float3   o, d, atten, color, N;
+  uint32_t seed, flags, tries;
+  int      mid;
+  float    brdf_w;
+};
+struct ChainEvent {
+  bool  shadow_ray, occluded;
+  float t, u, v;
+  int   prim;
+};
+struct ChainNext {
+  bool   end_sample, start_rad, start_shd;
+  float3 w;
+};
+struct EventCounters { uint32_t jobs, shadow, culled; };
+
+__device__ __forceinline__ ChainNext chain_event(const DScene& sc, const Tile& t, const uint32_t* lcg_a, const uint32_t* lcg_c,
+                                                 float4* jb /* this warp's 96 x float4 job buffer */, bool has_event,
+                                                 const ChainEvent& ev, ChainRegs& c, EventCounters& cnt) {
+  const unsigned lane = lane_id();
+  ChainNext nx;
+  nx.end_sample = nx.start_rad = nx.start_shd = false;
+  nx.w = f3(0, 0, 0);
+  bool finish = false, trying = false;
+  if (has_event) {
+    if (!ev.shadow_ray) {
+      // ---- (1) material dispatch of the finished radiance ray
+      if (ev.prim < 0) {
+        nx.end_sample = true;  // __miss__radiance (background 0, optix_wrapper.cc:354) or a null direction (Q7)
+      } else {
+        c.mid = __float_as_int(__ldg(sc.tri_v + 3 * ev.prim).w);
+        const DMaterial m = load_material(sc.mats, c.mid);
+        if (m.emit()) {  // shader.cu:216-218
+          c.color = add_emission(c.color, m.emission(), c.atten);
+          nx.end_sample = true;
+        } else {
+          const float3 P = madd(c.o, ev.t, c.d);  // shader.cu:221
+          Hit h;
+          h.t = ev.t; h.u = ev.u; h.v = ev.v; h.prim = ev.prim;
+          c.N = shading_normal(sc, h);
+          if (m.alpha() < 1.0f) {  // dielectric, shader.cu:226-246
+            float  cosI = dot(c.d, c.N), eta;
+            float3 Nn;
+            if (cosI < 0.0f) { cosI = -cosI; eta = 1.0f / m.ior(); Nn = c.N; }
+            else { c.atten = c.atten * m.diffuse(); eta = m.ior(); Nn = -c.N; }
+            float3 nd;
+            if (eta == 1.0f) nd = c.d;
+            else if (rnd(c.seed) <= bsdf::BTDF(cosI, eta)) nd = reflect(c.d, Nn);
+            else nd = refract(cosI, c.d, Nn, eta);
+            const uint32_t bounce = (c.flags & F_BOUNCE_MASK) + 1;
+            if (bounce >= t.bounces) nx.end_sample = true;
+            else {
+              c.flags = (c.flags & ~F_BOUNCE_MASK) | bounce;
+              c.o = P; c.d = nd;
+              nx.start_rad = true;
+            }
+          } else {  // opaque, shader.cu:248-253
+            c.atten = c.atten * m.diffuse();
+            c.o = P;
+            c.tries = 0;
+            trying = true;
+            cnt.jobs++;
+          }
+        }
+      }
+    } else {
+      // ---- (2) retire the finished shadow ray into RayState::hit
+      c.tries++;
+      if (ev.occluded) {               // a non-emitter decides: RayState::hit keeps its value (Q1)
+      } else if (ev.prim >= 0) {       // __closesthit__occlusion on an emitter
+        const int light = __float_as_int(__ldg(sc.tri_v + 3 * ev.prim).w);
+        c.flags = (c.flags & 0x0000ffffu) | F_STICKY | ((uint32_t)light << F_LIGHT_SHIFT);
+      } else c.flags &= ~F_STICKY;     // __miss__occlusion
+      if ((c.flags & F_STICKY) || c.tries == LISA_SHADOW_TRIES) finish = true;
+      else trying = true;
+    }
+  }
+  // ---- (3) shoot_ray_to_light
+  float3 cone_axis = f3(0, 0, 0);
+  float  cone_cos = 2.0f;
+  if (trying) {
+    emitter_cone(sc, c.o, cone_axis, cone_cos);
+    // every try lies in the hemisphere of N: if the whole cone is below that horizon no try can be a candidate
+    if (cone_cos > -1.0f && cone_cos <= 1.0f &&
+        dot(c.N, cone_axis) < -sqrtf(fmaxf(1.0f - cone_cos * cone_cos, 0.0f)) - 1e-3f) cone_cos = 2.0f;
+  }
+  if (trying && (c.flags & F_STICKY)) {  // RayState::hit is true (Q1), only at the first try of a bounce: a real ray
+    nx.w = shoot_ray_hemisphere(c.N, c.seed);
+    nx.start_shd = true; trying = false;
+  } else if (trying && cone_cos > 1.0f) {  // no try can reach an emitter: consume the draws of all that are left
+    const uint32_t k = LISA_SHADOW_TRIES - c.tries;
+    c.seed = lcg_a[k] * c.seed + lcg_c[k];
+    cnt.shadow += k; cnt.culled += k;
+    c.tries = LISA_SHADOW_TRIES;
+    finish = true; trying = false;
+  }
+  const unsigned jobs = __ballot_sync(FULL, trying);
+  if (jobs) {
+    if (trying) {
+      jb[3 * lane]     = make_float4(c.N.x, c.N.y, c.N.z, cone_cos * fabsf(cone_cos));
+      jb[3 * lane + 1] = make_float4(cone_axis.x, cone_axis.y, cone_axis.z, __uint_as_float(c.seed));
+      jb[3 * lane + 2].x = __uint_as_float(LISA_SHADOW_TRIES - c.tries);
+    }
+    __syncwarp();
+    const uint32_t my_a = lcg_a[lane], my_c = lcg_c[lane];
+    unsigned cone_mask = 0;
+    for (unsigned rem = jobs; rem; rem &= rem - 1u) {
+      const int      j  = __ffs(rem) - 1;
+      const float4   r0 = jb[3 * j], r1 = jb[3 * j + 1];
+      const uint32_t left = __float_as_uint(jb[3 * j + 2].x);
+      uint32_t       sd = my_a * __float_as_uint(r1.w) + my_c;  // LCG state before try (tries_j + lane)
+      const float    a = rng_fast(sd), b = rng_fast(sd), cc = rng_fast(sd);
+      // w = +-v/|v| with the sign of v.N (shoot_ray_hemisphere); w.A >= cos  <=>  q|q| >= cos|cos| * v.v with
+      // q = +-v.A, no normalisation needed.  Where the sign of v.N is within rounding of zero the try is kept.
+      const float    sN = fmaf(cc, r0.z, fmaf(b, r0.y, a * r0.x));
+      const float    qA = fmaf(cc, r1.z, fmaf(b, r1.y, a * r1.x));
+      const float    vv = fmaf(cc, cc, fmaf(b, b, a * a));
+      const float    q  = __uint_as_float(__float_as_uint(qA) ^ (__float_as_uint(sN) & 0x80000000u));
+      const bool     in_cone = q * fabsf(q) >= r0.w * vv || fabsf(sN) < 4e-6f;
+      const unsigned m = __ballot_sync(FULL, in_cone && lane < left);
+      if ((int)lane == j) cone_mask = m;
+    }
+    __syncwarp();
+    // the few cone hits are confirmed against the emitter box, in try order, by the job's owner, with the reference's
+    // own expression for the direction (measured: spreading these events over the warp's lanes gains nothing)
+    if (trying) {
+      int first = -1;
+      while (cone_mask) {
+        const int b = __ffs(cone_mask) - 1;
+        cone_mask &= cone_mask - 1u;
+        uint32_t     sd = lcg_a[b] * c.seed + lcg_c[b];
+        const float3 wb = shoot_ray_hemisphere(c.N, sd);
+        if (!sc.cull || hits_emitter_bounds(sc, c.o, wb, LISA_TMIN, LISA_TMAX)) { first = b; nx.w = wb; c.seed = sd; break; }
+      }
+      const uint32_t consumed = first >= 0 ? (uint32_t)first : LISA_SHADOW_TRIES - c.tries;
+      cnt.shadow += consumed; cnt.culled += consumed;
+      c.tries += consumed;
+      if (first >= 0) nx.start_shd = true;
+      else { c.seed = lcg_a[consumed] * c.seed + lcg_c[consumed]; finish = true; }
+    }
+  }
+  // ---- (4) end of the opaque branch (shader.cu:251-252): light term, BSDF bounce
+  if (finish) {
+    const MatRef m{sc.mats, c.mid};
+    if (c.flags & F_STICKY) {  // emission of the last light found (Q1) * BRDF(N, w) * attenuation
+      const DMaterial lm = load_material(sc.mats, (int)(c.flags >> F_LIGHT_SHIFT));
+      c.color = add_light(c.color, lm.emission(), c.brdf_w, c.atten);
+    }
+    const float3   nd = bsdf::bounce(c.d, c.N, c.seed, m);  // also after the last bounce: it consumes RNG
+    const uint32_t bounce = (c.flags & F_BOUNCE_MASK) + 1;
+    if (bounce >= t.bounces) nx.end_sample = true;
+    else {
+      c.flags = (c.flags & ~F_BOUNCE_MASK) | bounce;
+      c.d = nd;
+      nx.start_rad = true;
+    }
+  }
+  return nx;
+}
+
+// the warp's LCG jump tables: x -> A^(3k) x + C_(3k), k = threadIdx.x < 32 (call before a __syncthreads())
+__device__ __forceinline__ void fill_lcg_tables(uint32_t* lcg_a, uint32_t* lcg_c) {
+  if (threadIdx.x < 32) {
+    uint32_t a = 1u, c = 0u;
+    for (unsigned k = 0; k < 3 * threadIdx.x; k++) { c = 1664525u * c + 1013904223u; a *= 1664525u; }
+    lcg_a[threadIdx.x] = a; lcg_c[threadIdx.x] = c;
+  }
+}
+
 }  // namespace lisa

@@ -44,11 +44,7 @@ __global__ void __launch_bounds__(128, LISA_POOL_MIN_BLOCKS) k_pool(DScene sc, D
   Stack          stack(smem_stack);
   PoolWarp&      pw   = reinterpret_cast<PoolWarp*>(smem_stack + LISA_STACK_SM * 128)[threadIdx.x >> 5];
   const unsigned lane = lane_id();
-  if (threadIdx.x < 32) {
-    uint32_t a = 1u, c = 0u;
-    for (unsigned k = 0; k < 3 * threadIdx.x; k++) { c = 1664525u * c + 1013904223u; a *= 1664525u; }
-    lcg_a[threadIdx.x] = a; lcg_c[threadIdx.x] = c;
-  }
+  fill_lcg_tables(lcg_a, lcg_c);
   // every slot starts in the pending queue without a chain: the first management sections fetch chains for them
   for (unsigned k = lane; k < POOL_SLOTS; k += 32) {
     pw.pq[k] = (unsigned char)k;
@@ -75,7 +71,8 @@ __global__ void __launch_bounds__(128, LISA_POOL_MIN_BLOCKS) k_pool(DScene sc, D
   // chain queue
   unsigned wnext = 0, wend = 0;
   bool     exhausted = false;
-  uint32_t n_rad = 0, n_null = 0, n_samp = 0, n_done = 0, n_jobs = 0, nn = 0, nt = 0, n_sh = 0, n_cull = 0;
+  uint32_t n_rad = 0, n_null = 0, n_samp = 0, n_done = 0, nn = 0, nt = 0;
+  EventCounters ec = {0, 0, 0};
 
   while (true) {
     // ---- (a) lanes without a ray take ready slots
@@ -123,138 +120,19 @@ __global__ void __launch_bounds__(128, LISA_POOL_MIN_BLOCKS) k_pool(DScene sc, D
         r_t = f4.x; r_u = f4.y; r_v = f4.z; r_prim = __float_as_int(f4.w);
         chain = __float_as_int(g4.x); pixel = __float_as_uint(g4.y); done = __float_as_uint(g4.z);
       }
-      bool   end_sample = false, start_rad = false, start_shd = false, finish = false, trying = false;
-      float3 w = f3(0, 0, 0), cone_axis = f3(0, 0, 0);
-      float  cone_cos = 2.0f;
-      if (active && chain >= 0) {
-        if (!(kind & 1u)) {
-          // ---- (1) material dispatch of the finished radiance ray
-          if (r_prim < 0) {
-            end_sample = true;  // __miss__radiance (background 0, optix_wrapper.cc:354) or a null direction (Q7)
-          } else {
-            mid = __float_as_int(__ldg(sc.tri_v + 3 * r_prim).w);
-            const DMaterial m = load_material(sc.mats, mid);
-            if (m.emit()) {  // shader.cu:216-218
-              color = add_emission(color, m.emission(), atten);
-              end_sample = true;
-            } else {
-              const float3 P = madd(mo, r_t, d);  // shader.cu:221
-              Hit h;
-              h.t = r_t; h.u = r_u; h.v = r_v; h.prim = r_prim;
-              N = shading_normal(sc, h);
-              if (m.alpha() < 1.0f) {  // dielectric, shader.cu:226-246
-                float  cosI = dot(d, N), eta;
-                float3 Nn;
-                if (cosI < 0.0f) { cosI = -cosI; eta = 1.0f / m.ior(); Nn = N; }
-                else { atten = atten * m.diffuse(); eta = m.ior(); Nn = -N; }
-                float3 nd;
-                if (eta == 1.0f) nd = d;
-                else if (rnd(seed) <= bsdf::BTDF(cosI, eta)) nd = reflect(d, Nn);
-                else nd = refract(cosI, d, Nn, eta);
-                const uint32_t bounce = (flags & F_BOUNCE_MASK) + 1;
-                if (bounce >= t.bounces) end_sample = true;
-                else {
-                  flags = (flags & ~F_BOUNCE_MASK) | bounce;
-                  mo = P; d = nd;
-                  start_rad = true;
-                }
-              } else {  // opaque, shader.cu:248-253
-                atten = atten * m.diffuse();
-                mo = P;
-                tries = 0;
-                trying = true;
-                n_jobs++;
-              }
-            }
-          }
-        } else {
-          // ---- (2) retire the finished shadow ray into RayState::hit
-          tries++;
-          if (r_prim == -2) {              // a non-emitter decides: RayState::hit keeps its value (Q1)
-          } else if (r_prim >= 0) {        // __closesthit__occlusion on an emitter
-            const int light = __float_as_int(__ldg(sc.tri_v + 3 * r_prim).w);
-            flags = (flags & 0x0000ffffu) | F_STICKY | ((uint32_t)light << F_LIGHT_SHIFT);
-          } else flags &= ~F_STICKY;       // __miss__occlusion
-          if ((flags & F_STICKY) || tries == LISA_SHADOW_TRIES) finish = true;
-          else trying = true;
-        }
-      }
-      // ---- (3) shoot_ray_to_light (shader.cu:196-209), all the tries a job has left at once (see k_path)
-      if (trying) {
-        emitter_cone(sc, mo, cone_axis, cone_cos);
-        // every try lies in the hemisphere of N: if the whole cone is below that horizon no try can be a candidate
-        if (cone_cos > -1.0f && cone_cos <= 1.0f &&
-            dot(N, cone_axis) < -sqrtf(fmaxf(1.0f - cone_cos * cone_cos, 0.0f)) - 1e-3f) cone_cos = 2.0f;
-      }
-      if (trying && (flags & F_STICKY)) {  // RayState::hit is true (Q1), only at the first try of a bounce: a real ray
-        w = shoot_ray_hemisphere(N, seed);
-        start_shd = true; trying = false;
-      } else if (trying && cone_cos > 1.0f) {  // no try can reach an emitter: consume the draws of all that are left
-        const uint32_t k = LISA_SHADOW_TRIES - tries;
-        seed = lcg_a[k] * seed + lcg_c[k];
-        n_sh += k; n_cull += k;
-        tries = LISA_SHADOW_TRIES;
-        finish = true; trying = false;
-      }
-      const unsigned jobs = __ballot_sync(FULL, trying);
-      if (jobs) {
-        float4* jb = jobbuf[threadIdx.x >> 5];
-        if (trying) {
-          jb[3 * lane]     = make_float4(N.x, N.y, N.z, cone_cos * fabsf(cone_cos));
-          jb[3 * lane + 1] = make_float4(cone_axis.x, cone_axis.y, cone_axis.z, __uint_as_float(seed));
-          jb[3 * lane + 2].x = __uint_as_float(LISA_SHADOW_TRIES - tries);
-        }
-        __syncwarp();
-        const uint32_t my_a = lcg_a[lane], my_c = lcg_c[lane];
-        unsigned cone_mask = 0;
-        for (unsigned rem = jobs; rem; rem &= rem - 1u) {
-          const int      j  = __ffs(rem) - 1;
-          const float4   r0 = jb[3 * j], r1 = jb[3 * j + 1];
-          const uint32_t left = __float_as_uint(jb[3 * j + 2].x);
-          uint32_t       sd = my_a * __float_as_uint(r1.w) + my_c;  // LCG state before try (tries_j + lane)
-          const float    a = rng_fast(sd), b = rng_fast(sd), c = rng_fast(sd);
-          const float    sN = fmaf(c, r0.z, fmaf(b, r0.y, a * r0.x));
-          const float    qA = fmaf(c, r1.z, fmaf(b, r1.y, a * r1.x));
-          const float    vv = fmaf(c, c, fmaf(b, b, a * a));
-          const float    q  = __uint_as_float(__float_as_uint(qA) ^ (__float_as_uint(sN) & 0x80000000u));
-          const bool     in_cone = q * fabsf(q) >= r0.w * vv || fabsf(sN) < 4e-6f;
-          const unsigned m = __ballot_sync(FULL, in_cone && lane < left);
-          if ((int)lane == j) cone_mask = m;
-        }
-        __syncwarp();
-        if (trying) {
-          int first = -1;
-          while (cone_mask) {
-            const int b = __ffs(cone_mask) - 1;
-            cone_mask &= cone_mask - 1u;
-            uint32_t     sd = lcg_a[b] * seed + lcg_c[b];
-            const float3 wb = shoot_ray_hemisphere(N, sd);
-            if (!sc.cull || hits_emitter_bounds(sc, mo, wb, LISA_TMIN, LISA_TMAX)) { first = b; w = wb; seed = sd; break; }
-          }
-          const uint32_t consumed = first >= 0 ? (uint32_t)first : LISA_SHADOW_TRIES - tries;
-          n_sh += consumed; n_cull += consumed;
-          tries += consumed;
-          if (first >= 0) start_shd = true;
-          else { seed = lcg_a[consumed] * seed + lcg_c[consumed]; finish = true; }
-          trying = false;
-        }
-      }
-      // ---- (4) end of the opaque branch (shader.cu:251-252): light term, BSDF bounce
-      if (finish) {
-        const MatRef m{sc.mats, mid};
-        if (flags & F_STICKY) {  // emission of the last light found (Q1) * BRDF(N, w) * attenuation
-          const DMaterial lm = load_material(sc.mats, (int)(flags >> F_LIGHT_SHIFT));
-          color = add_light(color, lm.emission(), brdf_w, atten);
-        }
-        const float3   nd = bsdf::bounce(d, N, seed, m);  // also after the last bounce: it consumes RNG
-        const uint32_t bounce = (flags & F_BOUNCE_MASK) + 1;
-        if (bounce >= t.bounces) end_sample = true;
-        else {
-          flags = (flags & ~F_BOUNCE_MASK) | bounce;
-          d = nd;
-          start_rad = true;
-        }
-      }
+      // ---- (1)-(4) material dispatch / shadow-ray retirement, light sampling, light term + bounce (estimator.cuh)
+      ChainEvent ev;
+      ev.shadow_ray = kind & 1u; ev.occluded = r_prim == -2;
+      ev.t = r_t; ev.u = r_u; ev.v = r_v; ev.prim = r_prim;
+      ChainRegs cr;
+      cr.o = mo; cr.d = d; cr.atten = atten; cr.color = color; cr.N = N;
+      cr.seed = seed; cr.flags = flags; cr.tries = tries; cr.mid = mid; cr.brdf_w = brdf_w;
+      const ChainNext nx = chain_event(sc, t, lcg_a, lcg_c, jobbuf[threadIdx.x >> 5], active && chain >= 0, ev, cr, ec);
+      mo = cr.o; d = cr.d; atten = cr.atten; color = cr.color; N = cr.N;
+      seed = cr.seed; flags = cr.flags; tries = cr.tries; mid = cr.mid;
+      const bool   end_sample = nx.end_sample, start_shd = nx.start_shd;
+      bool         start_rad = nx.start_rad;
+      const float3 w = nx.w;  // direction of the shadow ray to start
       // ---- (5) end of the sample: the chain's sum lives in s.sum[chain]
       bool fresh = false;
       if (end_sample) {
@@ -309,7 +187,7 @@ __global__ void __launch_bounds__(128, LISA_POOL_MIN_BLOCKS) k_pool(DScene sc, D
           const float3 rd = start_rad ? d : w;
           kind = start_rad ? 0u : 1u;
           if (start_shd) {
-            n_sh++;
+            ec.shadow++;
             brdf_w = bsdf::BRDF(N, w, MatRef{sc.mats, mid});  // evaluated now (w is not kept), used if this try lights the job
           }
           if (start_rad && rd.x == 0.0f && rd.y == 0.0f && rd.z == 0.0f) { n_null++; to_pending = true; }
@@ -414,14 +292,14 @@ __global__ void __launch_bounds__(128, LISA_POOL_MIN_BLOCKS) k_pool(DScene sc, D
     }
   }
   warp_add(&s.stats[ST_RADIANCE], n_rad);
-  warp_add(&s.stats[ST_SHADOW], n_sh);
+  warp_add(&s.stats[ST_SHADOW], ec.shadow);
   warp_add(&s.stats[ST_SAMPLES], n_samp);
   warp_add(&s.stats[ST_NULLDIR], n_null);
   warp_add(&s.stats[ST_CHAINS_DONE], n_done);
   warp_add(&s.stats[ST_NODES], nn);
   warp_add(&s.stats[ST_TRIS], nt);
-  warp_add(&s.stats[ST_JOBS], n_jobs);
-  warp_add(&s.stats[ST_CULLED], n_cull);
+  warp_add(&s.stats[ST_JOBS], ec.jobs);
+  warp_add(&s.stats[ST_CULLED], ec.culled);
 }
 
 }  // namespace lisa
