@@ -36,6 +36,17 @@ __device__ __forceinline__ float3 perm3(const float3& v, int kz) {
   return f3(kz == 0 ? v.y : (kz == 1 ? v.z : v.x), kz == 0 ? v.z : (kz == 1 ? v.x : v.y),
             kz == 0 ? v.x : (kz == 1 ? v.y : v.z));
 }
+// the same rotation as six selects per vertex, never a branch: lanes of one warp hold rays of different kz, and the
+// compiler's if-conversion gives up on the three-component form above (it emitted ~13 instructions and a divergent
+// region per vertex).  k0 = (kz == 0), k1 = (kz == 1).
+__device__ __forceinline__ float sel_f(bool p, float a, float b) {
+  float r;
+  asm("{ .reg .pred q; setp.ne.u32 q, %3, 0; selp.f32 %0, %1, %2, q; }" : "=f"(r) : "f"(a), "f"(b), "r"((uint32_t)p));
+  return r;
+}
+__device__ __forceinline__ float3 perm3_sel(const float3& v, bool k0, bool k1) {
+  return f3(sel_f(k0, v.y, sel_f(k1, v.z, v.x)), sel_f(k0, v.z, sel_f(k1, v.x, v.y)), sel_f(k0, v.x, sel_f(k1, v.y, v.z)));
+}
 
 __device__ __forceinline__ RayPre ray_precompute(const float3& o, const float3& d) {
   RayPre r;
@@ -52,7 +63,8 @@ __device__ __forceinline__ RayPre ray_precompute(const float3& o, const float3& 
 // Returns true and updates (t, u, v) when the triangle is hit with tmin < t < tmax.
 __device__ __forceinline__ bool intersect_tri(const RayPre& r, const float3& v0, const float3& v1, const float3& v2,
                                               float tmin, float tmax, float& t_out, float& u_out, float& v_out) {
-  const float3 A = perm3(v0 - r.o, r.kz), B = perm3(v1 - r.o, r.kz), C = perm3(v2 - r.o, r.kz);
+  const bool   k0 = r.kz == 0, k1 = r.kz == 1;
+  const float3 A = perm3_sel(v0 - r.o, k0, k1), B = perm3_sel(v1 - r.o, k0, k1), C = perm3_sel(v2 - r.o, k0, k1);
   const float  Ax = fmaf(-r.Sx, A.z, A.x), Ay = fmaf(-r.Sy, A.z, A.y);
   const float  Bx = fmaf(-r.Sx, B.z, B.x), By = fmaf(-r.Sy, B.z, B.y);
   const float  Cx = fmaf(-r.Sx, C.z, C.x), Cy = fmaf(-r.Sy, C.z, C.y);
@@ -112,8 +124,7 @@ typedef TravStack<uint2, LISA_STACK_SM, LISA_STACK_LOC> Stack;
 // bytes of dynamic shared memory a traversal kernel needs per thread
 #define LISA_STACK_SMEM_PER_THREAD (LISA_STACK_SM * 8)
 
-__device__ __forceinline__ float3 safe_rcp_dir(const float3& d) {
-  const float eps = 1e-30f;
+__device__ __forceinline__ float3 safe_rcp_dir(const float3& d, const float eps = 1e-30f) {
   return f3(1.0f / (fabsf(d.x) > eps ? d.x : copysignf(eps, d.x)), 1.0f / (fabsf(d.y) > eps ? d.y : copysignf(eps, d.y)),
             1.0f / (fabsf(d.z) > eps ? d.z : copysignf(eps, d.z)));
 }
@@ -166,7 +177,7 @@ struct StepRay {        // per-ray constants kept in registers
 
 __device__ __forceinline__ StepRay step_ray(const float3& d) {
   StepRay r;
-  r.idir = safe_rcp_dir(d);
+  r.idir = safe_rcp_dir(d, 1e-20f);  // the wide node test scales it by 2^(e+15): keep that finite for any sane scene
   const float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
   r.kz = (ax > ay) ? (ax > az ? 0 : 2) : (ay > az ? 1 : 2);
   const float3 p = perm3(d, r.kz);
@@ -194,9 +205,14 @@ __device__ __forceinline__ bool step_tri_uv(const float3& o, const StepRay& r, c
   return intersect_tri(pre, f3(a), f3(b), f3(c), tmin, tmax, t_out, u_out, v_out);
 }
 
-// byte j of q -> float, on the ALU/FMA pipes (PRMT + FADD) instead of the slow conversion pipe
-__device__ __forceinline__ float byte_to_float(uint32_t q, int j) {
-  return __uint_as_float(__byte_perm(q, 0x4B000000u, 0x7650u | (uint32_t)j)) - 8388608.0f;
+// byte j of q -> the float 1 + q * 2^-15 in ONE instruction: PRMT drops the byte into bits 8..15 of the mantissa of 1.0f.
+// The plane equation q * a + o is then evaluated as fma(that, 2^15 a, o - 2^15 a): no int->float conversion (slow
+// pipe) and no subtraction of the magic.  The 1.0f comes from constant memory so that the SELECTOR is the immediate
+// operand of PRMT; with both operands literal, ptxas keeps the magic as the immediate and spends a MOV per PRMT on the
+// selector (48 per node visit).
+static __constant__ uint32_t c_unit_magic = 0x3F800000u;
+__device__ __forceinline__ float byte_to_unit(uint32_t q, int j, uint32_t magic) {
+  return __uint_as_float(__byte_perm(q, magic, 0x7604u | ((uint32_t)j << 4)));
 }
 
 // ---- compressed 8-wide --------------------------------------------------------------------------
@@ -224,14 +240,17 @@ __device__ __forceinline__ void wide_node_step(const float4* __restrict__ nodes,
   const float3 adir = f3(__uint_as_float((eimask & 0xffu) << 23) * r.idir.x, __uint_as_float(((eimask >> 8) & 0xffu) << 23) * r.idir.y,
                          __uint_as_float(((eimask >> 16) & 0xffu) << 23) * r.idir.z);
   const float3 org  = f3((w0.x - o.x) * r.idir.x, (w0.y - o.y) * r.idir.y, (w0.z - o.z) * r.idir.z);
-  // conservative planes: t = q*adir + org cancels when |org| and |q*adir| are large, and |t| <= |org| + 255 |adir|,
-  // so one absolute pad of 2^-20 of that bound
-  // covers both the cancellation in q*adir + org and the relative rounding of the result
+  // conservative planes.  With u = 1 + q 2^-15 (byte_to_unit) the plane is t = u * A + (org - A), A = 2^15 adir: the fma
+  // is exact up to its final rounding, org - A carries an error of 2^-24 max(|org|, 2^15 |adir|), and org itself two
+  // roundings; |t| <= |org| + 255 |adir|.  One absolute pad of 1.2e-6 (|org| + 3072 |adir|) covers all of it
+  // (3072 * 1.2e-6 = 3.7e-3 of a quantisation step, 2^-9 = 1.95e-3 needed).
   const float  kpad = 1.2e-6f;
-  const float3 pad  = f3(kpad * fmaf(256.0f, fabsf(adir.x), fabsf(org.x)), kpad * fmaf(256.0f, fabsf(adir.y), fabsf(org.y)),
-                         kpad * fmaf(256.0f, fabsf(adir.z), fabsf(org.z)));
-  const float3 an = adir, af = adir;
-  const float3 on = org - pad, of = org + pad;
+  const float3 pad  = f3(kpad * fmaf(3072.0f, fabsf(adir.x), fabsf(org.x)), kpad * fmaf(3072.0f, fabsf(adir.y), fabsf(org.y)),
+                         kpad * fmaf(3072.0f, fabsf(adir.z), fabsf(org.z)));
+  const float3 an = f3(adir.x * 32768.0f, adir.y * 32768.0f, adir.z * 32768.0f), af = an;
+  const float3 ob = org - an;
+  const float3 on = ob - pad, of = ob + pad;
+  const uint32_t magic = c_unit_magic;
   st.ng.x = __float_as_uint(w1.x);
   st.tg.x = __float_as_uint(w1.y);
   const bool negx = !(r.oct_inv4 & 4u), negy = !(r.oct_inv4 & 2u), negz = !(r.oct_inv4 & 1u);
@@ -252,9 +271,9 @@ __device__ __forceinline__ void wide_node_step(const float4* __restrict__ nodes,
     const uint32_t nz = negz ? qhiz : qloz, fz = negz ? qloz : qhiz;
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-      const float tnx = fmaf(byte_to_float(nx, j), an.x, on.x), tfx = fmaf(byte_to_float(fx, j), af.x, of.x);
-      const float tny = fmaf(byte_to_float(ny, j), an.y, on.y), tfy = fmaf(byte_to_float(fy, j), af.y, of.y);
-      const float tnz = fmaf(byte_to_float(nz, j), an.z, on.z), tfz = fmaf(byte_to_float(fz, j), af.z, of.z);
+      const float tnx = fmaf(byte_to_unit(nx, j, magic), an.x, on.x), tfx = fmaf(byte_to_unit(fx, j, magic), af.x, of.x);
+      const float tny = fmaf(byte_to_unit(ny, j, magic), an.y, on.y), tfy = fmaf(byte_to_unit(fy, j, magic), af.y, of.y);
+      const float tnz = fmaf(byte_to_unit(nz, j, magic), an.z, on.z), tfz = fmaf(byte_to_unit(fz, j, magic), af.z, of.z);
       const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
       const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tlimit));
       if (tn <= tf) hitmask |= extract_byte(child_bits4, j) << extract_byte(bit_index4, j);
