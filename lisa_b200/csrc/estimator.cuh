@@ -305,12 +305,11 @@ __device__ __forceinline__ ChainNext chain_event(const DScene& sc, const Tile& t
     // 3 instructions on the FMA pipe per draw instead of 6, 4 of them on the busier ALU pipe.  For |v| >= 0.01 that
     // moves the direction by < 2e-5 rad, well inside the 1e-4 the cone's cosine is widened by; shorter v are kept.
     const uint32_t my_a = lcg_a[lane], my_c8 = lcg_c[lane] << 8;
-    unsigned cone_mask = 0, n_cand = 0, my_off = 0;  // n_cand is warp-uniform
-    unsigned short* cand = reinterpret_cast<unsigned short*>(jb);  // candidate k = (job lane | try << 8) lives in the upper half of jb[3k+2].x
+    unsigned cone_mask = 0;
     for (unsigned rem = jobs; rem; rem &= rem - 1u) {
       const int      j  = __ffs(rem) - 1;
       const float4   r0 = jb[3 * j], r1 = jb[3 * j + 1];
-      const uint32_t left = __float_as_uint(jb[3 * j + 2].x) & 0xffffu;
+      const uint32_t left = __float_as_uint(jb[3 * j + 2].x);
       const uint32_t t0 = my_a * (__float_as_uint(r1.w) << 8) + my_c8;  // shifted LCG state before try (tries_j + lane)
       const uint32_t t1 = 1664525u * t0 + (1013904223u << 8);
       const uint32_t t2 = (1664525u * 1664525u) * t0 + ((1664525u * 1013904223u + 1013904223u) << 8);
@@ -324,55 +323,24 @@ __device__ __forceinline__ ChainNext chain_event(const DScene& sc, const Tile& t
       const float    qA = fmaf(cc, r1.z, fmaf(b, r1.y, a * r1.x));
       const float    vv = fmaf(cc, cc, fmaf(b, b, a * a));
       const float    q  = __uint_as_float(__float_as_uint(qA) ^ (__float_as_uint(sN) & 0x80000000u));
-      const bool     in_cone = (q * fabsf(q) >= r0.w * vv || fabsf(sN) < 4e-6f || vv < 1e-4f) && lane < left;
-      const unsigned m = __ballot_sync(FULL, in_cone);
-      // the cone hits of all jobs are compacted into one list, job by job and in try order within a job
-      const unsigned k = n_cand + __popc(m & lanemask_lt());
-      if (in_cone && k < 32u) cand[8 * (3 * k + 2) + 1] = (unsigned short)((unsigned)j | (lane << 8));
-      if ((int)lane == j) { cone_mask = m; my_off = n_cand; }
-      n_cand += __popc(m);
+      const bool     in_cone = q * fabsf(q) >= r0.w * vv || fabsf(sN) < 4e-6f || vv < 1e-4f;
+      const unsigned m = __ballot_sync(FULL, in_cone && lane < left);
+      if ((int)lane == j) cone_mask = m;
     }
     __syncwarp();
-    // The cone hits are confirmed against the emitter box with the reference's own expression for the direction.
-    int      first = -1;
-    float3   w_first = f3(0, 0, 0);
-    uint32_t sd_first = 0;
-    if (n_cand <= 32u) {
-      // one candidate per lane: up to 32 (job, try) pairs in ONE pass, whatever job they belong to (a lane walking
-      // its own job's cone hits runs ~4 passes at ~5 lanes: the cone around the emitters' bounding sphere passes
-      // 4x the tries that reach their box)
-      const bool     worker = lane < n_cand;
-      const unsigned desc = worker ? (unsigned)cand[8 * (3 * lane + 2) + 1] : 0u;
-      const int      wj = (int)(desc & 0xffu), wb_try = (int)(desc >> 8);
-      const float3   wo = f3(__shfl_sync(FULL, c.o.x, wj), __shfl_sync(FULL, c.o.y, wj), __shfl_sync(FULL, c.o.z, wj));
-      bool     ok = false;
-      float3   wdir = f3(0, 0, 0);
-      uint32_t wsd = 0;
-      if (worker) {
-        const float4 r0 = jb[3 * wj];
-        wsd  = lcg_a[wb_try] * __float_as_uint(jb[3 * wj + 1].w) + lcg_c[wb_try];
-        wdir = shoot_ray_hemisphere(f3(r0), wsd);
-        ok   = !sc.cull || hits_emitter_bounds(sc, wo, wdir, LISA_TMIN, LISA_TMAX);
-      }
-      const unsigned okm = __ballot_sync(FULL, ok);
-      const unsigned seg = trying ? ((okm >> (my_off & 31u)) & ((1u << __popc(cone_mask)) - 1u)) : 0u;  // a job has <= 30 tries
-      const unsigned src = seg ? my_off + (unsigned)__ffs(seg) - 1u : lane;
-      const float    fx = __shfl_sync(FULL, wdir.x, src), fy = __shfl_sync(FULL, wdir.y, src), fz = __shfl_sync(FULL, wdir.z, src);
-      const uint32_t fs = __shfl_sync(FULL, wsd, src);
-      const int      ft = __shfl_sync(FULL, wb_try, src);
-      if (seg) { first = ft; w_first = f3(fx, fy, fz); sd_first = fs; }
-    } else if (trying) {
-      // more cone hits than lanes (rare): each job's owner walks its own, in try order
+    // the few cone hits are confirmed against the emitter box, in try order, by the job's owner, with the reference's
+    // own expression for the direction.  Measured twice (k_path: 1143 vs 1152; k_pool: 1279 vs 1351 Msamples/s):
+    // compacting the cone hits of all jobs into one list and confirming one per lane in a single pass LOSES to this
+    // loop, although the cone around the emitters' bounding sphere passes 4x the tries that reach their box.
+    if (trying) {
+      int first = -1;
       while (cone_mask) {
         const int b = __ffs(cone_mask) - 1;
         cone_mask &= cone_mask - 1u;
         uint32_t     sd = lcg_a[b] * c.seed + lcg_c[b];
         const float3 wb = shoot_ray_hemisphere(c.N, sd);
-        if (!sc.cull || hits_emitter_bounds(sc, c.o, wb, LISA_TMIN, LISA_TMAX)) { first = b; w_first = wb; sd_first = sd; break; }
+        if (!sc.cull || hits_emitter_bounds(sc, c.o, wb, LISA_TMIN, LISA_TMAX)) { first = b; nx.w = wb; c.seed = sd; break; }
       }
-    }
-    if (trying) {
-      if (first >= 0) { nx.w = w_first; c.seed = sd_first; }
       const uint32_t consumed = first >= 0 ? (uint32_t)first : LISA_SHADOW_TRIES - c.tries;
       cnt.shadow += consumed; cnt.culled += consumed;
       c.tries += consumed;
