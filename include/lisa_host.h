@@ -28,6 +28,10 @@ const char* lisa_scene_mesh_file(const lisa_scene* scene, int i, int* mat_idx);
 int         lisa_scene_material_index(const lisa_scene* scene, const char* name);
 /* render() (progressive == 0) or display() (progressive != 0) on an existing context. */
 int         lisa_host_render(lisa_ctx* ctx, const lisa_scene* scene, int progressive);
+/* Binary soup cache for parse_obj (no counterpart in parse_obj.cc:24-69, which re-parses the text
+ * on every run): 1 = write/read <file>.obj.lisasoup next to each OBJ, 0 = off, -1 = as the environment variable
+ * LISA_OBJ_CACHE says (the default; unset = off). */
+void        lisa_host_set_obj_cache(int enabled);
 const char* lisa_host_last_error(void);
 int         lisa_host_last_exit_code(void);
 

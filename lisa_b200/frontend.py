@@ -26,11 +26,19 @@ _H.lisa_scene_mesh_file.argtypes = [_vp, ctypes.c_int, ctypes.POINTER(ctypes.c_i
 _H.lisa_scene_mesh_file.restype = ctypes.c_char_p
 _H.lisa_scene_material_index.argtypes = [_vp, ctypes.c_char_p]
 _H.lisa_host_render.argtypes = [_vp, _vp, ctypes.c_int]
+_H.lisa_host_set_obj_cache.argtypes = [ctypes.c_int]
+_H.lisa_host_set_obj_cache.restype = None
 _H.lisa_host_last_error.restype = ctypes.c_char_p
 _H.lisa_host_last_exit_code.restype = ctypes.c_int
 
 EXPORTS = ["lisa_scene_parse", "lisa_scene_free", "lisa_scene_get_desc", "lisa_scene_num_meshes", "lisa_scene_mesh_file",
-           "lisa_scene_material_index", "lisa_host_render", "lisa_host_last_error", "lisa_host_last_exit_code"]
+           "lisa_scene_material_index", "lisa_host_render", "lisa_host_set_obj_cache", "lisa_host_last_error",
+           "lisa_host_last_exit_code"]
+
+
+def set_obj_cache(enabled):
+    """Binary soup cache of the OBJ loader (<file>.lisasoup next to each OBJ): True/False, or None = as LISA_OBJ_CACHE says."""
+    _H.lisa_host_set_obj_cache(-1 if enabled is None else int(bool(enabled)))
 
 
 class SceneError(Exception):

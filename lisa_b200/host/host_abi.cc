@@ -4,6 +4,7 @@
 #include <string>
 
 #include "lisa_host.h"
+#include "parse_obj.hh"
 #include "render.hh"
 #include "scene_parser.hh"
 
@@ -61,3 +62,4 @@ extern "C" int lisa_host_render(lisa_ctx* ctx, const lisa_scene* s, int progress
     return LISA_ERR_STATE;
   }
 }
+extern "C" void lisa_host_set_obj_cache(int enabled) { parse_obj_set_cache(enabled); }

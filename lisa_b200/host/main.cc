@@ -2,7 +2,8 @@
 //   lisa -s scene.rto [-d]
 // -s <scene> is mandatory; without it the usage goes to stderr and the exit code is 1.  -d selects the
 // progressive mode (headless here).  Extra, optional: --gpus N renders N subframes of num_samples/N spp on N GPUs of
-// this box and reduces them over NVLink peer memory; --pfm <file> also writes the linear float image; with -d,
+// this box and reduces them over NVLink peer memory; --obj-cache keeps a binary copy of each OBJ's triangle soup next to
+// it (<file>.lisasoup) and loads that instead of the text when it is current; --pfm <file> also writes the linear float image; with -d,
 // --snapshot-every K rewrites the PPM every K subframes, --checkpoint <file> saves the accumulators then (and at the
 // end) and --resume <file> continues an interrupted render from such a file; --stats prints one JSON line with the counters of
 // include/lisa_rt.h:lisa_stats; environment variables LISA_BVH/LISA_SHADOW/LISA_MAX_CHAINS select
@@ -13,6 +14,7 @@
 #include <iostream>
 #include <string>
 
+#include "parse_obj.hh"
 #include "render.hh"
 #include "scene_parser.hh"
 
@@ -32,6 +34,7 @@ int main(int argc, char** argv) {
     return 1;
   }
   try {
+    if (cmdOptionExists(argv, argv + argc, "--obj-cache")) parse_obj_set_cache(1);
     SceneParser     parser(scene_path);
     lisa_scene_desc params = parser.get_params();
     if (char* g = getCmdOption(argv, argv + argc, "--gpus")) {  // sample-space partition over the GPUs of this box

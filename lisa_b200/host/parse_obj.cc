@@ -8,7 +8,16 @@
 // The whole file is read once and scanned in place (no per-line vector<string>) by one worker thread per chunk of
 // whole lines, in three passes (count, positions/normals, faces): what makes multi-million-triangle soups load in
 // seconds.  LISA_OBJ_THREADS overrides the worker count.
+//
+// Binary soup cache (opt-in: LISA_OBJ_CACHE=1, or `lisa --obj-cache`, or lisa_host_set_obj_cache(1)): after a text
+// parse the de-indexed soup is written next to the OBJ as <file>.lisasoup; the next load of the same OBJ (same size and
+// modification time) reads it back instead of parsing text — two freads of 36 bytes per triangle each.  A stale,
+// truncated or foreign file is ignored and rewritten; a directory that cannot be written to just means no cache.
+// Off by default: the reference never writes next to its inputs.
 #include "parse_obj.hh"
+
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <chrono>
@@ -46,7 +55,76 @@ float to_float(const char* b, const char* e, const std::string& path, long line)
   return v;
 }
 
+// ---- binary soup cache ---------------------------------------------------------------------------
+struct SoupHeader {           // 48 bytes, little endian
+  char     magic[8];          // "LISASOUP"
+  uint32_t version;           // 1
+  uint32_t header_bytes;      // sizeof(SoupHeader)
+  uint64_t source_size;       // the OBJ this was made from: size ...
+  int64_t  source_mtime_ns;   // ... and modification time
+  uint64_t num_triangles;     // then 9 T floats (vertices) and 9 T floats (normals)
+  uint64_t reserved;
+};
+static_assert(sizeof(SoupHeader) == 48, "SoupHeader layout");
+
+int g_obj_cache = -1;  // -1: ask the environment
+
+bool obj_cache_enabled() {
+  if (g_obj_cache >= 0) return g_obj_cache != 0;
+  const char* e = getenv("LISA_OBJ_CACHE");
+  return e && atoi(e) != 0;
+}
+
+bool source_stamp(const std::string& path, uint64_t& size, int64_t& mtime_ns) {
+  struct stat st;
+  if (stat(path.c_str(), &st) != 0) return false;
+  size = (uint64_t)st.st_size;
+  mtime_ns = (int64_t)st.st_mtim.tv_sec * 1000000000ll + (int64_t)st.st_mtim.tv_nsec;
+  return true;
+}
+
+// true: the soup of `path` was appended from its cache file
+bool soup_cache_load(const std::string& path, std::vector<float>& vertices, std::vector<float>& normals, size_t& num_tris) {
+  uint64_t size; int64_t mtime;
+  if (!source_stamp(path, size, mtime)) return false;
+  FILE* f = fopen((path + ".lisasoup").c_str(), "rb");
+  if (!f) return false;
+  SoupHeader h;
+  bool ok = fread(&h, sizeof(h), 1, f) == 1 && memcmp(h.magic, "LISASOUP", 8) == 0 && h.version == 1 && h.header_bytes == sizeof(h) &&
+            h.source_size == size && h.source_mtime_ns == mtime;
+  if (ok) {  // the file must hold exactly what the header promises
+    struct stat st;
+    ok = fstat(fileno(f), &st) == 0 && (uint64_t)st.st_size == sizeof(h) + h.num_triangles * 72ull;
+  }
+  if (ok) {
+    const size_t n = (size_t)h.num_triangles * 9, v0 = vertices.size(), n0 = normals.size();
+    vertices.resize(v0 + n);
+    normals.resize(n0 + n);
+    ok = (n == 0) || (fread(&vertices[v0], 4, n, f) == n && fread(&normals[n0], 4, n, f) == n);
+    if (!ok) { vertices.resize(v0); normals.resize(n0); }
+    else num_tris = (size_t)h.num_triangles;
+  }
+  fclose(f);
+  return ok;
+}
+
+void soup_cache_store(const std::string& path, const float* v, const float* n, size_t num_tris) {
+  SoupHeader h;
+  memset(&h, 0, sizeof(h));
+  memcpy(h.magic, "LISASOUP", 8);
+  h.version = 1; h.header_bytes = sizeof(h); h.num_triangles = num_tris;
+  if (!source_stamp(path, h.source_size, h.source_mtime_ns)) return;
+  const std::string dst = path + ".lisasoup", tmp = dst + ".tmp" + std::to_string((long)getpid());
+  FILE* f = fopen(tmp.c_str(), "wb");
+  if (!f) return;
+  const size_t cnt = num_tris * 9;
+  const bool ok = fwrite(&h, sizeof(h), 1, f) == 1 && (cnt == 0 || (fwrite(v, 4, cnt, f) == cnt && fwrite(n, 4, cnt, f) == cnt));
+  if (fclose(f) != 0 || !ok || rename(tmp.c_str(), dst.c_str()) != 0) remove(tmp.c_str());  // readers never see a partial file
+}
+
 }  // namespace
+
+void parse_obj_set_cache(int enabled) { g_obj_cache = enabled < 0 ? -1 : (enabled != 0); }
 
 namespace {
 
@@ -92,6 +170,17 @@ void parse_obj(const std::string& path, std::vector<float>& vertices, std::vecto
   auto T0 = tnow();
   FILE* f = fopen(path.c_str(), "rb");
   if (!f) throw SceneError(path + " not found.", -1);
+  const bool use_cache = obj_cache_enabled();
+  if (use_cache) {
+    size_t nt_cached = 0;
+    if (soup_cache_load(path, vertices, normals, nt_cached)) {
+      fclose(f);
+      mat_indices.resize(mat_indices.size() + nt_cached, mat_idx);
+      if (dbg) fprintf(stderr, "parse_obj: %zu triangles from %s.lisasoup in %.1f ms\n", nt_cached, path.c_str(), tms(T0, tnow()));
+      printf("Done. Imported %d triangles.\n", (int)nt_cached);
+      return;
+    }
+  }
   fseek(f, 0, SEEK_END);
   long size = ftell(f);
   fseek(f, 0, SEEK_SET);
@@ -192,6 +281,7 @@ void parse_obj(const std::string& path, std::vector<float>& vertices, std::vecto
     });
   });
   auto T5 = tnow();
+  if (use_cache) soup_cache_store(path, vertices.data() + v0, normals.data() + n0, tf);
   if (dbg) fprintf(stderr, "parse_obj: read %.1f chunk %.1f count %.1f v/vn %.1f faces %.1f ms (%zu chunks)\n", tms(T0, T1), tms(T1, T2), tms(T2, T3), tms(T3, T4), tms(T4, T5), chunks.size());
   printf("Done. Imported %d triangles.\n", (int)tf);
 }

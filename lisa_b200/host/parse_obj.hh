@@ -9,3 +9,6 @@
 // the file cannot be opened, like parse_obj.cc:66-67.
 void parse_obj(const std::string& obj_file_path, std::vector<float>& vertices, std::vector<float>& normals,
                std::vector<int32_t>& mat_indices, int mat_idx);
+
+// Binary soup cache next to the OBJ (<file>.lisasoup, see parse_obj.cc): 1 on, 0 off, -1 = as LISA_OBJ_CACHE says (default).
+void parse_obj_set_cache(int enabled);

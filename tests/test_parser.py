@@ -144,3 +144,48 @@ def test_parallel_obj_loader_matches_oracle(frontend, tmp_path, monkeypatch):
         np.testing.assert_array_equal(got["normals"], ref["normals"])
         np.testing.assert_array_equal(got["mat_indices"], ref["mat_indices"])
     assert got["vertices"].shape[0] == 3 * (2 * 60 * 16 + 1)
+
+
+def test_obj_soup_cache(frontend, tmp_path, capfd):
+    """Opt-in binary soup cache of the OBJ loader: written after a text parse, read back when the
+    OBJ is unchanged (same arrays, same two progress lines), ignored when stale or damaged, never written when off."""
+    obj = tmp_path / "t.obj"
+    obj.write_text("v 0 0 0\nv 1 0 0\nv 0 1 0\nv 0 0 1\nvn 0 0 1\nvn 1 0 0\nf 1//1 2//1 3//1\nf 1//2 3//2 4//2\n")
+    rto = tmp_path / "t.rto"
+    rto.write_text("material g { color = (1, 1, 1, 1)\n roughness = 1 }\nmesh { obj_file = %s\n material = g }\n"
+                   "mesh { obj_file = %s\n material = g }\n"
+                   "camera { position = (0,0,1) look_at = (0,0,0) fov = 40 }\nnum_samples = 1\nnum_bounces = 1\n"
+                   "width = 4\nheight = 4\noutput_image = x.ppm\n" % (obj, obj))
+    cache = tmp_path / "t.obj.lisasoup"
+    plain = frontend.parse_scene(str(rto))
+    assert not cache.exists()                      # off by default: nothing is written next to the inputs
+    frontend.set_obj_cache(True)
+    try:
+        capfd.readouterr()
+        first = frontend.parse_scene(str(rto))     # mesh 1 parses text and writes the cache, mesh 2 already reads it
+        out = capfd.readouterr().out
+        assert out == ("Importing %s...\nDone. Imported 2 triangles.\n" % obj) * 2
+        assert cache.exists() and cache.stat().st_size == 48 + 2 * 72
+        again = frontend.parse_scene(str(rto))
+        for k in ("vertices", "normals", "mat_indices"):
+            np.testing.assert_array_equal(first[k], plain[k])
+            np.testing.assert_array_equal(again[k], plain[k])
+        # the cache is really what is read: plant different numbers in it, keeping the header
+        raw = bytearray(cache.read_bytes())
+        raw[48:52] = np.float32(7.0).tobytes()
+        cache.write_bytes(bytes(raw))
+        assert frontend.parse_scene(str(rto))["vertices"][0, 0] == 7.0
+        # a truncated file is ignored (and rewritten from the text)
+        cache.write_bytes(bytes(raw[:100]))
+        np.testing.assert_array_equal(frontend.parse_scene(str(rto))["vertices"], plain["vertices"])
+        assert cache.stat().st_size == 48 + 2 * 72
+        # a changed OBJ makes it stale
+        obj.write_text(obj.read_text() + "f 2//1 3//1 4//1\n")
+        changed = frontend.parse_scene(str(rto))
+        assert changed["vertices"].shape[0] == 3 * 6 and cache.stat().st_size == 48 + 3 * 72
+        frontend.set_obj_cache(False)
+        cache.unlink()
+        frontend.parse_scene(str(rto))
+        assert not cache.exists()
+    finally:
+        frontend.set_obj_cache(None)
