@@ -124,7 +124,9 @@ typedef TravStack<uint2, LISA_STACK_SM, LISA_STACK_LOC> Stack;
 // bytes of dynamic shared memory a traversal kernel needs per thread
 #define LISA_STACK_SMEM_PER_THREAD (LISA_STACK_SM * 8)
 
-__device__ __forceinline__ float3 safe_rcp_dir(const float3& d, const float eps = 1e-30f) {
+// |component| clamped to 1e-20: the wide node test scales the reciprocal by 2^(e+15), which has to stay finite for any sane scene
+__device__ __forceinline__ float3 safe_rcp_dir(const float3& d) {
+  const float eps = 1e-20f;
   return f3(1.0f / (fabsf(d.x) > eps ? d.x : copysignf(eps, d.x)), 1.0f / (fabsf(d.y) > eps ? d.y : copysignf(eps, d.y)),
             1.0f / (fabsf(d.z) > eps ? d.z : copysignf(eps, d.z)));
 }
@@ -177,7 +179,7 @@ struct StepRay {        // per-ray constants kept in registers
 
 __device__ __forceinline__ StepRay step_ray(const float3& d) {
   StepRay r;
-  r.idir = safe_rcp_dir(d, 1e-20f);  // the wide node test scales it by 2^(e+15): keep that finite for any sane scene
+  r.idir = safe_rcp_dir(d);
   const float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
   r.kz = (ax > ay) ? (ax > az ? 0 : 2) : (ay > az ? 1 : 2);
   const float3 p = perm3(d, r.kz);
