@@ -2,6 +2,9 @@
 #include "devmem.h"
 
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <thread>
 #include <map>
 #include <mutex>
 #include <unordered_map>
@@ -109,6 +112,65 @@ void pinned_slot_free(void* p) {
   if (!p) return;
   std::lock_guard<std::mutex> lk(g_mu);
   g_pinned_free.push_back(p);
+}
+
+
+// ---- pinned, chunked upload ------------------------------------------------------------------------
+namespace {
+const size_t kChunk   = 16u << 20;
+const int    kWorkers = 4, kPerWorker = 2;  // 8 pinned buffers of 16 MB per process
+struct UploadRing {
+  std::mutex  mu;  // one upload at a time per process (the ring is shared)
+  char*       buf[kWorkers * kPerWorker] = {};
+  cudaEvent_t done[kWorkers * kPerWorker] = {};
+  bool        ok = false, tried = false;
+} g_ring;
+}  // namespace
+
+cudaError_t upload_async(void* dst, const void* src, size_t bytes, cudaStream_t st) {
+  size_t min_bytes = 1u << 30;  // measured on B200: 0.76 GB 70 ms plain vs 100-145 ms chunked (pinned ring set-up), 3.6 GB x 2: 675 vs 384 ms
+  if (const char* e = getenv("LISA_UPLOAD_CHUNKED_MIN")) min_bytes = (size_t)strtoull(e, nullptr, 10);
+  if (bytes == 0) return cudaSuccess;
+  if (bytes < min_bytes) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st);
+  std::lock_guard<std::mutex> lk(g_ring.mu);
+  if (!g_ring.tried) {
+    g_ring.tried = true;
+    g_ring.ok = true;
+    for (int k = 0; k < kWorkers * kPerWorker && g_ring.ok; k++)
+      g_ring.ok = cudaHostAlloc((void**)&g_ring.buf[k], kChunk, cudaHostAllocPortable) == cudaSuccess &&
+                  cudaEventCreateWithFlags(&g_ring.done[k], cudaEventDisableTiming) == cudaSuccess;
+    if (!g_ring.ok) (void)cudaGetLastError();  // no pinned memory to be had: plain copies from now on
+  }
+  if (!g_ring.ok) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st);
+  int device = 0;
+  cudaGetDevice(&device);
+  const char*  s = static_cast<const char*>(src);
+  char*        d = static_cast<char*>(dst);
+  const size_t chunks = (bytes + kChunk - 1) / kChunk;
+  cudaError_t  err[kWorkers];
+  // worker w stages chunks w, w + kWorkers, ... through its own two pinned buffers and issues their DMA itself: the
+  // destinations are disjoint, so the order in which the chunks reach the stream does not matter
+  auto work = [&](int w) {
+    err[w] = cudaSetDevice(device);
+    size_t mine = 0;
+    for (size_t k = (size_t)w; k < chunks && err[w] == cudaSuccess; k += kWorkers, mine++) {
+      const int    r   = w * kPerWorker + (int)(mine % kPerWorker);
+      const size_t off = k * kChunk, n = std::min(kChunk, bytes - off);
+      if (mine >= (size_t)kPerWorker) err[w] = cudaEventSynchronize(g_ring.done[r]);  // its previous DMA has drained
+      if (err[w] != cudaSuccess) break;
+      memcpy(g_ring.buf[r], s + off, n);
+      err[w] = cudaMemcpyAsync(d + off, g_ring.buf[r], n, cudaMemcpyHostToDevice, st);
+      if (err[w] == cudaSuccess) err[w] = cudaEventRecord(g_ring.done[r], st);
+    }
+  };
+  std::thread th[kWorkers];
+  for (int w = 1; w < kWorkers; w++) th[w] = std::thread(work, w);
+  work(0);
+  for (int w = 1; w < kWorkers; w++) th[w].join();
+  for (int w = 0; w < kWorkers; w++) if (err[w] != cudaSuccess) return err[w];
+  // the ring is reused by the next upload (possibly on another stream or device): wait until the DMA engine has
+  // drained it.  On return the copy is complete.
+  return cudaStreamSynchronize(st);
 }
 
 }  // namespace lisa

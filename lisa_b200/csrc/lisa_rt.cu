@@ -248,9 +248,10 @@ static int create_impl(const lisa_scene_desc* sd, const lisa_options* opt, lisa_
   CU(dev_alloc((void**)&d_emit, emit.size()));
   CU(dev_alloc((void**)&c->d_mats, sizeof(DMaterial) * mats.size()));
   if (T) {
-    CU(cudaMemcpyAsync(d_verts, sd->vertices, sizeof(float) * 9 * (size_t)T, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaMemcpyAsync(d_normals, sd->normals, sizeof(float) * 9 * (size_t)T, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaMemcpyAsync(d_mat_idx, sd->mat_indices, sizeof(int) * (size_t)T, cudaMemcpyHostToDevice, c->stream));
+    // large soups go through a ring of pinned buffers filled by worker threads (devmem.cu: upload_async)
+    CU(upload_async(d_verts, sd->vertices, sizeof(float) * 9 * (size_t)T, c->stream));
+    CU(upload_async(d_normals, sd->normals, sizeof(float) * 9 * (size_t)T, c->stream));
+    CU(upload_async(d_mat_idx, sd->mat_indices, sizeof(int) * (size_t)T, c->stream));
   }
   CU(cudaMemcpyAsync(d_emit, emit.data(), emit.size(), cudaMemcpyHostToDevice, c->stream));
   CU(cudaMemcpyAsync(c->d_mats, mats.data(), sizeof(DMaterial) * mats.size(), cudaMemcpyHostToDevice, c->stream));
