@@ -113,7 +113,7 @@ def test_node_planes_conservative_at_any_scale(rt, orc, scale, offset):
 
 def test_chunked_upload_is_exact(rt, monkeypatch):
     """lisa_create's pinned, chunked upload (devmem.cu: upload_async, used above 1 GB per array) forced on a 1.5M-triangle
-    soup (54 MB of vertices = 4 chunks over the 4 workers): same hits as the plain copy."""
+    soup (54 MB of vertices = 4 chunks over the 4 workers): same BVH and same hits as the plain copy."""
     rng = np.random.default_rng(5)
     T = 1_500_000
     c = rng.random((T, 1, 3), dtype=np.float32)
@@ -129,8 +129,8 @@ def test_chunked_upload_is_exact(rt, monkeypatch):
         R.close()
     np.testing.assert_array_equal(res[0][0], res[1][0])
     np.testing.assert_array_equal(res[0][1], res[1][1])
-    # (the PLOC builder's node count varies by a few nodes from build to build: merge order under atomics)
-    assert abs(res[0][2] - res[1][2]) <= 0.01 * res[1][2] and (res[0][0] >= 0).mean() > 0.05
+    assert res[0][2] == res[1][2]              # the builder is deterministic: same data, same tree
+    assert (res[0][0] >= 0).mean() > 0.05
 
 
 def rt_pack(mats):
