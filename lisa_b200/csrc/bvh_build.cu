@@ -249,7 +249,9 @@ __global__ void k_emit_binary(int n, const int2* __restrict__ child, const float
 }
 
 // ---- collapse to compressed 8-wide nodes --------------------------------------------------------
+#ifndef LEAF_MAX
 #define LEAF_MAX 3
+#endif
 struct WorkItem { int node2; int out; };  // binary node to expand -> index of the wide node to write
 
 __device__ __forceinline__ float half_area(const float4& lo, const float4& hi) {
