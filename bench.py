@@ -251,7 +251,7 @@ def main():
         agg["jobs"] += st["last_shadow_jobs"]
         agg["shadow_rays"] += st["last_shadow_rays"]
         agg["radiance_rays"] += st["last_radiance_rays"]
-        agg["launches"] += st["last_kernel_launches"] + 2  # + reset memsets are not kernels; finalize/init counted inside
+        agg["launches"] += st["last_kernel_launches"]  # our kernels only (k_pool/k_path + k_finalize; wavefront: every stage launch); R.reset() is a memset, the L2 flush is torch's fill
         agg["nodes"] += st["last_nodes_visited"]
         agg["tris"] += st["last_triangles_tested"]
         agg["culled"] += st["last_shadow_culled"]
