@@ -40,6 +40,29 @@ SCENE = "scenes/cornell_c2.rto"
 METRIC = "Msamples/s (Cornell 2000x2000, 7 bounces)"
 
 
+_JSON_FD = None
+
+
+def guard_stdout():
+    """From here on fd 1 is stderr for everybody (the OBJ loader's progress lines, NCCL's `NCCL version ...` banner when the
+    box sets NCCL_DEBUG): the ONE JSON line goes to the real stdout through emit()."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    sys.stdout.flush()
+    line = (json.dumps(obj) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, line)
+
+
 def parse_quiet(fe, path):
     """fe.parse_scene with the loader's `Importing ...` lines (the reference prints them on stdout, parse_obj.cc) sent to
     stderr, so that this script's stdout is the ONE JSON line."""
@@ -166,11 +189,12 @@ def run_reference(args, rank):
         out = dict(base, value=cb["value"], ms_per_step=round(w * h * S / (cb["value"] * 1e3), 1), cpu_baseline=cb, gpu_launches=0,
                    clocks={"sm_mhz": None, "sm_max_mhz": None, "reasons": []},
                    e2e={"value": cb["value"], "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
-    print(json.dumps(out))
+    emit(out)
     return 0
 
 
 def main():
+    guard_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=4)
@@ -381,7 +405,7 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(sc, S)
-        print(json.dumps(out))
+        emit(out)
     R.close()
     if world > 1:
         dist.barrier()
