@@ -16,6 +16,7 @@
 // Off by default: the reference never writes next to its inputs.
 #include "parse_obj.hh"
 
+#include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
 
@@ -44,7 +45,7 @@ struct Cursor {
   }
 };
 
-float to_float(const char* b, const char* e, const std::string& path, long line) {
+float to_float_slow(const char* b, const char* e, const std::string& path, long line) {
   char  buf[64];
   size_t n = (size_t)(e - b) < sizeof(buf) - 1 ? (size_t)(e - b) : sizeof(buf) - 1;
   memcpy(buf, b, n);
@@ -52,6 +53,64 @@ float to_float(const char* b, const char* e, const std::string& path, long line)
   char* q;
   float v = strtof(buf, &q);  // like std::stof: leading float, trailing characters ignored
   if (q == buf) throw SceneError(path + ":" + std::to_string(line) + ": not a number: '" + buf + "'", 1);
+  return v;
+}
+
+// The same value as strtof, without strtof, for the tokens OBJ files are made of: [+-]digits[.digits][e[+-]digits] with at
+// most 15 significant digits and a decimal exponent within +-22.  Then the decimal is w * 10^k with w < 2^53 and 10^|k|
+// exact in double, so ONE double multiplication or division gives the correctly rounded double (Clinger 1990), and
+// rounding that to float equals rounding the decimal itself to float unless the double sits exactly on the midpoint of two
+// floats (no float midpoint can lie strictly between a decimal and its nearest double: both are doubles).  Midpoints,
+// overflow, subnormal floats and every token of another shape (inf, nan, hex, trailing characters, too long) take the
+// strtof path, so the result is bit-identical to the reference's std::stof for every input.
+float to_float(const char* b, const char* e, const std::string& path, long line) {
+  static const double p10[23] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15, 1e16,
+                                 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
+  const char* p = b;
+  if (e - b > 40 || p >= e) return to_float_slow(b, e, path, line);
+  bool neg = false;
+  if (*p == '-' || *p == '+') { neg = *p == '-'; p++; }
+  uint64_t w = 0;
+  int      sig = 0, k = 0, ndig = 0;  // significant digits taken, decimal exponent, digits seen
+  for (; p < e && *p >= '0' && *p <= '9'; p++, ndig++) {
+    if (sig || *p != '0') { if (sig < 15) { w = w * 10 + (uint64_t)(*p - '0'); sig++; } else return to_float_slow(b, e, path, line); }
+  }
+  if (p < e && *p == '.') {
+    p++;
+    for (; p < e && *p >= '0' && *p <= '9'; p++, ndig++) {
+      if (sig || *p != '0') { if (sig < 15) { w = w * 10 + (uint64_t)(*p - '0'); sig++; } else return to_float_slow(b, e, path, line); }
+      k--;
+    }
+  }
+  if (ndig == 0) return to_float_slow(b, e, path, line);
+  if (p < e && (*p == 'e' || *p == 'E')) {
+    p++;
+    bool eneg = false;
+    if (p < e && (*p == '-' || *p == '+')) { eneg = *p == '-'; p++; }
+    int ex = 0, nd = 0;
+    for (; p < e && *p >= '0' && *p <= '9' && nd < 4; p++, nd++) ex = ex * 10 + (*p - '0');
+    if (nd == 0 || nd == 4) return to_float_slow(b, e, path, line);
+    k += eneg ? -ex : ex;
+  }
+  if (p != e || k < -22 || k > 22) return to_float_slow(b, e, path, line);
+  double d = (double)w;
+  d = k >= 0 ? d * p10[k] : d / p10[-k];
+  if (d != 0.0) {
+    uint64_t bits;
+    memcpy(&bits, &d, 8);
+    if (d > 3.0e38 || d < 2.0e-38 || (bits & 0x1fffffffull) == 0x10000000ull) return to_float_slow(b, e, path, line);
+  }
+  const float f = (float)d;
+  return neg ? -f : f;
+}
+
+// 1-based index at the start of [b, e): plain digits take the short way, anything else is strtol's business
+inline long to_index(const char* b, const char* e) {
+  const char* p = b;
+  long v = 0;
+  int  n = 0;
+  for (; p < e && *p >= '0' && *p <= '9' && n < 18; p++, n++) v = v * 10 + (*p - '0');
+  if (n == 0 || n == 18) return strtol(b, nullptr, 10);
   return v;
 }
 
@@ -184,13 +243,31 @@ void parse_obj(const std::string& path, std::vector<float>& vertices, std::vecto
   fseek(f, 0, SEEK_END);
   long size = ftell(f);
   fseek(f, 0, SEEK_SET);
-  std::vector<char> data((size_t)size + 1);
-  if (size > 0 && fread(data.data(), 1, (size_t)size, f) != (size_t)size) {
-    fclose(f);
-    throw SceneError(path + ": read error", -1);
+  // The text is scanned in place.  Mapped straight from the page cache when the file does not end on a page boundary (the
+  // zero tail of its last page then terminates a number that runs to the end of the file); read into a buffer with a
+  // newline sentinel otherwise.
+  struct Mapping {
+    void* p = MAP_FAILED; size_t n = 0;
+    ~Mapping() { if (p != MAP_FAILED) munmap(p, n); }
+  } map;
+  std::vector<char> buffer;
+  const char*       text = nullptr;
+  const long        page = sysconf(_SC_PAGESIZE);
+  if (size > 0 && page > 0 && size % page != 0 && !getenv("LISA_OBJ_NO_MMAP")) {
+    map.p = mmap(nullptr, (size_t)size, PROT_READ, MAP_PRIVATE | MAP_POPULATE, fileno(f), 0);
+    map.n = (size_t)size;
+    if (map.p != MAP_FAILED) text = static_cast<const char*>(map.p);
+  }
+  if (!text) {
+    buffer.resize((size_t)size + 1);
+    if (size > 0 && fread(buffer.data(), 1, (size_t)size, f) != (size_t)size) {
+      fclose(f);
+      throw SceneError(path + ": read error", -1);
+    }
+    buffer[(size_t)size] = '\n';
+    text = buffer.data();
   }
   fclose(f);
-  data[(size_t)size] = '\n';
 
   auto T1 = tnow();
   // chunks of whole lines, one per worker (a single chunk below 4 MB)
@@ -199,7 +276,7 @@ void parse_obj(const std::string& path, std::vector<float>& vertices, std::vecto
   if (const char* e = getenv("LISA_OBJ_THREADS")) nthreads = (unsigned)std::max(1, atoi(e));
   std::vector<Chunk> chunks;
   {
-    const char* base = data.data();
+    const char* base = text;
     const char* stop = base + size;
     const char* p = base;
     for (unsigned k = 0; k < nthreads && p < stop; k++) {
@@ -271,7 +348,7 @@ void parse_obj(const std::string& path, std::vector<float>& vertices, std::vecto
         const char* s1 = (const char*)memchr(b, '/', (size_t)(e - b));
         const char* s2 = s1 ? (const char*)memchr(s1 + 1, '/', (size_t)(e - s1 - 1)) : nullptr;
         if (!s2) throw SceneError(path + ":" + std::to_string(line_no) + ": face vertex without normal index", 1);
-        const long vi = strtol(b, nullptr, 10), ni = strtol(s2 + 1, nullptr, 10);
+        const long vi = to_index(b, s1), ni = to_index(s2 + 1, e);
         if (vi < 1 || (size_t)vi > tv || ni < 1 || (size_t)ni > tn)
           throw SceneError(path + ":" + std::to_string(line_no) + ": index out of range", 1);
         memcpy(&vertices[v0 + 9 * it + 3 * j], &vt[3 * (vi - 1)], 12);

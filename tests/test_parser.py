@@ -189,3 +189,55 @@ def test_obj_soup_cache(frontend, tmp_path, capfd):
         assert not cache.exists()
     finally:
         frontend.set_obj_cache(None)
+
+
+def test_obj_float_parsing_matches_strtof(frontend, tmp_path):
+    """The loader's own decimal -> float conversion (host/parse_obj.cc: to_float, one double operation + midpoint
+    check) must give the bits of strtof — what the reference's std::stof returns — for every token: random decimals
+    of every shape, exact float midpoints (where rounding through double would differ), range limits, signed zeros."""
+    import ctypes
+    from decimal import Decimal, getcontext
+    getcontext().prec = 60
+    libc = ctypes.CDLL(None)
+    libc.strtof.restype = ctypes.c_float
+    libc.strtof.argtypes = [ctypes.c_char_p, ctypes.c_void_p]
+    rng = np.random.default_rng(123)
+    toks = ["0", "-0", "+0.0", "1.", ".5", "-.25", "+3", "1e5", "1E-5", "2.5e+3", "123456789012345", "1234567890123456",
+            "0.000000000000000000001", "3.4028234e38", "3.4028236e38", "1.17549435e-38", "1e-45", "7e-46", "1e22", "1e23",
+            "16777217", "16777219", "0.1", "0.30000001192092896", "9007199254740993", "1e0005", "00012.5", "1.5000000000000000000"]
+    for _ in range(30000):
+        nd = int(rng.integers(1, 18))
+        digits = "".join(str(int(x)) for x in rng.integers(0, 10, nd))
+        dot = int(rng.integers(0, nd + 1))
+        t = digits[:dot] + ("." + digits[dot:] if rng.random() < 0.8 else digits[dot:])
+        if t in (".", ""):
+            t = "0"
+        if rng.random() < 0.3:
+            t += "eE"[int(rng.integers(0, 2))] + ["", "+", "-"][int(rng.integers(0, 3))] + str(int(rng.integers(0, 40)))
+        toks.append(["", "-", "+"][int(rng.integers(0, 3))] + t)
+    for _ in range(4000):  # exact midpoints between neighbouring floats, and their neighbourhood, at several lengths
+        f = np.float32(rng.standard_normal() * 10.0 ** float(rng.integers(-6, 7)))
+        g = np.nextafter(f, np.float32(np.inf))
+        mid = (Decimal(float(f)) + Decimal(float(g))) / 2
+        toks.append(format(mid, "f"))
+        toks.append(format(mid.quantize(Decimal(1).scaleb(mid.adjusted() - int(rng.integers(6, 16)))), "f"))
+        toks.append("%.9g" % float(f))
+    toks = [t for t in toks if len(t) < 60]
+    obj = tmp_path / "f.obj"
+    n = len(toks) // 3 * 3
+    with open(obj, "w") as fh:
+        for i in range(0, n, 3):
+            fh.write("v %s %s %s\n" % (toks[i], toks[i + 1], toks[i + 2]))
+        fh.write("vn 0 0 1\n")
+        for i in range(n // 3 // 3):
+            fh.write("f %d//1 %d//1 %d//1\n" % (3 * i + 1, 3 * i + 2, 3 * i + 3))
+    rto = tmp_path / "f.rto"
+    rto.write_text("material g { color = (1, 1, 1, 1)\n roughness = 1 }\nmesh { obj_file = %s\n material = g }\n"
+                   "camera { position = (0,0,1) look_at = (0,0,0) fov = 40 }\nnum_samples = 1\nnum_bounces = 1\n"
+                   "width = 4\nheight = 4\noutput_image = x.ppm\n" % obj)
+    got = frontend.parse_scene(str(rto))["vertices"].reshape(-1)
+    used = toks[:len(got)]
+    want = np.array([libc.strtof(t.encode(), None) for t in used], dtype=np.float32)
+    bad = np.nonzero(got.view(np.uint32) != want.view(np.uint32))[0]
+    assert len(bad) == 0, [(used[i], float(got[i]), float(want[i])) for i in bad[:10]]
+    assert len(got) > 40000
