@@ -158,6 +158,11 @@ int lisa_read_rgba8(lisa_ctx* ctx, uint8_t* rgba);
 /* Vertically flipped binary PPM as sutil::saveImage/savePPM (src/sutil/sutil.cpp:523-554, 97-117).
  * path == NULL uses scene->output_image. */
 int lisa_write_ppm(lisa_ctx* ctx, const char* path);
+/* save_image() -> sutil::saveImage (src/LiSA/src/render.cc:9-17, src/sutil/sutil.cpp:523-688) for the uchar4 frame the
+ * reference hands it: the last three characters of the name pick the format — "ppm"/"PPM" the flipped P6 above,
+ * "png"/"PNG" an 8-bit RGBA PNG (flipped, alpha 255), "exr"/"EXR" and anything else fail with the reference's message
+ * (LISA_ERR_ARG), as does a name shorter than 5 characters.  path == NULL uses scene->output_image. */
+int lisa_write_image(lisa_ctx* ctx, const char* path);
 /* Linear float image (Portable Float Map, RGB, little endian): the accumulators without the 8-bit sRGB quantisation,
  * for parity tooling (the reference can only write the quantised PPM; README.md:183 lists float output as a TODO). */
 int lisa_write_pfm(lisa_ctx* ctx, const char* path);

@@ -181,21 +181,27 @@ __device__ __forceinline__ float merged_half_area(const float4& l0, const float4
   return dx * dy + dy * dz + dz * dx;
 }
 
-// nearest neighbour of cluster i among positions [i-r, i+r]; ties go to the smaller position, which guarantees
-// that at least one mutual pair exists every round
+// nearest neighbour of cluster i among positions [i-r, i+r] by merged surface area.  Ties are broken by a key that is
+// SYMMETRIC in the pair — (distance in the order, parity of the lower position, lower position) — so candidate pairs
+// are totally ordered, the best pair overall is always mutual (progress every round), and a run of coincident boxes
+// (equal areas everywhere) pairs up (0,1), (2,3), ... and halves per round: a balanced tree, where "smallest position
+// wins" made every cluster point at the start of the run and merged ONE pair per round into a chain.
 __global__ void k_ploc_nn(const int* __restrict__ C, int m, const float4* __restrict__ box_lo, const float4* __restrict__ box_hi,
                           int r, int* nn) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m) return;
   const float4 l = box_lo[C[i]], h = box_hi[C[i]];
-  float best = FLT_MAX;
-  int   bj = -1;
+  float    best = FLT_MAX;
+  unsigned bkey = 0xffffffffu;
+  int      bj = -1;
   const int j0 = max(0, i - r), j1 = min(m - 1, i + r);
   for (int j = j0; j <= j1; j++) {
     if (j == i) continue;
-    const int   c = C[j];
-    const float a = merged_half_area(l, h, box_lo[c], box_hi[c]);
-    if (a < best) { best = a; bj = j; }
+    const int      c = C[j];
+    const float    a = merged_half_area(l, h, box_lo[c], box_hi[c]);
+    const int      lo = min(i, j);
+    const unsigned key = ((unsigned)abs(j - i) << 1) | ((unsigned)lo & 1u);  // same distance + same parity: the lower j comes first in the scan
+    if (a < best || (a == best && key < bkey)) { best = a; bkey = key; bj = j; }
   }
   nn[i] = bj;
 }

@@ -121,8 +121,7 @@ const size_t kChunk   = 16u << 20;
 const int    kWorkers = 4, kPerWorker = 2;  // 8 pinned buffers of 16 MB per process
 struct UploadRing {
   std::mutex  mu;  // one upload at a time per process (the ring is shared)
-  char*       buf[kWorkers * kPerWorker] = {};
-  cudaEvent_t done[kWorkers * kPerWorker] = {};
+  char*       buf[kWorkers * kPerWorker] = {};  // portable pinned memory: usable from any device
   bool        ok = false, tried = false;
 } g_ring;
 }  // namespace
@@ -137,13 +136,22 @@ cudaError_t upload_async(void* dst, const void* src, size_t bytes, cudaStream_t 
     g_ring.tried = true;
     g_ring.ok = true;
     for (int k = 0; k < kWorkers * kPerWorker && g_ring.ok; k++)
-      g_ring.ok = cudaHostAlloc((void**)&g_ring.buf[k], kChunk, cudaHostAllocPortable) == cudaSuccess &&
-                  cudaEventCreateWithFlags(&g_ring.done[k], cudaEventDisableTiming) == cudaSuccess;
+      g_ring.ok = cudaHostAlloc((void**)&g_ring.buf[k], kChunk, cudaHostAllocPortable) == cudaSuccess;
     if (!g_ring.ok) (void)cudaGetLastError();  // no pinned memory to be had: plain copies from now on
   }
   if (!g_ring.ok) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st);
   int device = 0;
   cudaGetDevice(&device);
+  // an event can only be recorded on a stream of the device it was created on, and the ring serves every device of the
+  // process (render_multi creates one context per GPU): the "buffer drained" events are made per call, on `st`'s device
+  struct Events {
+    cudaEvent_t e[kWorkers * kPerWorker] = {};
+    ~Events() { for (cudaEvent_t x : e) if (x) cudaEventDestroy(x); }
+  } done;
+  for (cudaEvent_t& x : done.e) {
+    const cudaError_t ce = cudaEventCreateWithFlags(&x, cudaEventDisableTiming);
+    if (ce != cudaSuccess) return ce;
+  }
   const char*  s = static_cast<const char*>(src);
   char*        d = static_cast<char*>(dst);
   const size_t chunks = (bytes + kChunk - 1) / kChunk;
@@ -156,11 +164,11 @@ cudaError_t upload_async(void* dst, const void* src, size_t bytes, cudaStream_t 
     for (size_t k = (size_t)w; k < chunks && err[w] == cudaSuccess; k += kWorkers, mine++) {
       const int    r   = w * kPerWorker + (int)(mine % kPerWorker);
       const size_t off = k * kChunk, n = std::min(kChunk, bytes - off);
-      if (mine >= (size_t)kPerWorker) err[w] = cudaEventSynchronize(g_ring.done[r]);  // its previous DMA has drained
+      if (mine >= (size_t)kPerWorker) err[w] = cudaEventSynchronize(done.e[r]);  // its previous DMA has drained
       if (err[w] != cudaSuccess) break;
       memcpy(g_ring.buf[r], s + off, n);
       err[w] = cudaMemcpyAsync(d + off, g_ring.buf[r], n, cudaMemcpyHostToDevice, st);
-      if (err[w] == cudaSuccess) err[w] = cudaEventRecord(g_ring.done[r], st);
+      if (err[w] == cudaSuccess) err[w] = cudaEventRecord(done.e[r], st);
     }
   };
   std::thread th[kWorkers];
@@ -169,7 +177,7 @@ cudaError_t upload_async(void* dst, const void* src, size_t bytes, cudaStream_t 
   for (int w = 1; w < kWorkers; w++) th[w].join();
   for (int w = 0; w < kWorkers; w++) if (err[w] != cudaSuccess) return err[w];
   // the ring is reused by the next upload (possibly on another stream or device): wait until the DMA engine has
-  // drained it.  On return the copy is complete.
+  // drained it (which also makes it safe to destroy this call's events).  On return the copy is complete.
   return cudaStreamSynchronize(st);
 }
 

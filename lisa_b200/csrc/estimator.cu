@@ -240,6 +240,14 @@ void launch_trace_shadow(const DScene& sc, const float* d_org, const float* d_di
 void launch_primary_rays(const DCamera& cam, uint32_t subframe, float* d_dirs, uint32_t* d_seeds, cudaStream_t st) {
   k_primary_rays<<<cdiv(cam.width * cam.height, 256), 256, 0, st>>>(cam, subframe, d_dirs, d_seeds);
 }
+// traversal-stack overflow flag of the current device (traverse.cuh): copied into *h_pinned on `st`, then cleared
+cudaError_t fetch_trav_overflow(unsigned int* h_pinned, cudaStream_t st) {
+  cudaError_t e = cudaMemcpyFromSymbolAsync(h_pinned, g_trav_overflow, sizeof(unsigned int), 0, cudaMemcpyDeviceToHost, st);
+  if (e != cudaSuccess) return e;
+  static const unsigned int zero = 0u;
+  return cudaMemcpyToSymbolAsync(g_trav_overflow, &zero, sizeof(unsigned int), 0, cudaMemcpyHostToDevice, st);
+}
+int traversal_stack_entries() { return LISA_STACK_TOTAL; }
 int launch_kat(int what, uint32_t n, const float* in_f, const uint32_t* in_u, float* out_f, uint32_t* out_u, cudaStream_t st) {
   if (what < 0 || what > 9) return -1;
   if (n) k_kat<<<cdiv(n, 128), 128, 0, st>>>(what, n, in_f, in_u, out_f, out_u);

@@ -70,6 +70,11 @@ void launch_pool(const DScene& sc, const DState& s, const DCamera& cam, const Ti
 // the whole tile in one persistent launch (chains fetched from a cursor in s.ring[0]; only s.sum, s.ring, s.stats are used)
 void launch_path(const DScene& sc, const DState& s, const DCamera& cam, const Tile& t, const LaunchCfg& cfg, cudaStream_t st);
 
+// Copies the device's "a traversal stack was full" flag (traverse.cuh: g_trav_overflow) to pinned host memory on `st` and
+// clears it.  Non-zero after the stream is synchronised means some ray skipped a subtree: the caller must fail.
+cudaError_t fetch_trav_overflow(unsigned int* h_pinned, cudaStream_t st);
+int         traversal_stack_entries();  // capacity of a ray's traversal stack (LISA_STACK_TOTAL)
+
 // diagnostics
 void launch_trace_closest(const DScene& sc, const float* d_org, const float* d_dir, uint32_t n, float tmin, float tmax,
                           int* d_prim, float* d_t, cudaStream_t st);

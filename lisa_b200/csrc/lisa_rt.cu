@@ -90,6 +90,13 @@ static void drain_stage_events(lisa_ctx* c) {
   c->ev_used = 0;
 }
 
+// the pinned slot behind h_stats is 256 bytes: the 16 counters, then the traversal-stack overflow flag
+static unsigned int* overflow_slot(lisa_ctx* c) { return reinterpret_cast<unsigned int*>(c->h_stats + 16); }
+static int stack_overflow_error() {
+  return fail(LISA_ERR_STATE, "traversal stack overflow: the BVH is deeper than %d levels of 8-wide nodes (a chain-shaped "
+              "hierarchy); some rays skipped a subtree, so the result is discarded", traversal_stack_entries());
+}
+
 extern "C" const char* lisa_last_error(void) { return g_err; }
 extern "C" int         lisa_version(void) { return LISA_RT_VERSION; }
 
@@ -317,7 +324,7 @@ static int create_impl(const lisa_scene_desc* sd, const lisa_options* opt, lisa_
   CU(cudaMemsetAsync(c->state.stats, 0, sizeof(unsigned long long) * 16, c->stream));
   c->h_stats = (unsigned long long*)pinned_slot_alloc();
   if (!c->h_stats) return fail(LISA_ERR_NOMEM, "pinned host allocation failed");
-  memset(c->h_stats, 0, sizeof(unsigned long long) * 16);
+  memset(c->h_stats, 0, 256);
 
   c->cfg.sm_count = di.sms;
   c->cfg.extend_block = 128;  // __launch_bounds__(128, 6): 80 registers/thread, 6 CTAs = 24 warps per SM
@@ -493,8 +500,10 @@ extern "C" int lisa_render_subframes(lisa_ctx* c, uint32_t first, uint32_t count
   }
   CU(cudaEventRecord(c->ev1, c->stream));
   CU(cudaMemcpyAsync(c->h_stats, c->state.stats, sizeof(before), cudaMemcpyDeviceToHost, c->stream));
+  CU(fetch_trav_overflow(overflow_slot(c), c->stream));
   CU(cudaStreamSynchronize(c->stream));
   CU(cudaGetLastError());
+  if (*overflow_slot(c)) return stack_overflow_error();
   float ms = 0;
   cudaEventElapsedTime(&ms, c->ev0, c->ev1);
   lisa_stats& s = c->stats;
@@ -572,6 +581,82 @@ extern "C" int lisa_write_ppm(lisa_ctx* c, const char* path) {
   }
   fclose(f);
   return LISA_OK;
+}
+
+// ---- PNG (RGBA8, no compression: zlib "stored" blocks) --------------------------------------------------------
+static uint32_t crc32_update(uint32_t crc, const uint8_t* p, size_t n) {
+  static uint32_t table[256];
+  static bool     ready = false;
+  if (!ready) {
+    for (uint32_t i = 0; i < 256; i++) {
+      uint32_t c = i;
+      for (int k = 0; k < 8; k++) c = (c & 1u) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
+      table[i] = c;
+    }
+    ready = true;
+  }
+  for (size_t i = 0; i < n; i++) crc = table[(crc ^ p[i]) & 0xffu] ^ (crc >> 8);
+  return crc;
+}
+static void put_be32(std::vector<uint8_t>& v, uint32_t x) { for (int s = 24; s >= 0; s -= 8) v.push_back((uint8_t)(x >> s)); }
+static bool png_chunk(FILE* f, const char* type, const std::vector<uint8_t>& data) {
+  std::vector<uint8_t> head;
+  put_be32(head, (uint32_t)data.size());
+  uint32_t crc = crc32_update(0xffffffffu, (const uint8_t*)type, 4);
+  crc = crc32_update(crc, data.data(), data.size()) ^ 0xffffffffu;
+  std::vector<uint8_t> tail;
+  put_be32(tail, crc);
+  return fwrite(head.data(), 1, 4, f) == 4 && fwrite(type, 1, 4, f) == 4 &&
+         (data.empty() || fwrite(data.data(), 1, data.size(), f) == data.size()) && fwrite(tail.data(), 1, 4, f) == 4;
+}
+
+// sutil::saveImage's PNG branch (sutil.cpp:600-613): the uchar4 frame, all four components, flipped vertically
+static int write_png(lisa_ctx* c, const char* path) {
+  std::vector<uint8_t> px((size_t)c->width * c->height * 4);
+  int rc = lisa_read_rgba8(c, px.data());
+  if (rc) return rc;
+  const size_t row = (size_t)c->width * 4;
+  std::vector<uint8_t> raw;  // filter byte 0 + row, rows top to bottom
+  raw.reserve((row + 1) * c->height);
+  for (int y = (int)c->height - 1; y >= 0; y--) {
+    raw.push_back(0);
+    raw.insert(raw.end(), px.begin() + (size_t)y * row, px.begin() + (size_t)(y + 1) * row);
+  }
+  std::vector<uint8_t> z;  // zlib stream of stored blocks
+  z.push_back(0x78); z.push_back(0x01);
+  uint32_t a = 1, b = 0;  // adler32
+  for (size_t off = 0; off < raw.size() || off == 0; off += 65535) {
+    const size_t n = std::min<size_t>(65535, raw.size() - off);
+    z.push_back(off + n >= raw.size() ? 1 : 0);
+    z.push_back((uint8_t)(n & 0xff)); z.push_back((uint8_t)(n >> 8));
+    z.push_back((uint8_t)(~n & 0xff)); z.push_back((uint8_t)((~n >> 8) & 0xff));
+    z.insert(z.end(), raw.begin() + off, raw.begin() + off + n);
+    for (size_t i = off; i < off + n; i++) { a = (a + raw[i]) % 65521u; b = (b + a) % 65521u; }
+    if (raw.empty()) break;
+  }
+  put_be32(z, (b << 16) | a);
+  FILE* f = fopen(path, "wb");
+  if (!f) return fail(LISA_ERR_IO, "cannot open %s for writing", path);
+  static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', '\r', '\n', 0x1a, '\n'};
+  std::vector<uint8_t> ihdr;
+  put_be32(ihdr, c->width); put_be32(ihdr, c->height);
+  ihdr.push_back(8); ihdr.push_back(6); ihdr.push_back(0); ihdr.push_back(0); ihdr.push_back(0);  // 8 bit RGBA
+  bool ok = fwrite(sig, 1, 8, f) == 8 && png_chunk(f, "IHDR", ihdr) && png_chunk(f, "IDAT", z) && png_chunk(f, "IEND", {});
+  ok = (fclose(f) == 0) && ok;
+  return ok ? LISA_OK : fail(LISA_ERR_IO, "short write to %s", path);
+}
+
+extern "C" int lisa_write_image(lisa_ctx* c, const char* path) {
+  if (!c) return fail(LISA_ERR_ARG, "null ctx");
+  if (!path) path = c->output_image.c_str();
+  const std::string filename(path ? path : "");
+  // sutil::saveImage (sutil.cpp:523-530, 600, 636, 685-688): the LAST THREE characters name the format
+  if (filename.length() < 5) return fail(LISA_ERR_ARG, "sutil::saveImage(): Failed to determine filename extension");
+  const std::string ext = filename.substr(filename.length() - 3);
+  if (ext == "PPM" || ext == "ppm") return lisa_write_ppm(c, filename.c_str());
+  if (ext == "PNG" || ext == "png") return write_png(c, filename.c_str());
+  if (ext == "EXR" || ext == "exr") return fail(LISA_ERR_ARG, "sutil::saveImage(): saving of uchar4 images to EXR not implemented yet");
+  return fail(LISA_ERR_ARG, "sutil::saveImage(): Failed unsupported filetype '%s'", ext.c_str());
 }
 
 extern "C" int lisa_write_pfm(lisa_ctx* c, const char* path) {
@@ -712,8 +797,10 @@ extern "C" int lisa_trace_closest(lisa_ctx* c, const float* org, const float* di
   std::vector<int> f2o((size_t)c->scene.num_tris);
   if (c->scene.num_tris)
     CU(cudaMemcpyAsync(f2o.data(), c->bvh.d_final_to_orig, sizeof(int) * f2o.size(), cudaMemcpyDeviceToHost, c->stream));
+  CU(fetch_trav_overflow(overflow_slot(c), c->stream));
   CU(cudaStreamSynchronize(c->stream));
   CU(cudaGetLastError());
+  if (*overflow_slot(c)) return stack_overflow_error();
   for (uint32_t i = 0; i < n; i++) prim[i] = fp[i] >= 0 ? f2o[fp[i]] : -1;
   return LISA_OK;
 }
@@ -730,8 +817,10 @@ extern "C" int lisa_trace_shadow(lisa_ctx* c, const float* org, const float* dir
   launch_trace_shadow(c->scene, d_o.p, d_d.p, n, tmin, tmax, d_oc.p, d_l.p, c->stream);
   CU(cudaMemcpyAsync(outcome, d_oc.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
   if (light) CU(cudaMemcpyAsync(light, d_l.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+  CU(fetch_trav_overflow(overflow_slot(c), c->stream));
   CU(cudaStreamSynchronize(c->stream));
   CU(cudaGetLastError());
+  if (*overflow_slot(c)) return stack_overflow_error();
   return LISA_OK;
 }
 

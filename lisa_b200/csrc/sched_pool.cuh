@@ -193,12 +193,16 @@ __global__ void __launch_bounds__(128, LISA_POOL_MIN_BLOCKS) k_pool(DScene sc, D
           if (start_rad && rd.x == 0.0f && rd.y == 0.0f && rd.z == 0.0f) { n_null++; to_pending = true; }
           else {
             if (start_rad) n_rad++;
-            const StepRay r = step_ray(rd);
-            f4 = make_float4(r.idir.x, r.idir.y, r.idir.z, __uint_as_float(r.oct_inv4));
-            h4 = make_float4(r.Sx, r.Sy, r.Sz, __int_as_float(r.kz));
             if (!hits_emitter_bounds(sc, mo, rd, LISA_TMIN, LISA_TMAX)) kind |= 2u;
-            if ((kind & 2u) && sc.root_other < 0) to_pending = true;  // nothing to traverse: a miss
-            else to_ready = true;
+            // nothing to traverse (no emitter in reach and no other triangle at all): the slot goes straight back to the
+            // pending queue and F must keep the MISS record (0, 0, 0, -1) — the ray set-up is stored only for the ready queue
+            if ((kind & 2u) && sc.root_other < 0) to_pending = true;
+            else {
+              const StepRay r = step_ray(rd);
+              f4 = make_float4(r.idir.x, r.idir.y, r.idir.z, __uint_as_float(r.oct_inv4));
+              h4 = make_float4(r.Sx, r.Sy, r.Sz, __int_as_float(r.kz));
+              to_ready = true;
+            }
           }
         } else if (chain < 0 && !(exhausted && wnext == wend)) {
           to_pending = true;  // this batch ran dry mid-fetch: ask again

@@ -93,6 +93,11 @@ __device__ __forceinline__ bool intersect_tri(const RayPre& r, const float3& v0,
 // ------------------------------------------------------------------------------------------------
 // Traversal stack: NS entries in shared memory, NL more in local memory
 // ------------------------------------------------------------------------------------------------
+// Set when a push finds the stack full (NS + NL entries): that subtree is then NOT traversed, so the host fails the
+// call that ran the kernel (lisa_rt.cu: LISA_ERR_STATE) instead of returning an image with hits missing.  The builders do
+// not bound the depth of the tree; a full stack takes a chain-shaped hierarchy of depth > NS + NL 8-wide levels.
+static __device__ unsigned int g_trav_overflow = 0u;
+
 template <typename T, int NS, int NL>
 struct TravStack {
   T*  sm;      // this thread's column of the block's shared array
@@ -103,7 +108,8 @@ struct TravStack {
   __device__ __forceinline__ void push(const T& v) {
     if (sp < NS) sm[sp * stride] = v;
     else if (sp < NS + NL) loc[sp - NS] = v;
-    sp++;  // beyond NS+NL entries are dropped (cannot happen: builders bound the depth, see bvh_build.cu)
+    else { g_trav_overflow = 1u; return; }  // full: the entry is dropped (pop stays in bounds) and the call fails
+    sp++;
   }
   __device__ __forceinline__ T pop() {
     sp--;
@@ -119,7 +125,10 @@ struct TravStack {
 #ifndef LISA_STACK_SM
 #define LISA_STACK_SM 4
 #endif
-#define LISA_STACK_LOC (64 - LISA_STACK_SM)
+#ifndef LISA_STACK_TOTAL
+#define LISA_STACK_TOTAL 64  // entries before a push overflows (the test build liblisa_rt_tinystack.so shrinks it to provoke that)
+#endif
+#define LISA_STACK_LOC (LISA_STACK_TOTAL - LISA_STACK_SM)
 typedef TravStack<uint2, LISA_STACK_SM, LISA_STACK_LOC> Stack;
 // bytes of dynamic shared memory a traversal kernel needs per thread
 #define LISA_STACK_SMEM_PER_THREAD (LISA_STACK_SM * 8)

@@ -104,14 +104,22 @@ float to_float(const char* b, const char* e, const std::string& path, long line)
   return neg ? -f : f;
 }
 
-// 1-based index at the start of [b, e): plain digits take the short way, anything else is strtol's business
+// 1-based index held by the field [b, e)
 inline long to_index(const char* b, const char* e) {
+  // the field is [b, e): nothing outside it is ever read (the text may end right behind the last token).  An empty
+  // field ("f 1// 2//2 3//3") yields 0, which the caller reports as an index out of range — the reference's
+  // std::stoi throws on it (parse_obj.cc:52-54).  A sign is accepted like stoi does; negative indices are out of range.
   const char* p = b;
+  bool neg = false;
+  if (p < e && (*p == '+' || *p == '-')) { neg = *p == '-'; p++; }
   long v = 0;
   int  n = 0;
-  for (; p < e && *p >= '0' && *p <= '9' && n < 18; p++, n++) v = v * 10 + (*p - '0');
-  if (n == 0 || n == 18) return strtol(b, nullptr, 10);
-  return v;
+  for (; p < e && *p >= '0' && *p <= '9'; p++, n++) {
+    if (n >= 18) return neg ? -1 : (long)0x7fffffffffffffffL;  // more digits than any index can have: out of range either way
+    v = v * 10 + (*p - '0');
+  }
+  if (n == 0) return 0;
+  return neg ? -v : v;
 }
 
 // ---- binary soup cache ---------------------------------------------------------------------------

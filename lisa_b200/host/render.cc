@@ -13,8 +13,8 @@ static void check(int rc, const char* what) {
   if (rc != LISA_OK) throw std::runtime_error(std::string(what) + ": " + lisa_last_error());
 }
 
-static void save_image(lisa_ctx* ctx, const lisa_scene_desc& params) {  // render.cc:9-17
-  check(lisa_write_ppm(ctx, params.output_image), "save_image");
+static void save_image(lisa_ctx* ctx, const lisa_scene_desc& params) {  // render.cc:9-17: sutil::saveImage picks the format by extension
+  check(lisa_write_image(ctx, params.output_image), "save_image");
 }
 
 void render(lisa_ctx* ctx, const lisa_scene_desc& params) {

@@ -85,6 +85,7 @@ _L.lisa_read_accum.argtypes = [_vp, _vp]
 _L.lisa_read_rgba8.argtypes = [_vp, _vp]
 _L.lisa_write_ppm.argtypes = [_vp, ctypes.c_char_p]
 _L.lisa_write_pfm.argtypes = [_vp, ctypes.c_char_p]
+_L.lisa_write_image.argtypes = [_vp, ctypes.c_char_p]
 _L.lisa_save_accum.argtypes = [_vp, ctypes.c_char_p]
 _L.lisa_load_accum.argtypes = [_vp, ctypes.c_char_p, ctypes.POINTER(ctypes.c_uint32)]
 _L.lisa_get_stats.argtypes = [_vp, ctypes.POINTER(Stats)]
@@ -101,7 +102,7 @@ _L.lisa_primary_rays.argtypes = [_vp, ctypes.c_uint32, _vp, _vp]
 _L.lisa_kat_eval.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_uint32, _vp, _vp, _vp, _vp]
 
 EXPORTS = ["lisa_create", "lisa_destroy", "lisa_last_error", "lisa_version", "lisa_render_subframes",
-           "lisa_reset_accum", "lisa_read_accum", "lisa_read_rgba8", "lisa_write_ppm", "lisa_write_pfm", "lisa_save_accum", "lisa_load_accum", "lisa_get_stats",
+           "lisa_reset_accum", "lisa_read_accum", "lisa_read_rgba8", "lisa_write_ppm", "lisa_write_pfm", "lisa_write_image", "lisa_save_accum", "lisa_load_accum", "lisa_get_stats",
            "lisa_accum_add_peer", "lisa_accum_device_ptr", "lisa_accum_bytes", "lisa_device", "lisa_sync", "lisa_trace_closest",
            "lisa_trace_shadow", "lisa_primary_rays", "lisa_kat_eval", "lisa_debug_sort_pairs", "lisa_debug_scan_compact"]
 
@@ -216,6 +217,10 @@ class Renderer:
 
     def write_ppm(self, path=None):
         _check(_L.lisa_write_ppm(self._h, path.encode() if path else None))
+
+    def write_image(self, path=None):
+        """save_image() of the reference: the format follows the extension (ppm, png; anything else is an error)."""
+        _check(_L.lisa_write_image(self._h, path.encode() if path else None))
 
     def write_pfm(self, path):
         _check(_L.lisa_write_pfm(self._h, path.encode()))

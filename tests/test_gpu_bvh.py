@@ -238,3 +238,85 @@ def test_builder_primitives(rt, n):
     np.testing.assert_array_equal(s, (np.cumsum(a, dtype=np.uint64) - a).astype(np.uint32))
     assert tot == int(a.sum(dtype=np.uint64)) & 0xffffffff
     np.testing.assert_array_equal(kept, c[c >= 0])
+
+
+@pytest.mark.parametrize("pipe", ["pool", "path", "wavefront"])
+def test_every_schedule_on_empty_and_emitter_only_scenes(rt, pipe, monkeypatch):
+    """No non-emitter triangle at all (root_other < 0): a ray that misses the emitter bounds has nothing to traverse and
+    must come back as a MISS.  k_pool used to park such a slot with the ray set-up in the hit record and read a bogus
+    primitive; small images go to k_path by default, so every schedule is forced here."""
+    monkeypatch.setenv("LISA_PIPELINE", pipe)
+    z3 = np.zeros((0, 3), np.float32)
+    R = rt.Renderer(z3, z3, np.zeros(0, np.int32), [MAT_W], 64, 48, (0, 0, 5), (0, 0, 0), 45.0, 1, 3)
+    R.render_subframes(0, 2, 3)
+    assert float(np.abs(R.read_accum()[..., :3]).max()) == 0.0
+    R.close()
+    # one small emitter triangle in the middle of the view: most camera rays miss its bounds, the others see it
+    tri = np.float32([[-0.5, -0.5, 0], [0.5, -0.5, 0], [0, 0.5, 0]])
+    nrm = np.float32([[0, 0, 1]] * 3)
+    R = rt.Renderer(tri, nrm, np.zeros(1, np.int32), [MAT_L], 64, 48, (0, 0, 5), (0, 0, 0), 45.0, 1, 3)
+    R.render_subframes(0, 2, 3)
+    a = R.read_accum()[..., :3]
+    st = R.stats()
+    assert np.isfinite(a).all() and a.max() == 1.0 and a.min() == 0.0
+    assert 0.005 < (a[..., 0] > 0).mean() < 0.2           # the triangle covers a small part of the image
+    assert a[24, 32, 0] == 1.0 and a[0, 0, 0] == 0.0      # centre pixel sees the emitter (emission 1), corner misses
+    assert st["last_samples"] == 64 * 48 * 6 and st["last_radiance_rays"] == st["last_samples"]
+    assert st["last_shadow_rays"] == 0                    # no opaque hit, no light sampling
+    R.close()
+
+
+@pytest.mark.parametrize("bvh", [0, 1], ids=["wide8", "binary"])
+def test_ten_thousand_coincident_triangles(rt, bvh):
+    """10,000 copies of one triangle (identical Morton keys, identical boxes, every merged area a tie) plus a floor: the
+    PLOC tie-break pairs such runs up, so the hierarchy stays balanced — it builds in ~14 rounds instead of ~10,000 and
+    no ray overflows its traversal stack.  Every ray through the stack hits one of the copies at the exact distance."""
+    tri = np.float32([[-1, -1, 0], [1, -1, 0], [0, 1, 0]])
+    floor = np.float32([[-5, -5, -1], [5, -5, -1], [0, 5, -1]])
+    T = 10000
+    v = np.concatenate([np.tile(tri, (T, 1)), floor])
+    n = np.tile(np.float32([[0, 0, 1]]), (3 * (T + 1), 1))
+    m = np.zeros(T + 1, np.int32)
+    R = _mk(rt, v, n, m, [MAT_W], bvh)
+    o = np.float32([[0, 0, 2], [0.1, -0.3, 3], [3, -3, 2], [9, 9, 2]])
+    d = np.float32([[0, 0, -1], [0, 0, -2], [0, 0, -1], [0, 0, -1]])
+    prim, t = R.trace_closest(o, d)
+    assert 0 <= prim[0] < T and 0 <= prim[1] < T and prim[2] == T and prim[3] == -1
+    np.testing.assert_allclose(t[:3], [2.0, 1.5, 3.0], rtol=1e-6)
+    R.render_subframes(0, 1, 1)                           # the render kernels traverse it too
+    assert np.isfinite(R.read_accum()).all()
+
+
+def test_traversal_stack_overflow_is_loud(built, tmp_path):
+    """A traversal stack that fills up drops a subtree; the call that ran the kernel must then FAIL (LISA_ERR_STATE) instead
+    of returning hits that may be wrong.  The builders do not bound the depth of the tree, so the condition is provoked
+    with a test build of the same sources whose stacks hold 5 entries (make liblisa_rt_tinystack.so): a 50k-triangle soup
+    overflows them on most rays, in the diagnostic queries and in the render kernels alike."""
+    import os, subprocess, sys
+    from conftest import ROOT
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "lisa_b200"), "liblisa_rt_tinystack.so"])
+    code = ("import numpy as np, lisa_b200.rt as rt\n"
+            "rng = np.random.default_rng(1); T = 50000\n"
+            "c = rng.uniform(-1, 1, size=(T, 1, 3)); v = (c + rng.normal(scale=0.3, size=(T, 3, 3))).astype(np.float32).reshape(-1, 3)\n"
+            "n = np.tile(np.float32([[0, 0, 1]]), (3 * T, 1)); m = np.zeros(T, np.int32)\n"
+            "mats = [dict(emit=False, alpha=1.0, diffuse=(0.8, 0.8, 0.8), roughness=1.0)]\n"
+            "R = rt.Renderer(v, n, m, mats, 32, 32, (0, 0, 5), (0, 0, 0), 45.0, 1, 3)\n"
+            "o = rng.uniform(-2, 2, size=(4096, 3)).astype(np.float32); d = rng.normal(size=(4096, 3)).astype(np.float32)\n"
+            "out = []\n"
+            "for call in (lambda: R.trace_closest(o, d), lambda: R.trace_shadow(o, d), lambda: R.render_subframes(0, 1, 2)):\n"
+            "    try:\n"
+            "        call(); out.append('ok')\n"
+            "    except rt.LisaError as e:\n"
+            "        out.append('%d %s' % (e.code, e))\n"
+            "print('\\n'.join(out))\n")
+    for lib, expect_fail in (("liblisa_rt_tinystack.so", True), ("liblisa_rt.so", False)):
+        env = dict(os.environ, LISA_RT_LIB=os.path.join(ROOT, "lisa_b200", lib))
+        r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        assert r.returncode == 0, r.stderr[-2000:]
+        lines = r.stdout.strip().splitlines()
+        assert len(lines) == 3
+        for ln in lines:
+            if expect_fail:
+                assert ln.startswith("-5 ") and "traversal stack overflow" in ln, ln
+            else:
+                assert ln == "ok", ln

@@ -168,6 +168,32 @@ def test_rgba8_and_ppm(rt, orc, cornell, tmp_path):
     np.testing.assert_array_equal(img, px[::-1, :, :3])  # rows reversed, alpha dropped
 
 
+def test_write_image_follows_the_extension(rt, cornell, tmp_path):
+    """save_image -> sutil::saveImage (render.cc:9-17, sutil.cpp:523-688): "ppm" writes the flipped P6, "png" an 8-bit RGBA
+    PNG of the same frame (flipped, alpha 255); "exr", unknown extensions and names shorter than 5 characters fail with
+    the reference's messages instead of writing a PPM under another name."""
+    from PIL import Image
+    R = rt.Renderer.from_scene(resized(cornell, 72, 40))
+    R.render_subframes(0, 1, 4)
+    px = R.read_rgba8()
+    p = str(tmp_path / "o.ppm")
+    R.write_image(p)
+    q = str(tmp_path / "ref.ppm")
+    R.write_ppm(q)
+    assert open(p, "rb").read() == open(q, "rb").read()
+    for name in ("o.png", "o.PNG"):
+        p = str(tmp_path / name)
+        R.write_image(p)
+        im = Image.open(p)
+        assert im.mode == "RGBA" and im.size == (72, 40)
+        np.testing.assert_array_equal(np.asarray(im), px[::-1])
+    for name, msg in (("o.exr", "saving of uchar4 images to EXR not implemented yet"), ("o.jpg", "Failed unsupported filetype 'jpg'"),
+                      ("a.pp", "Failed unsupported filetype '.pp'"), ("ppm", "Failed to determine filename extension")):
+        with pytest.raises(rt.LisaError, match=msg):
+            R.write_image(str(tmp_path / name) if len(name) > 3 else name)
+    R.close()
+
+
 def test_host_render_and_display(rt, frontend, tmp_path, capfd):
     """render()/display() of the reference (render.cc:133-148, 75-131) through liblisa_host.so."""
     os.makedirs(os.path.join(ROOT, "out"), exist_ok=True)

@@ -241,3 +241,25 @@ def test_obj_float_parsing_matches_strtof(frontend, tmp_path):
     bad = np.nonzero(got.view(np.uint32) != want.view(np.uint32))[0]
     assert len(bad) == 0, [(used[i], float(got[i]), float(want[i])) for i in bad[:10]]
     assert len(got) > 40000
+
+
+@pytest.mark.parametrize("face,tail", [("f 1// 2//2 3//3", "\n"), ("f 1//1 2//1 3//", ""), ("f 1//1 2//1 3//", "\n"),
+                                       ("f 1//1 2//1 -3//1", "\n"), ("f 1//1 2//1 3//1234567890123456789012", "\n"),
+                                       ("f 1//1 2//1 3/1", "\n")])
+@pytest.mark.parametrize("nommap", ["0", "1"])
+def test_obj_malformed_face_indices_are_errors(frontend, tmp_path, monkeypatch, face, tail, nommap):
+    """An empty, negative or absurdly long index field is an error confined to its own field: the loader never reads the
+    next token (or past the end of the text, with the file ending right behind the field) to find a number.  The
+    reference's std::stoi throws on the same input (parse_obj.cc:52-54)."""
+    if nommap == "1":
+        monkeypatch.setenv("LISA_OBJ_NO_MMAP", "1")   # heap buffer instead of the page-cache mapping
+    else:
+        monkeypatch.delenv("LISA_OBJ_NO_MMAP", raising=False)
+    obj = tmp_path / "bad.obj"
+    obj.write_text("v 0 0 0\nv 1 0 0\nv 0 1 0\nvn 0 0 1\nvn 0 1 0\nvn 1 0 0\n" + face + tail)
+    rto = tmp_path / "bad.rto"
+    rto.write_text("material g { color = (1, 1, 1, 1)\n roughness = 1 }\nmesh { obj_file = %s\n material = g }\n"
+                   "camera { position = (0,0,1) look_at = (0,0,0) fov = 40 }\nnum_samples = 1\nnum_bounces = 1\n"
+                   "width = 4\nheight = 4\noutput_image = x.ppm\n" % obj)
+    with pytest.raises(frontend.SceneError, match="index out of range|without normal index"):
+        frontend.parse_scene(str(rto))
