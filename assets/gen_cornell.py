@@ -141,6 +141,9 @@ def main():
         tv += [(xa, Y1, za), (xb, Y1, za), (xb, Y1, zb), (xa, Y1, zb)]
         tf += [((b, 0), (b + 1, 0), (b + 2, 0)), ((b, 0), (b + 2, 0), (b + 3, 0))]
     W("top.obj", (tv, [(0, -1, 0)], tf), "ceiling (frame around the light's footprint), normal -y")
+    # The ORIGINAL ceiling (one quad, 1 mm behind the light), kept as a fixture: scenes/c3_knot_q2.rto uses it to pin the
+    # measured sensitivity of Q2 (first-found vs closest shadow hits) against the reference's OptiX build.
+    W("top_full.obj", quad((X0, Y1, Z0), (X1, Y1, Z0), (X1, Y1, Z1), (X0, Y1, Z1), (0, -1, 0)), "ceiling as first authored (full quad behind the light), normal -y")
     W("back.obj", quad((X0, Y0, Z0), (X1, Y0, Z0), (X1, Y1, Z0), (X0, Y1, Z0), (0, 0, 1)), "back wall, normal +z")
     W("right.obj", quad((X1, Y0, Z0), (X1, Y0, Z1), (X1, Y1, Z1), (X1, Y1, Z0), (-1, 0, 0)), "right wall, normal -x")
     W("left.obj", quad((X0, Y0, Z1), (X0, Y0, Z0), (X0, Y1, Z0), (X0, Y1, Z1), (1, 0, 0)), "left wall, normal +x")

@@ -12,9 +12,16 @@ subframe index, so no step can reuse an earlier result.
   value   Msamples/s with the scene and its BVH resident in HBM (device time, CUDA events).
   e2e     the same metric through the C ABI with HOST buffers every step: lisa_create (H2D of the soup +
           device BVH build) + lisa_render_subframes + lisa_read_accum (D2H of the float4 image) + destroy.
-  roofline  dominant kernel k_pool (the whole estimator, one persistent launch per step): algorithmic bytes per
-          launch / its launch time (CUDA events around the launch, LISA_FLAG_PROFILE_STAGES) against the
-          measured HBM peak, plus the issue-slot figures of the committed ncu capture (the kernel is issue bound).
+  roofline  dominant kernel k_pool (the whole estimator, one persistent launch per step).  What binds it is instruction
+          ISSUE (L2-resident scene), so: achieved = thread instructions per launch / the launch's
+          duration measured live (CUDA events around the launch, LISA_FLAG_PROFILE_STAGES); peak = SMs x 4 schedulers
+          x 32 lanes x the SM clock sampled during the timed region; frac = issue-slot utilisation x active lanes / 32.
+          The instruction counts per launch are a property of (kernel, workload): they come from the ncu capture of
+          the same launch committed under profiles/, which records a hash of the kernel sources — `stale` says whether
+          the sources have changed since.  HBM traffic of the launch is reported beside it (secondary).
+  multi_gpu_parity  (N > 1) after the timed loop a 128x128 job is rendered partitioned over the N ranks + reduced, and
+          again by rank 0 alone over the same subframes; the line carries the largest difference.
+  strong_scaling    the same workload with a FIXED total of samples per step split over the N ranks.
   --pipeline path|pool|wavefront  forces one schedule of the estimator (ablation; same images).  Default: the
           library's own choice per tile, which is k_pool for this workload.
   cpu_baseline  the oracle (oracle/cpu_ref.c, OpenMP) on a bounded pixel sample of the same workload.
@@ -25,8 +32,10 @@ N > 1 (torchrun, one rank per GPU): sample-space partition — every rank render
 full image each step, then ONE reduce of the float4 sums onto rank 0 (weak scaling).
 """
 import argparse
+import hashlib
 import json
 import os
+import re
 import subprocess
 import sys
 import threading
@@ -38,6 +47,37 @@ os.chdir(ROOT)
 
 SCENE = "scenes/cornell_c2.rto"
 METRIC = "Msamples/s (Cornell 2000x2000, 7 bounces)"
+
+
+STRONG_SPP = 48          # strong-scaling leg: samples per pixel and step over ALL ranks (divisible by 1, 2, 4, 8)
+
+
+def scene_header(path=SCENE):
+    """width / height / num_bounces straight from the scene text (the grammar's `name = <uint>`, scene_parser.cc:85-87):
+    all the reference arm needs to name its config, without loading any library."""
+    txt = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, path)).read(), flags=re.S)
+    g = lambda name: int(re.search(name + r"\s*=\s*([0-9]+)", txt).group(1))
+    return g("width"), g("height"), g("num_bounces")
+
+
+def config_dict(w, h, bounces, S):
+    """The workload, byte-identical in both arms."""
+    return {"workload": "BASELINE configs[1]: README Cornell box %dx%d, %d bounces, 1002 authored triangles; step = one subframe "
+                        "of %d spp per GPU (2000 spp = %d steps)" % (w, h, bounces, S, max(1, 2000 // S)),
+            "width": w, "height": h, "bounces": bounces, "spp_per_step": S,
+            "l2": "flushed between steps (256 MB rewritten; L2 is 126 MB)"}
+
+
+def kernel_source_hash():
+    """sha256 over the sources the render kernels are built from (what an ncu capture under profiles/ is valid for)."""
+    h = hashlib.sha256()
+    base = os.path.join(ROOT, "lisa_b200")
+    names = ["Makefile"] + sorted(os.path.join("csrc", f) for f in os.listdir(os.path.join(base, "csrc")) if f.endswith((".cuh", ".h")) or f == "estimator.cu")
+    names += [os.path.join("csrc", "bsdf", "lambertian.cuh")]
+    for n in names:
+        h.update(n.encode())
+        h.update(open(os.path.join(base, n), "rb").read())
+    return h.hexdigest()[:16]
 
 
 _JSON_FD = None
@@ -148,17 +188,16 @@ def cpu_baseline(sc, spp, target_s=12.0):
 
 
 def run_reference(args, rank):
-    """Reference arm: the unmodified reference's OptiX renderer (it has no CPU implementation)."""
+    """Reference arm: the unmodified reference's OptiX renderer (it has no CPU implementation).  Nothing of the product is
+    imported or loaded here: the config comes from the scene text, the numbers from the harness's own JSON line."""
     if rank != 0:
         return 0
-    import lisa_b200.frontend as fe
-    sc = fe.parse_scene(SCENE, load_meshes=False)
-    w, h, S, K, W = sc["width"], sc["height"], args.spp_per_step, args.steps, args.warmup
+    w, h, bounces = scene_header()
+    S, K, W = args.spp_per_step, args.steps, args.warmup
     exe = os.path.join(ROOT, "oracle", "_ref", "lisa_optix_ref")
     base = {"metric": METRIC, "unit": "Msamples/s", "n_gpus": 1, "steps": K, "warmup": W, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
-            "config": {"workload": "BASELINE configs[1]: README Cornell box 2000x2000, 7 bounces; step = one subframe of %d spp" % S,
-                       "width": w, "height": h, "bounces": sc["num_bounces"], "spp_per_step": S}}
+            "config": config_dict(w, h, bounces, S)}
     out = None
     if os.path.exists(exe):
         try:
@@ -170,25 +209,33 @@ def run_reference(args, rank):
             line = [l for l in r.stdout.splitlines() if l.startswith("{")]
             if r.returncode == 0 and line:
                 j = json.loads(line[-1])
+                assert (j["width"], j["height"], j["bounces"], j["spp"]) == (w, h, bounces, S), j
                 ms = sum(j["step_ms"])
                 v = w * h * S * K / ms / 1e3
                 out = dict(base, value=round(v, 4), ms_per_step=round(ms / K, 3), clocks=clocks, gpu_launches=K,
                            cpu_baseline={"value": round(v, 4), "unit": "Msamples/s", "cores": 1, "kind": "reference",
                                          "sample": "unmodified gaetanserre/LiSA OptiX 7.4 renderer (oracle/_ref/lisa_optix_ref) on "
                                                    "1 B200 (software traversal, no RT cores), 1 host thread; %d launches of %d spp, "
-                                                   "std::chrono around optixLaunch+sync" % (K, S)},
+                                                   "std::chrono around optixLaunch+sync; setup (upload + optixAccelBuild + pipeline) %.1f ms"
+                                                   % (K, S, j.get("setup_ms", 0.0))},
                            e2e={"value": round(v, 4), "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
             else:
                 sys.stderr.write("reference OptiX harness failed (rc %d): %s\n" % (r.returncode, r.stderr[-400:]))
         except Exception as e:  # noqa: BLE001
             sys.stderr.write("reference OptiX harness failed: %r\n" % (e,))
     if out is None:
-        # OptiX could not start: time the CPU restatement instead (labelled as a port)
-        sc = parse_quiet(fe, SCENE)
+        # OptiX could not start: time the CPU restatement instead (labelled as a port); scene through the oracle's own parser
+        from oracle import scene_py
+        sys.stderr.write("reference arm: OptiX unavailable, timing the CPU restatement (oracle/) on %s\n" % SCENE)
+        sc = scene_py.parse_scene(SCENE)
         cb = cpu_baseline(sc, S, target_s=float(os.environ.get("LISA_BENCH_CPU_TARGET_S", "20")))  # env: the CPU tests shorten it
         out = dict(base, value=cb["value"], ms_per_step=round(w * h * S / (cb["value"] * 1e3), 1), cpu_baseline=cb, gpu_launches=0,
                    clocks={"sm_mhz": None, "sm_max_mhz": None, "reasons": []},
                    e2e={"value": cb["value"], "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
+    # evidence for the driver's hygiene check: this arm must not map any of the product's libraries
+    mapped = sorted({l.split()[-1] for l in open("/proc/self/maps") if "lisa_b200" in l}) if os.path.exists("/proc/self/maps") else []
+    sys.stderr.write("reference arm: product libraries mapped in this process: %s; product modules imported: %s\n"
+                     % (mapped, sorted(m for m in sys.modules if m.startswith("lisa_b200"))))
     emit(out)
     return 0
 
@@ -201,6 +248,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--spp-per-step", type=int, default=50)
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="which leg is the line's `value`: weak = one subframe of --spp-per-step per GPU and step (default), "
+                         "strong = a fixed %d spp per step split over the GPUs; the other leg is reported beside it" % STRONG_SPP)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--pipeline", default="auto", choices=["auto", "pool", "path", "wavefront"])
@@ -233,6 +283,7 @@ def main():
 
     sc = parse_quiet(fe, SCENE)
     w, h, S, K, W = sc["width"], sc["height"], args.spp_per_step, args.steps, max(args.warmup, 0)
+    assert (w, h, sc["num_bounces"]) == scene_header()
     npix = w * h
     pipe_flag = rt.FLAG_WAVEFRONT if args.pipeline == "wavefront" else 0
     if args.pipeline != "auto":
@@ -244,53 +295,93 @@ def main():
     acc_t = ldist.accum_tensor(R) if world > 1 else None
     total = torch.zeros_like(acc_t) if (world > 1 and rank == 0) else None
 
-    def step(i):
+    def step(i, spp):
         """One pass of the hot path: this rank's subframe of step i (+ the one reduce when N > 1)."""
         R.reset()
         flush.fill_(i & 0xff)
         torch.cuda.current_stream().synchronize()
-        R.render_subframes(i * world + rank, 1, S)
+        R.render_subframes(i * world + rank, 1, spp)
         if world > 1:
             dist.reduce(acc_t, dst=0, op=dist.ReduceOp.SUM)
             if rank == 0:
                 total.add_(acc_t)
         return R.stats()
 
+    def timed_leg(first_step, spp, sample_clocks):
+        """K timed steps of `spp` samples per pixel and rank, bracketed by barrier + synchronize; device time, max over ranks."""
+        barrier()
+        clk = ClockSampler(local_rank) if (rank == 0 and sample_clocks) else None
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        agg = dict(render_ms=0.0, shadow_ms=0.0, extend_ms=0.0, shadow_launches=0, extend_launches=0, jobs=0, shadow_rays=0,
+                   radiance_rays=0, launches=0, nodes=0, tris=0, culled=0)
+        e0.record()
+        t0 = time.perf_counter()
+        for i in range(first_step, first_step + K):
+            st = step(i, spp)
+            agg["render_ms"] += st["last_render_ms"]
+            agg["shadow_ms"] += st["last_shadow_ms"]
+            agg["extend_ms"] += st["last_extend_ms"]
+            agg["shadow_launches"] += st["last_shadow_launches"]
+            agg["extend_launches"] += st["last_extend_launches"]
+            agg["jobs"] += st["last_shadow_jobs"]
+            agg["shadow_rays"] += st["last_shadow_rays"]
+            agg["radiance_rays"] += st["last_radiance_rays"]
+            agg["launches"] += st["last_kernel_launches"]  # our kernels only (k_pool/k_path + k_finalize; wavefront: every stage launch); R.reset() is a memset, the L2 flush is torch's fill
+            agg["nodes"] += st["last_nodes_visited"]
+            agg["tris"] += st["last_triangles_tested"]
+            agg["culled"] += st["last_shadow_culled"]
+        torch.cuda.synchronize()
+        e1.record()
+        e1.synchronize()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        barrier()
+        clocks = clk.stop() if clk else None
+        # whole device-synchronised bracket; every call inside is blocking, so event time == wall time up to microseconds
+        t_ms = torch.tensor([max(e0.elapsed_time(e1), agg["render_ms"])], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+        T = float(t_ms.item())
+        return dict(T=T, value=world * npix * spp * K / T / 1e3, wall_ms=wall_ms, agg=agg, clocks=clocks)
+
+    # ---- weak leg: every rank renders its own subframe of S spp each step
     for i in range(W):
-        step(i)
-    barrier()
-    clk = ClockSampler(local_rank) if rank == 0 else None
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    agg = dict(render_ms=0.0, shadow_ms=0.0, extend_ms=0.0, shadow_launches=0, extend_launches=0, jobs=0, shadow_rays=0,
-               radiance_rays=0, launches=0, nodes=0, tris=0, culled=0)
-    e0.record()
-    t0 = time.perf_counter()
-    for i in range(W, W + K):
-        st = step(i)
-        agg["render_ms"] += st["last_render_ms"]
-        agg["shadow_ms"] += st["last_shadow_ms"]
-        agg["extend_ms"] += st["last_extend_ms"]
-        agg["shadow_launches"] += st["last_shadow_launches"]
-        agg["extend_launches"] += st["last_extend_launches"]
-        agg["jobs"] += st["last_shadow_jobs"]
-        agg["shadow_rays"] += st["last_shadow_rays"]
-        agg["radiance_rays"] += st["last_radiance_rays"]
-        agg["launches"] += st["last_kernel_launches"]  # our kernels only (k_pool/k_path + k_finalize; wavefront: every stage launch); R.reset() is a memset, the L2 flush is torch's fill
-        agg["nodes"] += st["last_nodes_visited"]
-        agg["tris"] += st["last_triangles_tested"]
-        agg["culled"] += st["last_shadow_culled"]
-    torch.cuda.synchronize()
-    e1.record()
-    e1.synchronize()
-    wall_ms = (time.perf_counter() - t0) * 1e3
-    barrier()
-    clocks = clk.stop() if clk else None
-    # whole device-synchronised bracket; every call inside is blocking, so event time == wall time up to microseconds
-    t_ms = torch.tensor([max(e0.elapsed_time(e1), agg["render_ms"])], device="cuda", dtype=torch.float64)
+        step(i, S)
+    weak = timed_leg(W, S, True)
+    # ---- strong leg: a FIXED total of STRONG_SPP samples per pixel and step, split over the ranks (each renders its own
+    # subframe of STRONG_SPP / N spp).  At N = 1 it is the weak leg with another spp.
+    strong_spp = max(1, STRONG_SPP // world)
+    for i in range(min(W, 2)):
+        step(W + K + i, strong_spp)
+    strong = timed_leg(W + K + 2, strong_spp, False)
+    strong_obj = {"value": round(strong["value"], 4), "unit": "Msamples/s", "ms_per_step": round(strong["T"] / K, 3),
+                  "spp_per_step_all_gpus": strong_spp * world, "spp_per_step_per_gpu": strong_spp,
+                  "note": "fixed total work per step split over the ranks (sample-space), one reduce per step"}
+    weak_obj = {"value": round(weak["value"], 4), "unit": "Msamples/s", "ms_per_step": round(weak["T"] / K, 3), "spp_per_step_per_gpu": S}
+    main = strong if args.scaling == "strong" else weak
+    T, value, agg, wall_ms, clocks = main["T"], main["value"], main["agg"], main["wall_ms"], weak["clocks"]
+    S_main = strong_spp if args.scaling == "strong" else S
+
+    # ---- multi-GPU parity, where the driver can see it (its GPU-test box has one GPU): the N-rank partition + reduce of a
+    # small job against rank 0 rendering the same subframes alone
+    parity = None
     if world > 1:
-        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-    T = float(t_ms.item())
-    value = world * npix * S * K / T / 1e3
+        small = dict(sc, width=128, height=128)
+        first, count, spp_p = 5, 2 * world + 1, 4      # ragged: the blocks differ in size
+        Rp = rt.Renderer.from_scene(small, device=local_rank, flags=pipe_flag)
+        ldist.render_partitioned(Rp, first, count, spp_p)
+        if rank == 0:
+            multi = Rp.read_accum()
+            Rs = rt.Renderer.from_scene(small, device=local_rank, flags=pipe_flag)
+            Rs.render_subframes(first, count, spp_p)
+            single = Rs.read_accum()
+            Rs.close()
+            diff = float(np.abs(multi - single).max())
+            # same samples, another order of the float additions: 2e-6 relative (tests/test_gpu_multi.py uses the same bar)
+            ok = bool(np.allclose(multi, single, rtol=2e-6, atol=1e-7)) and bool((single[..., :3] > 0).mean() > 0.5)
+            parity = {"max_abs_diff": diff, "ok": ok, "ranks": world, "job": "128x128, subframes [%d, %d) x %d spp in contiguous blocks per rank, one NCCL reduce" % (first, first + count, spp_p),
+                      "image_mean": float(single[..., :3].mean())}
+        Rp.close()
+        barrier()
 
     # ---- end to end: host buffers in, host image out, every step
     e2e = None
@@ -312,7 +403,7 @@ def main():
             ts = [time.perf_counter()]
             R2 = rt.Renderer.from_scene(sc_pinned, device=local_rank, flags=pipe_flag)     # H2D + BVH build
             ts.append(time.perf_counter())
-            R2.render_subframes((W + K + i) * world + rank, 1, S)
+            R2.render_subframes((W + 3 * K + 8 + i) * world + rank, 1, S_main)
             ts.append(time.perf_counter())
             if world > 1:
                 t2 = ldist.accum_tensor(R2)
@@ -331,78 +422,87 @@ def main():
         te = torch.tensor([(time.perf_counter() - t0) * 1e3], device="cuda", dtype=torch.float64)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e = {"value": round(world * npix * S * K / float(te.item()) / 1e3, 4), "unit": "Msamples/s",
+        e2e = {"value": round(world * npix * S_main * K / float(te.item()) / 1e3, 4), "unit": "Msamples/s",
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": round(float(te.item()) / K, 3),
                "warmup": We}
 
     if rank == 0:
-        peak, peak_src = measured_peaks()
+        hbm_peak, hbm_src = measured_peaks()
         ref_rays = agg["shadow_rays"] + agg["radiance_rays"]          # rays the reference's programs would trace
         rays = ref_rays - agg["culled"]                                # rays actually traversed here
         nn, nt = agg["nodes"] / max(rays, 1), agg["tris"] / max(rays, 1)
         ext_launches = max(agg["extend_launches"], 1)
         avg_ms = agg["extend_ms"] / ext_launches
         if args.pipeline != "wavefront":
-            # dominant kernel: k_pool (the default picks it for this workload: 4 M chains per step) or k_path.  Algorithmic bytes (DESIGN.md "Kernels"): per traversed ray 80 B per node visited
-            # and 48 B per triangle tested; per radiance hit 48 B of vertex normals + 48 B of material; per chain one
-            # 16 B sum written.  All of it but the sums is served by L1/L2 (BVH 11 KB + triangles 96 KB).
-            kname, prof_name = ("k_path<wide8>", "r01_k_path.json") if args.pipeline == "path" else ("k_pool<wide8>", "r01_k_pool.json")
+            # dominant kernel: k_pool (the default picks it for this workload: 4 M chains per step) or k_path
+            kname, prof_name = ("k_path<wide8>", "r01_k_path.json") if args.pipeline == "path" else ("k_pool<wide8>", "r02_k_pool.json")
+            # L1-level algorithmic bytes (DESIGN.md "Kernels"): per traversed ray 80 B per node visited and 48 B per triangle
+            # tested; per radiance hit 48 B of vertex normals + 48 B of material; per chain one 16 B sum written
             alg_bytes = (rays * (80 * nn + 48 * nt) + agg["radiance_rays"] * 96 + npix * K * 16) / ext_launches
-            per_unit = alg_bytes / (npix * S)
-            per_unit_name = "algorithmic_bytes_per_sample"
-            note = ("one persistent launch per step; chain state never leaves the SM (registers for k_path, shared memory for "
-                    "k_pool), BVH (11 KB) + triangles (96 KB) are L1/L2 resident: the kernel is issue bound, HBM sees only the "
-                    "16-byte sum per chain. `issue` (issue-slot utilisation x active lanes / 32, committed ncu capture) is the "
-                    "roofline that binds.")
         else:
-            # k_extend (one radiance ray + material dispatch per live chain and iteration): chain state 16 (sum) + 32 (a, c)
-            # + 32 (o, d) read, 64 written, hit shading 96, ray 32, BVH 80 B per node visited and 48 B per triangle tested
             kname, prof_name = "k_extend<wide8>", "r01_k_extend.json"
-            chains_per_launch = agg["radiance_rays"] / ext_launches
-            per_unit = 144 + 96 + 32 + 80 * nn + 48 * nt
-            per_unit_name = "algorithmic_bytes_per_chain"
-            alg_bytes = chains_per_launch * per_unit
-            note = ("wavefront pipeline (ablation): BVH + triangles are L1/L2 resident, HBM traffic is the chain state; "
-                    "latency/issue bound.")
-        achieved = alg_bytes / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else None
-        traffic, issue = None, None
-        prof = os.path.join(ROOT, "profiles", prof_name)
+            alg_bytes = (agg["radiance_rays"] / ext_launches) * (144 + 96 + 32 + 80 * nn + 48 * nt)
+        # ---- the roofline that binds: instruction issue.  Instruction counts per launch from the committed ncu capture of
+        # this very launch (one step of S spp), valid while the kernel sources hash the same; its duration and the SM clock are
+        # measured in THIS run.
+        prof, pj = os.path.join(ROOT, "profiles", prof_name), None
+        if not os.path.exists(prof) and prof_name.startswith("r02_"):
+            prof = os.path.join(ROOT, "profiles", "r01_" + prof_name[4:])
         if os.path.exists(prof):
             try:
                 pj = json.load(open(prof))["launches"][0]
-                traffic = pj.get("dram_bytes_per_launch")
-                issue = {"issue_slot_utilisation_pct": pj.get("issue_slot_utilisation_pct"),
-                         "avg_active_lanes_per_instruction": pj.get("avg_active_lanes_per_instruction"),
-                         "frac_of_issue_roofline": pj.get("issue_roofline_frac"),
-                         "capture": pj.get("capture", "profiles/%s (ncu --set full)" % prof_name)}
-            except Exception:
-                pass
+            except Exception:  # noqa: BLE001
+                pj = None
+        sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
+        sm_mhz = (clocks or {}).get("sm_mhz") or (clocks or {}).get("sm_max_mhz") or 1965.0
+        peak_thread = sm_count * 4 * 32 * sm_mhz * 1e6                 # thread instructions / s
+        src_hash = kernel_source_hash()
+        roof = {"bound": "issue", "kernel": kname, "achieved": None, "peak": round(peak_thread / 1e12, 4), "unit": "Tthread-inst/s",
+                "frac": None, "traffic": None,
+                "peak_source": "%d SMs x 4 schedulers x 32 lanes x %.0f MHz (SM clock sampled by nvidia-smi during the timed region)" % (sm_count, sm_mhz),
+                "avg_launch_ms": round(avg_ms, 4), "launches": int(ext_launches),
+                "share_of_step": round(agg["extend_ms"] / max(agg["render_ms"], 1e-9), 4),
+                "nodes_per_ray": round(nn, 2), "tris_per_ray": round(nt, 2)}
+        if pj and pj.get("warp_instructions") and avg_ms > 0 and args.scaling == "weak" and S == int(pj.get("spp_per_launch", 50)):
+            warp_i = float(pj["warp_instructions"])
+            thread_i = float(pj.get("thread_instructions") or warp_i * pj["avg_active_lanes_per_instruction"])
+            ach = thread_i / (avg_ms * 1e-3)
+            roof.update(achieved=round(ach / 1e12, 4), frac=round(ach / peak_thread, 4), traffic=pj.get("dram_bytes_per_launch"),
+                        issue={"warp_instructions_per_launch": warp_i, "thread_instructions_per_launch": thread_i,
+                               "issue_slot_utilisation": round(warp_i / (avg_ms * 1e-3) / (sm_count * 4 * sm_mhz * 1e6), 4),
+                               "active_lanes_per_instruction": round(thread_i / warp_i, 2),
+                               "source": "profiles/%s (ncu --set full of one launch of %d spp)" % (os.path.basename(prof), S),
+                               "source_kernel_hash": pj.get("kernel_source_sha256"), "kernel_hash": src_hash,
+                               "stale": pj.get("kernel_source_sha256") != src_hash,
+                               "under_ncu": {"duration_ms": pj.get("duration"), "issue_slot_utilisation_pct": pj.get("issue_slot_utilisation_pct"),
+                                             "frac": pj.get("issue_roofline_frac")}})
+            if roof["traffic"]:
+                gbs = roof["traffic"] / (avg_ms * 1e-3) / 1e9
+                roof["hbm"] = {"achieved": round(gbs, 2), "peak": hbm_peak, "unit": "GB/s", "frac": round(gbs / hbm_peak, 6), "peak_source": hbm_src,
+                               "note": "HBM sees the 16-byte sum per chain and the first touch of the scene: not the bound"}
+        roof["l1_level_algorithmic_bytes_per_launch"] = int(alg_bytes)
+        roof["note"] = ("one persistent launch per step; chain state never leaves the SM, BVH (11 KB) + triangles (96 KB) are L1/L2 "
+                        "resident: instruction issue binds (SURVEY.md 8d), frac = issue-slot utilisation x active lanes / 32")
+        cfg = config_dict(w, h, sc["num_bounces"], S)
         out = {
             "metric": METRIC, "value": round(value, 4), "unit": "Msamples/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": round(T / K, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic",
-            "config": {"workload": "BASELINE configs[1]: README Cornell box 2000x2000, 7 bounces, 1002 authored triangles; "
-                                   "step = one subframe of %d spp per GPU (2000 spp = %d steps)" % (S, max(1, 2000 // S)),
-                       "width": w, "height": h, "bounces": sc["num_bounces"], "spp_per_step": S, "parallelism": "sample-space x%d" % world,
-                       "pipeline": args.pipeline, "l2": "flushed between steps (256 MB rewritten; L2 is 126 MB)"},
+            "ms_per_step": round(T / K, 3), "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": cfg,
+            "parallelism": "sample-space x%d" % world, "pipeline": args.pipeline,
+            "weak_scaling": weak_obj, "strong_scaling": strong_obj,
             "mrays_per_s": round(world * rays / T / 1e3, 1),
-            "rays_per_sample": round(rays / (npix * S * K), 2),
-            "reference_rays_per_sample": round(ref_rays / (npix * S * K), 2),
+            "rays_per_sample": round(rays / (npix * S_main * K), 2),
+            "reference_rays_per_sample": round(ref_rays / (npix * S_main * K), 2),
             "reference_equivalent_mrays_per_s": round(world * ref_rays / T / 1e3, 1),
             "shadow_tries_resolved_without_traversal": round(agg["culled"] / max(agg["shadow_rays"], 1), 4),
             "wall_ms_per_step": round(wall_ms / K, 3), "device_render_ms_per_step": round(agg["render_ms"] / K, 3),
             "gpu_launches": int(agg["launches"]),
             "clocks": clocks,
             "e2e": e2e,
-            "roofline": {"bound": "hbm", "kernel": kname, "achieved": round(achieved, 1) if achieved else None, "peak": peak,
-                         "unit": "GB/s", "frac": round(achieved / peak, 4) if achieved else None, "traffic": traffic,
-                         "peak_source": peak_src, "algorithmic_bytes_per_launch": int(alg_bytes),
-                         per_unit_name: round(per_unit, 1), "avg_launch_ms": round(avg_ms, 4),
-                         "launches": int(ext_launches), "share_of_step": round(agg["extend_ms"] / max(agg["render_ms"], 1e-9), 4),
-                         "light_sampling_share_of_step": round(agg["shadow_ms"] / max(agg["render_ms"], 1e-9), 4),
-                         "nodes_per_ray": round(nn, 2), "tris_per_ray": round(nt, 2), "issue": issue,
-                         "note": note},
+            "roofline": roof,
         }
+        if parity is not None:
+            out["multi_gpu_parity"] = parity
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(sc, S)
         emit(out)

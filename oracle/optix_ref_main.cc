@@ -15,6 +15,13 @@
  *     selected with --subframes.
  * It dumps the raw float4 accumulators (row 0 = image bottom) so parity is
  * judged on linear radiance, not on 8-bit sRGB.
+ *   --soup-bin FILE --soup-material K   appends a procedural triangle soup
+ *     (BASELINE C4: 1M-100M triangles; as OBJ text that is hundreds of MB and
+ *     minutes in the reference's line-by-line loader) to the RendererParams the
+ *     reference's SceneParser produced: FILE = u64 T, then 9T floats of
+ *     vertices, 9T floats of normals (de-indexed, like parse_obj's output);
+ *     every soup triangle gets material index K.  The arrays are handed to the
+ *     unmodified OptixWrapper exactly as SceneParser's would be.
  */
 #include <chrono>
 #include <cstdio>
@@ -90,6 +97,26 @@ int main(int argc, char** argv) {
   }
   SceneParser    parser(const_cast<char*>(scene));
   RendererParams params = parser.get_params();
+  std::vector<float3> soup_v, soup_n;
+  std::vector<int>    soup_m;
+  if (const char* sb = opt(argc, argv, "--soup-bin")) {
+    const int k = opt(argc, argv, "--soup-material") ? atoi(opt(argc, argv, "--soup-material")) : 0;
+    FILE* f = fopen(sb, "rb");
+    unsigned long long T = 0;
+    if (!f || fread(&T, sizeof(T), 1, f) != 1) { fprintf(stderr, "optix_ref: cannot read %s\n", sb); return 3; }
+    const size_t nv0 = (size_t)params.num_vertices, nt0 = nv0 / 3;
+    soup_v.resize(nv0 + 3 * T); soup_n.resize(nv0 + 3 * T); soup_m.assign(nv0 + 3 * T, k);  /* optix_wrapper.cc:67 copies num_vertices ints (Q11): keep that read in bounds */
+    /* the soup first, the scene file's own meshes (the light) after it */
+    if (fread(soup_v.data(), sizeof(float3), 3 * T, f) != 3 * T || fread(soup_n.data(), sizeof(float3), 3 * T, f) != 3 * T) {
+      fprintf(stderr, "optix_ref: %s is truncated\n", sb); return 3;
+    }
+    fclose(f);
+    memcpy(soup_v.data() + 3 * T, params.vertices, sizeof(float3) * nv0);
+    memcpy(soup_n.data() + 3 * T, params.normals, sizeof(float3) * nv0);
+    memcpy(soup_m.data() + T, params.mat_indices, sizeof(int) * nt0);
+    params.vertices = soup_v.data(); params.normals = soup_n.data(); params.mat_indices = soup_m.data();
+    params.num_vertices = (int)(nv0 + 3 * T);
+  }
 
   auto         t_setup0 = std::chrono::steady_clock::now();
   OptixWrapper wrapper(params);

@@ -31,7 +31,12 @@ def test_reference_arm_prints_one_json_line():
     assert d["impl"] == "reference" and d["unit"] == "Msamples/s" and d["higher_is_better"] is True
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["value"] > 0
     assert d["e2e"] == {"value": d["value"], "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert "Importing" in r.stderr.decode()          # the loader's lines went to stderr, not into the JSON stream
+    # the reference arm neither imports the product package nor maps its libraries (the config comes from the scene text)
+    assert "product libraries mapped in this process: []; product modules imported: []" in r.stderr.decode()
+    # both arms name the workload with the same dictionary
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"] == bench.config_dict(2000, 2000, 7, 50) and bench.scene_header() == (2000, 2000, 7)
 
 
 @pytest.mark.skipif(_has_cuda(), reason="exercises the no-GPU paths")
