@@ -143,8 +143,9 @@ const char* lisa_last_error(void);
 int  lisa_version(void);
 
 /* B3.  Renders subframes first .. first+count-1, each with spp samples per pixel, seeded
- * tea<16>(pixel, subframe) exactly as shader.cu:141, and merges them into the accumulators with equal
- * weights (what the reference's running mean, shader.cu:160-164, converges to).
+ * tea<16>(pixel, subframe) exactly as shader.cu:141, and adds their samples to the accumulators (sum of
+ * samples | number of samples per pixel): the image is the mean over ALL samples rendered since the last reset, which is
+ * what the reference's running mean of equally sized subframes, shader.cu:160-164, computes.
  *   reference `-s`  ==  lisa_render_subframes(ctx, 0, 1, num_samples)            (render.cc:140)
  *   reference `-d`  ==  for f = 0.. : lisa_render_subframes(ctx, f, 1, min(16, num_samples))
  * Blocking: returns when the accumulators on the device are final. */
@@ -167,8 +168,8 @@ int lisa_write_image(lisa_ctx* ctx, const char* path);
  * for parity tooling (the reference can only write the quantised PPM; README.md:183 lists float output as a TODO). */
 int lisa_write_pfm(lisa_ctx* ctx, const char* path);
 /* Checkpoint / resume of a progressive render (the reference keeps its accum_buffer only in device
- * memory, src/LiSA/src/render.cc:75-131).  lisa_save_accum writes the raw accumulators (W*H float4: sum of subframe
- * means | subframe count) with a header naming the image size and the number of subframes accumulated;
+ * memory, src/LiSA/src/render.cc:75-131).  lisa_save_accum writes the raw accumulators (W*H float4: sum of
+ * all samples | number of samples) with a header naming the image size and the number of subframes accumulated;
  * lisa_load_accum replaces the accumulators of a context of the same size with a saved file and reports through
  * *subframes how many subframes it holds, so that rendering resumes at that subframe index: the resumed image is
  * bit-identical to an uninterrupted one. */
@@ -178,14 +179,43 @@ int lisa_get_stats(lisa_ctx* ctx, lisa_stats* stats /* struct_size set by caller
 
 /* Multi-GPU plumbing: every rank renders a disjoint subframe set into its own sums; the
  * caller reduces the sum buffers (one NCCL reduce) and the root reads the image.  The buffer holds W*H
- * float4 = (sum of subframe means .xyz, number of subframes .w) and lives on the context's device. */
+ * float4 = (sum of all samples .xyz, number of samples .w; the image is .xyz / .w) and lives on the context's device. */
 /* Same-process alternative to the NCCL reduce: dst's accumulators += src's, as ONE kernel on dst's device that reads
  * src's buffer over NVLink through the peer mapping (falls back to a peer copy where P2P is unavailable). */
 int    lisa_accum_add_peer(lisa_ctx* dst, lisa_ctx* src);
+/* Bookkeeping after the CALLER summed other contexts' accumulators into ctx's buffer (e.g. one ncclReduce onto
+ * lisa_accum_device_ptr): adds `subframes` / `samples` to ctx's counters, so that lisa_get_stats and the header written by
+ * lisa_save_accum describe what the buffer now holds. */
+int    lisa_accum_note_merged(lisa_ctx* ctx, uint32_t subframes, uint64_t samples);
 void*  lisa_accum_device_ptr(lisa_ctx* ctx);
 size_t lisa_accum_bytes(lisa_ctx* ctx);
 int    lisa_device(lisa_ctx* ctx);
 int    lisa_sync(lisa_ctx* ctx);
+
+/* B3 on several GPUs of one box, ONE process (SURVEY.md §8b B3 "internally splits subframes over GPUs and reduces", §8e):
+ * a lisa_multi owns one context per GPU (replicated scene, each GPU builds its own BVH from the same upload) and one NCCL
+ * communicator per GPU (ncclCommInitAll).  lisa_multi_render_subframes partitions subframes [first, first+count) into
+ * contiguous blocks, one per GPU (block sizes differ by at most one), renders them concurrently (one host thread per GPU)
+ * and combines the float4 accumulators with ONE ncclReduce(sum, fp32, root = GPU 0) of W*H*4 floats over NVLink inside an
+ * ncclGroupStart/End; afterwards GPU 0's accumulators hold everything rendered so far and the others are cleared.
+ * lisa_multi_render_samples is the `-s` call for G GPUs: num_samples split into G subframes of floor/ceil(N/G) spp (exactly
+ * N samples in total — the accumulators weigh by sample count).  Read the image through lisa_multi_root(...) with the
+ * single-GPU calls.  NCCL is loaded at run time (libnccl.so.2); where it is missing the reduce falls back to
+ * lisa_accum_add_peer (one kernel per peer reading over NVLink) and lisa_multi_backend() says "peer" instead of "nccl".
+ * num_gpus <= 0 means every visible device.  Deterministic: the N-GPU image equals the 1-GPU image over the same subframes
+ * up to the order of the float additions. */
+typedef struct lisa_multi lisa_multi;
+int         lisa_multi_create(const lisa_scene_desc* scene, const lisa_options* options /* device is ignored */, int num_gpus, lisa_multi** out);
+void        lisa_multi_destroy(lisa_multi* m);
+int         lisa_multi_num_gpus(const lisa_multi* m);
+lisa_ctx*   lisa_multi_root(lisa_multi* m);
+lisa_ctx*   lisa_multi_ctx(lisa_multi* m, int gpu);
+const char* lisa_multi_backend(const lisa_multi* m);
+int         lisa_multi_reset_accum(lisa_multi* m);
+int         lisa_multi_render_subframes(lisa_multi* m, uint32_t first_subframe, uint32_t count, uint32_t spp_per_subframe);
+int         lisa_multi_render_samples(lisa_multi* m, uint32_t first_subframe, uint32_t num_samples);
+/* last lisa_multi_render_* call: wall time of the render phase (slowest GPU) and of the reduce, in ms */
+int         lisa_multi_last_times(const lisa_multi* m, double* render_ms, double* reduce_ms);
 
 /* Diagnostics used by the parity tests (not part of the reference surface).
  * Batched queries against the context's BVH; host arrays; n rays.  org/dir: n*3 floats.

@@ -9,16 +9,17 @@
 namespace lisa {
 
 // ------------------------------------------------------------------------------------------------
-// Chain sums -> accumulators.  accum.xyz += mean of every subframe of the tile, accum.w += subframes,
-// in subframe order (fixed order => deterministic sums).
+// Chain sums -> accumulators.  accum.xyz += the SUM of the samples of every subframe of the tile, accum.w += their number,
+// in subframe order (fixed order => deterministic sums).  The image is accum.xyz / accum.w: the mean over all samples,
+// which is what the reference's running mean of equally sized subframes is (shader.cu:158-164) — and stays the plain
+// sample mean when subframes differ in size (N samples split over G GPUs with G not dividing N).
 __global__ void k_finalize(DState s, Tile t, float4* accum) {
   uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= t.npix) return;
   float4 acc = accum[t.pix0 + k];
   for (uint32_t f = 0; f < t.nf; f++) {
     const float4 sm = s.sum[f * t.npix + k];
-    const float  inv = 1.0f / (float)t.spp;  // shader.cu:158
-    acc.x = fmaf(sm.x, inv, acc.x); acc.y = fmaf(sm.y, inv, acc.y); acc.z = fmaf(sm.z, inv, acc.z); acc.w += 1.0f;
+    acc.x = __fadd_rn(acc.x, sm.x); acc.y = __fadd_rn(acc.y, sm.y); acc.z = __fadd_rn(acc.z, sm.z); acc.w += (float)t.spp;
   }
   accum[t.pix0 + k] = acc;
 }

@@ -22,6 +22,7 @@
 #include "sort_scan.h"
 #include "scene.cuh"
 #include "estimator.h"
+#include "internal.h"
 
 using namespace lisa;
 
@@ -49,7 +50,7 @@ struct lisa_ctx {
   DCamera      cam{};
   BuildOutput  bvh{};
   DMaterial*   d_mats = nullptr;
-  float4*      d_accum = nullptr;   // W*H float4: sum of subframe means | subframe count
+  float4*      d_accum = nullptr;   // W*H float4: sum of all samples | number of samples
   float4*      d_mean = nullptr;    // scratch for read-back
   uint32_t*    d_rgba8 = nullptr;
   DState       state{};
@@ -98,6 +99,7 @@ static int stack_overflow_error() {
 }
 
 extern "C" const char* lisa_last_error(void) { return g_err; }
+extern "C" void        lisa_internal_set_last_error(const char* msg) { snprintf(g_err, sizeof(g_err), "%s", msg ? msg : ""); }
 extern "C" int         lisa_version(void) { return LISA_RT_VERSION; }
 
 // src/sutil/Camera.cpp:34-45 with up = (0,1,0) and aspect = width/height (optix_wrapper.cc:433-442)
@@ -760,6 +762,13 @@ extern "C" int lisa_accum_add_peer(lisa_ctx* dst, lisa_ctx* src) {
   dev_free(staged);
   dst->stats.subframes_accumulated += src->stats.subframes_accumulated;
   dst->stats.samples += src->stats.samples;
+  return LISA_OK;
+}
+
+extern "C" int lisa_accum_note_merged(lisa_ctx* c, uint32_t subframes, uint64_t samples) {
+  if (!c) return fail(LISA_ERR_ARG, "null ctx");
+  c->stats.subframes_accumulated += subframes;
+  c->stats.samples += samples;
   return LISA_OK;
 }
 

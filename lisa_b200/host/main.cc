@@ -1,8 +1,8 @@
 // lisa_b200/host/main.cc — the CLI (src/LiSA/src/main.cc:6-28, include/parse_args.hh:3-16).
 //   lisa -s scene.rto [-d]
 // -s <scene> is mandatory; without it the usage goes to stderr and the exit code is 1.  -d selects the
-// progressive mode (headless here).  Extra, optional: --gpus N renders N subframes of num_samples/N spp on N GPUs of
-// this box and reduces them over NVLink peer memory; --obj-cache keeps a binary copy of each OBJ's triangle soup next to
+// progressive mode (headless here).  Extra, optional: --gpus N splits num_samples over N GPUs of this box (one context each, in
+// this process) and combines the accumulators with one ncclReduce (lisa_multi_*); --obj-cache keeps a binary copy of each OBJ's triangle soup next to
 // it (<file>.lisasoup) and loads that instead of the text when it is current; --pfm <file> also writes the linear float image; with -d,
 // --snapshot-every K rewrites the PPM every K subframes, --checkpoint <file> saves the accumulators then (and at the
 // end) and --resume <file> continues an interrupted render from such a file; --stats prints one JSON line with the counters of

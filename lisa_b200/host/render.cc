@@ -65,29 +65,20 @@ void display(lisa_ctx* ctx, const lisa_scene_desc& params, const DisplayOptions&
 
 double render_multi(const lisa_scene_desc& params, int ngpus) {
   if (ngpus < 1) ngpus = 1;
-  const unsigned spp = (params.num_samples + ngpus - 1) / ngpus;
-  std::vector<lisa_ctx*>   ctx(ngpus, nullptr);
-  std::vector<std::string> err(ngpus);
+  lisa_multi* m = nullptr;
   auto start = std::chrono::system_clock::now();
-  std::vector<std::thread> th;
-  for (int g = 0; g < ngpus; g++)
-    th.emplace_back([&, g] {
-      lisa_options o{};
-      o.struct_size = sizeof(o);
-      o.device = g;
-      if (lisa_create(&params, &o, &ctx[g]) != LISA_OK) { err[g] = lisa_last_error(); return; }
-      if (lisa_render_subframes(ctx[g], (uint32_t)g, 1, spp) != LISA_OK) err[g] = lisa_last_error();
-    });
-  for (auto& t : th) t.join();
-  for (int g = 0; g < ngpus; g++)
-    if (!err[g].empty()) {
-      for (lisa_ctx* c : ctx) lisa_destroy(c);
-      throw std::runtime_error("GPU " + std::to_string(g) + ": " + err[g]);
-    }
-  for (int g = 1; g < ngpus; g++) check(lisa_accum_add_peer(ctx[0], ctx[g]), "reduce");
-  save_image(ctx[0], params);
+  check(lisa_multi_create(&params, nullptr, ngpus, &m), "create");
+  // num_samples split into one subframe per GPU of floor/ceil(N / G) spp — exactly N samples — then ONE ncclReduce
+  int rc = lisa_multi_render_samples(m, 0, params.num_samples);
+  if (rc == LISA_OK) rc = lisa_write_image(lisa_multi_root(m), params.output_image);
+  const std::string err = rc == LISA_OK ? "" : lisa_last_error();
+  double render_ms = 0, reduce_ms = 0;
+  lisa_multi_last_times(m, &render_ms, &reduce_ms);
+  const std::string backend = lisa_multi_backend(m);
+  lisa_multi_destroy(m);
+  if (rc != LISA_OK) throw std::runtime_error("render_multi: " + err);
   std::chrono::duration<double> total = std::chrono::system_clock::now() - start;
-  for (lisa_ctx* c : ctx) lisa_destroy(c);
+  printf("%d GPUs: render %.2f ms, reduce (%s) %.2f ms\n", ngpus, render_ms, backend.c_str(), reduce_ms);
   printf("Rendering finished in %.2f mn.\n", total.count() / 60.0);
   return total.count();
 }

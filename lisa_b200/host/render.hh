@@ -22,8 +22,8 @@ struct DisplayOptions {
 };
 void display(lisa_ctx* ctx, const lisa_scene_desc& params, const DisplayOptions& opt);
 
-// Sample-space partition over `ngpus` GPUs of this box, single process: the num_samples are split into
-// `ngpus` subframes of ceil(num_samples / ngpus) spp; GPU g (own context: full scene, own BVH) renders subframe g on
-// its own host thread; the sums are added onto GPU 0 by lisa_accum_add_peer (one kernel reading peer memory over
-// NVLink) and GPU 0 writes the PPM.  Returns the render wall time in seconds.
+// Sample-space partition over `ngpus` GPUs of this box, single process, through lisa_multi (include/lisa_rt.h):
+// one context per GPU (full scene, own BVH), num_samples split into `ngpus` subframes of floor/ceil(num_samples / ngpus) spp
+// (exactly num_samples in total), rendered concurrently, ONE ncclReduce of the float4 accumulators onto GPU 0, which writes
+// the image.  Returns the wall time in seconds.
 double render_multi(const lisa_scene_desc& params, int ngpus);

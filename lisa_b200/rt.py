@@ -90,6 +90,21 @@ _L.lisa_save_accum.argtypes = [_vp, ctypes.c_char_p]
 _L.lisa_load_accum.argtypes = [_vp, ctypes.c_char_p, ctypes.POINTER(ctypes.c_uint32)]
 _L.lisa_get_stats.argtypes = [_vp, ctypes.POINTER(Stats)]
 _L.lisa_accum_add_peer.argtypes = [_vp, _vp]
+_L.lisa_accum_note_merged.argtypes = [_vp, ctypes.c_uint32, ctypes.c_uint64]
+_L.lisa_multi_create.argtypes = [ctypes.POINTER(SceneDesc), ctypes.POINTER(Options), ctypes.c_int, ctypes.POINTER(_vp)]
+_L.lisa_multi_destroy.argtypes = [_vp]
+_L.lisa_multi_destroy.restype = None
+_L.lisa_multi_num_gpus.argtypes = [_vp]
+_L.lisa_multi_root.argtypes = [_vp]
+_L.lisa_multi_root.restype = _vp
+_L.lisa_multi_ctx.argtypes = [_vp, ctypes.c_int]
+_L.lisa_multi_ctx.restype = _vp
+_L.lisa_multi_backend.argtypes = [_vp]
+_L.lisa_multi_backend.restype = ctypes.c_char_p
+_L.lisa_multi_reset_accum.argtypes = [_vp]
+_L.lisa_multi_render_subframes.argtypes = [_vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32]
+_L.lisa_multi_render_samples.argtypes = [_vp, ctypes.c_uint32, ctypes.c_uint32]
+_L.lisa_multi_last_times.argtypes = [_vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
 _L.lisa_accum_device_ptr.argtypes = [_vp]
 _L.lisa_accum_device_ptr.restype = _vp
 _L.lisa_accum_bytes.argtypes = [_vp]
@@ -103,7 +118,9 @@ _L.lisa_kat_eval.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_uint32, _vp, _
 
 EXPORTS = ["lisa_create", "lisa_destroy", "lisa_last_error", "lisa_version", "lisa_render_subframes",
            "lisa_reset_accum", "lisa_read_accum", "lisa_read_rgba8", "lisa_write_ppm", "lisa_write_pfm", "lisa_write_image", "lisa_save_accum", "lisa_load_accum", "lisa_get_stats",
-           "lisa_accum_add_peer", "lisa_accum_device_ptr", "lisa_accum_bytes", "lisa_device", "lisa_sync", "lisa_trace_closest",
+           "lisa_accum_add_peer", "lisa_accum_note_merged", "lisa_multi_create", "lisa_multi_destroy", "lisa_multi_num_gpus", "lisa_multi_root",
+           "lisa_multi_ctx", "lisa_multi_backend", "lisa_multi_reset_accum", "lisa_multi_render_subframes", "lisa_multi_render_samples",
+           "lisa_multi_last_times", "lisa_accum_device_ptr", "lisa_accum_bytes", "lisa_device", "lisa_sync", "lisa_trace_closest",
            "lisa_trace_shadow", "lisa_primary_rays", "lisa_kat_eval", "lisa_debug_sort_pairs", "lisa_debug_scan_compact"]
 
 
@@ -140,7 +157,7 @@ class Renderer:
 
     def __init__(self, vertices, normals, mat_indices, materials, width, height, eye, look_at, fov, num_samples=1,
                  num_bounces=7, output_image=None, device=-1, shadow_mode=SHADOW_CLOSEST, bvh_kind=BVH_WIDE8, max_chains=0,
-                 flags=0):
+                 flags=0, _multi_gpus=None):
         self._v = np.ascontiguousarray(vertices, dtype=np.float32).reshape(-1, 3)
         self._n = np.ascontiguousarray(normals, dtype=np.float32).reshape(-1, 3)
         self._m = np.ascontiguousarray(mat_indices, dtype=np.int32).reshape(-1)
@@ -167,7 +184,12 @@ class Renderer:
         self.width, self.height = width, height
         self.num_samples, self.num_bounces = num_samples, num_bounces
         self._h = _vp()
-        _check(_L.lisa_create(ctypes.byref(sd), ctypes.byref(opt), ctypes.byref(self._h)))
+        self._m = _vp()
+        if _multi_gpus is None:
+            _check(_L.lisa_create(ctypes.byref(sd), ctypes.byref(opt), ctypes.byref(self._h)))
+        else:   # MultiRenderer: one context per GPU behind a lisa_multi; self._h is the root's (borrowed)
+            _check(_L.lisa_multi_create(ctypes.byref(sd), ctypes.byref(opt), _multi_gpus, ctypes.byref(self._m)))
+            self._h = _vp(_L.lisa_multi_root(self._m))
 
     @classmethod
     def from_scene(cls, sc, **kw):
@@ -180,7 +202,10 @@ class Renderer:
         return cls(sc["vertices"], sc["normals"], sc["mat_indices"], mats, **args)
 
     def close(self):
-        if getattr(self, "_h", None) and self._h.value:
+        if getattr(self, "_m", None) is not None and self._m.value:
+            _L.lisa_multi_destroy(self._m)
+            self._m, self._h = _vp(), _vp()
+        elif getattr(self, "_h", None) and self._h.value:
             _L.lisa_destroy(self._h)
             self._h = _vp()
 
@@ -244,6 +269,10 @@ class Renderer:
         """self += other (another Renderer, possibly on another GPU of this process)."""
         _check(_L.lisa_accum_add_peer(self._h, other._h))
 
+    def accum_note_merged(self, subframes, samples):
+        """Bookkeeping after the caller reduced other contexts' accumulators into this one's buffer (e.g. NCCL)."""
+        _check(_L.lisa_accum_note_merged(self._h, subframes, samples))
+
     def accum_device_ptr(self):
         return _L.lisa_accum_device_ptr(self._h)
 
@@ -279,6 +308,45 @@ class Renderer:
         s = np.empty((self.height, self.width), dtype=np.uint32)
         _check(_L.lisa_primary_rays(self._h, subframe, d.ctypes.data, s.ctypes.data))
         return d, s
+
+
+class MultiRenderer(Renderer):
+    """lisa_multi: ONE process, one context per GPU, subframes partitioned over them and combined by one ncclReduce
+    (include/lisa_rt.h).  Image read-back and statistics go through the root context (GPU 0) with Renderer's methods."""
+
+    def __init__(self, *a, num_gpus=0, **kw):
+        kw.pop("device", None)
+        super().__init__(*a, _multi_gpus=num_gpus, **kw)
+
+    @classmethod
+    def from_scene(cls, sc, num_gpus=0, **kw):
+        cam = sc["camera"]
+        args = dict(width=sc["width"], height=sc["height"], eye=cam["eye"], look_at=cam["look_at"], fov=cam["fov"],
+                    num_samples=sc["num_samples"], num_bounces=sc["num_bounces"], output_image=sc.get("output_image"))
+        args.update(kw)
+        mats = sc["materials_packed"] if "materials_packed" in sc else sc["materials"]
+        return cls(sc["vertices"], sc["normals"], sc["mat_indices"], mats, num_gpus=num_gpus, **args)
+
+    def num_gpus(self):
+        return _L.lisa_multi_num_gpus(self._m)
+
+    def backend(self):
+        return _L.lisa_multi_backend(self._m).decode()
+
+    def reset(self):
+        _check(_L.lisa_multi_reset_accum(self._m))
+
+    def render_subframes(self, first=0, count=1, spp=None):
+        _check(_L.lisa_multi_render_subframes(self._m, first, count, self.num_samples if spp is None else spp))
+
+    def render_samples(self, first=0, num_samples=None):
+        """`-s` over G GPUs: num_samples split into G subframes of floor/ceil(N / G) spp, exactly N in total."""
+        _check(_L.lisa_multi_render_samples(self._m, first, self.num_samples if num_samples is None else num_samples))
+
+    def last_times(self):
+        a, b = ctypes.c_double(0), ctypes.c_double(0)
+        _L.lisa_multi_last_times(self._m, ctypes.byref(a), ctypes.byref(b))
+        return a.value, b.value
 
 
 _L.lisa_debug_sort_pairs.argtypes = [ctypes.c_int, _vp, _vp, ctypes.c_uint32]

@@ -51,10 +51,16 @@ def lib():
         L.orc_render.argtypes = [ctypes.c_void_p, c_fp, c_fp, c_f, c_u32, c_u32, c_u32, c_u32, c_u32, c_u32,
                                  ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
         L.orc_primary_ray.argtypes = [c_fp, c_fp, c_f, c_u32, c_u32, c_u32, c_u32, c_u32, c_fp, c_u32p]
+        L.orc_set_bsdf.argtypes = [ctypes.c_int]
         L.orc_write_ppm.restype = ctypes.c_int
         L.orc_write_ppm.argtypes = [ctypes.c_char_p, ctypes.c_void_p, c_u32, c_u32]
         _LIB = L
     return _LIB
+
+
+def set_bsdf(name):
+    """Which BSDF the oracle's estimator uses: "lambertian" (the reference's, default) or "ggx" (the product's variant)."""
+    lib().orc_set_bsdf({"lambertian": 0, "ggx": 1}[name])
 
 
 def f3(v):

@@ -128,8 +128,41 @@ void orc_barycentric_normal(const float* P, const float* n, const float* v, floa
                             mk(v[0], v[1], v[2]), mk(v[3], v[4], v[5]), mk(v[6], v[7], v[8]));
   out[0] = r.x; out[1] = r.y; out[2] = r.z;
 }
+/* The interchangeable BSDF (seam B4, shader.cu:4 `#include "bsdfs/lambertian.cu"`): 0 = the reference's Lambertian
+ * (lambertian.cu:7-27), 1 = the GGX variant the product can be built with (lisa_b200/csrc/bsdf/ggx.cuh; GGX is on the
+ * reference's TODO list, README.md:183-184, so there is no reference code to follow for it: the oracle restates the
+ * variant's own definition so that the GGX kernel is checked against something, same seeds, same estimator). */
+static int g_bsdf = 0;
+void orc_set_bsdf(int which) { g_bsdf = which; }
+
+/* ggx.cuh: half vector from the GGX normal distribution of width a = roughness^2 (two rnd() draws), the incoming direction
+ * mirrored about it; a sample below the surface falls back to the plain mirror direction */
+static f3 ggx_bounce(f3 d, f3 N, uint32_t* seed, float roughness) {
+  float a  = fmaxf(roughness * roughness, 1e-3f);
+  float u1 = orc_rnd(seed), u2 = orc_rnd(seed);
+  float ct = sqrtf((1.0f - u1) / (1.0f + (a * a - 1.0f) * u1)), st = sqrtf(fmaxf(1.0f - ct * ct, 0.0f));
+  float ph = 6.283185307179586f * u2;
+  f3    up = fabsf(N.z) < 0.999f ? mk(0, 0, 1) : mk(1, 0, 0);
+  f3    T = normalize(cross(up, N)), B = cross(N, T);
+  f3    h = add(add(scale(T, st * cosf(ph)), scale(B, st * sinf(ph))), scale(N, ct));
+  f3    out = reflect3(d, h);
+  if (dot(out, N) * dot(d, N) > 0.0f) out = reflect3(d, N);
+  return out;
+}
+/* ggx.cuh: the GGX lobe D for the half vector between N and L, times clamp(N.L)^2 like the Lambertian term */
+static float ggx_brdf(f3 N, f3 L, float roughness) {
+  float a   = fmaxf(roughness * roughness, 1e-3f);
+  float ndl = clampf(dot(N, L), 0.0f, 1.0f);
+  f3    h   = normalize(add(N, L));
+  float ndh = clampf(dot(N, h), 0.0f, 1.0f);
+  float d   = ndh * ndh * (a * a - 1.0f) + 1.0f;
+  float D   = (a * a) / (3.14159265358979f * d * d);
+  return ndl * D * ndl;
+}
+
 /* lambertian.cu:7-13 */
 static f3 bounce(f3 d, f3 N, uint32_t* seed, float roughness) {
+  if (g_bsdf == 1) return ggx_bounce(d, N, seed, roughness);
   f3 refl = reflect3(d, N);
   f3 h    = hemisphere(N, seed);
   return lerp3(refl, h, roughness);
@@ -382,7 +415,7 @@ static f3 trace_path(const orc_ctx* c, f3 org, f3 dir, uint32_t* seed, orc_count
         /* else: unchanged (Q1) */
         if (hit) {
           const orc_material* lm = &s->mats[light];
-          L = scale(mk(lm->emission[0], lm->emission[1], lm->emission[2]), brdf(N, w));
+          L = scale(mk(lm->emission[0], lm->emission[1], lm->emission[2]), g_bsdf == 1 ? ggx_brdf(N, w, m->roughness) : brdf(N, w));
           t_flags |= 16;
           break;
         }

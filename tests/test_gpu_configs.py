@@ -1,0 +1,144 @@
+"""Every BASELINE.json config, where the driver's GPU-test box can see it: the CUDA path through the C ABI against
+accumulators dumped by the UNMODIFIED reference OptiX renderer on a B200 (oracle/make_golden_gpu.py; the figures it
+measured are committed as profiles/r02_parity_vs_optix.json and the bars below sit under them with margin).
+
+  configs[0]  README Cornell 512x512, 64 spp ................ test_gpu_parity.py, and here with k_pool forced
+  configs[1]  README Cornell 2000x2000 (4 of the 2000 spp) .. test_c2_resolution_against_optix (k_pool: 4M chains)
+  configs[2]  871,200-triangle glass knot, 12 bounces ....... test_c3_knot_against_optix (480x270, 1 and 16 spp)
+  configs[3]  1M-triangle soup .............................. test_c4_soup_1m_against_optix (256x256, 4 spp)
+  configs[4]  sample-partitioned 4K ......................... same kernels as configs[1]; the N-GPU partition is verified
+                                                              by test_gpu_multi.py (>= 2 GPUs) and by bench.py's
+                                                              multi_gpu_parity in every SCALE run
+  Q2          the ORIGINAL ceiling asset .................... test_q2_original_ceiling_sensitivity: measured deviation
+                                                              of both shadow policies from the OptiX image, asserted
+Bars, per pixel at equal spp with the reference's seeding: a pixel whose decisions all agree reproduces the reference to
+1e-4; chains diverge for good after one differing decision, so the matching fraction decays with spp.  Means within 1 %
+(north_star).  Block means within the Monte-Carlo noise of the few samples a block holds."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, golden, resized
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(acc, g, crop_frac, block_tol, mean_rtol=0.01):
+    y0, x0 = g["crop_origin"]
+    d = np.abs(acc[y0:y0 + 128, x0:x0 + 128] - g["crop"]).max(axis=2)
+    frac = float((d < 1e-4).mean())
+    assert frac >= crop_frac, frac
+    np.testing.assert_allclose(acc.reshape(-1, 3).mean(0), g["mean_rgb"], rtol=mean_rtol)
+    b = int(g["block"])
+    hb, wb = acc.shape[0] // b * b, acc.shape[1] // b * b
+    bm = acc[:hb, :wb].reshape(hb // b, b, wb // b, b, 3).mean(axis=(1, 3))
+    assert float(np.abs(bm - g["block_mean"]).max()) < block_tol
+    return frac
+
+
+def _render(rt, sc, spp, **kw):
+    R = rt.Renderer.from_scene(sc, **kw)
+    R.render_subframes(0, 1, spp)
+    acc, st = R.read_accum()[..., :3], R.stats()
+    R.close()
+    return acc, st
+
+
+def test_c1_config_with_k_pool_forced(rt, cornell, monkeypatch):
+    """BASELINE configs[0] through the bench kernel: 512x512 is below the default switch to k_pool (378,880 chains), so
+    the OptiX-golden tests of test_gpu_parity.py run k_path; here the same comparison with LISA_PIPELINE=pool."""
+    monkeypatch.setenv("LISA_PIPELINE", "pool")
+    acc, st = _render(rt, resized(cornell, 512), 64)
+    g64, g1024 = golden("optix_c1"), golden("optix_c1_1024")
+    o = g64["crop_origin"]
+    assert (np.abs(acc[o[0]:o[0] + 128, o[1]:o[1] + 128] - g64["crop"]).max(axis=2) < 1e-4).mean() >= 0.85
+    np.testing.assert_allclose(acc.reshape(-1, 3).mean(0), g64["mean_rgb"], rtol=0.01)
+    np.testing.assert_allclose(acc.reshape(-1, 3).mean(0), g1024["mean_rgb"], rtol=0.01)
+    b8 = acc.reshape(64, 8, 64, 8, 3).mean(axis=(1, 3))
+    conv = g1024["block8"]
+    relmse = lambda a: float((((a - conv) ** 2) / (conv ** 2 + 1e-4)).mean())
+    assert relmse(b8) <= 1.25 * relmse(g64["block8"]) + 1e-6
+    acc1, _ = _render(rt, resized(cornell, 512), 1)
+    g1 = golden("optix_c1_1")
+    assert (np.abs(acc1[o[0]:o[0] + 128, o[1]:o[1] + 128] - g1["crop"]).max(axis=2) < 1e-4).mean() >= 0.995
+
+
+def test_c2_resolution_against_optix(rt, cornell):
+    """BASELINE configs[1] at its own resolution (2000x2000 = 4M chains: the default picks k_pool, the bench kernel).
+    Measured: 99.43 % of the crop within 1e-4 at 4 spp, means 0.9999 / 1.0002 / 0.9997, 8x8 block means within 0.019."""
+    acc, st = _render(rt, resized(cornell, 2000), 4)
+    _check(acc, golden("optix_c2_4"), 0.985, 0.04)
+    assert st["last_samples"] == 2000 * 2000 * 4
+
+
+@pytest.fixture(scope="module")
+def knot_obj(tmp_path_factory):
+    """The 871,200-triangle knot as OBJ text (75 MB, generated: never committed), in a temporary directory."""
+    p = tmp_path_factory.mktemp("knot") / "knot.obj"
+    subprocess.check_call([sys.executable, os.path.join(ROOT, "assets", "gen_knot.py"), str(p)], stdout=subprocess.DEVNULL)
+    return str(p)
+
+
+def _knot_scene(frontend, knot_obj, tmp_path, rto, w, h):
+    txt = open(os.path.join(ROOT, "scenes", rto)).read().replace("out/knot.obj", knot_obj)
+    txt = re.sub(r"width = \d+", "width = %d" % w, txt)
+    txt = re.sub(r"height = \d+", "height = %d" % h, txt)
+    p = tmp_path / rto
+    p.write_text(txt)
+    return frontend.parse_scene(str(p))
+
+
+def test_c3_knot_against_optix(rt, frontend, knot_obj, tmp_path):
+    """BASELINE configs[2]: the glass knot (871,218 triangles with the walls and the light) in the Cornell box, 12 bounces,
+    through the product's own parser and OBJ loader.  Measured: 99.97 % / 99.13 % of the crop within 1e-4 at 1 / 16 spp."""
+    sc = _knot_scene(frontend, knot_obj, tmp_path, "c3_knot.rto", 480, 270)
+    assert sc["vertices"].shape[0] == 3 * 871218 and sc["num_bounces"] == 12
+    acc, st = _render(rt, sc, 1)
+    assert st["num_triangles"] == 871218
+    _check(acc, golden("optix_c3_1"), 0.997, 0.03)
+    acc, _ = _render(rt, sc, 16)
+    _check(acc, golden("optix_c3_16"), 0.975, 0.012)
+
+
+def test_q2_original_ceiling_sensitivity(rt, frontend, knot_obj, tmp_path):
+    """Q2, pinned.  The reference asks OptiX for the first-FOUND hit of a shadow ray (shader.cu:69).  With the
+    ceiling as first authored — one quad 1 mm BEHIND the light (scenes/c3_knot_q2.rto) — OptiX's traversal finds the
+    ceiling before the emitter for part of the light samples on this 871k-triangle scene and loses them: its image is
+    ~4 % darker than a traversal-order-independent answer.  Measured against its accumulators at 16 spp: closest-hit policy
+    (default) mean ratio 1.038 / 1.042 / 1.035 (R, G, B), first-found with emitters first 1.062 / 1.067 / 1.070, 76 % / 72 %
+    of pixels identical.  Neither policy can reproduce a closed-source traversal order; this is why the shipped assets keep
+    nothing behind the emitter (assets/gen_cornell.py), where all three agree to 1e-4 (test_c3_knot_against_optix)."""
+    sc = _knot_scene(frontend, knot_obj, tmp_path, "c3_knot_q2.rto", 480, 270)
+    g = golden("optix_c3q2_16")
+    ratios = {}
+    for mode in (0, 1):
+        acc, _ = _render(rt, sc, 16, shadow_mode=mode)
+        ratios[mode] = acc.reshape(-1, 3).mean(0) / g["mean_rgb"]
+    assert (ratios[0] > 1.025).all() and (ratios[0] < 1.055).all(), ratios[0]      # closest hit decides (default)
+    assert (ratios[1] > 1.045).all() and (ratios[1] < 1.085).all(), ratios[1]      # first found, emitters first
+    assert (ratios[1] > ratios[0]).all()   # ignoring occluders in front of a light can only brighten
+    # the frame-shaped ceiling changes the reference's own mean by that much, and ours by (almost) nothing
+    fixed = golden("optix_c3_16")["mean_rgb"]
+    np.testing.assert_allclose(ratios[0] * g["mean_rgb"], fixed, rtol=0.01)
+
+
+def test_c4_soup_1m_against_optix(rt, frontend, tmp_path):
+    """BASELINE configs[3] in small: the 1M-triangle procedural soup (seed 0x5EED, oracle/make_golden_gpu.py: soup) under
+    one emissive quad, 256x256, 4 spp, 7 bounces.  Measured: 99.49 % of the crop within 1e-4, mean ratio 1.00007."""
+    from oracle import make_golden_gpu as mg
+    light = tmp_path / "light.obj"
+    light.write_text(mg.LIGHT_OBJ)
+    rto = tmp_path / "soup.rto"
+    rto.write_text(mg.SOUP_RTO % dict(light=str(light), spp=4, w=256, h=256))
+    sc = frontend.parse_scene(str(rto))
+    v, n = mg.soup(1_000_000)
+    sc["vertices"] = np.concatenate([v, sc["vertices"]])
+    sc["normals"] = np.concatenate([n, sc["normals"]])
+    sc["mat_indices"] = np.concatenate([np.zeros(1_000_000, np.int32), sc["mat_indices"]])
+    acc, st = _render(rt, sc, 4)
+    assert st["num_triangles"] == 1_000_002 and st["num_emitter_triangles"] == 2
+    _check(acc, golden("optix_c4_1m_4"), 0.985, 0.015)

@@ -254,24 +254,53 @@ def test_pfm_output(rt, cornell, tmp_path):
     np.testing.assert_array_equal(img, R.read_accum()[..., :3])
 
 
-def test_ggx_variant_renders(built, tmp_path):
-    """Second BSDF (bsdf/ggx.cuh) behind the compile-time seam: renders, differs from the Lambertian image where
-    materials are rough-specular, and leaves emitter/miss pixels untouched."""
+def test_ggx_variant_matches_its_oracle(built, orc, tmp_path):
+    """Second BSDF (bsdf/ggx.cuh) behind the compile-time seam, checked like the first one: the GGX build of the library
+    (liblisa_rt_ggx.so) against the oracle switched to the same BSDF (oracle/cpu_ref.c: ggx_bounce / ggx_brdf), same
+    seeds, same estimator — the Lambertian bars of test_matches_oracle_same_seeds (a pixel whose decisions all agree
+    reproduces the oracle to 1e-4; ray counts within 0.5 % / 2 %).  The GGX image must also differ from the Lambertian one
+    where materials are rough-specular, and leave emitter/miss pixels untouched."""
     import subprocess, sys
     subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "lisa_b200"), "BSDF=ggx", "variant"])
-    code = ("import numpy as np, lisa_b200.frontend as fe, lisa_b200.rt as rt\n"
+    code = ("import json, numpy as np, lisa_b200.frontend as fe, lisa_b200.rt as rt\n"
             "sc = fe.parse_scene('scenes/cornell_c1.rto'); sc['width'] = sc['height'] = 64\n"
             "for m in sc['materials']:\n"
             "    if 'roughness' in m: m['roughness'] = 0.4\n"
             "sc.pop('materials_packed')\n"
-            "R = rt.Renderer.from_scene(sc); R.render_subframes(0, 1, 16); np.save(r'%s', R.read_accum())\n")
+            "res = {}\n"
+            "for spp in (1, 8):\n"
+            "    R = rt.Renderer.from_scene(sc); R.render_subframes(0, 1, spp); res['a%d' %% spp] = R.read_accum(); st = R.stats()\n"
+            "    res['rays%d' %% spp] = np.array([st['last_radiance_rays'], st['last_shadow_rays']])\n"
+            "np.savez(r'%s', **res)\n")
     imgs = []
     for lib in ("liblisa_rt.so", "liblisa_rt_ggx.so"):
-        out = str(tmp_path / (lib + ".npy"))
+        out = str(tmp_path / (lib + ".npz"))
         env = dict(os.environ, LISA_RT_LIB=os.path.join(ROOT, "lisa_b200", lib))
         subprocess.check_call([sys.executable, "-c", code % out], cwd=ROOT, env=env)
         imgs.append(np.load(out))
-    a, b = imgs
+    lam, ggx = imgs
+    # the oracle with the same materials
+    from oracle import scene_py
+    sc = scene_py.parse_scene("scenes/cornell_c1.rto")
+    mats = [dict(m, roughness=0.4) if "roughness" in m else m for m in sc["materials"]]
+    mp = b"".join(scene_py.pack_material(roughness=m.get("roughness", 0.0), alpha=m["alpha"], n=m.get("n", 0.0), diffuse=m.get("diffuse", (0, 0, 0)),
+                                         emit=m["emit"], emission=m.get("emission", (0, 0, 0))) for m in mats)
+    S = orc.Scene(sc["vertices"], sc["normals"], sc["mat_indices"], mp)
+    cam = sc["camera"]
+    try:
+        for name, img in (("lambertian", lam), ("ggx", ggx)):
+            orc.set_bsdf(name)
+            for spp, frac in ((1, 0.995), (8, 0.97)):
+                ref, cnt = S.render(cam["eye"], cam["look_at"], cam["fov"], 64, 64, 7, spp)
+                acc = img["a%d" % spp]
+                assert (np.abs(acc[..., :3] - ref[..., :3]).max(axis=2) < 1e-4).mean() >= frac, (name, spp)
+                np.testing.assert_allclose(acc[..., :3].mean(), ref[..., :3].mean(), rtol=0.01)
+                rays = img["rays%d" % spp]
+                assert abs(int(rays[0]) - cnt["radiance_rays"]) <= 0.005 * cnt["radiance_rays"] + 8
+                assert abs(int(rays[1]) - cnt["shadow_rays"]) <= 0.02 * cnt["shadow_rays"] + 8
+    finally:
+        orc.set_bsdf("lambertian")
+    a, b = lam["a8"], ggx["a8"]
     assert np.isfinite(b).all() and (b[..., :3] >= 0).all() and b[..., :3].max() < 50
     assert np.abs(a[..., :3] - b[..., :3]).mean() > 1e-3          # a different BSDF gives a different image
     np.testing.assert_array_equal(a[:, :2], b[:, :2])             # border pixels miss everything: black in both
