@@ -4,10 +4,12 @@
 //   1. k_centroid_bounds   scene bounds of triangle centroids (block reduce + ordered-int atomics)
 //   2. k_morton            63-bit Morton key per triangle; bit 63 = "triangle emits", so one sort also
 //                          partitions the soup into non-emitters | emitters
-//   3. radix sort          (key, triangle id) pairs, own LSD sort, 8 passes of 8 bits  (sort_scan.cu)
+//   3. radix sort          (key, triangle id) pairs, own LSD sort, 8 bits per pass over the key bits that matter
+//                          (emitter bit + ceil(log2 T / 3) + 6 bits per axis; sort_scan.cu)
 //   4a. PLOC (default)     parallel locally-ordered clustering over the Morton order (Meister & Bittner 2018):
-//                          per round k_ploc_nn (nearest neighbour by merged surface area within +-radius),
-//                          k_ploc_merge (mutual pairs become a node), stream compaction; ~log n rounds.
+//                          ONE kernel per round (k_ploc_round: nearest neighbour by merged surface area within +-radius,
+//                          mutual pairs become a node, survivors compacted in order by a single-pass look-back scan),
+//                          k_ploc_tail finishes the last <= 512 clusters in one CTA; ~log n rounds.
 //                          Near-SAH quality: large wall triangles stay near the root, small ones cluster first.
 //   4b. LBVH (fast build)  k_karras hierarchy per partition (Karras 2012), one thread per internal node,
 //   5.                     then k_refit: leaf boxes + bottom-up box refit with arrival counters
@@ -16,8 +18,8 @@
 //                          greedy largest-area child opening, octant-affinity slot assignment,
 //                          8-bit box quantisation, leaf triangles made contiguous per node
 //   7. k_pack_triangles    soup -> (tri_v, tri_n) float4 arrays in final leaf order
-// Algorithmic bytes per triangle: 72 read soup + 12 key/id + sort 8 passes x 24 +
-// 2 x 80 hierarchy/refit + ~40 collapse + 96 packed write.
+// Algorithmic bytes per triangle: bounds 36 + keys 36 + 12, sort 32 per pass, leaf records 36 + 4 + 96,
+// PLOC ~2.7 rounds-worth of (64 read + 64 written) + 44 per node, collapse ~100, pack 72 + 72 + 8 read and 100 written.
 #include <algorithm>
 #include <cfloat>
 #include <chrono>
@@ -165,14 +167,32 @@ __global__ void k_refit(const float* __restrict__ verts, const unsigned int* __r
 }
 
 // ---- PLOC ------------------------------------------------------------------------------------------
-__global__ void k_leaf_boxes(const float* __restrict__ verts, const unsigned int* __restrict__ ids, int n, float4* box_lo,
-                             float4* box_hi, int* C) {
+// Clusters are kept as RECORDS in position (Morton) order — two float4 per cluster: (box lo | node id), (box hi | number
+// of triangles below) — so that a round reads its neighbourhood with coalesced 16-byte loads instead of gathering boxes
+// through an index array.  One kernel per round (k_ploc_round) does what took five launches: a CTA stages its tile of
+// 256 clusters plus a halo of 2r on either side in shared memory, finds every cluster's nearest neighbour within +-r
+// (for the tile AND a halo of r, so that mutual pairs across tile borders are seen identically by both tiles), merges
+// mutual pairs (the lower position creates the node and keeps the place, the higher one is dropped) and compacts the
+// survivors in order: the output offset of a tile is the sum over the tiles before it, obtained by a single-pass scan
+// with decoupled look-back (tiles take tickets, publish their aggregate, and look back over their predecessors'
+// aggregates / inclusive prefixes).  The same scan carries the number of merges, which numbers the new nodes
+// deterministically (same input, same node ids).  Once 512 or fewer clusters remain, ONE CTA finishes all remaining
+// rounds in shared memory (k_ploc_tail).
+#define PLOC_TILE 256
+#define PLOC_RMAX 32
+#define PLOC_TAIL 512
+
+__global__ void k_leaf_records(const float* __restrict__ verts, const unsigned int* __restrict__ ids, int n, float4* box_lo,
+                               float4* box_hi, float4* rec) {
   int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
   const float* p = verts + 9ll * ids[j];
-  box_lo[(n - 1) + j] = make_float4(fminf(p[0], fminf(p[3], p[6])), fminf(p[1], fminf(p[4], p[7])), fminf(p[2], fminf(p[5], p[8])), 0.0f);
-  box_hi[(n - 1) + j] = make_float4(fmaxf(p[0], fmaxf(p[3], p[6])), fmaxf(p[1], fmaxf(p[4], p[7])), fmaxf(p[2], fmaxf(p[5], p[8])), 0.0f);
-  C[j] = (n - 1) + j;
+  const float4 lo = make_float4(fminf(p[0], fminf(p[3], p[6])), fminf(p[1], fminf(p[4], p[7])), fminf(p[2], fminf(p[5], p[8])), 0.0f);
+  const float4 hi = make_float4(fmaxf(p[0], fmaxf(p[3], p[6])), fmaxf(p[1], fmaxf(p[4], p[7])), fmaxf(p[2], fmaxf(p[5], p[8])), 0.0f);
+  box_lo[(n - 1) + j] = lo;
+  box_hi[(n - 1) + j] = hi;
+  rec[2ll * j]     = make_float4(lo.x, lo.y, lo.z, __int_as_float((n - 1) + j));
+  rec[2ll * j + 1] = make_float4(hi.x, hi.y, hi.z, __int_as_float(1));
 }
 
 __device__ __forceinline__ float merged_half_area(const float4& l0, const float4& h0, const float4& l1, const float4& h1) {
@@ -181,52 +201,180 @@ __device__ __forceinline__ float merged_half_area(const float4& l0, const float4
   return dx * dy + dy * dz + dz * dx;
 }
 
-// nearest neighbour of cluster i among positions [i-r, i+r] by merged surface area.  Ties are broken by a key that is
-// SYMMETRIC in the pair — (distance in the order, parity of the lower position, lower position) — so candidate pairs
-// are totally ordered, the best pair overall is always mutual (progress every round), and a run of coincident boxes
-// (equal areas everywhere) pairs up (0,1), (2,3), ... and halves per round: a balanced tree, where "smallest position
-// wins" made every cluster point at the start of the run and merged ONE pair per round into a chain.
-__global__ void k_ploc_nn(const int* __restrict__ C, int m, const float4* __restrict__ box_lo, const float4* __restrict__ box_hi,
-                          int r, int* nn) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= m) return;
-  const float4 l = box_lo[C[i]], h = box_hi[C[i]];
+// Nearest neighbour of the cluster at position p among positions [p-r, p+r] of [0, m) by merged surface area; slo / shi
+// hold the records of positions lo0, lo0 + 1, ...  Ties are broken by a key that is SYMMETRIC in the pair — (distance in
+// the order, parity of the lower position, lower position) — so candidate pairs are totally ordered, the best pair overall
+// is always mutual (progress every round), and a run of coincident boxes (equal areas everywhere) pairs up (0,1), (2,3),
+// ... and halves per round: a balanced tree, where "smallest position wins" made every cluster point at the start of
+// the run and merged ONE pair per round into a chain.
+__device__ __forceinline__ int ploc_nearest(const float4* slo, const float4* shi, int lo0, int p, int m, int r) {
+  const float4 l = slo[p - lo0], h = shi[p - lo0];
   float    best = FLT_MAX;
   unsigned bkey = 0xffffffffu;
   int      bj = -1;
-  const int j0 = max(0, i - r), j1 = min(m - 1, i + r);
+  const int j0 = max(0, p - r), j1 = min(m - 1, p + r);
   for (int j = j0; j <= j1; j++) {
-    if (j == i) continue;
-    const int      c = C[j];
-    const float    a = merged_half_area(l, h, box_lo[c], box_hi[c]);
-    const int      lo = min(i, j);
-    const unsigned key = ((unsigned)abs(j - i) << 1) | ((unsigned)lo & 1u);  // same distance + same parity: the lower j comes first in the scan
+    if (j == p) continue;
+    const float    a = merged_half_area(l, h, slo[j - lo0], shi[j - lo0]);
+    const unsigned key = ((unsigned)abs(j - p) << 1) | ((unsigned)min(p, j) & 1u);  // same distance + parity: the lower j comes first in the scan
     if (a < best || (a == best && key < bkey)) { best = a; bkey = key; bj = j; }
   }
-  nn[i] = bj;
+  return bj;
 }
 
-__global__ void k_ploc_merge(const int* __restrict__ C, int m, const int* __restrict__ nn, float4* box_lo, float4* box_hi,
-                             int2* child, int* cnt, int n, int* next_internal, int* Cout) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= m) return;
-  const int j = nn[i];
-  if (j >= 0 && nn[j] == i) {
-    if (i < j) {
-      const int id = atomicAdd(next_internal, 1);
-      const int a = C[i], b = C[j];
-      const float4 l0 = box_lo[a], h0 = box_hi[a], l1 = box_lo[b], h1 = box_hi[b];
-      box_lo[id] = make_float4(fminf(l0.x, l1.x), fminf(l0.y, l1.y), fminf(l0.z, l1.z), 0.0f);
-      box_hi[id] = make_float4(fmaxf(h0.x, h1.x), fmaxf(h0.y, h1.y), fmaxf(h0.z, h1.z), 0.0f);
-      child[id]  = make_int2(a, b);
-      cnt[id]    = (a >= n - 1 ? 1 : cnt[a]) + (b >= n - 1 ? 1 : cnt[b]);
-      Cout[i]    = id;
-    } else {
-      Cout[i] = -1;
-    }
-  } else {
-    Cout[i] = C[i];
+// creates the node that merges the clusters (la, ha) and (lb, hb) — a at the lower position — and returns its record
+__device__ __forceinline__ void ploc_make_node(int id, const float4& la, const float4& ha, const float4& lb, const float4& hb,
+                                               float4* node_lo, float4* node_hi, int2* child, int* cnt, float4& rlo, float4& rhi) {
+  const int c = __float_as_int(ha.w) + __float_as_int(hb.w);
+  rlo = make_float4(fminf(la.x, lb.x), fminf(la.y, lb.y), fminf(la.z, lb.z), __int_as_float(id));
+  rhi = make_float4(fmaxf(ha.x, hb.x), fmaxf(ha.y, hb.y), fmaxf(ha.z, hb.z), __int_as_float(c));
+  node_lo[id] = make_float4(rlo.x, rlo.y, rlo.z, 0.0f);
+  node_hi[id] = make_float4(rhi.x, rhi.y, rhi.z, 0.0f);
+  child[id]   = make_int2(__float_as_int(la.w), __float_as_int(lb.w));
+  cnt[id]     = c;
+}
+
+// tile state of the look-back scan: bits 0..29 survivors, 30..59 merges, 60..61 status (1 aggregate, 2 inclusive prefix), 62..63 round tag
+#define PLOC_ST_AGG (1ull << 60)
+#define PLOC_ST_PFX (2ull << 60)
+#define PLOC_VAL_MASK ((1ull << 60) - 1ull)
+__device__ __forceinline__ unsigned long long ploc_ld(const unsigned long long* p) { return *reinterpret_cast<const volatile unsigned long long*>(p); }
+__device__ __forceinline__ void ploc_st(unsigned long long* p, unsigned long long v) { *reinterpret_cast<volatile unsigned long long*>(p) = v; }
+
+__global__ void __launch_bounds__(PLOC_TILE) k_ploc_round(const float4* __restrict__ in, int m, int r, float4* __restrict__ out,
+                                                          float4* node_lo, float4* node_hi, int2* child, int* cnt, int node_base,
+                                                          unsigned long long* state, unsigned int* ticket, int* m_out, unsigned tag) {
+  __shared__ float4             slo[PLOC_TILE + 4 * PLOC_RMAX], shi[PLOC_TILE + 4 * PLOC_RMAX];
+  __shared__ int                snn[PLOC_TILE + 2 * PLOC_RMAX];
+  __shared__ unsigned           s_tile, s_warp[PLOC_TILE / 32];
+  __shared__ unsigned long long s_excl;
+  const int t = threadIdx.x;
+  if (t == 0) s_tile = atomicAdd(ticket, 1u);  // tiles are numbered in the order they START: a tile only ever waits for earlier ones
+  __syncthreads();
+  const int tile = (int)s_tile, ntiles = (m + PLOC_TILE - 1) / PLOC_TILE;
+  const int base = tile * PLOC_TILE, lo0 = base - 2 * r;
+  for (int k = t; k < PLOC_TILE + 4 * r; k += PLOC_TILE) {
+    const int p = lo0 + k;
+    if (p >= 0 && p < m) { slo[k] = in[2ll * p]; shi[k] = in[2ll * p + 1]; }
   }
+  __syncthreads();
+  for (int e = t; e < PLOC_TILE + 2 * r; e += PLOC_TILE) {  // the tile and a halo of r on either side
+    const int p = base - r + e;
+    snn[e] = (p >= 0 && p < m) ? ploc_nearest(slo, shi, lo0, p, m, r) : -1;
+  }
+  __syncthreads();
+  const int p = base + t;
+  int  j = -1;
+  bool valid = false, owner = false;
+  if (p < m) {
+    j = snn[t + r];
+    const bool mutual = j >= 0 && snn[j - (base - r)] == p;
+    owner = mutual && p < j;
+    valid = !(mutual && p > j);
+  }
+  // CTA-wide exclusive scan of (survivor, merge) flags, packed 16 | 16
+  const unsigned lane = t & 31, w = t >> 5;
+  const unsigned v = (valid ? 1u : 0u) | (owner ? 0x10000u : 0u);
+  unsigned inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const unsigned x = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= (unsigned)o) inc += x; }
+  if (lane == 31) s_warp[w] = inc;
+  __syncthreads();
+  unsigned wbase = 0, tot = 0;
+#pragma unroll
+  for (int k = 0; k < PLOC_TILE / 32; k++) { const unsigned x = s_warp[k]; if ((unsigned)k < w) wbase += x; tot += x; }
+  const unsigned excl = wbase + inc - v;
+  // decoupled look-back over the tiles before this one (warp 0)
+  if (t < 32) {
+    const unsigned long long TAG = (unsigned long long)(tag & 3u) << 62;
+    const unsigned long long agg = (unsigned long long)(tot & 0xffffu) | ((unsigned long long)(tot >> 16) << 30);
+    unsigned long long       before = 0;
+    if (tile == 0) {
+      if (t == 0) ploc_st(&state[0], TAG | PLOC_ST_PFX | agg);
+    } else {
+      if (t == 0) ploc_st(&state[tile], TAG | PLOC_ST_AGG | agg);
+      int look = tile - 1;
+      while (true) {
+        const int          idx = look - t;
+        unsigned long long sv = TAG | PLOC_ST_PFX;  // in front of tile 0: an inclusive prefix of zero
+        if (idx >= 0) {
+          do { sv = ploc_ld(&state[idx]); } while ((sv >> 62) != (unsigned long long)(tag & 3u) || ((sv >> 60) & 3ull) == 0ull);
+        }
+        const unsigned pm = __ballot_sync(0xffffffffu, ((sv >> 60) & 3ull) == 2ull);
+        const int      first = pm ? __ffs(pm) - 1 : 31;  // nearest predecessor that already knows its inclusive prefix
+        unsigned long long val = t <= first ? (sv & PLOC_VAL_MASK) : 0ull;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+        before += val;
+        if (pm) break;
+        look -= 32;
+      }
+      if (t == 0) ploc_st(&state[tile], TAG | PLOC_ST_PFX | (before + agg));
+    }
+    if (t == 0) s_excl = before;
+  }
+  __syncthreads();
+  const unsigned valid_before = (unsigned)(s_excl & 0x3fffffffull), merges_before = (unsigned)((s_excl >> 30) & 0x3fffffffull);
+  if (valid) {
+    const long long q = (long long)valid_before + (excl & 0xffffu);
+    float4 rlo = slo[p - lo0], rhi = shi[p - lo0];
+    if (owner)
+      ploc_make_node(node_base + (int)(merges_before + (excl >> 16)), rlo, rhi, slo[j - lo0], shi[j - lo0], node_lo, node_hi, child, cnt, rlo, rhi);
+    out[2 * q]     = rlo;
+    out[2 * q + 1] = rhi;
+  }
+  if (tile == ntiles - 1 && t == 0) {  // the holder of the last ticket started last: every ticket of this round is taken
+    *m_out  = (int)(valid_before + (tot & 0xffffu));
+    *ticket = 0u;
+  }
+}
+
+// all remaining rounds for m <= PLOC_TAIL clusters, in one CTA; *root_out = node id of the last cluster standing
+__global__ void __launch_bounds__(PLOC_TAIL) k_ploc_tail(const float4* __restrict__ in, int m, int r, float4* node_lo, float4* node_hi,
+                                                         int2* child, int* cnt, int node_base, int* root_out) {
+  __shared__ float4   slo[2][PLOC_TAIL], shi[2][PLOC_TAIL];
+  __shared__ int      snn[PLOC_TAIL];
+  __shared__ unsigned s_warp[PLOC_TAIL / 32];
+  const int      t = threadIdx.x;
+  const unsigned lane = t & 31, w = t >> 5;
+  int cur = 0;
+  if (t < m) { slo[0][t] = in[2 * t]; shi[0][t] = in[2 * t + 1]; }
+  __syncthreads();
+  while (m > 1) {
+    if (t < m) snn[t] = ploc_nearest(slo[cur], shi[cur], 0, t, m, r);
+    __syncthreads();
+    int  j = -1;
+    bool valid = false, owner = false;
+    if (t < m) {
+      j = snn[t];
+      const bool mutual = j >= 0 && snn[j] == t;
+      owner = mutual && t < j;
+      valid = !(mutual && t > j);
+    }
+    const unsigned v = (valid ? 1u : 0u) | (owner ? 0x10000u : 0u);
+    unsigned inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned x = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= (unsigned)o) inc += x; }
+    if (lane == 31) s_warp[w] = inc;
+    __syncthreads();
+    unsigned wbase = 0, tot = 0;
+#pragma unroll
+    for (int k = 0; k < PLOC_TAIL / 32; k++) { const unsigned x = s_warp[k]; if ((unsigned)k < w) wbase += x; tot += x; }
+    const unsigned excl = wbase + inc - v;
+    if (valid) {
+      const unsigned q = excl & 0xffffu;
+      float4 rlo = slo[cur][t], rhi = shi[cur][t];
+      if (owner) ploc_make_node(node_base + (int)(excl >> 16), rlo, rhi, slo[cur][j], shi[cur][j], node_lo, node_hi, child, cnt, rlo, rhi);
+      slo[cur ^ 1][q] = rlo;
+      shi[cur ^ 1][q] = rhi;
+    }
+    __syncthreads();
+    if ((tot >> 16) == 0u) break;  // no mutual pair (NaN boxes): the host reports it
+    m = (int)(tot & 0xffffu);
+    node_base += (int)(tot >> 16);
+    cur ^= 1;
+  }
+  if (t == 0) { root_out[0] = __float_as_int(slo[cur][0].w); root_out[1] = m; }
 }
 
 // ---- binary traversal nodes -----------------------------------------------------------------------
@@ -468,7 +616,20 @@ int build_bvh(const BuildInput& in, BuildOutput* out, cudaStream_t st, char* err
   const size_t tmp_bytes = radix_sort_temp_bytes((size_t)T);
   void* d_tmp;
   CK(dev_alloc((void**)&d_tmp, tmp_bytes));
-  if (radix_sort_pairs(d_keys, d_keys2, d_ids, d_ids2, (size_t)T, 0, 64, d_tmp, st) == 0) {  // 8 passes: ends in *_in
+  // PLOC only needs the Morton ORDER to be a good one: its window search looks +-radius positions around every cluster.
+  // The sort therefore covers the emitter bit and the top ceil(log2(T) / 3) + 6 bits per axis — 64 cells per axis finer
+  // than the mean triangle spacing, so a region 2^18 times denser than average still resolves — and leaves triangles that
+  // agree in all of those in input order (stable sort): 6 passes instead of 8 at 100M triangles, 4 at 1k.  The Karras
+  // hierarchy needs fully sorted keys; LISA_MORTON_BITS=21 sorts everything.
+  int bits_axis = 21;
+  if (!in.lbvh) {
+    int lg = 0;
+    while ((1ll << lg) < (long long)T) lg++;
+    bits_axis = std::min(21, (lg + 2) / 3 + 6);
+    if (const char* e = getenv("LISA_MORTON_BITS")) bits_axis = std::max(1, std::min(21, atoi(e)));
+  }
+  const int sort_passes = (3 * bits_axis + 1 + 7) / 8, begin_bit = 64 - 8 * sort_passes;
+  if (radix_sort_pairs(d_keys, d_keys2, d_ids, d_ids2, (size_t)T, begin_bit, 64, d_tmp, st) == 0) {  // even number of passes: ends in *_in
     std::swap(d_keys, d_keys2);
     std::swap(d_ids, d_ids2);
   }
@@ -481,28 +642,31 @@ int build_bvh(const BuildInput& in, BuildOutput* out, cudaStream_t st, char* err
 
   // hierarchy storage for both partitions: partition p uses node slice [base_p, base_p + 2 n_p - 1)
   int2*   d_child;
-  int *   d_range, *d_parent, *d_flags;  // d_range: triangles below each internal node
+  int *   d_range, *d_parent = nullptr, *d_flags = nullptr;  // d_range: triangles below each internal node
   float4 *d_lo, *d_hi;
   const size_t NN = 2ull * T + 2;
   CK(dev_alloc((void**)&d_child, sizeof(int2) * NN));
   CK(dev_alloc((void**)&d_range, sizeof(int) * NN));
-  CK(dev_alloc((void**)&d_parent, sizeof(int) * NN));
-  CK(dev_alloc((void**)&d_flags, sizeof(int) * NN));
   CK(dev_alloc((void**)&d_lo, sizeof(float4) * NN));
   CK(dev_alloc((void**)&d_hi, sizeof(float4) * NN));
-  CK(cudaMemsetAsync(d_flags, 0, sizeof(int) * NN, st));
+  if (in.lbvh) {
+    CK(dev_alloc((void**)&d_parent, sizeof(int) * NN));
+    CK(dev_alloc((void**)&d_flags, sizeof(int) * NN));
+    CK(cudaMemsetAsync(d_flags, 0, sizeof(int) * NN, st));
+  }
 
   struct Part { int n, sorted_base, slice, root; } parts[2] = {{n_other, 0, 0, 0}, {n_emit, n_other, 2 * n_other + 1, 0}};
-  int *d_C[2] = {nullptr, nullptr}, *d_nn = nullptr, *d_sel = nullptr;
-  void*  d_sel_tmp = nullptr;
-  size_t sel_bytes = 0;
+  float4*             d_rec[2] = {nullptr, nullptr};  // PLOC cluster records, ping-pong
+  unsigned long long* d_tile_state = nullptr;
+  int*                d_ploc_ctl = nullptr;           // [0] ticket, [1] clusters after the round, [2] root id, [3] clusters left by the tail
+  const int radius = std::max(1, std::min(in.ploc_radius, PLOC_RMAX));
+  const size_t max_tiles = ((size_t)T + PLOC_TILE - 1) / PLOC_TILE + 1;
   if (!in.lbvh) {
-    CK(dev_alloc((void**)&d_C[0], sizeof(int) * (size_t)T));
-    CK(dev_alloc((void**)&d_C[1], sizeof(int) * (size_t)T));
-    CK(dev_alloc((void**)&d_nn, sizeof(int) * (size_t)T));
-    CK(dev_alloc((void**)&d_sel, sizeof(int) * 2));
-    sel_bytes = compact_temp_bytes((size_t)T);
-    CK(dev_alloc((void**)&d_sel_tmp, sel_bytes));
+    CK(dev_alloc((void**)&d_rec[0], sizeof(float4) * 2 * (size_t)T));
+    CK(dev_alloc((void**)&d_rec[1], sizeof(float4) * 2 * (size_t)T));
+    CK(dev_alloc((void**)&d_tile_state, sizeof(unsigned long long) * max_tiles));
+    CK(dev_alloc((void**)&d_ploc_ctl, sizeof(int) * 4));
+    CK(cudaMemsetAsync(d_ploc_ctl, 0, sizeof(int) * 4, st));
   }
   for (int p = 0; p < 2; p++) {
     Part& P = parts[p];
@@ -515,28 +679,30 @@ int build_bvh(const BuildInput& in, BuildOutput* out, cudaStream_t st, char* err
                                               d_parent + P.slice, d_lo + P.slice, d_hi + P.slice, d_flags + P.slice);
       P.root = 0;
     } else {
-      k_leaf_boxes<<<cdiv(P.n, 256), 256, 0, st>>>(in.d_verts, d_ids2 + P.sorted_base, P.n, d_lo + P.slice, d_hi + P.slice, d_C[0]);
-      int m = P.n, cur = 0, h_next = 0, rounds = 0;
-      int* d_next = d_sel + 1;
-      CK(cudaMemcpyAsync(d_next, &h_next, sizeof(int), cudaMemcpyHostToDevice, st));
-      while (m > 1) {
-        k_ploc_nn<<<cdiv(m, 128), 128, 0, st>>>(d_C[cur], m, d_lo + P.slice, d_hi + P.slice, in.ploc_radius, d_nn);
-        k_ploc_merge<<<cdiv(m, 256), 256, 0, st>>>(d_C[cur], m, d_nn, d_lo + P.slice, d_hi + P.slice, d_child + P.slice,
-                                                   d_range + P.slice, P.n, d_next, d_C[cur ^ 1]);
-        // compact in place of the old array: valid entries of d_C[cur^1] -> d_C[cur]
-        compact_nonneg(d_C[cur ^ 1], d_C[cur], (size_t)m, d_sel, d_sel_tmp, st);
+      k_leaf_records<<<cdiv(P.n, 256), 256, 0, st>>>(in.d_verts, d_ids2 + P.sorted_base, P.n, d_lo + P.slice, d_hi + P.slice, d_rec[0]);
+      int m = P.n, cur = 0, rounds = 0;
+      // stale tile states of the other partition must not be taken for this one's
+      CK(cudaMemsetAsync(d_tile_state, 0, sizeof(unsigned long long) * (((size_t)P.n + PLOC_TILE - 1) / PLOC_TILE), st));
+      while (m > PLOC_TAIL) {
+        k_ploc_round<<<cdiv(m, PLOC_TILE), PLOC_TILE, 0, st>>>(d_rec[cur], m, radius, d_rec[cur ^ 1], d_lo + P.slice, d_hi + P.slice,
+                                                             d_child + P.slice, d_range + P.slice, P.n - m, d_tile_state,
+                                                             (unsigned int*)d_ploc_ctl, d_ploc_ctl + 1, (unsigned)rounds);
         int m2 = 0;
-        CK(cudaMemcpyAsync(&m2, d_sel, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&m2, d_ploc_ctl + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         if (m2 >= m || m2 < 1) { snprintf(err, errlen, "PLOC made no progress (%d -> %d clusters)", m, m2); return -5; }
         m = m2;
+        cur ^= 1;
         rounds++;
       }
-      if (dbg) fprintf(stderr, "  ploc partition %d: %d leaves, %d rounds\n", p, P.n, rounds);
-      int root = 0;
-      CK(cudaMemcpyAsync(&root, d_C[cur], sizeof(int), cudaMemcpyDeviceToHost, st));
+      k_ploc_tail<<<1, PLOC_TAIL, 0, st>>>(d_rec[cur], m, radius, d_lo + P.slice, d_hi + P.slice, d_child + P.slice, d_range + P.slice,
+                                          P.n - m, d_ploc_ctl + 2);
+      int tail[2] = {0, 0};
+      CK(cudaMemcpyAsync(tail, d_ploc_ctl + 2, sizeof(tail), cudaMemcpyDeviceToHost, st));
       CK(cudaStreamSynchronize(st));
-      P.root = P.n > 1 ? root : 0;
+      if (tail[1] != 1) { snprintf(err, errlen, "PLOC made no progress (%d clusters left)", tail[1]); return -5; }
+      if (dbg) fprintf(stderr, "  ploc partition %d: %d leaves, %d rounds + tail from %d clusters\n", p, P.n, rounds, m);
+      P.root = P.n > 1 ? tail[0] : 0;
     }
   }
 
@@ -622,7 +788,7 @@ int build_bvh(const BuildInput& in, BuildOutput* out, cudaStream_t st, char* err
   tick("pack");
 
   dev_free(d_acc); dev_free(d_keys); dev_free(d_keys2); dev_free(d_ids); dev_free(d_ids2); dev_free(d_final_to_sorted);
-  dev_free(d_C[0]); dev_free(d_C[1]); dev_free(d_nn); dev_free(d_sel); dev_free(d_sel_tmp);
+  dev_free(d_rec[0]); dev_free(d_rec[1]); dev_free(d_tile_state); dev_free(d_ploc_ctl);
   dev_free(d_tmp); dev_free(d_child); dev_free(d_range); dev_free(d_parent); dev_free(d_flags); dev_free(d_lo); dev_free(d_hi);
 
   out->d_nodes = d_nodes;

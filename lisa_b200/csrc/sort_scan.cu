@@ -4,7 +4,8 @@
 //           (recursively tiled when there are more than 4096 of them), then a second sweep adds the offsets.
 // sort:     per 8-bit pass: k_rs_hist (per-tile digit histogram, layout [digit][tile]), exclusive scan of the
 //           histogram = global base of every (digit, tile), k_rs_scatter (stable: a warp owns a contiguous chunk of
-//           the tile, ranks equal digits with __match_any_sync + running per-warp counters in shared memory).
+//           the tile, ranks equal digits with __match_any_sync + running per-warp counters in shared memory, the tile
+//           is sorted by digit in shared memory and written out in runs).
 //           Algorithmic bytes per key and pass: 8 (hist) + 12 read + 12 written.
 // compact:  per-CTA ballot counts -> scan -> scatter.
 #include "sort_scan.h"
@@ -91,11 +92,20 @@ void exclusive_scan_u32(const uint32_t* in, uint32_t* out, size_t n, uint32_t* t
 }
 
 // ---- radix sort ---------------------------------------------------------------------------------------
+// A CTA owns a tile of 4096 consecutive keys (256 threads x 16), a warp a contiguous chunk of 512 of them.
+//   k_rs_hist     digit histogram of every tile, layout [digit][tile] (so that ONE exclusive scan of the whole array is
+//                 the global base of every (digit, tile) bucket)
+//   k_rs_scatter  ranks the keys of the tile stably (per warp: __match_any_sync + running per-warp digit counters), sorts
+//                 the tile by digit INTO SHARED MEMORY, and writes it out position by position: a warp's 32 stores then
+//                 fall into a few long runs (one per digit: ~16 keys = 128 B on uniform digits) instead of 32 scattered
+//                 sectors.  Algorithmic bytes per key and pass: 8 (hist) + 12 read + 12 written.
 #define RS_THREADS 256
-#define RS_ITEMS 8
-#define RS_TILE (RS_THREADS * RS_ITEMS)  // 2048 keys per CTA; a warp owns 256 consecutive keys
+#define RS_ITEMS 16
+#define RS_TILE (RS_THREADS * RS_ITEMS)  // 4096 keys per CTA; a warp owns 512 consecutive keys
+#define RS_WARPS (RS_THREADS / 32)
 
-__global__ void k_rs_hist(const unsigned long long* __restrict__ keys, size_t n, int shift, uint32_t* hist, uint32_t ntiles) {
+__global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const unsigned long long* __restrict__ keys, size_t n, int shift, uint32_t* hist,
+                                                        uint32_t ntiles) {
   __shared__ uint32_t h[256];
   h[threadIdx.x] = 0;
   __syncthreads();
@@ -109,14 +119,25 @@ __global__ void k_rs_hist(const unsigned long long* __restrict__ keys, size_t n,
   hist[(size_t)threadIdx.x * ntiles + blockIdx.x] = h[threadIdx.x];
 }
 
-__global__ void k_rs_scatter(const unsigned long long* __restrict__ keys, const unsigned int* __restrict__ vals, size_t n, int shift,
-                             const uint32_t* __restrict__ hist_scanned, uint32_t ntiles, unsigned long long* keys_out,
-                             unsigned int* vals_out) {
-  __shared__ uint32_t cnt[RS_THREADS / 32][256];  // running count of each digit inside each warp's chunk
-  for (int k = threadIdx.x; k < (RS_THREADS / 32) * 256; k += RS_THREADS) (&cnt[0][0])[k] = 0;
+struct RsSmem {
+  unsigned long long key[RS_TILE];
+  unsigned int       val[RS_TILE];
+  uint32_t           cnt[RS_WARPS][256];  // running count of each digit inside each warp's chunk -> start of (warp, digit) in the digit's run
+  uint32_t           dstart[256];         // start of the digit's run in the sorted tile
+  uint32_t           gdelta[256];         // global index of the digit's run minus dstart (mod 2^32)
+  uint32_t           scan[33];
+};
+
+__global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const unsigned long long* __restrict__ keys, const unsigned int* __restrict__ vals,
+                                                           size_t n, int shift, const uint32_t* __restrict__ hist_scanned, uint32_t ntiles,
+                                                           unsigned long long* keys_out, unsigned int* vals_out) {
+  extern __shared__ unsigned char rs_raw[];
+  RsSmem& sm = *reinterpret_cast<RsSmem*>(rs_raw);
+  for (int k = threadIdx.x; k < RS_WARPS * 256; k += RS_THREADS) (&sm.cnt[0][0])[k] = 0;
   __syncthreads();
   const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const size_t   chunk = (size_t)blockIdx.x * RS_TILE + (size_t)w * (RS_ITEMS * 32);
+  const size_t   tile0 = (size_t)blockIdx.x * RS_TILE;
+  const size_t   chunk = tile0 + (size_t)w * (RS_ITEMS * 32);
   unsigned long long key[RS_ITEMS];
   uint32_t           off[RS_ITEMS];
 #pragma unroll
@@ -128,19 +149,23 @@ __global__ void k_rs_scatter(const unsigned long long* __restrict__ keys, const 
     const unsigned same = __match_any_sync(0xffffffffu, d);
     const unsigned rank = __popc(same & ((1u << lane) - 1u));
     uint32_t       before = 0;
-    if (ok) before = cnt[w][d];
+    if (ok) before = sm.cnt[w][d];
     __syncwarp();
-    if (ok && rank == 0) cnt[w][d] = before + __popc(same);
+    if (ok && rank == 0) sm.cnt[w][d] = before + __popc(same);
     __syncwarp();
     off[r] = before + rank;
   }
   __syncthreads();
-  // per digit: exclusive prefix over the warps + global base of (digit, tile); thread d owns digit d
+  // thread d owns digit d: exclusive prefix of its counts over the warps, then the digit's place in the sorted tile
   {
     const unsigned d = threadIdx.x;
-    uint32_t run = hist_scanned[(size_t)d * ntiles + blockIdx.x];
+    uint32_t run = 0;
 #pragma unroll
-    for (int ww = 0; ww < RS_THREADS / 32; ww++) { const uint32_t c = cnt[ww][d]; cnt[ww][d] = run; run += c; }
+    for (int ww = 0; ww < RS_WARPS; ww++) { const uint32_t c = sm.cnt[ww][d]; sm.cnt[ww][d] = run; run += c; }
+    uint32_t tot;
+    const uint32_t start = block_excl_scan(run, sm.scan, &tot);
+    sm.dstart[d] = start;
+    sm.gdelta[d] = hist_scanned[(size_t)d * ntiles + blockIdx.x] - start;
   }
   __syncthreads();
 #pragma unroll
@@ -148,9 +173,21 @@ __global__ void k_rs_scatter(const unsigned long long* __restrict__ keys, const 
     const size_t i = chunk + (size_t)r * 32 + lane;
     if (i < n) {
       const unsigned d = (unsigned)(key[r] >> shift) & 255u;
-      const size_t   dst = (size_t)cnt[w][d] + off[r];
-      keys_out[dst] = key[r];
-      vals_out[dst] = vals[i];
+      const uint32_t pos = sm.dstart[d] + sm.cnt[w][d] + off[r];
+      sm.key[pos] = key[r];
+      sm.val[pos] = vals[i];
+    }
+  }
+  __syncthreads();
+  const uint32_t n_tile = (uint32_t)(n - tile0 < (size_t)RS_TILE ? n - tile0 : (size_t)RS_TILE);
+#pragma unroll
+  for (int k = 0; k < RS_ITEMS; k++) {
+    const uint32_t pos = (uint32_t)k * RS_THREADS + threadIdx.x;
+    if (pos < n_tile) {
+      const unsigned long long kk = sm.key[pos];
+      const size_t dst = (size_t)(uint32_t)(sm.gdelta[(unsigned)(kk >> shift) & 255u] + pos);
+      keys_out[dst] = kk;
+      vals_out[dst] = sm.val[pos];
     }
   }
 }
@@ -165,6 +202,13 @@ size_t radix_sort_temp_bytes(size_t n) {
 int radix_sort_pairs(unsigned long long* keys_in, unsigned long long* keys_out, unsigned int* vals_in, unsigned int* vals_out,
                      size_t n, int begin_bit, int end_bit, void* temp, cudaStream_t st) {
   if (n == 0) return 0;
+  static bool configured[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!configured[dev & 63]) {  // 58 KB of shared memory per CTA: above the 48 KB a kernel gets without asking
+    cudaFuncSetAttribute(k_rs_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmem));
+    configured[dev & 63] = true;
+  }
   const uint32_t tiles = (uint32_t)rs_tiles(n);
   const size_t   h = 256 * (size_t)tiles;
   uint32_t*      hist = (uint32_t*)temp;
@@ -177,7 +221,7 @@ int radix_sort_pairs(unsigned long long* keys_in, unsigned long long* keys_out, 
     unsigned int*       vo = flip ? vals_in : vals_out;
     k_rs_hist<<<tiles, RS_THREADS, 0, st>>>(ki, n, shift, hist, tiles);
     exclusive_scan_u32(hist, hist, h, nullptr, scan_tmp, st);
-    k_rs_scatter<<<tiles, RS_THREADS, 0, st>>>(ki, vi, n, shift, hist, tiles, ko, vo);
+    k_rs_scatter<<<tiles, RS_THREADS, sizeof(RsSmem), st>>>(ki, vi, n, shift, hist, tiles, ko, vo);
     flip ^= 1;
   }
   return flip;

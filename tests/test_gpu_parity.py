@@ -112,15 +112,15 @@ def test_primary_rays_bitwise_seeds(rt, orc, cornell):
 
 
 def test_shadow_policy_sensitivity(rt, cornell):
-    """Q2: closest-hit-decides (default) vs first-found (emitters first): report the mean shift."""
+    """Q2: closest-hit-decides (default) vs first-found with emitters first, on the README Cornell box: the second policy
+    ignores the sphere and the blocks where they stand between a surface and the light, so it can only brighten.  Measured
+    (128x128, 32 spp): x1.139 / 1.066 / 1.105 (R, G, B).  The sensitivity against the reference's own OptiX image, with the
+    original ceiling asset, is pinned in test_gpu_configs.py::test_q2_original_ceiling_sensitivity."""
     a, _ = _render(rt, cornell, 128, 32, shadow_mode=0)
     b, _ = _render(rt, cornell, 128, 32, shadow_mode=1)
     shift = b.reshape(-1, 3).mean(0) / a.reshape(-1, 3).mean(0)
-    import os
-    if os.path.isdir("gpurun_out"):
-        open("gpurun_out/q2_shift_cornell.txt", "w").write(repr(shift.tolist()))
-    assert (shift >= 0.999).all()      # ignoring occluders in front of the light can only brighten
-    assert (shift < 1.5).all()
+    assert (shift > 1.03).all() and (shift < 1.2).all(), shift
+    assert shift[0] > shift[2] > shift[1]   # the red wall's side of the box is the one the props shadow most
 
 
 def _knot_scene(cornell, nu, nv):

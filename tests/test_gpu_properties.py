@@ -269,14 +269,14 @@ def test_ggx_variant_matches_its_oracle(built, orc, tmp_path):
             "sc.pop('materials_packed')\n"
             "res = {}\n"
             "for spp in (1, 8):\n"
-            "    R = rt.Renderer.from_scene(sc); R.render_subframes(0, 1, spp); res['a%d' %% spp] = R.read_accum(); st = R.stats()\n"
-            "    res['rays%d' %% spp] = np.array([st['last_radiance_rays'], st['last_shadow_rays']])\n"
-            "np.savez(r'%s', **res)\n")
+            "    R = rt.Renderer.from_scene(sc); R.render_subframes(0, 1, spp); res['a' + str(spp)] = R.read_accum(); st = R.stats()\n"
+            "    res['rays' + str(spp)] = np.array([st['last_radiance_rays'], st['last_shadow_rays']])\n"
+            "np.savez(r'OUTFILE', **res)\n")
     imgs = []
     for lib in ("liblisa_rt.so", "liblisa_rt_ggx.so"):
         out = str(tmp_path / (lib + ".npz"))
         env = dict(os.environ, LISA_RT_LIB=os.path.join(ROOT, "lisa_b200", lib))
-        subprocess.check_call([sys.executable, "-c", code % out], cwd=ROOT, env=env)
+        subprocess.check_call([sys.executable, "-c", code.replace("OUTFILE", out)], cwd=ROOT, env=env)
         imgs.append(np.load(out))
     lam, ggx = imgs
     # the oracle with the same materials
