@@ -223,15 +223,19 @@ __device__ __forceinline__ int ploc_nearest(const float4* slo, const float4* shi
 }
 
 // creates the node that merges the clusters (la, ha) and (lb, hb) — a at the lower position — and returns its record
-__device__ __forceinline__ void ploc_make_node(int id, const float4& la, const float4& ha, const float4& lb, const float4& hb,
+// (inputs by value: callers pass the record they are about to overwrite)
+__device__ __forceinline__ void ploc_make_node(int id, const float4 la, const float4 ha, const float4 lb, const float4 hb,
                                                float4* node_lo, float4* node_hi, int2* child, int* cnt, float4& rlo, float4& rhi) {
-  const int c = __float_as_int(ha.w) + __float_as_int(hb.w);
-  rlo = make_float4(fminf(la.x, lb.x), fminf(la.y, lb.y), fminf(la.z, lb.z), __int_as_float(id));
-  rhi = make_float4(fmaxf(ha.x, hb.x), fmaxf(ha.y, hb.y), fmaxf(ha.z, hb.z), __int_as_float(c));
-  node_lo[id] = make_float4(rlo.x, rlo.y, rlo.z, 0.0f);
-  node_hi[id] = make_float4(rhi.x, rhi.y, rhi.z, 0.0f);
-  child[id]   = make_int2(__float_as_int(la.w), __float_as_int(lb.w));
+  const int  c = __float_as_int(ha.w) + __float_as_int(hb.w);
+  const int2 ch = make_int2(__float_as_int(la.w), __float_as_int(lb.w));
+  const float4 mlo = make_float4(fminf(la.x, lb.x), fminf(la.y, lb.y), fminf(la.z, lb.z), 0.0f);
+  const float4 mhi = make_float4(fmaxf(ha.x, hb.x), fmaxf(ha.y, hb.y), fmaxf(ha.z, hb.z), 0.0f);
+  node_lo[id] = mlo;
+  node_hi[id] = mhi;
+  child[id]   = ch;
   cnt[id]     = c;
+  rlo = make_float4(mlo.x, mlo.y, mlo.z, __int_as_float(id));
+  rhi = make_float4(mhi.x, mhi.y, mhi.z, __int_as_float(c));
 }
 
 // tile state of the look-back scan: bits 0..29 survivors, 30..59 merges, 60..61 status (1 aggregate, 2 inclusive prefix), 62..63 round tag
@@ -773,6 +777,16 @@ int build_bvh(const BuildInput& in, BuildOutput* out, cudaStream_t st, char* err
     }
     total_nodes = node_next;
     dev_free(d_q[0]); dev_free(d_q[1]); dev_free(d_counters);
+    // the node array was sized for the worst case (one wide node per triangle: 8 GB at 100M triangles); keep what is used
+    // (typically T / 7 nodes) and hand the rest back
+    if ((size_t)total_nodes * 4 < max_nodes) {
+      float4* d_fit = nullptr;
+      CK(dev_alloc((void**)&d_fit, sizeof(float4) * 5 * (size_t)std::max(total_nodes, 1)));
+      CK(cudaMemcpyAsync(d_fit, d_nodes, sizeof(float4) * 5 * (size_t)total_nodes, cudaMemcpyDeviceToDevice, st));
+      CK(cudaStreamSynchronize(st));
+      dev_free(d_nodes);
+      d_nodes = d_fit;
+    }
   }
 
   tick("collapse");

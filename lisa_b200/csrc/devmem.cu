@@ -22,7 +22,15 @@ std::mutex                                      g_mu;
 std::multimap<Key, void*>                       g_free;    // parked blocks by (device, class size)
 std::unordered_map<void*, Key>                  g_live;    // every block handed out
 size_t                                          g_cached = 0;
-const size_t                                    kBudget = 24ull << 30;  // parked bytes per process
+// parked bytes per process: 64 GB by default (a 100M-triangle build holds ~50 GB at its peak; anything above the budget
+// goes back to the driver, and the next build then pays cudaMalloc again: 20-30 ms per multi-GB block); LISA_CACHE_GB overrides
+size_t budget() {
+  static size_t b = [] {
+    const char* e = getenv("LISA_CACHE_GB");
+    return (size_t)(e ? std::max(0, atoi(e)) : 64) << 30;
+  }();
+  return b;
+}
 
 size_t size_class(size_t b) {
   if (b < 512) return 512;
@@ -83,7 +91,7 @@ void dev_free(void* p) {
   if (it == g_live.end()) { cudaFree(p); return; }  // not ours
   const Key k = it->second;
   g_live.erase(it);
-  if (g_cached + k.bytes <= kBudget) {
+  if (g_cached + k.bytes <= budget()) {
     g_free.emplace(k, p);
     g_cached += k.bytes;
   } else {

@@ -167,6 +167,11 @@ struct TravState<true> : WideState {};
 template <>
 struct TravState<false> : BinState {};
 
+// component (i mod 3) of v, by selects (a runtime index into a local array would live in local memory)
+__device__ __forceinline__ float pick3(const float3& v, int i) {
+  return (i == 0 || i == 3) ? v.x : ((i == 1 || i == 4) ? v.y : v.z);
+}
+
 // cone (axis, cos half-angle) around the sphere that bounds all emitters, seen from P
 __device__ __forceinline__ void emitter_cone(const DScene& sc, const float3& P, float3& axis, float& cosa) {
   const float3 v  = sc.emit_c - P;
@@ -273,18 +278,62 @@ __device__ __forceinline__ ChainNext chain_event(const DScene& sc, const Tile& t
     }
   }
   // ---- (3) shoot_ray_to_light
-  float3 cone_axis = f3(0, 0, 0);
-  float  cone_cos = 2.0f;
+  // Per job, the filter that decides which tries CAN reach an emitter (everything else is resolved by consuming its draws):
+  //   flat bounds (a quad light, sc.emit_flat = k): the try's direction w crosses the slab |X_k - plane| <= hh for
+  //     t in [(|dy| - hh) / u, (|dy| + hh) / u] with u = +-w_k > 0 towards the plane, dy = plane - P_k; it can reach the
+  //     rectangle [A0, B0] x [A2, B2] (relative to P, on the other two axes) only if, on each axis,
+  //     |dy| w_i + hh |w_i| >= A_i u  and  |dy| w_i - hh |w_i| <= B_i u.  No division, no normalisation (homogeneous in w),
+  //     and as tight as the box test itself: ~1 in 4 of the tries the bounding-sphere cone lets through.
+  //   otherwise: the cone around the sphere that bounds all emitters (q|q| >= cos|cos| v.v).
+  // Both are conservative with respect to hits_emitter_bounds(), which confirms the survivors in try order.
+  // The job's row of the warp's job buffer is written right here (three float4: N | LCG state, the filter's four
+  // parameters — flat: A0, B0, A2, B2; cone: axis.xyz, cos|cos| — and |dy|, flag bits (sign of dy | 1 = every try passes),
+  // tries left, slack), so that none of it stays live in registers; rows of lanes that stop trying below are never read.
+  bool      nothing = false;                           // no try of this job can reach an emitter
+  const int fk = sc.emit_flat;
   if (trying) {
-    emitter_cone(sc, c.o, cone_axis, cone_cos);
-    // every try lies in the hemisphere of N: if the whole cone is below that horizon no try can be a candidate
-    if (cone_cos > -1.0f && cone_cos <= 1.0f &&
-        dot(c.N, cone_axis) < -sqrtf(fmaxf(1.0f - cone_cos * cone_cos, 0.0f)) - 1e-3f) cone_cos = 2.0f;
+    float4   fpar = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    float    f_ady = 0.0f, f_sl = 0.0f;
+    uint32_t f_bits = 0u;
+    if (sc.emit_r2 < 0.0f) nothing = true;             // no emitters at all
+    else if (fk >= 0) {
+      // components along the flat axis (k), and along the two axes of the rectangle (k + 1, k + 2 mod 3)
+      const float Pk = pick3(c.o, fk), P0 = pick3(c.o, fk + 1), P2 = pick3(c.o, fk + 2);
+      const float Nk = pick3(c.N, fk), N0 = pick3(c.N, fk + 1), N2 = pick3(c.N, fk + 2);
+      const float dy = sc.emit_plane - Pk;
+      float A0 = pick3(sc.emit_lo, fk + 1) - P0, B0 = pick3(sc.emit_hi, fk + 1) - P0;
+      float A2 = pick3(sc.emit_lo, fk + 2) - P2, B2 = pick3(sc.emit_hi, fk + 2) - P2;
+      f_ady = fabsf(dy);
+      const float sum = fabsf(A0) + fabsf(B0) + fabsf(A2) + fabsf(B2) + f_ady;
+      const float mrg = 4e-6f * sum;  // hits_emitter_bounds accepts with a relative slack of 1e-6 on its slab distances
+      A0 -= mrg; B0 += mrg; A2 -= mrg; B2 += mrg;
+      fpar = make_float4(A0, B0, A2, B2);
+      f_sl = 1e-6f * sum;             // the draws below are within 2^-23 of the true ones; the test is linear in them
+      f_bits = __float_as_uint(dy) & 0x80000000u;
+      if (!sc.cull || f_ady <= sc.emit_hh) f_bits |= 1u;  // culling off, or P inside the slab of the light's plane
+      else {
+        // every try lies in the hemisphere of N: if the whole light is below that horizon no try can reach it
+        const float top = fmaxf(N0 * A0, N0 * B0) + fmaxf(N2 * A2, N2 * B2) + Nk * dy + sc.emit_hh * fabsf(Nk);
+        if (top < -1e-4f * sum) nothing = true;
+      }
+    } else {
+      float3 cone_axis;
+      float  cone_cos;
+      emitter_cone(sc, c.o, cone_axis, cone_cos);
+      // every try lies in the hemisphere of N: if the whole cone is below that horizon no try can be a candidate
+      if (cone_cos > -1.0f && cone_cos <= 1.0f &&
+          dot(c.N, cone_axis) < -sqrtf(fmaxf(1.0f - cone_cos * cone_cos, 0.0f)) - 1e-3f) cone_cos = 2.0f;
+      if (cone_cos > 1.0f) nothing = true;
+      fpar = make_float4(cone_axis.x, cone_axis.y, cone_axis.z, cone_cos * fabsf(cone_cos));
+    }
+    jb[3 * lane]     = make_float4(c.N.x, c.N.y, c.N.z, __uint_as_float(c.seed));
+    jb[3 * lane + 1] = fpar;
+    jb[3 * lane + 2] = make_float4(f_ady, __uint_as_float(f_bits), __uint_as_float(LISA_SHADOW_TRIES - c.tries), f_sl);
   }
   if (trying && (c.flags & F_STICKY)) {  // RayState::hit is true (Q1), only at the first try of a bounce: a real ray
     nx.w = shoot_ray_hemisphere(c.N, c.seed);
     nx.start_shd = true; trying = false;
-  } else if (trying && cone_cos > 1.0f) {  // no try can reach an emitter: consume the draws of all that are left
+  } else if (trying && nothing) {  // no try can reach an emitter: consume the draws of all that are left
     const uint32_t k = LISA_SHADOW_TRIES - c.tries;
     c.seed = lcg_a[k] * c.seed + lcg_c[k];
     cnt.shadow += k; cnt.culled += k;
@@ -293,45 +342,70 @@ __device__ __forceinline__ ChainNext chain_event(const DScene& sc, const Tile& t
   }
   const unsigned jobs = __ballot_sync(FULL, trying);
   if (jobs) {
-    if (trying) {
-      jb[3 * lane]     = make_float4(c.N.x, c.N.y, c.N.z, cone_cos * fabsf(cone_cos));
-      jb[3 * lane + 1] = make_float4(cone_axis.x, cone_axis.y, cone_axis.z, __uint_as_float(c.seed));
-      jb[3 * lane + 2].x = __uint_as_float(LISA_SHADOW_TRIES - c.tries);
-    }
     __syncwarp();
-    // The cone test only has to be conservative (its hits are confirmed below with the reference's own expression), so a
+    // The filter only has to be conservative (its hits are confirmed below with the reference's own expression), so a
     // draw is taken from the LCG state shifted left by 8 bits (t = s << 8 obeys t' = A t + (C << 8), and holds the 24
     // bits rnd() uses in its top 24): 2 + (u >> 1) 2^-22 is one IMAD.HI, minus 3 gives rng() to within 2^-23 —
-    // 3 instructions on the FMA pipe per draw instead of 6, 4 of them on the busier ALU pipe.  For |v| >= 0.01 that
-    // moves the direction by < 2e-5 rad, well inside the 1e-4 the cone's cosine is widened by; shorter v are kept.
+    // 3 instructions on the FMA pipe per draw instead of 6, 4 of them on the busier ALU pipe.
     const uint32_t my_a = lcg_a[lane], my_c8 = lcg_c[lane] << 8;
     unsigned cone_mask = 0;
-    for (unsigned rem = jobs; rem; rem &= rem - 1u) {
-      const int      j  = __ffs(rem) - 1;
-      const float4   r0 = jb[3 * j], r1 = jb[3 * j + 1];
-      const uint32_t left = __float_as_uint(jb[3 * j + 2].x);
-      const uint32_t t0 = my_a * (__float_as_uint(r1.w) << 8) + my_c8;  // shifted LCG state before try (tries_j + lane)
-      const uint32_t t1 = 1664525u * t0 + (1013904223u << 8);
-      const uint32_t t2 = (1664525u * 1664525u) * t0 + ((1664525u * 1013904223u + 1013904223u) << 8);
-      const uint32_t t3 = (1664525u * 1664525u * 1664525u) * t0 + (((1664525u * 1664525u) * 1013904223u + 1664525u * 1013904223u + 1013904223u) << 8);
-      const float    a = __uint_as_float(__umulhi(t1, 0x00800000u) + 0x40000000u) - 3.0f;
-      const float    b = __uint_as_float(__umulhi(t2, 0x00800000u) + 0x40000000u) - 3.0f;
-      const float    cc = __uint_as_float(__umulhi(t3, 0x00800000u) + 0x40000000u) - 3.0f;
-      // w = +-v/|v| with the sign of v.N (shoot_ray_hemisphere); w.A >= cos  <=>  q|q| >= cos|cos| * v.v with
-      // q = +-v.A, no normalisation needed.  Where the sign of v.N is within rounding of zero the try is kept.
-      const float    sN = fmaf(cc, r0.z, fmaf(b, r0.y, a * r0.x));
-      const float    qA = fmaf(cc, r1.z, fmaf(b, r1.y, a * r1.x));
-      const float    vv = fmaf(cc, cc, fmaf(b, b, a * a));
-      const float    q  = __uint_as_float(__float_as_uint(qA) ^ (__float_as_uint(sN) & 0x80000000u));
-      const bool     in_cone = q * fabsf(q) >= r0.w * vv || fabsf(sN) < 4e-6f || vv < 1e-4f;
-      const unsigned m = __ballot_sync(FULL, in_cone && lane < left);
-      if ((int)lane == j) cone_mask = m;
+    if (fk >= 0) {
+      const float hh = sc.emit_hh;
+      for (unsigned rem = jobs; rem; rem &= rem - 1u) {
+        const int      j  = __ffs(rem) - 1;
+        const float4   r0 = jb[3 * j], r1 = jb[3 * j + 1], r2 = jb[3 * j + 2];
+        const uint32_t left = __float_as_uint(r2.z), bits = __float_as_uint(r2.y);
+        const uint32_t t0 = my_a * (__float_as_uint(r0.w) << 8) + my_c8;  // shifted LCG state before try (tries_j + lane)
+        const uint32_t t1 = 1664525u * t0 + (1013904223u << 8);
+        const uint32_t t2 = (1664525u * 1664525u) * t0 + ((1664525u * 1013904223u + 1013904223u) << 8);
+        const uint32_t t3 = (1664525u * 1664525u * 1664525u) * t0 + (((1664525u * 1664525u) * 1013904223u + 1664525u * 1013904223u + 1013904223u) << 8);
+        const float    a = __uint_as_float(__umulhi(t1, 0x00800000u) + 0x40000000u) - 3.0f;
+        const float    b = __uint_as_float(__umulhi(t2, 0x00800000u) + 0x40000000u) - 3.0f;
+        const float    cc = __uint_as_float(__umulhi(t3, 0x00800000u) + 0x40000000u) - 3.0f;
+        // w = +-v with the sign of v.N (shoot_ray_hemisphere); where that sign is within rounding of zero the try is kept
+        const float    sN = fmaf(cc, r0.z, fmaf(b, r0.y, a * r0.x));
+        const uint32_t sb = __float_as_uint(sN) & 0x80000000u;
+        const float    vk = fk == 0 ? a : (fk == 1 ? b : cc), v0 = fk == 0 ? b : (fk == 1 ? cc : a), v2 = fk == 0 ? cc : (fk == 1 ? a : b);
+        const float    u  = __uint_as_float(__float_as_uint(vk) ^ sb ^ (bits & 0x80000000u));  // component towards the plane
+        const float    w0 = __uint_as_float(__float_as_uint(v0) ^ sb), w2 = __uint_as_float(__float_as_uint(v2) ^ sb);
+        const float    c0 = r2.x * w0, c2 = r2.x * w2;
+        const float    p0 = fmaf(hh, fabsf(w0), c0), q0 = fmaf(-hh, fabsf(w0), c0);
+        const float    p2 = fmaf(hh, fabsf(w2), c2), q2 = fmaf(-hh, fabsf(w2), c2);
+        const bool     reach = u > -2.4e-7f && fmaf(-r1.x, u, p0) >= -r2.w && fmaf(-r1.y, u, q0) <= r2.w &&
+                               fmaf(-r1.z, u, p2) >= -r2.w && fmaf(-r1.w, u, q2) <= r2.w;
+        const bool     keep = reach || fabsf(sN) < 4e-6f || (bits & 1u);
+        const unsigned m = __ballot_sync(FULL, keep && lane < left);
+        if ((int)lane == j) cone_mask = m;
+      }
+    } else {
+      for (unsigned rem = jobs; rem; rem &= rem - 1u) {
+        const int      j  = __ffs(rem) - 1;
+        const float4   r0 = jb[3 * j], r1 = jb[3 * j + 1];
+        const uint32_t left = __float_as_uint(jb[3 * j + 2].z);
+        const uint32_t t0 = my_a * (__float_as_uint(r0.w) << 8) + my_c8;  // shifted LCG state before try (tries_j + lane)
+        const uint32_t t1 = 1664525u * t0 + (1013904223u << 8);
+        const uint32_t t2 = (1664525u * 1664525u) * t0 + ((1664525u * 1013904223u + 1013904223u) << 8);
+        const uint32_t t3 = (1664525u * 1664525u * 1664525u) * t0 + (((1664525u * 1664525u) * 1013904223u + 1664525u * 1013904223u + 1013904223u) << 8);
+        const float    a = __uint_as_float(__umulhi(t1, 0x00800000u) + 0x40000000u) - 3.0f;
+        const float    b = __uint_as_float(__umulhi(t2, 0x00800000u) + 0x40000000u) - 3.0f;
+        const float    cc = __uint_as_float(__umulhi(t3, 0x00800000u) + 0x40000000u) - 3.0f;
+        // w = +-v/|v| with the sign of v.N (shoot_ray_hemisphere); w.A >= cos  <=>  q|q| >= cos|cos| * v.v with
+        // q = +-v.A, no normalisation needed.  Where the sign of v.N is within rounding of zero the try is kept; so are
+        // very short v (the draws' 2^-23 becomes a direction error above the 1e-4 the cone's cosine is widened by).
+        const float    sN = fmaf(cc, r0.z, fmaf(b, r0.y, a * r0.x));
+        const float    qA = fmaf(cc, r1.z, fmaf(b, r1.y, a * r1.x));
+        const float    vv = fmaf(cc, cc, fmaf(b, b, a * a));
+        const float    q  = __uint_as_float(__float_as_uint(qA) ^ (__float_as_uint(sN) & 0x80000000u));
+        const bool     in_cone = q * fabsf(q) >= r1.w * vv || fabsf(sN) < 4e-6f || vv < 1e-4f;
+        const unsigned m = __ballot_sync(FULL, in_cone && lane < left);
+        if ((int)lane == j) cone_mask = m;
+      }
     }
     __syncwarp();
-    // the few cone hits are confirmed against the emitter box, in try order, by the job's owner, with the reference's
-    // own expression for the direction.  Measured twice (k_path: 1143 vs 1152; k_pool: 1279 vs 1351 Msamples/s):
-    // compacting the cone hits of all jobs into one list and confirming one per lane in a single pass LOSES to this
-    // loop, although the cone around the emitters' bounding sphere passes 4x the tries that reach their box.
+    // the survivors are confirmed against the emitter box, in try order, by the job's owner, with the reference's own
+    // expression for the direction (with flat bounds the first survivor almost always is one: ~1.1 passes of this loop
+    // per management section instead of 4).  Measured twice (k_path: 1143 vs 1152; k_pool: 1279 vs 1351 Msamples/s):
+    // compacting the survivors of all jobs into one list and confirming one per lane in a single pass LOSES to this loop.
     if (trying) {
       int first = -1;
       while (cone_mask) {

@@ -272,10 +272,13 @@ static int create_impl(const lisa_scene_desc* sd, const lisa_options* opt, lisa_
   if (const char* e = getenv("LISA_PLOC_RADIUS")) radius = std::max(1, atoi(e));
   BuildInput bi{d_verts, d_normals, d_mat_idx, d_emit, T, sd->num_materials, o.bvh_kind == LISA_BVH_WIDE8 ? 1 : 0, lbvh, radius};
   int rc = build_bvh(bi, &c->bvh, c->stream, g_err, sizeof(g_err));
+  if (rc) {  // keep the builder's message: a sticky CUDA error would otherwise be reported by the next call instead
+    dev_free(d_verts); dev_free(d_normals); dev_free(d_mat_idx); dev_free(d_emit);
+    return rc;
+  }
   CU(cudaEventRecord(t2, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   dev_free(d_verts); dev_free(d_normals); dev_free(d_mat_idx); dev_free(d_emit);
-  if (rc) return rc;
   cudaEventElapsedTime(&c->stats.upload_ms, t0, t1);
   cudaEventElapsedTime(&c->stats.bvh_build_ms, t1, t2);
 
@@ -304,6 +307,22 @@ static int create_impl(const lisa_scene_desc* sd, const lisa_options* opt, lisa_
     } else {  // no emitter: nothing can ever be lit; an empty sphere culls every non-sticky try
       c->scene.emit_c = make_float3(0, 0, 0);
       c->scene.emit_r2 = -1.0f;
+    }
+    // a quad light: the (unpadded) emitter bounds are flat along one axis
+    c->scene.emit_flat = -1;
+    c->scene.emit_plane = 0.0f;
+    c->scene.emit_hh = 0.0f;
+    if (c->bvh.num_emit_tris > 0 && !(getenv("LISA_FLAT_LIGHT") && !atoi(getenv("LISA_FLAT_LIGHT")))) {
+      const float ext[3] = {b[3] - b[0], b[4] - b[1], b[5] - b[2]};
+      const float big = std::max(ext[0], std::max(ext[1], ext[2]));
+      for (int k = 0; k < 3; k++)
+        if (big > 0.0f && ext[k] <= 1e-6f * big && ext[(k + 1) % 3] > 0.0f && ext[(k + 2) % 3] > 0.0f) {
+          const float lo = (&c->scene.emit_lo.x)[k], hi = (&c->scene.emit_hi.x)[k];  // the PADDED bounds, which the confirmation tests
+          c->scene.emit_flat = k;
+          c->scene.emit_plane = 0.5f * (lo + hi);
+          c->scene.emit_hh = 0.5f * (hi - lo) * 1.01f + 4e-6f * (big + fabsf(lo) + fabsf(hi));
+          break;
+        }
     }
     c->scene.cull = (o.flags & LISA_FLAG_NO_CULL) ? 0 : 1;
     if (const char* e = getenv("LISA_CULL")) c->scene.cull = atoi(e) != 0;

@@ -35,6 +35,11 @@ struct DScene {
   float3           emit_c;             // centre and squared radius of the sphere around those bounds:
   float            emit_r2;            //   a shadow ray outside the cone (P, sphere) cannot reach an emitter
   int              cull;               // 1: resolve shadow tries that provably cannot change RayState::hit without traversal
+  int              emit_flat;          // axis (0, 1, 2) along which the emitter bounds are flat (a quad light: all emitter
+                                       //   triangles in one axis-aligned plane), -1 otherwise; flat bounds get an (almost)
+                                       //   exact, division-free filter for shadow tries instead of the cone test
+  float            emit_plane;         // the plane's coordinate on that axis
+  float            emit_hh;            // half thickness of the padded bounds on that axis, plus slack
 };
 
 }  // namespace lisa
