@@ -177,6 +177,16 @@ int lisa_save_accum(lisa_ctx* ctx, const char* path);
 int lisa_load_accum(lisa_ctx* ctx, const char* path, uint32_t* subframes);
 int lisa_get_stats(lisa_ctx* ctx, lisa_stats* stats /* struct_size set by caller */);
 
+/* Serialisable BVH (the reference rebuilds its GAS on every start, optix_wrapper.cc:105-145).
+ * lisa_save_bvh writes what lisa_create built: the node array, the packed triangles (positions + material ids, normals +
+ * original indices) in leaf order, the roots and bounds of the emitter / non-emitter partitions.  lisa_create_from_bvh makes
+ * a context from such a file: no soup upload, no build — scene->vertices / normals / mat_indices may be NULL (num_vertices 0),
+ * everything else of the scene (materials, camera, size) is used; the file is refused if it is truncated, if the triangle
+ * count disagrees with a scene that does carry geometry, or if the materials' emitter flags differ from those the BVH was
+ * built for (the partition is baked in).  Images are bit-identical to those of the context that saved the file. */
+int lisa_save_bvh(lisa_ctx* ctx, const char* path);
+int lisa_create_from_bvh(const lisa_scene_desc* scene, const lisa_options* options /* may be NULL */, const char* path, lisa_ctx** out);
+
 /* Multi-GPU plumbing: every rank renders a disjoint subframe set into its own sums; the
  * caller reduces the sum buffers (one NCCL reduce) and the root reads the image.  The buffer holds W*H
  * float4 = (sum of all samples .xyz, number of samples .w; the image is .xyz / .w) and lives on the context's device. */

@@ -22,6 +22,7 @@ struct BuildOutput {
   float4* d_tri_v;          // 3 float4 per triangle, final order
   float4* d_tri_n;          // 3 float4 per triangle, final order
   int*    d_final_to_orig;  // final index -> caller's triangle index
+  int     num_tris;
   int     num_nodes, nodes_other, nodes_emit;
   int     root_other, root_emit;
   int     num_emit_tris;

@@ -601,6 +601,8 @@ int build_bvh(const BuildInput& in, BuildOutput* out, cudaStream_t st, char* err
   tick(nullptr);
   memset(out, 0, sizeof(*out));
   out->root_other = out->root_emit = -1;
+  out->num_tris = T;
+  for (int k = 0; k < 3; k++) { out->box_other[k] = out->box_emit[k] = FLT_MAX; out->box_other[3 + k] = out->box_emit[3 + k] = -FLT_MAX; }
   if (T == 0) return 0;
 
   BoundsAcc*          d_acc;

@@ -294,15 +294,17 @@ __device__ __forceinline__ ChainNext chain_event(const DScene& sc, const Tile& t
   if (trying) {
     float4   fpar = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     float    f_ady = 0.0f, f_sl = 0.0f;
+    float    Nk = c.N.x, N0 = c.N.y, N2 = c.N.z;  // the normal as the loop wants it: permuted (k, k+1, k+2) for flat bounds
     uint32_t f_bits = 0u;
     if (sc.emit_r2 < 0.0f) nothing = true;             // no emitters at all
     else if (fk >= 0) {
-      // components along the flat axis (k), and along the two axes of the rectangle (k + 1, k + 2 mod 3)
-      const float Pk = pick3(c.o, fk), P0 = pick3(c.o, fk + 1), P2 = pick3(c.o, fk + 2);
-      const float Nk = pick3(c.N, fk), N0 = pick3(c.N, fk + 1), N2 = pick3(c.N, fk + 2);
+      // components along the flat axis (k) and along the two axes of the rectangle (k + 1, k + 2 mod 3); fk is uniform
+      float Pk, P0, P2, l0, h0, l2, h2;
+      if (fk == 0)      { Pk = c.o.x; P0 = c.o.y; P2 = c.o.z; Nk = c.N.x; N0 = c.N.y; N2 = c.N.z; l0 = sc.emit_lo.y; h0 = sc.emit_hi.y; l2 = sc.emit_lo.z; h2 = sc.emit_hi.z; }
+      else if (fk == 1) { Pk = c.o.y; P0 = c.o.z; P2 = c.o.x; Nk = c.N.y; N0 = c.N.z; N2 = c.N.x; l0 = sc.emit_lo.z; h0 = sc.emit_hi.z; l2 = sc.emit_lo.x; h2 = sc.emit_hi.x; }
+      else              { Pk = c.o.z; P0 = c.o.x; P2 = c.o.y; Nk = c.N.z; N0 = c.N.x; N2 = c.N.y; l0 = sc.emit_lo.x; h0 = sc.emit_hi.x; l2 = sc.emit_lo.y; h2 = sc.emit_hi.y; }
       const float dy = sc.emit_plane - Pk;
-      float A0 = pick3(sc.emit_lo, fk + 1) - P0, B0 = pick3(sc.emit_hi, fk + 1) - P0;
-      float A2 = pick3(sc.emit_lo, fk + 2) - P2, B2 = pick3(sc.emit_hi, fk + 2) - P2;
+      float A0 = l0 - P0, B0 = h0 - P0, A2 = l2 - P2, B2 = h2 - P2;
       f_ady = fabsf(dy);
       const float sum = fabsf(A0) + fabsf(B0) + fabsf(A2) + fabsf(B2) + f_ady;
       const float mrg = 4e-6f * sum;  // hits_emitter_bounds accepts with a relative slack of 1e-6 on its slab distances
@@ -326,7 +328,7 @@ __device__ __forceinline__ ChainNext chain_event(const DScene& sc, const Tile& t
       if (cone_cos > 1.0f) nothing = true;
       fpar = make_float4(cone_axis.x, cone_axis.y, cone_axis.z, cone_cos * fabsf(cone_cos));
     }
-    jb[3 * lane]     = make_float4(c.N.x, c.N.y, c.N.z, __uint_as_float(c.seed));
+    jb[3 * lane]     = make_float4(Nk, N0, N2, __uint_as_float(c.seed));
     jb[3 * lane + 1] = fpar;
     jb[3 * lane + 2] = make_float4(f_ady, __uint_as_float(f_bits), __uint_as_float(LISA_SHADOW_TRIES - c.tries), f_sl);
   }
@@ -350,31 +352,38 @@ __device__ __forceinline__ ChainNext chain_event(const DScene& sc, const Tile& t
     const uint32_t my_a = lcg_a[lane], my_c8 = lcg_c[lane] << 8;
     unsigned cone_mask = 0;
     if (fk >= 0) {
-      const float hh = sc.emit_hh;
+      // The three draws of a try are x, y, z of its direction, in that order (maths.cu:10-15); the loop wants them as
+      // (k, k + 1, k + 2): it steps the LCG by the matching number of draws — multipliers and increments chosen once, per
+      // kernel-uniform fk — and the job's normal is stored in the same order.  No select in the loop, and no branch: the
+      // four margins are folded with min.
+      const uint32_t A1 = 1664525u, A2 = 1664525u * 1664525u, A3 = 1664525u * 1664525u * 1664525u;
+      const uint32_t C1 = 1013904223u << 8, C2 = (1664525u * 1013904223u + 1013904223u) << 8,
+                     C3 = ((1664525u * 1664525u) * 1013904223u + 1664525u * 1013904223u + 1013904223u) << 8;
+      const uint32_t mk = fk == 0 ? A1 : (fk == 1 ? A2 : A3), ck = fk == 0 ? C1 : (fk == 1 ? C2 : C3);
+      const uint32_t m0 = fk == 0 ? A2 : (fk == 1 ? A3 : A1), c0i = fk == 0 ? C2 : (fk == 1 ? C3 : C1);
+      const uint32_t m2 = fk == 0 ? A3 : (fk == 1 ? A1 : A2), c2i = fk == 0 ? C3 : (fk == 1 ? C1 : C2);
+      const float    hh = sc.emit_hh;
       for (unsigned rem = jobs; rem; rem &= rem - 1u) {
         const int      j  = __ffs(rem) - 1;
         const float4   r0 = jb[3 * j], r1 = jb[3 * j + 1], r2 = jb[3 * j + 2];
         const uint32_t left = __float_as_uint(r2.z), bits = __float_as_uint(r2.y);
         const uint32_t t0 = my_a * (__float_as_uint(r0.w) << 8) + my_c8;  // shifted LCG state before try (tries_j + lane)
-        const uint32_t t1 = 1664525u * t0 + (1013904223u << 8);
-        const uint32_t t2 = (1664525u * 1664525u) * t0 + ((1664525u * 1013904223u + 1013904223u) << 8);
-        const uint32_t t3 = (1664525u * 1664525u * 1664525u) * t0 + (((1664525u * 1664525u) * 1013904223u + 1664525u * 1013904223u + 1013904223u) << 8);
-        const float    a = __uint_as_float(__umulhi(t1, 0x00800000u) + 0x40000000u) - 3.0f;
-        const float    b = __uint_as_float(__umulhi(t2, 0x00800000u) + 0x40000000u) - 3.0f;
-        const float    cc = __uint_as_float(__umulhi(t3, 0x00800000u) + 0x40000000u) - 3.0f;
+        const float    vk = __uint_as_float(__umulhi(mk * t0 + ck, 0x00800000u) + 0x40000000u) - 3.0f;
+        const float    v0 = __uint_as_float(__umulhi(m0 * t0 + c0i, 0x00800000u) + 0x40000000u) - 3.0f;
+        const float    v2 = __uint_as_float(__umulhi(m2 * t0 + c2i, 0x00800000u) + 0x40000000u) - 3.0f;
         // w = +-v with the sign of v.N (shoot_ray_hemisphere); where that sign is within rounding of zero the try is kept
-        const float    sN = fmaf(cc, r0.z, fmaf(b, r0.y, a * r0.x));
+        const float    sN = fmaf(v2, r0.z, fmaf(v0, r0.y, vk * r0.x));
         const uint32_t sb = __float_as_uint(sN) & 0x80000000u;
-        const float    vk = fk == 0 ? a : (fk == 1 ? b : cc), v0 = fk == 0 ? b : (fk == 1 ? cc : a), v2 = fk == 0 ? cc : (fk == 1 ? a : b);
         const float    u  = __uint_as_float(__float_as_uint(vk) ^ sb ^ (bits & 0x80000000u));  // component towards the plane
         const float    w0 = __uint_as_float(__float_as_uint(v0) ^ sb), w2 = __uint_as_float(__float_as_uint(v2) ^ sb);
         const float    c0 = r2.x * w0, c2 = r2.x * w2;
-        const float    p0 = fmaf(hh, fabsf(w0), c0), q0 = fmaf(-hh, fabsf(w0), c0);
-        const float    p2 = fmaf(hh, fabsf(w2), c2), q2 = fmaf(-hh, fabsf(w2), c2);
-        const bool     reach = u > -2.4e-7f && fmaf(-r1.x, u, p0) >= -r2.w && fmaf(-r1.y, u, q0) <= r2.w &&
-                               fmaf(-r1.z, u, p2) >= -r2.w && fmaf(-r1.w, u, q2) <= r2.w;
-        const bool     keep = reach || fabsf(sN) < 4e-6f || (bits & 1u);
-        const unsigned m = __ballot_sync(FULL, keep && lane < left);
+        const float    g1 = fmaf(-r1.x, u, fmaf(hh, fabsf(w0), c0));   // |dy| w0 + hh |w0| - A0 u  >= -slack
+        const float    g2 = fmaf(r1.y, u, -fmaf(-hh, fabsf(w0), c0));  // B0 u - (|dy| w0 - hh |w0|) >= -slack
+        const float    g3 = fmaf(-r1.z, u, fmaf(hh, fabsf(w2), c2));
+        const float    g4 = fmaf(r1.w, u, -fmaf(-hh, fabsf(w2), c2));
+        const float    g  = fminf(fminf(g1, g2), fminf(g3, g4));
+        const unsigned keep = ((unsigned)(g >= -r2.w) & (unsigned)(u > -2.4e-7f)) | (unsigned)(fabsf(sN) < 4e-6f) | (bits & 1u);
+        const unsigned m = __ballot_sync(FULL, keep != 0u && lane < left);
         if ((int)lane == j) cone_mask = m;
       }
     } else {

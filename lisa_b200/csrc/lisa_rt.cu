@@ -61,6 +61,7 @@ struct lisa_ctx {
   lisa_stats   stats{};
   uint32_t     width = 0, height = 0, num_samples = 0, num_bounces = 0;
   std::string  output_image;
+  uint32_t     emit_hash = 0;       // of the materials' emitter flags (what a serialised BVH is valid for)
   bool         profile_stages = false;
   int          pipeline = 3;        // 3: per tile, k_pool when the tile has enough chains to fill its slots twice, else k_path;
                                     // 2: k_pool, 1: k_path (one persistent launch per tile either way), 0: wavefront (three kernels per bounce)
@@ -195,7 +196,72 @@ extern "C" void lisa_destroy(lisa_ctx* c) {
   delete c;
 }
 
-static int create_impl(const lisa_scene_desc* sd, const lisa_options* opt, lisa_ctx* c) {
+// ---- serialised BVH -------------------------------------------------------------------
+// File: BvhFileHeader, then the node array, tri_v, tri_n (3 float4 per triangle each, leaf order), final_to_orig.
+struct BvhFileHeader {
+  char     magic[8];  // "LISABVH1"
+  uint32_t version, header_bytes;
+  uint64_t num_tris, num_nodes;
+  int32_t  nodes_other, nodes_emit, root_other, root_emit, num_emit_tris, wide;
+  int32_t  num_materials;
+  uint32_t emit_hash;  // FNV-1a over the materials' emitter flags: the emitter / non-emitter partition is baked into the file
+  float    box_other[6], box_emit[6];
+  uint64_t file_bytes;
+};
+static uint32_t emit_flags_hash(const lisa_scene_desc* sd) {
+  uint32_t h = 2166136261u;
+  for (int i = 0; i < sd->num_materials; i++) h = (h ^ (sd->materials[i].emit ? 1u : 0u)) * 16777619u;
+  return h;
+}
+static uint64_t bvh_file_bytes(const BvhFileHeader& h) {
+  return sizeof(BvhFileHeader) + h.num_nodes * (h.wide ? 80ull : 64ull) + h.num_tris * (48ull + 48ull + 4ull);
+}
+
+// reads a file written by lisa_save_bvh into device arrays (c->bvh), in place of the upload of the soup and the build
+static int load_bvh_file(const lisa_scene_desc* sd, const char* path, lisa_ctx* c, int* wide_out) {
+  FILE* f = fopen(path, "rb");
+  if (!f) return fail(LISA_ERR_IO, "cannot open %s", path);
+  struct Closer { FILE* f; ~Closer() { fclose(f); } } closer{f};
+  BvhFileHeader h;
+  if (fread(&h, sizeof(h), 1, f) != 1 || memcmp(h.magic, "LISABVH1", 8) != 0 || h.version != 1 || h.header_bytes != sizeof(h))
+    return fail(LISA_ERR_IO, "%s is not a serialised BVH of this library", path);
+  if (fseek(f, 0, SEEK_END) != 0 || (uint64_t)ftell(f) != h.file_bytes || h.file_bytes != bvh_file_bytes(h))
+    return fail(LISA_ERR_IO, "%s is truncated or damaged", path);
+  if (sd->num_vertices && (uint64_t)(sd->num_vertices / 3) != h.num_tris)
+    return fail(LISA_ERR_ARG, "%s holds %llu triangles, the scene has %d", path, (unsigned long long)h.num_tris, sd->num_vertices / 3);
+  if (h.num_materials != sd->num_materials || h.emit_hash != emit_flags_hash(sd))
+    return fail(LISA_ERR_ARG, "%s was built for %d materials with other emitter flags (the emitter partition is part of the BVH)", path, h.num_materials);
+  fseek(f, (long)sizeof(h), SEEK_SET);
+  BuildOutput& b = c->bvh;
+  memset(&b, 0, sizeof(b));
+  const size_t T = (size_t)h.num_tris, nb = (size_t)h.num_nodes * (h.wide ? 80 : 64);
+  b.num_nodes = (int)h.num_nodes; b.nodes_other = h.nodes_other; b.nodes_emit = h.nodes_emit;
+  b.root_other = h.root_other; b.root_emit = h.root_emit; b.num_emit_tris = h.num_emit_tris; b.node_bytes = nb;
+  b.num_tris = (int)h.num_tris;
+  memcpy(b.box_other, h.box_other, sizeof(b.box_other));
+  memcpy(b.box_emit, h.box_emit, sizeof(b.box_emit));
+  *wide_out = h.wide;
+  if (T == 0) return LISA_OK;
+  CU(dev_alloc((void**)&b.d_nodes, std::max<size_t>(nb, 16)));
+  CU(dev_alloc((void**)&b.d_tri_v, 48 * T));
+  CU(dev_alloc((void**)&b.d_tri_n, 48 * T));
+  CU(dev_alloc((void**)&b.d_final_to_orig, 4 * T));
+  std::vector<char> buf(std::min<size_t>(64u << 20, std::max<size_t>(48 * T, nb)));
+  auto pump = [&](void* dst, size_t bytes) -> int {  // file -> device in chunks (the copy of a chunk overlaps the read of the next)
+    for (size_t off = 0; off < bytes; off += buf.size()) {
+      const size_t n = std::min(buf.size(), bytes - off);
+      if (fread(buf.data(), 1, n, f) != n) return fail(LISA_ERR_IO, "%s: short read", path);
+      CU(cudaMemcpyAsync((char*)dst + off, buf.data(), n, cudaMemcpyHostToDevice, c->stream));
+      CU(cudaStreamSynchronize(c->stream));
+    }
+    return LISA_OK;
+  };
+  int rc;
+  if ((rc = pump(b.d_nodes, nb)) || (rc = pump(b.d_tri_v, 48 * T)) || (rc = pump(b.d_tri_n, 48 * T)) || (rc = pump(b.d_final_to_orig, 4 * T))) return rc;
+  return LISA_OK;
+}
+
+static int create_impl(const lisa_scene_desc* sd, const lisa_options* opt, lisa_ctx* c, const char* bvh_path = nullptr) {
   lisa_options o{};
   o.struct_size = sizeof(o);
   o.device = -1;
@@ -223,22 +289,12 @@ static int create_impl(const lisa_scene_desc* sd, const lisa_options* opt, lisa_
   CU(cudaEventCreate(&c->ev0));
   CU(cudaEventCreate(&c->ev1));
 
-  const int T = sd->num_vertices / 3;
+  int T = sd->num_vertices / 3;
   c->width = sd->width; c->height = sd->height;
   c->num_samples = sd->num_samples; c->num_bounces = sd->num_bounces;
   if (sd->output_image) c->output_image = sd->output_image;
   camera_frame(sd->camera, sd->width, sd->height, &c->cam);
 
-  // ---- upload (Q11: one material index per triangle; Q12: the caller zero-fills unused material fields)
-  struct Ev3 {  // destroyed on every exit path
-    cudaEvent_t e[3] = {nullptr, nullptr, nullptr};
-    ~Ev3() { for (cudaEvent_t x : e) if (x) cudaEventDestroy(x); }
-  } ev3;
-  for (cudaEvent_t& x : ev3.e) CU(cudaEventCreate(&x));
-  cudaEvent_t t0 = ev3.e[0], t1 = ev3.e[1], t2 = ev3.e[2];
-  float *d_verts = nullptr, *d_normals = nullptr;
-  int*   d_mat_idx = nullptr;
-  unsigned char* d_emit = nullptr;
   std::vector<DMaterial>     mats((size_t)std::max(sd->num_materials, 1));
   std::vector<unsigned char> emit((size_t)std::max(sd->num_materials, 1), 0);
   int first_light = -1, single_light = 1;
@@ -250,12 +306,35 @@ static int create_impl(const lisa_scene_desc* sd, const lisa_options* opt, lisa_
     emit[i]   = m.emit ? 1 : 0;
     if (m.emit) { if (first_light < 0) first_light = i; else single_light = 0; }
   }
+  c->emit_hash = emit_flags_hash(sd);
+  CU(dev_alloc((void**)&c->d_mats, sizeof(DMaterial) * mats.size()));
+  CU(cudaMemcpyAsync(c->d_mats, mats.data(), sizeof(DMaterial) * mats.size(), cudaMemcpyHostToDevice, c->stream));
+  int wide = o.bvh_kind == LISA_BVH_WIDE8 ? 1 : 0;
+  if (bvh_path) {
+    // ---- a BVH built earlier (lisa_save_bvh): no soup upload, no build
+    const auto t_load = std::chrono::steady_clock::now();
+    int rc = load_bvh_file(sd, bvh_path, c, &wide);
+    if (rc) return rc;
+    T = c->bvh.num_tris;
+    CU(cudaStreamSynchronize(c->stream));
+    c->stats.upload_ms = (float)std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_load).count();
+    c->stats.bvh_build_ms = 0.0f;
+  } else {
+  // ---- upload (Q11: one material index per triangle; Q12: the caller zero-fills unused material fields)
+  struct Ev3 {  // destroyed on every exit path
+    cudaEvent_t e[3] = {nullptr, nullptr, nullptr};
+    ~Ev3() { for (cudaEvent_t x : e) if (x) cudaEventDestroy(x); }
+  } ev3;
+  for (cudaEvent_t& x : ev3.e) CU(cudaEventCreate(&x));
+  cudaEvent_t t0 = ev3.e[0], t1 = ev3.e[1], t2 = ev3.e[2];
+  float *d_verts = nullptr, *d_normals = nullptr;
+  int*   d_mat_idx = nullptr;
+  unsigned char* d_emit = nullptr;
   CU(cudaEventRecord(t0, c->stream));
   const size_t vb = sizeof(float) * 9 * (size_t)std::max(T, 1);
   CU(dev_alloc((void**)&d_verts, vb)); CU(dev_alloc((void**)&d_normals, vb));
   CU(dev_alloc((void**)&d_mat_idx, sizeof(int) * (size_t)std::max(T, 1)));
   CU(dev_alloc((void**)&d_emit, emit.size()));
-  CU(dev_alloc((void**)&c->d_mats, sizeof(DMaterial) * mats.size()));
   if (T) {
     // large soups go through a ring of pinned buffers filled by worker threads (devmem.cu: upload_async)
     CU(upload_async(d_verts, sd->vertices, sizeof(float) * 9 * (size_t)T, c->stream));
@@ -263,14 +342,13 @@ static int create_impl(const lisa_scene_desc* sd, const lisa_options* opt, lisa_
     CU(upload_async(d_mat_idx, sd->mat_indices, sizeof(int) * (size_t)T, c->stream));
   }
   CU(cudaMemcpyAsync(d_emit, emit.data(), emit.size(), cudaMemcpyHostToDevice, c->stream));
-  CU(cudaMemcpyAsync(c->d_mats, mats.data(), sizeof(DMaterial) * mats.size(), cudaMemcpyHostToDevice, c->stream));
   CU(cudaEventRecord(t1, c->stream));
 
   // ---- BVH
   int lbvh = (o.flags & LISA_FLAG_LBVH) ? 1 : 0, radius = 16;
   if (const char* e = getenv("LISA_BUILDER")) lbvh = !strcmp(e, "lbvh");
   if (const char* e = getenv("LISA_PLOC_RADIUS")) radius = std::max(1, atoi(e));
-  BuildInput bi{d_verts, d_normals, d_mat_idx, d_emit, T, sd->num_materials, o.bvh_kind == LISA_BVH_WIDE8 ? 1 : 0, lbvh, radius};
+  BuildInput bi{d_verts, d_normals, d_mat_idx, d_emit, T, sd->num_materials, wide, lbvh, radius};
   int rc = build_bvh(bi, &c->bvh, c->stream, g_err, sizeof(g_err));
   if (rc) {  // keep the builder's message: a sticky CUDA error would otherwise be reported by the next call instead
     dev_free(d_verts); dev_free(d_normals); dev_free(d_mat_idx); dev_free(d_emit);
@@ -281,6 +359,7 @@ static int create_impl(const lisa_scene_desc* sd, const lisa_options* opt, lisa_
   dev_free(d_verts); dev_free(d_normals); dev_free(d_mat_idx); dev_free(d_emit);
   cudaEventElapsedTime(&c->stats.upload_ms, t0, t1);
   cudaEventElapsedTime(&c->stats.bvh_build_ms, t1, t2);
+  }
 
   c->scene.tri_v = c->bvh.d_tri_v;
   c->scene.tri_n = c->bvh.d_tri_n;
@@ -288,7 +367,7 @@ static int create_impl(const lisa_scene_desc* sd, const lisa_options* opt, lisa_
   c->scene.bvh = c->bvh.d_nodes;
   c->scene.root_other = c->bvh.root_other;
   c->scene.root_emit = c->bvh.root_emit;
-  c->scene.wide = bi.wide;
+  c->scene.wide = wide;
   c->scene.num_tris = T;
   c->scene.num_mats = sd->num_materials;
   c->scene.single_light = single_light;
@@ -363,7 +442,7 @@ static int create_impl(const lisa_scene_desc* sd, const lisa_options* opt, lisa_
   if (const char* e2 = getenv("LISA_DEFER")) c->cfg.defer_retries = atoi(e2) != 0;
   if (const char* e2 = getenv("LISA_SHADOW_PASSES")) c->cfg.shadow_passes = atoi(e2);
   {
-    const int w = bi.wide != 0;
+    const int w = wide != 0;
     if (!di.ok || getenv("LISA_EXTEND_BLOCK") || getenv("LISA_SHADOW_BLOCK")) {
       di.occ_tries = tries_occupancy(256);
       for (int k = 0; k < 2; k++) { di.occ_ext[k] = extend_occupancy(k != 0, c->cfg.extend_block); di.occ_rays[k] = shadow_occupancy(k != 0, c->cfg.shadow_block); di.occ_path[k] = path_occupancy(k != 0, 128); di.occ_pool[k] = pool_occupancy(k != 0); }
@@ -416,6 +495,63 @@ extern "C" int lisa_create(const lisa_scene_desc* sd, const lisa_options* opt, l
     return rc;
   }
   *out = c;
+  return LISA_OK;
+}
+
+extern "C" int lisa_create_from_bvh(const lisa_scene_desc* sd, const lisa_options* opt, const char* path, lisa_ctx** out) {
+  if (!sd || !out || !path || !*path) return fail(LISA_ERR_ARG, "lisa_create_from_bvh: null argument");
+  *out = nullptr;
+  if (sd->num_vertices < 0 || sd->num_vertices % 3) return fail(LISA_ERR_ARG, "num_vertices (%d) must be a non-negative multiple of 3", sd->num_vertices);
+  if (sd->num_materials < 0 || (sd->num_materials && !sd->materials)) return fail(LISA_ERR_ARG, "bad materials");
+  if (!sd->width || !sd->height) return fail(LISA_ERR_ARG, "width and height must be positive");
+  if ((uint64_t)sd->width * sd->height > (1ull << 31)) return fail(LISA_ERR_ARG, "image too large");
+  lisa_ctx* c = new lisa_ctx();
+  int rc = create_impl(sd, opt, c, path);
+  if (rc != LISA_OK) {
+    std::string keep = g_err;
+    lisa_destroy(c);
+    snprintf(g_err, sizeof(g_err), "%s", keep.c_str());
+    return rc;
+  }
+  *out = c;
+  return LISA_OK;
+}
+
+extern "C" int lisa_save_bvh(lisa_ctx* c, const char* path) {
+  if (!c || !path || !*path) return fail(LISA_ERR_ARG, "null argument");
+  CU(cudaSetDevice(c->device));
+  BvhFileHeader h{};
+  memcpy(h.magic, "LISABVH1", 8);
+  h.version = 1; h.header_bytes = sizeof(h);
+  h.num_tris = (uint64_t)c->scene.num_tris; h.num_nodes = (uint64_t)c->bvh.num_nodes;
+  h.nodes_other = c->bvh.nodes_other; h.nodes_emit = c->bvh.nodes_emit;
+  h.root_other = c->bvh.root_other; h.root_emit = c->bvh.root_emit;
+  h.num_emit_tris = c->bvh.num_emit_tris; h.wide = c->scene.wide;
+  h.num_materials = c->scene.num_mats; h.emit_hash = c->emit_hash;
+  memcpy(h.box_other, c->bvh.box_other, sizeof(h.box_other));
+  memcpy(h.box_emit, c->bvh.box_emit, sizeof(h.box_emit));
+  h.file_bytes = bvh_file_bytes(h);
+  const std::string tmp = std::string(path) + ".tmp";  // written aside and renamed
+  FILE* f = fopen(tmp.c_str(), "wb");
+  if (!f) return fail(LISA_ERR_IO, "cannot open %s for writing", tmp.c_str());
+  bool ok = fwrite(&h, sizeof(h), 1, f) == 1;
+  const size_t T = (size_t)h.num_tris;
+  std::vector<char> buf(std::min<size_t>(64u << 20, std::max<size_t>(48 * std::max<size_t>(T, 1), 80)));
+  auto pump = [&](const void* src, size_t bytes) {
+    for (size_t off = 0; off < bytes && ok; off += buf.size()) {
+      const size_t n = std::min(buf.size(), bytes - off);
+      ok = cudaMemcpyAsync(buf.data(), (const char*)src + off, n, cudaMemcpyDeviceToHost, c->stream) == cudaSuccess &&
+           cudaStreamSynchronize(c->stream) == cudaSuccess && fwrite(buf.data(), 1, n, f) == n;
+    }
+  };
+  if (T) {
+    pump(c->bvh.d_nodes, (size_t)h.num_nodes * (h.wide ? 80 : 64));
+    pump(c->bvh.d_tri_v, 48 * T);
+    pump(c->bvh.d_tri_n, 48 * T);
+    pump(c->bvh.d_final_to_orig, 4 * T);
+  }
+  ok = (fclose(f) == 0) && ok;
+  if (!ok || rename(tmp.c_str(), path) != 0) { remove(tmp.c_str()); return fail(LISA_ERR_IO, "short write to %s", path); }
   return LISA_OK;
 }
 

@@ -3,7 +3,8 @@
 // -s <scene> is mandatory; without it the usage goes to stderr and the exit code is 1.  -d selects the
 // progressive mode (headless here).  Extra, optional: --gpus N splits num_samples over N GPUs of this box (one context each, in
 // this process) and combines the accumulators with one ncclReduce (lisa_multi_*); --obj-cache keeps a binary copy of each OBJ's triangle soup next to
-// it (<file>.lisasoup) and loads that instead of the text when it is current; --pfm <file> also writes the linear float image; with -d,
+// it (<file>.lisasoup) and loads that instead of the text when it is current; --pfm <file> also writes the linear float image; --save-bvh <file> serialises the BVH after the build and
+// --load-bvh <file> starts from such a file instead of loading the OBJ meshes and building (lisa_save_bvh / lisa_create_from_bvh); with -d,
 // --snapshot-every K rewrites the PPM every K subframes, --checkpoint <file> saves the accumulators then (and at the
 // end) and --resume <file> continues an interrupted render from such a file; --stats prints one JSON line with the counters of
 // include/lisa_rt.h:lisa_stats; environment variables LISA_BVH/LISA_SHADOW/LISA_MAX_CHAINS select
@@ -35,7 +36,8 @@ int main(int argc, char** argv) {
   }
   try {
     if (cmdOptionExists(argv, argv + argc, "--obj-cache")) parse_obj_set_cache(1);
-    SceneParser     parser(scene_path);
+    char* load_bvh = getCmdOption(argv, argv + argc, "--load-bvh");
+    SceneParser     parser(scene_path, load_bvh == nullptr);  // with a serialised BVH the OBJ files are not even opened
     lisa_scene_desc params = parser.get_params();
     if (char* g = getCmdOption(argv, argv + argc, "--gpus")) {  // sample-space partition over the GPUs of this box
       if (atoi(g) > 1) {
@@ -45,10 +47,13 @@ int main(int argc, char** argv) {
       }
     }
     lisa_ctx*       ctx = nullptr;
-    if (lisa_create(&params, nullptr, &ctx) != LISA_OK) {
+    if ((load_bvh ? lisa_create_from_bvh(&params, nullptr, load_bvh, &ctx) : lisa_create(&params, nullptr, &ctx)) != LISA_OK) {
       // the reference throws sutil::Exception out of OptixWrapper's constructor and aborts
       std::cerr << "lisa: " << lisa_last_error() << std::endl;
       return 134;
+    }
+    if (char* save_bvh = getCmdOption(argv, argv + argc, "--save-bvh")) {
+      if (lisa_save_bvh(ctx, save_bvh) != LISA_OK) std::cerr << "lisa: " << lisa_last_error() << std::endl;
     }
     printf("Starting rendering...\n");
     if (cmdOptionExists(argv, argv + argc, "-d")) {

@@ -89,6 +89,8 @@ _L.lisa_write_image.argtypes = [_vp, ctypes.c_char_p]
 _L.lisa_save_accum.argtypes = [_vp, ctypes.c_char_p]
 _L.lisa_load_accum.argtypes = [_vp, ctypes.c_char_p, ctypes.POINTER(ctypes.c_uint32)]
 _L.lisa_get_stats.argtypes = [_vp, ctypes.POINTER(Stats)]
+_L.lisa_save_bvh.argtypes = [_vp, ctypes.c_char_p]
+_L.lisa_create_from_bvh.argtypes = [ctypes.POINTER(SceneDesc), ctypes.POINTER(Options), ctypes.c_char_p, ctypes.POINTER(_vp)]
 _L.lisa_accum_add_peer.argtypes = [_vp, _vp]
 _L.lisa_accum_note_merged.argtypes = [_vp, ctypes.c_uint32, ctypes.c_uint64]
 _L.lisa_multi_create.argtypes = [ctypes.POINTER(SceneDesc), ctypes.POINTER(Options), ctypes.c_int, ctypes.POINTER(_vp)]
@@ -117,7 +119,7 @@ _L.lisa_primary_rays.argtypes = [_vp, ctypes.c_uint32, _vp, _vp]
 _L.lisa_kat_eval.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_uint32, _vp, _vp, _vp, _vp]
 
 EXPORTS = ["lisa_create", "lisa_destroy", "lisa_last_error", "lisa_version", "lisa_render_subframes",
-           "lisa_reset_accum", "lisa_read_accum", "lisa_read_rgba8", "lisa_write_ppm", "lisa_write_pfm", "lisa_write_image", "lisa_save_accum", "lisa_load_accum", "lisa_get_stats",
+           "lisa_reset_accum", "lisa_read_accum", "lisa_read_rgba8", "lisa_write_ppm", "lisa_write_pfm", "lisa_write_image", "lisa_save_accum", "lisa_load_accum", "lisa_get_stats", "lisa_save_bvh", "lisa_create_from_bvh",
            "lisa_accum_add_peer", "lisa_accum_note_merged", "lisa_multi_create", "lisa_multi_destroy", "lisa_multi_num_gpus", "lisa_multi_root",
            "lisa_multi_ctx", "lisa_multi_backend", "lisa_multi_reset_accum", "lisa_multi_render_subframes", "lisa_multi_render_samples",
            "lisa_multi_last_times", "lisa_accum_device_ptr", "lisa_accum_bytes", "lisa_device", "lisa_sync", "lisa_trace_closest",
@@ -157,7 +159,7 @@ class Renderer:
 
     def __init__(self, vertices, normals, mat_indices, materials, width, height, eye, look_at, fov, num_samples=1,
                  num_bounces=7, output_image=None, device=-1, shadow_mode=SHADOW_CLOSEST, bvh_kind=BVH_WIDE8, max_chains=0,
-                 flags=0, _multi_gpus=None):
+                 flags=0, _multi_gpus=None, _bvh_file=None):
         self._v = np.ascontiguousarray(vertices, dtype=np.float32).reshape(-1, 3)
         self._n = np.ascontiguousarray(normals, dtype=np.float32).reshape(-1, 3)
         self._m = np.ascontiguousarray(mat_indices, dtype=np.int32).reshape(-1)
@@ -185,7 +187,9 @@ class Renderer:
         self.num_samples, self.num_bounces = num_samples, num_bounces
         self._h = _vp()
         self._m = _vp()
-        if _multi_gpus is None:
+        if _bvh_file is not None:   # a BVH serialised by save_bvh(): the geometry arrays may be empty
+            _check(_L.lisa_create_from_bvh(ctypes.byref(sd), ctypes.byref(opt), _bvh_file.encode(), ctypes.byref(self._h)))
+        elif _multi_gpus is None:
             _check(_L.lisa_create(ctypes.byref(sd), ctypes.byref(opt), ctypes.byref(self._h)))
         else:   # MultiRenderer: one context per GPU behind a lisa_multi; self._h is the root's (borrowed)
             _check(_L.lisa_multi_create(ctypes.byref(sd), ctypes.byref(opt), _multi_gpus, ctypes.byref(self._m)))
@@ -200,6 +204,21 @@ class Renderer:
         args.update(kw)
         mats = sc["materials_packed"] if "materials_packed" in sc else sc["materials"]
         return cls(sc["vertices"], sc["normals"], sc["mat_indices"], mats, **args)
+
+    @classmethod
+    def from_bvh(cls, sc, path, with_geometry=False, **kw):
+        """A context from a BVH file written by save_bvh(): materials, camera and size from `sc`; no soup upload, no build."""
+        cam = sc["camera"]
+        args = dict(width=sc["width"], height=sc["height"], eye=cam["eye"], look_at=cam["look_at"], fov=cam["fov"],
+                    num_samples=sc["num_samples"], num_bounces=sc["num_bounces"], output_image=sc.get("output_image"))
+        args.update(kw)
+        mats = sc["materials_packed"] if "materials_packed" in sc else sc["materials"]
+        z = np.zeros((0, 3), np.float32)
+        geo = (sc["vertices"], sc["normals"], sc["mat_indices"]) if with_geometry else (z, z, np.zeros(0, np.int32))
+        return cls(*geo, mats, _bvh_file=path, **args)
+
+    def save_bvh(self, path):
+        _check(_L.lisa_save_bvh(self._h, path.encode()))
 
     def close(self):
         if getattr(self, "_m", None) is not None and self._m.value:

@@ -320,3 +320,53 @@ def test_traversal_stack_overflow_is_loud(built, tmp_path):
                 assert ln.startswith("-5 ") and "traversal stack overflow" in ln, ln
             else:
                 assert ln == "ok", ln
+
+
+def test_serialised_bvh_round_trip(rt, cornell, tmp_path):
+    """lisa_save_bvh / lisa_create_from_bvh: a context made from the file — no geometry handed over,
+    no build — answers closest-hit queries and renders bit-identically to the context that wrote it; truncated files, files
+    for another triangle count and files built for other emitter flags are refused."""
+    sc = resized(cornell, 96)
+    A = rt.Renderer.from_scene(sc)
+    path = str(tmp_path / "cornell.lisabvh")
+    A.save_bvh(path)
+    stA = A.stats()
+    import os
+    assert os.path.getsize(path) == 120 + stA["bvh_bytes"] + stA["num_triangles"] * 100   # header, nodes, 48 + 48 + 4 bytes per triangle
+    B = rt.Renderer.from_bvh(sc, path)
+    stB = B.stats()
+    for k in ("num_triangles", "num_emitter_triangles", "bvh_nodes", "bvh_emitter_nodes", "bvh_bytes"):
+        assert stA[k] == stB[k], k
+    assert stB["bvh_build_ms"] == 0.0
+    rng = np.random.default_rng(9)
+    o, d = _rays(rng, cornell["vertices"].min(0), cornell["vertices"].max(0), 50000)
+    pa, ta = A.trace_closest(o, d)
+    pb, tb = B.trace_closest(o, d)
+    np.testing.assert_array_equal(pa, pb)
+    np.testing.assert_array_equal(ta, tb)
+    A.render_subframes(0, 2, 8)
+    B.render_subframes(0, 2, 8)
+    np.testing.assert_array_equal(A.read_accum(), B.read_accum())
+    C = rt.Renderer.from_bvh(sc, path, with_geometry=True)   # geometry present: only its triangle count is checked
+    C.render_subframes(0, 2, 8)
+    np.testing.assert_array_equal(A.read_accum(), C.read_accum())
+    for R in (A, B, C):
+        R.close()
+    raw = open(path, "rb").read()
+    bad = str(tmp_path / "cut.lisabvh")
+    open(bad, "wb").write(raw[:-1000])
+    with pytest.raises(rt.LisaError, match="truncated or damaged"):
+        rt.Renderer.from_bvh(sc, bad)
+    open(bad, "wb").write(b"P6\n" + raw[3:])
+    with pytest.raises(rt.LisaError, match="not a serialised BVH"):
+        rt.Renderer.from_bvh(sc, bad)
+    other = dict(sc)
+    other["vertices"], other["normals"], other["mat_indices"] = sc["vertices"][:-3], sc["normals"][:-3], sc["mat_indices"][:-1]
+    with pytest.raises(rt.LisaError, match="holds 1002 triangles, the scene has 1001"):
+        rt.Renderer.from_bvh(other, path, with_geometry=True)
+    swapped = dict(sc)
+    swapped.pop("materials_packed", None)
+    swapped["materials"] = [dict(m) for m in sc["materials"]]
+    swapped["materials"][0], swapped["materials"][4] = swapped["materials"][4], swapped["materials"][0]   # the light becomes material 0
+    with pytest.raises(rt.LisaError, match="other emitter flags"):
+        rt.Renderer.from_bvh(swapped, path)
