@@ -245,40 +245,113 @@ __device__ __forceinline__ void ploc_make_node(int id, const float4 la, const fl
 __device__ __forceinline__ unsigned long long ploc_ld(const unsigned long long* p) { return *reinterpret_cast<const volatile unsigned long long*>(p); }
 __device__ __forceinline__ void ploc_st(unsigned long long* p, unsigned long long v) { *reinterpret_cast<volatile unsigned long long*>(p) = v; }
 
-__global__ void __launch_bounds__(PLOC_TILE) k_ploc_round(const float4* __restrict__ in, int m, int r, float4* __restrict__ out,
+// One thread searches the neighbourhoods of PLOC_K consecutive clusters at once: the window of candidates
+// [p0 - r, p0 + PLOC_K - 1 + r] is read from shared memory ONCE and every candidate is tried against the (up to) four
+// clusters it is a neighbour of — a quarter of the shared-memory traffic of one cluster per thread, which is what bounded
+// the search.  A CTA's 256 threads cover exactly the tile plus its halo of r on either side: tile = 1024 - 2 r positions.
+#define PLOC_K 4
+#define PLOC_SPAN (PLOC_TILE * PLOC_K)  // positions whose nearest neighbour a CTA computes: tile + 2 r
+__host__ __device__ inline int ploc_tile_size(int r) { return PLOC_SPAN - 2 * r; }
+// Shared-memory slot of the record staged for window index i: thread t reads indices 4 t + c, so the records are kept in
+// four planes by i mod 4 — the lanes of a warp then read CONSECUTIVE 16-byte slots (no bank conflicts), where the plain
+// layout had them 64 bytes apart (4-way conflicts: 70 % of the kernel's shared-memory wavefronts, ncu).
+#define PLOC_PLANE ((PLOC_SPAN + 2 * PLOC_RMAX) / 4 + 1)
+__device__ __forceinline__ int ploc_slot(int i) { return (i & 3) * PLOC_PLANE + (i >> 2); }
+
+// RT > 0: the radius is the compile-time constant RT and the candidate loop is unrolled completely — distances, range checks and
+// the tie-break keys of all 4 x (2 RT + 4) pairs become constants (up to the CTA-uniform parity of the window's start), and
+// positions outside [0, m) are staged as boxes of infinite extent that no cluster ever prefers.  RT == 0: any radius.
+template <int RT>
+__global__ void __launch_bounds__(PLOC_TILE) k_ploc_round(const float4* __restrict__ in, int m, int r_arg, float4* __restrict__ out,
                                                           float4* node_lo, float4* node_hi, int2* child, int* cnt, int node_base,
                                                           unsigned long long* state, unsigned int* ticket, int* m_out, unsigned tag) {
-  __shared__ float4             slo[PLOC_TILE + 4 * PLOC_RMAX], shi[PLOC_TILE + 4 * PLOC_RMAX];
-  __shared__ int                snn[PLOC_TILE + 2 * PLOC_RMAX];
+  __shared__ float4             slo[4 * PLOC_PLANE], shi[4 * PLOC_PLANE];  // positions [base - 2r, base + tile + 2r), by ploc_slot()
+  __shared__ int                snn[PLOC_SPAN];                                                  // positions [base - r, base + tile + r)
   __shared__ unsigned           s_tile, s_warp[PLOC_TILE / 32];
   __shared__ unsigned long long s_excl;
   const int t = threadIdx.x;
+  const int r = RT > 0 ? RT : r_arg;
   if (t == 0) s_tile = atomicAdd(ticket, 1u);  // tiles are numbered in the order they START: a tile only ever waits for earlier ones
   __syncthreads();
-  const int tile = (int)s_tile, ntiles = (m + PLOC_TILE - 1) / PLOC_TILE;
-  const int base = tile * PLOC_TILE, lo0 = base - 2 * r;
-  for (int k = t; k < PLOC_TILE + 4 * r; k += PLOC_TILE) {
-    const int p = lo0 + k;
-    if (p >= 0 && p < m) { slo[k] = in[2ll * p]; shi[k] = in[2ll * p + 1]; }
+  const int tsize = ploc_tile_size(r);
+  const int tile = (int)s_tile, ntiles = (m + tsize - 1) / tsize;
+  const int base = tile * tsize, lo0 = base - 2 * r;
+  for (int k = t; k < PLOC_SPAN + 2 * r; k += PLOC_TILE) {
+    const int p = lo0 + k, sl = ploc_slot(k);
+    if (p >= 0 && p < m) { slo[sl] = in[2ll * p]; shi[sl] = in[2ll * p + 1]; }
+    else {  // beyond the ends of the array: merging with this costs an infinite area
+      slo[sl] = make_float4(-INFINITY, -INFINITY, -INFINITY, 0.0f);
+      shi[sl] = make_float4(INFINITY, INFINITY, INFINITY, 0.0f);
+    }
   }
   __syncthreads();
-  for (int e = t; e < PLOC_TILE + 2 * r; e += PLOC_TILE) {  // the tile and a halo of r on either side
-    const int p = base - r + e;
-    snn[e] = (p >= 0 && p < m) ? ploc_nearest(slo, shi, lo0, p, m, r) : -1;
+  {  // nearest neighbours of positions p0 .. p0 + 3 (the tile and its halo of r: PLOC_SPAN positions, four per thread)
+    const int p0 = base - r + PLOC_K * t;
+    float4   l[PLOC_K], h[PLOC_K];
+    float    best[PLOC_K];
+    unsigned bkey[PLOC_K];
+    int      bj[PLOC_K];
+#pragma unroll
+    for (int k = 0; k < PLOC_K; k++) {
+      const int q = ploc_slot(min(max(p0 + k, 0), m - 1) - lo0);  // clamped: out-of-range positions are computed and discarded
+      l[k] = slo[q]; h[k] = shi[q];
+      best[k] = FLT_MAX; bkey[k] = 0xffffffffu; bj[k] = -1;
+    }
+    if (RT > 0) {
+      const unsigned pb = (unsigned)p0 & 1u;  // parity of the window's first cluster (the same for the whole CTA: p0 = base - r + 4 t)
+      const int      w0 = p0 - RT - lo0;      // shared-memory index of the first candidate
+#pragma unroll
+      for (int o = -RT; o <= PLOC_K - 1 + RT; o++) {  // candidate p0 + o
+        const int    sl = ploc_slot(w0 + o + RT);  // w0 = 4 t: plane (o + RT) & 3, slot t + ((o + RT) >> 2)
+        const float4 cl = slo[sl], ch = shi[sl];
+#pragma unroll
+        for (int k = 0; k < PLOC_K; k++) {
+          const int d = o - k < 0 ? k - o : o - k;  // compile-time
+          if (d == 0 || d > RT) continue;
+          const float    a = merged_half_area(l[k], h[k], cl, ch);
+          const unsigned key = ((unsigned)d << 1) | ((((unsigned)(o < k ? o : k)) & 1u) ^ pb);  // parity of min(p, j) = p0 + min(k, o)
+          if (a < best[k] || (a == best[k] && key < bkey[k])) { best[k] = a; bkey[k] = key; bj[k] = p0 + o; }
+        }
+      }
+    } else {
+      const int j0 = max(0, p0 - r), j1 = min(m - 1, p0 + PLOC_K - 1 + r);
+      for (int j = j0; j <= j1; j++) {
+        const float4 cl = slo[ploc_slot(j - lo0)], ch = shi[ploc_slot(j - lo0)];
+#pragma unroll
+        for (int k = 0; k < PLOC_K; k++) {
+          const int p = p0 + k, d = abs(j - p);
+          const float    a = merged_half_area(l[k], h[k], cl, ch);
+          const unsigned key = ((unsigned)d << 1) | ((unsigned)min(p, j) & 1u);
+          // candidates of p: the positions within r of it, except p itself; best by (area, key), see ploc_nearest
+          if (d != 0 && d <= r && (a < best[k] || (a == best[k] && key < bkey[k]))) { best[k] = a; bkey[k] = key; bj[k] = j; }
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < PLOC_K; k++) {
+      const int p = p0 + k;
+      snn[PLOC_K * t + k] = (p >= 0 && p < m) ? bj[k] : -1;
+    }
   }
   __syncthreads();
-  const int p = base + t;
-  int  j = -1;
-  bool valid = false, owner = false;
-  if (p < m) {
-    j = snn[t + r];
-    const bool mutual = j >= 0 && snn[j - (base - r)] == p;
-    owner = mutual && p < j;
-    valid = !(mutual && p > j);
+  // decisions for the tile's own positions: thread t owns base + 4 t .. base + 4 t + 3
+  int      jn[PLOC_K];
+  unsigned vmask = 0, omask = 0;
+#pragma unroll
+  for (int k = 0; k < PLOC_K; k++) {
+    const int p = base + PLOC_K * t + k;
+    jn[k] = -1;
+    if (PLOC_K * t + k < tsize && p < m) {
+      const int j = snn[p - (base - r)];
+      const bool mutual = j >= 0 && snn[j - (base - r)] == p;
+      jn[k] = j;
+      if (mutual && p < j) omask |= 1u << k;
+      if (!(mutual && p > j)) vmask |= 1u << k;
+    }
   }
-  // CTA-wide exclusive scan of (survivor, merge) flags, packed 16 | 16
+  // CTA-wide exclusive scan of (survivors, merges) per thread, packed 16 | 16
   const unsigned lane = t & 31, w = t >> 5;
-  const unsigned v = (valid ? 1u : 0u) | (owner ? 0x10000u : 0u);
+  const unsigned v = (unsigned)__popc(vmask) | ((unsigned)__popc(omask) << 16);
   unsigned inc = v;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) { const unsigned x = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= (unsigned)o) inc += x; }
@@ -319,13 +392,18 @@ __global__ void __launch_bounds__(PLOC_TILE) k_ploc_round(const float4* __restri
   }
   __syncthreads();
   const unsigned valid_before = (unsigned)(s_excl & 0x3fffffffull), merges_before = (unsigned)((s_excl >> 30) & 0x3fffffffull);
-  if (valid) {
-    const long long q = (long long)valid_before + (excl & 0xffffu);
-    float4 rlo = slo[p - lo0], rhi = shi[p - lo0];
-    if (owner)
-      ploc_make_node(node_base + (int)(merges_before + (excl >> 16)), rlo, rhi, slo[j - lo0], shi[j - lo0], node_lo, node_hi, child, cnt, rlo, rhi);
+  long long q = (long long)valid_before + (excl & 0xffffu);
+  int       id = node_base + (int)(merges_before + (excl >> 16));
+#pragma unroll
+  for (int k = 0; k < PLOC_K; k++) {
+    if (!(vmask >> k & 1u)) continue;
+    const int p = base + PLOC_K * t + k;
+    float4 rlo = slo[ploc_slot(p - lo0)], rhi = shi[ploc_slot(p - lo0)];
+    if (omask >> k & 1u)
+      ploc_make_node(id++, rlo, rhi, slo[ploc_slot(jn[k] - lo0)], shi[ploc_slot(jn[k] - lo0)], node_lo, node_hi, child, cnt, rlo, rhi);
     out[2 * q]     = rlo;
     out[2 * q + 1] = rhi;
+    q++;
   }
   if (tile == ntiles - 1 && t == 0) {  // the holder of the last ticket started last: every ticket of this round is taken
     *m_out  = (int)(valid_before + (tot & 0xffffu));
@@ -439,39 +517,45 @@ __global__ void k_collapse8(const WorkItem* __restrict__ in, int n_in, WorkItem*
   int w = blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= n_in) return;
   const WorkItem item = in[w];
-  int            ch[8];
-  int            nc = 0;
-  float4         plo, phi;
+  // the children gathered so far, with everything the steps below need of them read ONCE (the kernel waits on these
+  // gathers: 10.6 of its stall cycles per instruction were global loads when every step fetched the boxes again)
+  int    ch[8], ccnt[8];
+  float4 clo[8], chi[8];
+  int    nc = 0;
+  float4 plo, phi;
+  auto add_child = [&](int k, int node) {
+    ch[k] = node; ccnt[k] = node_count(node, n, range); clo[k] = box_lo[node]; chi[k] = box_hi[node];
+  };
   if (n == 1) {  // degenerate partition: one triangle, no binary internal node
-    ch[nc++] = 0;
-    plo = box_lo[0]; phi = box_hi[0];
+    add_child(nc++, 0);
+    plo = clo[0]; phi = chi[0];
   } else {
     int2 c = child[item.node2];
-    ch[nc++] = c.x; ch[nc++] = c.y;
+    add_child(nc++, c.x); add_child(nc++, c.y);
     plo = box_lo[item.node2]; phi = box_hi[item.node2];
     while (nc < 8) {
       int   best = -1;
       float ba   = -1.0f;
       for (int k = 0; k < nc; k++) {
-        if (node_count(ch[k], n, range) <= LEAF_MAX) continue;  // stays a leaf
-        float a = half_area(box_lo[ch[k]], box_hi[ch[k]]);
+        if (ccnt[k] <= LEAF_MAX) continue;  // stays a leaf
+        float a = half_area(clo[k], chi[k]);
         if (a > ba) { ba = a; best = k; }
       }
       if (best < 0) break;
-      int2 c2  = child[ch[best]];
-      ch[best] = c2.x;
-      ch[nc++] = c2.y;
+      int2 c2 = child[ch[best]];
+      add_child(best, c2.x);
+      add_child(nc++, c2.y);
     }
   }
   // octant-affinity slot assignment (greedy): slot bit 4/2/1 set = child lies on the +x/+y/+z side
   const float3 pc = f3((plo.x + phi.x) * 0.5f, (plo.y + phi.y) * 0.5f, (plo.z + phi.z) * 0.5f);
   float3 rel[8];
   for (int k = 0; k < nc; k++) {
-    float4 l = box_lo[ch[k]], h = box_hi[ch[k]];
+    const float4 l = clo[k], h = chi[k];
     rel[k] = f3((l.x + h.x) * 0.5f - pc.x, (l.y + h.y) * 0.5f - pc.y, (l.z + h.z) * 0.5f - pc.z);
   }
-  int slot_child[8];
-  for (int s = 0; s < 8; s++) slot_child[s] = -1;
+  int slot_k[8];  // slot -> index into ch / ccnt / clo / chi, -1 = empty
+  for (int s = 0; s < 8; s++) slot_k[s] = -1;
   unsigned int child_done = 0, slot_done = 0;
   for (int it = 0; it < nc; it++) {
     float bc = -FLT_MAX;
@@ -484,7 +568,7 @@ __global__ void k_collapse8(const WorkItem* __restrict__ in, int n_in, WorkItem*
         if (c > bc) { bc = c; bk = k; bs = s; }
       }
     }
-    slot_child[bs] = ch[bk];
+    slot_k[bs] = bk;
     child_done |= 1u << bk;
     slot_done |= 1u << bs;
   }
@@ -506,8 +590,8 @@ __global__ void k_collapse8(const WorkItem* __restrict__ in, int n_in, WorkItem*
   // counts
   int n_inner = 0, n_tri = 0;
   for (int s = 0; s < 8; s++) {
-    if (slot_child[s] < 0) continue;
-    int cnt = node_count(slot_child[s], n, range);
+    if (slot_k[s] < 0) continue;
+    const int cnt = ccnt[slot_k[s]];
     if (cnt <= LEAF_MAX) n_tri += cnt; else n_inner++;
   }
   int child_base = n_inner ? atomicAdd(&counters[0], n_inner) : 0;
@@ -519,9 +603,9 @@ __global__ void k_collapse8(const WorkItem* __restrict__ in, int n_in, WorkItem*
   for (int s = 0; s < 8; s++) {
     meta[s] = 0;
     for (int a = 0; a < 3; a++) { qlo[a][s] = 255; qhi[a][s] = 0; }  // empty: inverted box, never hit
-    int c = slot_child[s];
-    if (c < 0) continue;
-    float4 l = box_lo[c], h = box_hi[c];
+    if (slot_k[s] < 0) continue;
+    const int    c = ch[slot_k[s]];
+    const float4 l = clo[slot_k[s]], h = chi[slot_k[s]];
     const float l3[3] = {l.x, l.y, l.z}, h3[3] = {h.x, h.y, h.z};
     for (int a = 0; a < 3; a++) {
       float step = __int_as_float((ex[a] + 127) << 23);  // 2^e, exact
@@ -533,7 +617,7 @@ __global__ void k_collapse8(const WorkItem* __restrict__ in, int n_in, WorkItem*
       while (qh < 255 && (double)plo3[a] + (double)qh * (double)step < (double)h3[a]) qh++;
       qlo[a][s] = (unsigned)ql; qhi[a][s] = (unsigned)qh;
     }
-    int cnt = node_count(c, n, range);
+    const int cnt = ccnt[slot_k[s]];
     if (cnt <= LEAF_MAX) {
       meta[s]   = (((1u << cnt) - 1u) << 5) | (unsigned)tri_off;
       int leaves[LEAF_MAX];
@@ -666,7 +750,7 @@ int build_bvh(const BuildInput& in, BuildOutput* out, cudaStream_t st, char* err
   unsigned long long* d_tile_state = nullptr;
   int*                d_ploc_ctl = nullptr;           // [0] ticket, [1] clusters after the round, [2] root id, [3] clusters left by the tail
   const int radius = std::max(1, std::min(in.ploc_radius, PLOC_RMAX));
-  const size_t max_tiles = ((size_t)T + PLOC_TILE - 1) / PLOC_TILE + 1;
+  const size_t max_tiles = ((size_t)T + ploc_tile_size(radius) - 1) / ploc_tile_size(radius) + 1;
   if (!in.lbvh) {
     CK(dev_alloc((void**)&d_rec[0], sizeof(float4) * 2 * (size_t)T));
     CK(dev_alloc((void**)&d_rec[1], sizeof(float4) * 2 * (size_t)T));
@@ -688,11 +772,12 @@ int build_bvh(const BuildInput& in, BuildOutput* out, cudaStream_t st, char* err
       k_leaf_records<<<cdiv(P.n, 256), 256, 0, st>>>(in.d_verts, d_ids2 + P.sorted_base, P.n, d_lo + P.slice, d_hi + P.slice, d_rec[0]);
       int m = P.n, cur = 0, rounds = 0;
       // stale tile states of the other partition must not be taken for this one's
-      CK(cudaMemsetAsync(d_tile_state, 0, sizeof(unsigned long long) * (((size_t)P.n + PLOC_TILE - 1) / PLOC_TILE), st));
+      CK(cudaMemsetAsync(d_tile_state, 0, sizeof(unsigned long long) * (((size_t)P.n + ploc_tile_size(radius) - 1) / ploc_tile_size(radius)), st));
       while (m > PLOC_TAIL) {
-        k_ploc_round<<<cdiv(m, PLOC_TILE), PLOC_TILE, 0, st>>>(d_rec[cur], m, radius, d_rec[cur ^ 1], d_lo + P.slice, d_hi + P.slice,
-                                                             d_child + P.slice, d_range + P.slice, P.n - m, d_tile_state,
-                                                             (unsigned int*)d_ploc_ctl, d_ploc_ctl + 1, (unsigned)rounds);
+        auto round_kernel = radius == 16 ? k_ploc_round<16> : k_ploc_round<0>;  // the default radius has its own, fully unrolled instance
+        round_kernel<<<cdiv(m, ploc_tile_size(radius)), PLOC_TILE, 0, st>>>(d_rec[cur], m, radius, d_rec[cur ^ 1], d_lo + P.slice, d_hi + P.slice,
+                                                                           d_child + P.slice, d_range + P.slice, P.n - m, d_tile_state,
+                                                                           (unsigned int*)d_ploc_ctl, d_ploc_ctl + 1, (unsigned)rounds);
         int m2 = 0;
         CK(cudaMemcpyAsync(&m2, d_ploc_ctl + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
