@@ -128,13 +128,16 @@ int configure_kernels(char* err, size_t errlen) {
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_extend<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_rays<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_rays<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_path<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_path<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   const int psm = smem + 4 * (int)sizeof(PoolWarp);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_pool<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, psm);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_pool<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, psm);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_pool<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_pool<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  auto path_attr = [&](const void* f) { if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); };
+  auto pool_attr = [&](const void* f) {
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, psm);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  };
+  path_attr((const void*)k_path<true, true>); path_attr((const void*)k_path<true, false>);
+  path_attr((const void*)k_path<false, true>); path_attr((const void*)k_path<false, false>);
+  pool_attr((const void*)k_pool<true, true>); pool_attr((const void*)k_pool<true, false>);
+  pool_attr((const void*)k_pool<false, true>); pool_attr((const void*)k_pool<false, false>);
   if (e != cudaSuccess) { snprintf(err, errlen, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -2; }
   return 0;
 }
@@ -143,22 +146,23 @@ static inline size_t pool_smem() { return stack_smem(128) + 4 * sizeof(PoolWarp)
 int pool_chains_per_cta() { return POOL_SLOTS * 4; }
 int pool_occupancy(bool wide) {
   int n = 0;
-  cudaError_t e = wide ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_pool<true>, 128, pool_smem())
-                       : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_pool<false>, 128, pool_smem());
+  cudaError_t e = wide ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_pool<true, true>, 128, pool_smem())
+                       : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_pool<false, true>, 128, pool_smem());
   return (e == cudaSuccess && n > 0) ? n : 1;
 }
 void launch_pool(const DScene& sc, const DState& s, const DCamera& cam, const Tile& t, const LaunchCfg& cfg, cudaStream_t st) {
   unsigned grid = (unsigned)(cfg.sm_count * cfg.pool_blocks_per_sm);
   grid = min(grid, max(1u, cdiv(t.n_chains, POOL_SLOTS * 4u)));
   cudaMemsetAsync(s.ring, 0, sizeof(unsigned int), st);  // chain fetch cursor
-  if (sc.wide) k_pool<true><<<grid, 128, pool_smem(), st>>>(sc, s, cam, t, (uint32_t)cfg.pool_dry_thresh);
-  else k_pool<false><<<grid, 128, pool_smem(), st>>>(sc, s, cam, t, (uint32_t)cfg.pool_dry_thresh);
+  const bool flat = sc.emit_flat >= 0;  // each kernel is instantiated with and without the flat-bounds filter of the shadow tries
+  auto k = sc.wide ? (flat ? k_pool<true, true> : k_pool<true, false>) : (flat ? k_pool<false, true> : k_pool<false, false>);
+  k<<<grid, 128, pool_smem(), st>>>(sc, s, cam, t, (uint32_t)cfg.pool_dry_thresh);
 }
 
 int path_occupancy(bool wide, int block) {
   int n = 0;
-  cudaError_t e = wide ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_path<true>, block, stack_smem(block))
-                       : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_path<false>, block, stack_smem(block));
+  cudaError_t e = wide ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_path<true, true>, block, stack_smem(block))
+                       : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_path<false, true>, block, stack_smem(block));
   return (e == cudaSuccess && n > 0) ? n : 2;
 }
 void launch_path(const DScene& sc, const DState& s, const DCamera& cam, const Tile& t, const LaunchCfg& cfg, cudaStream_t st) {
@@ -166,8 +170,9 @@ void launch_path(const DScene& sc, const DState& s, const DCamera& cam, const Ti
   unsigned grid = (unsigned)(cfg.sm_count * cfg.path_blocks_per_sm);
   grid = min(grid, max(1u, cdiv(t.n_chains, 32u * (b / 32))));
   cudaMemsetAsync(s.ring, 0, sizeof(unsigned int), st);  // chain fetch cursor
-  if (sc.wide) k_path<true><<<grid, b, stack_smem(b), st>>>(sc, s, cam, t, (uint32_t)cfg.path_wait_thresh);
-  else k_path<false><<<grid, b, stack_smem(b), st>>>(sc, s, cam, t, (uint32_t)cfg.path_wait_thresh);
+  const bool flat = sc.emit_flat >= 0;
+  auto k = sc.wide ? (flat ? k_path<true, true> : k_path<true, false>) : (flat ? k_path<false, true> : k_path<false, false>);
+  k<<<grid, b, stack_smem(b), st>>>(sc, s, cam, t, (uint32_t)cfg.path_wait_thresh);
 }
 
 int shadow_occupancy(bool wide, int block) {

@@ -216,6 +216,9 @@ struct ChainNext {
 };
 struct EventCounters { uint32_t jobs, shadow, culled; };
 
+// FLAT: the scene's emitter bounds are flat (sc.emit_flat >= 0): the kernels are instantiated for both cases, so that each
+// carries only its own filter loop.
+template <bool FLAT>
 __device__ __forceinline__ ChainNext chain_event(const DScene& sc, const Tile& t, const uint32_t* lcg_a, const uint32_t* lcg_c,
                                                  float4* jb /* this warp's 96 x float4 job buffer */, bool has_event,
                                                  const ChainEvent& ev, ChainRegs& c, EventCounters& cnt) {
@@ -297,7 +300,7 @@ __device__ __forceinline__ ChainNext chain_event(const DScene& sc, const Tile& t
     float    Nk = c.N.x, N0 = c.N.y, N2 = c.N.z;  // the normal as the loop wants it: permuted (k, k+1, k+2) for flat bounds
     uint32_t f_bits = 0u;
     if (sc.emit_r2 < 0.0f) nothing = true;             // no emitters at all
-    else if (fk >= 0) {
+    else if (FLAT) {
       // components along the flat axis (k) and along the two axes of the rectangle (k + 1, k + 2 mod 3); fk is uniform
       float Pk, P0, P2, l0, h0, l2, h2;
       if (fk == 0)      { Pk = c.o.x; P0 = c.o.y; P2 = c.o.z; Nk = c.N.x; N0 = c.N.y; N2 = c.N.z; l0 = sc.emit_lo.y; h0 = sc.emit_hi.y; l2 = sc.emit_lo.z; h2 = sc.emit_hi.z; }
@@ -328,9 +331,11 @@ __device__ __forceinline__ ChainNext chain_event(const DScene& sc, const Tile& t
       if (cone_cos > 1.0f) nothing = true;
       fpar = make_float4(cone_axis.x, cone_axis.y, cone_axis.z, cone_cos * fabsf(cone_cos));
     }
-    jb[3 * lane]     = make_float4(Nk, N0, N2, __uint_as_float(c.seed));
-    jb[3 * lane + 1] = fpar;
-    jb[3 * lane + 2] = make_float4(f_ady, __uint_as_float(f_bits), __uint_as_float(LISA_SHADOW_TRIES - c.tries), f_sl);
+    if (!nothing && !(c.flags & F_STICKY)) {  // the lanes that stay in `trying` below
+      jb[3 * lane]     = make_float4(Nk, N0, N2, __uint_as_float(c.seed));
+      jb[3 * lane + 1] = fpar;
+      jb[3 * lane + 2] = make_float4(f_ady, __uint_as_float(f_bits), __uint_as_float(LISA_SHADOW_TRIES - c.tries), f_sl);
+    }
   }
   if (trying && (c.flags & F_STICKY)) {  // RayState::hit is true (Q1), only at the first try of a bounce: a real ray
     nx.w = shoot_ray_hemisphere(c.N, c.seed);
@@ -351,7 +356,7 @@ __device__ __forceinline__ ChainNext chain_event(const DScene& sc, const Tile& t
     // 3 instructions on the FMA pipe per draw instead of 6, 4 of them on the busier ALU pipe.
     const uint32_t my_a = lcg_a[lane], my_c8 = lcg_c[lane] << 8;
     unsigned cone_mask = 0;
-    if (fk >= 0) {
+    if (FLAT) {
       // The three draws of a try are x, y, z of its direction, in that order (maths.cu:10-15); the loop wants them as
       // (k, k + 1, k + 2): it steps the LCG by the matching number of draws — multipliers and increments chosen once, per
       // kernel-uniform fk — and the job's normal is stored in the same order.  No select in the loop, and no branch: the

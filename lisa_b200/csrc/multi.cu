@@ -143,8 +143,21 @@ extern "C" int lisa_multi_create(const lisa_scene_desc* sd, const lisa_options* 
   }
   if (num_gpus > 1 && nccl().ok) {
     const ncclResult_t r = nccl().CommInitAll(m->comm.data(), num_gpus, m->dev.data());
-    if (r == 0) m->use_nccl = true;
-    else {  // keep going with the peer-kernel reduce, and say so
+    if (r == 0) {
+      m->use_nccl = true;
+      // the first collective of a communicator sets up its channels (tens of ms): pay that here, not in the first render
+      std::vector<float*> tiny(num_gpus, nullptr);
+      ncclResult_t w = 0;
+      for (int g = 0; g < num_gpus; g++) { cudaSetDevice(g); if (cudaMalloc((void**)&tiny[g], 64) != cudaSuccess) w = 1; else cudaMemsetAsync(tiny[g], 0, 64, m->stream[g]); }
+      if (w == 0) {
+        w = nccl().GroupStart();
+        for (int g = 0; g < num_gpus && w == 0; g++) { cudaSetDevice(g); w = nccl().Reduce(tiny[g], tiny[g], 16, kNcclFloat, kNcclSum, 0, m->comm[g], m->stream[g]); }
+        const ncclResult_t w2 = nccl().GroupEnd();
+        if (w == 0) w = w2;
+      }
+      for (int g = 0; g < num_gpus; g++) { cudaSetDevice(g); cudaStreamSynchronize(m->stream[g]); if (tiny[g]) cudaFree(tiny[g]); }
+      if (w != 0) fprintf(stderr, "lisa_multi: NCCL warm-up reduce failed (%s)\n", nccl().GetErrorString(w));
+    } else {  // keep going with the peer-kernel reduce, and say so
       fprintf(stderr, "lisa_multi: ncclCommInitAll failed (%s); reducing through peer-memory kernels\n", nccl().GetErrorString(r));
       m->comm.assign(num_gpus, nullptr);
     }

@@ -22,7 +22,7 @@ namespace lisa {
 #ifndef LISA_PATH_MIN_BLOCKS
 #define LISA_PATH_MIN_BLOCKS 5
 #endif
-template <bool WIDE>
+template <bool WIDE, bool FLAT>
 __global__ void __launch_bounds__(128, LISA_PATH_MIN_BLOCKS) k_path(DScene sc, DState s, DCamera cam, Tile t, uint32_t wait_thresh) {
   extern __shared__ uint2 smem_stack[];
   __shared__ uint32_t lcg_a[32], lcg_c[32];  // x -> A^(3k) x + C_(3k): skip k tries
@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(128, LISA_PATH_MIN_BLOCKS) k_path(DScene sc, D
       cr.seed = seed; cr.flags = flags; cr.tries = tries; cr.mid = mid; cr.brdf_w = brdf_w;
       const bool      has_event = pending;
       pending = false;
-      const ChainNext nx = chain_event(sc, t, lcg_a, lcg_c, jobbuf[threadIdx.x >> 5], has_event, ev, cr, ec);
+      const ChainNext nx = chain_event<FLAT>(sc, t, lcg_a, lcg_c, jobbuf[threadIdx.x >> 5], has_event, ev, cr, ec);
       o = cr.o; d = cr.d; atten = cr.atten; color = cr.color; N = cr.N;
       seed = cr.seed; flags = cr.flags; tries = cr.tries; mid = cr.mid;
       const bool   end_sample = nx.end_sample, start_shd = nx.start_shd;

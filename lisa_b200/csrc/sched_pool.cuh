@@ -29,14 +29,16 @@ namespace lisa {
 #ifndef LISA_POOL_MIN_BLOCKS
 #define LISA_POOL_MIN_BLOCKS 5
 #endif
-#define POOL_SLOTS 64
+#ifndef POOL_SLOTS
+#define POOL_SLOTS 64  // chains per warp (ring positions wrap with % POOL_SLOTS: a power of two costs one AND)
+#endif
 
 struct PoolWarp {
   float4        A[POOL_SLOTS], B[POOL_SLOTS], C[POOL_SLOTS], D[POOL_SLOTS], E[POOL_SLOTS], F[POOL_SLOTS], H[POOL_SLOTS], G[POOL_SLOTS];
   unsigned char rq[POOL_SLOTS], pq[POOL_SLOTS];
 };
 
-template <bool WIDE>
+template <bool WIDE, bool FLAT>
 __global__ void __launch_bounds__(128, LISA_POOL_MIN_BLOCKS) k_pool(DScene sc, DState s, DCamera cam, Tile t, uint32_t dry_thresh) {
   extern __shared__ uint2 smem_stack[];  // [LISA_STACK_SM][128] traversal stacks, then 4 x PoolWarp
   __shared__ uint32_t lcg_a[32], lcg_c[32];  // x -> A^(3k) x + C_(3k): skip k tries
@@ -80,7 +82,7 @@ __global__ void __launch_bounds__(128, LISA_POOL_MIN_BLOCKS) k_pool(DScene sc, D
     if (freemask && rq_cnt) {
       const unsigned rank = __popc(freemask & lanemask_lt());
       if (!in_flight && rank < rq_cnt) {
-        slot = pw.rq[(rq_head + rank) & (POOL_SLOTS - 1)];
+        slot = pw.rq[(rq_head + rank) % POOL_SLOTS];
         const float4   a4 = pw.A[slot], f4 = pw.F[slot], h4 = pw.H[slot];
         const uint32_t kind = __float_as_uint(pw.E[slot].w);
         o = f3(a4);
@@ -101,7 +103,7 @@ __global__ void __launch_bounds__(128, LISA_POOL_MIN_BLOCKS) k_pool(DScene sc, D
     if (pq_cnt >= 32u || (rq_cnt == 0u && (pq_cnt >= dry_thresh || (fly == 0u && pq_cnt > 0u)))) {
       const unsigned np = min(pq_cnt, 32u);
       const bool     active = lane < np;
-      const int      ms = active ? (int)pw.pq[(pq_head + lane) & (POOL_SLOTS - 1)] : -1;
+      const int      ms = active ? (int)pw.pq[(pq_head + lane) % POOL_SLOTS] : -1;
       pq_head += np; pq_cnt -= np;
       // slot -> registers
       int      chain = -1;
@@ -127,7 +129,7 @@ __global__ void __launch_bounds__(128, LISA_POOL_MIN_BLOCKS) k_pool(DScene sc, D
       ChainRegs cr;
       cr.o = mo; cr.d = d; cr.atten = atten; cr.color = color; cr.N = N;
       cr.seed = seed; cr.flags = flags; cr.tries = tries; cr.mid = mid; cr.brdf_w = brdf_w;
-      const ChainNext nx = chain_event(sc, t, lcg_a, lcg_c, jobbuf[threadIdx.x >> 5], active && chain >= 0, ev, cr, ec);
+      const ChainNext nx = chain_event<FLAT>(sc, t, lcg_a, lcg_c, jobbuf[threadIdx.x >> 5], active && chain >= 0, ev, cr, ec);
       mo = cr.o; d = cr.d; atten = cr.atten; color = cr.color; N = cr.N;
       seed = cr.seed; flags = cr.flags; tries = cr.tries; mid = cr.mid;
       const bool   end_sample = nx.end_sample, start_shd = nx.start_shd;
@@ -220,8 +222,8 @@ __global__ void __launch_bounds__(128, LISA_POOL_MIN_BLOCKS) k_pool(DScene sc, D
       }
       {
         const unsigned rm = __ballot_sync(FULL, to_ready), pm = __ballot_sync(FULL, to_pending);
-        if (to_ready) pw.rq[(rq_head + rq_cnt + __popc(rm & lanemask_lt())) & (POOL_SLOTS - 1)] = (unsigned char)ms;
-        if (to_pending) pw.pq[(pq_head + pq_cnt + __popc(pm & lanemask_lt())) & (POOL_SLOTS - 1)] = (unsigned char)ms;
+        if (to_ready) pw.rq[(rq_head + rq_cnt + __popc(rm & lanemask_lt())) % POOL_SLOTS] = (unsigned char)ms;
+        if (to_pending) pw.pq[(pq_head + pq_cnt + __popc(pm & lanemask_lt())) % POOL_SLOTS] = (unsigned char)ms;
         rq_cnt += __popc(rm); pq_cnt += __popc(pm);
       }
       __syncwarp();
@@ -290,7 +292,7 @@ __global__ void __launch_bounds__(128, LISA_POOL_MIN_BLOCKS) k_pool(DScene sc, D
     // the slots whose ray has just finished join the pending queue
     const unsigned fm = __ballot_sync(FULL, finished);
     if (fm) {
-      if (finished) pw.pq[(pq_head + pq_cnt + __popc(fm & lanemask_lt())) & (POOL_SLOTS - 1)] = (unsigned char)slot;
+      if (finished) pw.pq[(pq_head + pq_cnt + __popc(fm & lanemask_lt())) % POOL_SLOTS] = (unsigned char)slot;
       pq_cnt += __popc(fm);
       __syncwarp();
     }
