@@ -285,7 +285,7 @@ __device__ __forceinline__ ChainNext chain_event(const DScene& sc, const Tile& t
   //   flat bounds (a quad light, sc.emit_flat = k): the try's direction w crosses the slab |X_k - plane| <= hh for
   //     t in [(|dy| - hh) / u, (|dy| + hh) / u] with u = +-w_k > 0 towards the plane, dy = plane - P_k; it can reach the
   //     rectangle [A0, B0] x [A2, B2] (relative to P, on the other two axes) only if, on each axis,
-  //     |dy| w_i + hh |w_i| >= A_i u  and  |dy| w_i - hh |w_i| <= B_i u.  No division, no normalisation (homogeneous in w),
+  //     |dy| w_i + hh |w_i| >= A_i u  and  |dy| w_i - hh |w_i| <= B_i u (hh |w_i| <= hh goes into the slack).  No division, no normalisation (homogeneous in w),
   //     and as tight as the box test itself: ~1 in 4 of the tries the bounding-sphere cone lets through.
   //   otherwise: the cone around the sphere that bounds all emitters (q|q| >= cos|cos| v.v).
   // Both are conservative with respect to hits_emitter_bounds(), which confirms the survivors in try order.
@@ -313,7 +313,7 @@ __device__ __forceinline__ ChainNext chain_event(const DScene& sc, const Tile& t
       const float mrg = 4e-6f * sum;  // hits_emitter_bounds accepts with a relative slack of 1e-6 on its slab distances
       A0 -= mrg; B0 += mrg; A2 -= mrg; B2 += mrg;
       fpar = make_float4(A0, B0, A2, B2);
-      f_sl = 1e-6f * sum;             // the draws below are within 2^-23 of the true ones; the test is linear in them
+      f_sl = 1e-6f * sum + sc.emit_hh;  // the draws below are within 2^-23 of the true ones and the test is linear in them; + the slab's half thickness
       f_bits = __float_as_uint(dy) & 0x80000000u;
       if (!sc.cull || f_ady <= sc.emit_hh) f_bits |= 1u;  // culling off, or P inside the slab of the light's plane
       else {
@@ -367,7 +367,6 @@ __device__ __forceinline__ ChainNext chain_event(const DScene& sc, const Tile& t
       const uint32_t mk = fk == 0 ? A1 : (fk == 1 ? A2 : A3), ck = fk == 0 ? C1 : (fk == 1 ? C2 : C3);
       const uint32_t m0 = fk == 0 ? A2 : (fk == 1 ? A3 : A1), c0i = fk == 0 ? C2 : (fk == 1 ? C3 : C1);
       const uint32_t m2 = fk == 0 ? A3 : (fk == 1 ? A1 : A2), c2i = fk == 0 ? C3 : (fk == 1 ? C1 : C2);
-      const float    hh = sc.emit_hh;
       for (unsigned rem = jobs; rem; rem &= rem - 1u) {
         const int      j  = __ffs(rem) - 1;
         const float4   r0 = jb[3 * j], r1 = jb[3 * j + 1], r2 = jb[3 * j + 2];
@@ -381,11 +380,12 @@ __device__ __forceinline__ ChainNext chain_event(const DScene& sc, const Tile& t
         const uint32_t sb = __float_as_uint(sN) & 0x80000000u;
         const float    u  = __uint_as_float(__float_as_uint(vk) ^ sb ^ (bits & 0x80000000u));  // component towards the plane
         const float    w0 = __uint_as_float(__float_as_uint(v0) ^ sb), w2 = __uint_as_float(__float_as_uint(v2) ^ sb);
+        // |w_i| <= 1 (the draws lie in [-1, 1]), so hh |w_i| <= hh: the half thickness is part of the job's slack
         const float    c0 = r2.x * w0, c2 = r2.x * w2;
-        const float    g1 = fmaf(-r1.x, u, fmaf(hh, fabsf(w0), c0));   // |dy| w0 + hh |w0| - A0 u  >= -slack
-        const float    g2 = fmaf(r1.y, u, -fmaf(-hh, fabsf(w0), c0));  // B0 u - (|dy| w0 - hh |w0|) >= -slack
-        const float    g3 = fmaf(-r1.z, u, fmaf(hh, fabsf(w2), c2));
-        const float    g4 = fmaf(r1.w, u, -fmaf(-hh, fabsf(w2), c2));
+        const float    g1 = fmaf(-r1.x, u, c0);   // |dy| w0 - A0 u  >= -(slack + hh)
+        const float    g2 = fmaf(r1.y, u, -c0);   // B0 u - |dy| w0  >= -(slack + hh)
+        const float    g3 = fmaf(-r1.z, u, c2);
+        const float    g4 = fmaf(r1.w, u, -c2);
         const float    g  = fminf(fminf(g1, g2), fminf(g3, g4));
         const unsigned keep = ((unsigned)(g >= -r2.w) & (unsigned)(u > -2.4e-7f)) | (unsigned)(fabsf(sN) < 4e-6f) | (bits & 1u);
         const unsigned m = __ballot_sync(FULL, keep != 0u && lane < left);
