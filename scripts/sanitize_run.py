@@ -13,3 +13,31 @@ for bvh in (0, 1):
         img = R.read_accum(); px = R.read_rgba8()
         print(bvh, flags, float(img[..., :3].mean()), R.stats()["last_kernel_launches"])
         R.close()
+# round 2: every persistent schedule, the 20k-triangle soup (several PLOC rounds with the look-back scan, two sort tiles),
+# a non-flat emitter set (cone filter) and the serialised BVH
+import numpy as np
+rng = np.random.default_rng(3)
+T = 20000
+c = rng.uniform(-1, 1, size=(T, 1, 3))
+v = (c + rng.normal(scale=0.05, size=(T, 3, 3))).astype(np.float32).reshape(-1, 3)
+n = rng.normal(size=(3 * T, 3)).astype(np.float32); n /= np.linalg.norm(n, axis=1, keepdims=True)
+m = (rng.random(T) < 0.02).astype(np.int32)
+mats = [dict(emit=False, alpha=1.0, diffuse=(0.8, 0.8, 0.8), roughness=1.0), dict(emit=True, alpha=1.0, emission=(1, 1, 1))]
+for pipe in ("pool", "path", "wavefront"):
+    os.environ["LISA_PIPELINE"] = pipe
+    R = rt.Renderer(v, n, m, mats, 40, 32, (0, 0, 4), (0, 0, 0), 45.0, 1, 3)
+    R.render_subframes(0, 1, 2)
+    print("soup", pipe, float(R.read_accum()[..., :3].mean()), R.stats()["bvh_nodes"])
+    if pipe == "pool":
+        R.save_bvh("/tmp/sanitize.lisabvh")
+    R.close()
+    R = rt.Renderer.from_scene(sc)                      # flat quad light: the flat-bounds filter
+    R.render_subframes(0, 1, 2)
+    print("cornell", pipe, float(R.read_accum()[..., :3].mean()))
+    R.close()
+os.environ.pop("LISA_PIPELINE")
+R = rt.Renderer(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.float32), np.zeros(0, np.int32), mats, 40, 32, (0, 0, 4), (0, 0, 0), 45.0, 1, 3,
+                _bvh_file="/tmp/sanitize.lisabvh")
+R.render_subframes(0, 1, 1)
+print("from file", float(R.read_accum()[..., :3].mean()))
+R.close()
