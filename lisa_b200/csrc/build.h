@@ -15,6 +15,7 @@ struct BuildInput {
   int                  wide;       // 1: compressed 8-wide nodes, 0: binary nodes
   int                  lbvh;       // 1: plain LBVH hierarchy (fast build), 0: PLOC (default, near-SAH quality)
   int                  ploc_radius;
+  int                  rotate_passes;  // SAH tree-rotation passes over the binary hierarchy before the collapse (0 = none)
 };
 
 struct BuildOutput {

@@ -459,6 +459,75 @@ __global__ void __launch_bounds__(PLOC_TAIL) k_ploc_tail(const float4* __restric
   if (t == 0) { root_out[0] = __float_as_int(slo[cur][0].w); root_out[1] = m; }
 }
 
+// ---- SAH restructuring of the binary hierarchy: tree rotations ------------------------------------------------------
+// (Kensler 2008, "Tree Rotations for Improving Bounding Volume Hierarchies".)  At an internal node X = (L, R) a rotation swaps
+// one child with a grandchild on the other side — L <-> RL, L <-> RR, R <-> LL or R <-> LR — which changes exactly one
+// bounding box, that of the child whose pair is re-formed.  With the surface-area heuristic (a node's cost is proportional
+// to its area) the best of the four is the one that shrinks that box's area most; it is applied when it shrinks it at all.
+// The pass is bottom-up, one thread per leaf climbing through arrival counters like a refit: the thread that arrives
+// second at X owns X's whole subtree (every node below has been processed, nobody else is inside), so rotations need no
+// locks.  Triangle counts and boxes of the re-formed node are updated in place; parents are recomputed per pass.
+__global__ void k_parents(const int2* __restrict__ child, int n, int root, int* parent) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n - 1) return;
+  const int2 c = child[i];
+  parent[c.x] = i;
+  parent[c.y] = i;
+  if (i == root) parent[i] = -1;
+}
+
+__device__ __forceinline__ float union_half_area(const float4& l0, const float4& h0, const float4& l1, const float4& h1) {
+  return merged_half_area(l0, h0, l1, h1);
+}
+
+__global__ void k_rotate(int n, int2* child, const int* __restrict__ parent, float4* box_lo, float4* box_hi, int* cnt, int* flags,
+                         unsigned int* n_rotations) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  int cur = parent[(n - 1) + j];
+  while (cur >= 0) {
+    __threadfence();
+    if (atomicAdd(&flags[cur], 1) == 0) return;  // first arrival: the sibling's thread will continue
+    __threadfence();
+    const int2 c = __ldcg(&child[cur]);
+    const int  L = c.x, R = c.y;
+    const float4 lL = __ldcg(box_lo + L), hL = __ldcg(box_hi + L), lR = __ldcg(box_lo + R), hR = __ldcg(box_hi + R);
+    float best = 0.0f;  // area saved
+    int   which = -1;
+    int2  cR = make_int2(-1, -1), cL = make_int2(-1, -1);
+    float4 lRL, hRL, lRR, hRR, lLL, hLL, lLR, hLR;
+    if (R < n - 1) {  // R is internal: L <-> RL (R' = L + RR) or L <-> RR (R' = RL + L)
+      cR = __ldcg(&child[R]);
+      lRL = __ldcg(box_lo + cR.x); hRL = __ldcg(box_hi + cR.x); lRR = __ldcg(box_lo + cR.y); hRR = __ldcg(box_hi + cR.y);
+      const float aR = union_half_area(lR, hR, lR, hR);
+      const float s0 = aR - union_half_area(lL, hL, lRR, hRR), s1 = aR - union_half_area(lRL, hRL, lL, hL);
+      if (s0 > best) { best = s0; which = 0; }
+      if (s1 > best) { best = s1; which = 1; }
+    }
+    if (L < n - 1) {  // L is internal: R <-> LL (L' = R + LR) or R <-> LR (L' = LL + R)
+      cL = __ldcg(&child[L]);
+      lLL = __ldcg(box_lo + cL.x); hLL = __ldcg(box_hi + cL.x); lLR = __ldcg(box_lo + cL.y); hLR = __ldcg(box_hi + cL.y);
+      const float aL = union_half_area(lL, hL, lL, hL);
+      const float s2 = aL - union_half_area(lR, hR, lLR, hLR), s3 = aL - union_half_area(lLL, hLL, lR, hR);
+      if (s2 > best) { best = s2; which = 2; }
+      if (s3 > best) { best = s3; which = 3; }
+    }
+    auto count = [&](int node) { return node >= n - 1 ? 1 : __ldcg(&cnt[node]); };
+    auto remake = [&](int node, int a, int b, const float4& la, const float4& ha, const float4& lb, const float4& hb) {
+      child[node]  = make_int2(a, b);
+      box_lo[node] = make_float4(fminf(la.x, lb.x), fminf(la.y, lb.y), fminf(la.z, lb.z), 0.0f);
+      box_hi[node] = make_float4(fmaxf(ha.x, hb.x), fmaxf(ha.y, hb.y), fmaxf(ha.z, hb.z), 0.0f);
+      cnt[node]    = count(a) + count(b);
+    };
+    if (which == 0) { remake(R, L, cR.y, lL, hL, lRR, hRR); child[cur] = make_int2(cR.x, R); }
+    else if (which == 1) { remake(R, cR.x, L, lRL, hRL, lL, hL); child[cur] = make_int2(cR.y, R); }
+    else if (which == 2) { remake(L, R, cL.y, lR, hR, lLR, hLR); child[cur] = make_int2(L, cL.x); }
+    else if (which == 3) { remake(L, cL.x, R, lLL, hLL, lR, hR); child[cur] = make_int2(L, cL.y); }
+    if (which >= 0) atomicAdd(n_rotations, 1u);
+    cur = parent[cur];
+  }
+}
+
 // ---- binary traversal nodes -----------------------------------------------------------------------
 // One node per internal Karras node; tri_base = first final triangle index of the partition.
 __global__ void k_emit_binary(int n, const int2* __restrict__ child, const float4* __restrict__ box_lo,
@@ -798,6 +867,31 @@ int build_bvh(const BuildInput& in, BuildOutput* out, cudaStream_t st, char* err
   }
 
   tick(in.lbvh ? "lbvh" : "ploc");
+  if (in.rotate_passes > 0) {
+    int *d_par = nullptr, *d_arr = nullptr;
+    unsigned int* d_nrot = nullptr;
+    CK(dev_alloc((void**)&d_par, sizeof(int) * NN));
+    CK(dev_alloc((void**)&d_arr, sizeof(int) * NN));
+    CK(dev_alloc((void**)&d_nrot, sizeof(unsigned int)));
+    CK(cudaMemsetAsync(d_nrot, 0, sizeof(unsigned int), st));
+    for (int pass = 0; pass < in.rotate_passes; pass++)
+      for (int p = 0; p < 2; p++) {
+        const Part& P = parts[p];
+        if (P.n < 3) continue;
+        k_parents<<<cdiv(P.n - 1, 256), 256, 0, st>>>(d_child + P.slice, P.n, P.root, d_par + P.slice);
+        CK(cudaMemsetAsync(d_arr + P.slice, 0, sizeof(int) * (size_t)(P.n - 1), st));
+        k_rotate<<<cdiv(P.n, 256), 256, 0, st>>>(P.n, d_child + P.slice, d_par + P.slice, d_lo + P.slice, d_hi + P.slice,
+                                                 d_range + P.slice, d_arr + P.slice, d_nrot);
+      }
+    if (dbg) {
+      unsigned int nrot = 0;
+      CK(cudaMemcpyAsync(&nrot, d_nrot, sizeof(nrot), cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      fprintf(stderr, "  tree rotations: %u in %d pass(es)\n", nrot, in.rotate_passes);
+    }
+    dev_free(d_par); dev_free(d_arr); dev_free(d_nrot);
+    tick("rotations");
+  }
   for (int p = 0; p < 2; p++) {  // root bounds of each partition (node 0 of its slice)
     float* dst = p == 0 ? out->box_other : out->box_emit;
     for (int k = 0; k < 3; k++) { dst[k] = FLT_MAX; dst[3 + k] = -FLT_MAX; }

@@ -348,7 +348,9 @@ static int create_impl(const lisa_scene_desc* sd, const lisa_options* opt, lisa_
   int lbvh = (o.flags & LISA_FLAG_LBVH) ? 1 : 0, radius = 16;
   if (const char* e = getenv("LISA_BUILDER")) lbvh = !strcmp(e, "lbvh");
   if (const char* e = getenv("LISA_PLOC_RADIUS")) radius = std::max(1, atoi(e));
-  BuildInput bi{d_verts, d_normals, d_mat_idx, d_emit, T, sd->num_materials, wide, lbvh, radius};
+  int rotate = 0;
+  if (const char* e = getenv("LISA_BVH_ROTATE")) rotate = std::max(0, std::min(8, atoi(e)));
+  BuildInput bi{d_verts, d_normals, d_mat_idx, d_emit, T, sd->num_materials, wide, lbvh, radius, rotate};
   int rc = build_bvh(bi, &c->bvh, c->stream, g_err, sizeof(g_err));
   if (rc) {  // keep the builder's message: a sticky CUDA error would otherwise be reported by the next call instead
     dev_free(d_verts); dev_free(d_normals); dev_free(d_mat_idx); dev_free(d_emit);
