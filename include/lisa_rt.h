@@ -130,6 +130,9 @@ typedef struct lisa_stats {
   uint64_t nodes_visited, triangles_tested;           /* cumulative traversal work (both stages) */
   uint64_t last_nodes_visited, last_triangles_tested;
   uint64_t shadow_culled, last_shadow_culled;         /* shadow tries resolved without traversal (counted in shadow_rays too) */
+  /* stages of the device BVH build (CUDA events; they add up to bvh_build_ms): Morton keys + radix sort, hierarchy (PLOC rounds
+   * or LBVH, optional rotations), collapse to 8-wide nodes, triangle packing */
+  float    build_sort_ms, build_hierarchy_ms, build_collapse_ms, build_pack_ms;
 } lisa_stats;
 
 typedef struct lisa_ctx lisa_ctx;

@@ -29,6 +29,7 @@ struct BuildOutput {
   int     num_emit_tris;
   size_t  node_bytes;
   float   box_other[6], box_emit[6];  // root bounds (lo.xyz, hi.xyz) of the two partitions
+  float   stage_ms[4];                // CUDA-event time of the build stages: Morton + sort, hierarchy (PLOC / LBVH, rotations), collapse, pack
 };
 
 // Returns 0 or a negative lisa_status; on failure err holds a message.  Synchronises the stream.

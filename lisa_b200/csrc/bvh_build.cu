@@ -25,6 +25,9 @@
 #include <chrono>
 #include <cstdlib>
 #include <cstdio>
+#include <cstring>
+
+#include <nvtx3/nvToolsExt.h>
 
 #include "build.h"
 #include "devmem.h"
@@ -743,20 +746,33 @@ static inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
 int build_bvh(const BuildInput& in, BuildOutput* out, cudaStream_t st, char* err, size_t errlen) {
   const int T = in.num_tris;
   const bool dbg = getenv("LISA_DEBUG_TIMING") != nullptr;
-  auto tick = [&](const char* what) {
+  // stage boundaries: a CUDA event each (BuildOutput::stage_ms, always), an NVTX range each (visible to nsys / ncu --nvtx when
+  // a tool is attached, free otherwise), and under LISA_DEBUG_TIMING a synchronised wall-clock line on stderr
+  struct StageEvents {
+    cudaEvent_t e[8] = {};
+    int         n = 0;
+    const char* name[8] = {};
+    ~StageEvents() { for (cudaEvent_t x : e) if (x) cudaEventDestroy(x); }
+  } sev;
+  bool range_open = false;
+  auto tick = [&](const char* what) {  // closes the stage `what` (nullptr: the start of the build)
     static std::chrono::steady_clock::time_point last;
+    if (range_open) { nvtxRangePop(); range_open = false; }
+    if (sev.n < 8 && cudaEventCreate(&sev.e[sev.n]) == cudaSuccess) { cudaEventRecord(sev.e[sev.n], st); sev.name[sev.n] = what; sev.n++; }
     if (!dbg) return;
     cudaStreamSynchronize(st);
     auto now = std::chrono::steady_clock::now();
     if (what) fprintf(stderr, "  build %-10s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(now - last).count());
     last = now;
   };
-  tick(nullptr);
+  auto stage = [&](const char* name) { nvtxRangePushA(name); range_open = true; };
   memset(out, 0, sizeof(*out));
+  tick(nullptr);
   out->root_other = out->root_emit = -1;
   out->num_tris = T;
   for (int k = 0; k < 3; k++) { out->box_other[k] = out->box_emit[k] = FLT_MAX; out->box_other[3 + k] = out->box_emit[3 + k] = -FLT_MAX; }
   if (T == 0) return 0;
+  stage("lisa: bvh morton + sort");
 
   BoundsAcc*          d_acc;
   unsigned long long *d_keys, *d_keys2;
@@ -793,6 +809,7 @@ int build_bvh(const BuildInput& in, BuildOutput* out, cudaStream_t st, char* err
     std::swap(d_ids, d_ids2);
   }
   tick("morton+sort");
+  stage("lisa: bvh hierarchy");
   BoundsAcc h_acc;
   CK(cudaMemcpyAsync(&h_acc, d_acc, sizeof(h_acc), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
@@ -868,6 +885,7 @@ int build_bvh(const BuildInput& in, BuildOutput* out, cudaStream_t st, char* err
 
   tick(in.lbvh ? "lbvh" : "ploc");
   if (in.rotate_passes > 0) {
+    stage("lisa: bvh rotations");
     int *d_par = nullptr, *d_arr = nullptr;
     unsigned int* d_nrot = nullptr;
     CK(dev_alloc((void**)&d_par, sizeof(int) * NN));
@@ -892,6 +910,7 @@ int build_bvh(const BuildInput& in, BuildOutput* out, cudaStream_t st, char* err
     dev_free(d_par); dev_free(d_arr); dev_free(d_nrot);
     tick("rotations");
   }
+  stage("lisa: bvh collapse");
   for (int p = 0; p < 2; p++) {  // root bounds of each partition (node 0 of its slice)
     float* dst = p == 0 ? out->box_other : out->box_emit;
     for (int k = 0; k < 3; k++) { dst[k] = FLT_MAX; dst[3 + k] = -FLT_MAX; }
@@ -971,6 +990,7 @@ int build_bvh(const BuildInput& in, BuildOutput* out, cudaStream_t st, char* err
   }
 
   tick("collapse");
+  stage("lisa: bvh pack");
   float4 *d_tri_v, *d_tri_n;
   int*    d_final_to_orig;
   CK(dev_alloc((void**)&d_tri_v, sizeof(float4) * 3 * (size_t)T));
@@ -981,6 +1001,17 @@ int build_bvh(const BuildInput& in, BuildOutput* out, cudaStream_t st, char* err
   CK(cudaStreamSynchronize(st));
   CK(cudaGetLastError());
   tick("pack");
+  for (int k = 1; k < sev.n; k++) {  // the stream is synchronised: every event has completed
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, sev.e[k - 1], sev.e[k]);
+    const char* w = sev.name[k];
+    if (!w) continue;
+    if (!strcmp(w, "morton+sort")) out->stage_ms[0] = ms;
+    else if (!strcmp(w, "ploc") || !strcmp(w, "lbvh")) out->stage_ms[1] = ms;
+    else if (!strcmp(w, "rotations")) out->stage_ms[1] += ms;
+    else if (!strcmp(w, "collapse")) out->stage_ms[2] = ms;
+    else if (!strcmp(w, "pack")) out->stage_ms[3] = ms;
+  }
 
   dev_free(d_acc); dev_free(d_keys); dev_free(d_keys2); dev_free(d_ids); dev_free(d_ids2); dev_free(d_final_to_sorted);
   dev_free(d_rec[0]); dev_free(d_rec[1]); dev_free(d_tile_state); dev_free(d_ploc_ctl);

@@ -24,6 +24,8 @@
 #include "estimator.h"
 #include "internal.h"
 
+#include <nvtx3/nvToolsExt.h>
+
 using namespace lisa;
 
 static thread_local char g_err[512] = "";
@@ -361,6 +363,8 @@ static int create_impl(const lisa_scene_desc* sd, const lisa_options* opt, lisa_
   dev_free(d_verts); dev_free(d_normals); dev_free(d_mat_idx); dev_free(d_emit);
   cudaEventElapsedTime(&c->stats.upload_ms, t0, t1);
   cudaEventElapsedTime(&c->stats.bvh_build_ms, t1, t2);
+  c->stats.build_sort_ms = c->bvh.stage_ms[0]; c->stats.build_hierarchy_ms = c->bvh.stage_ms[1];
+  c->stats.build_collapse_ms = c->bvh.stage_ms[2]; c->stats.build_pack_ms = c->bvh.stage_ms[3];
   }
 
   c->scene.tri_v = c->bvh.d_tri_v;
@@ -580,8 +584,10 @@ static int run_tile(lisa_ctx* c, const Tile& t, uint64_t* launches, uint64_t* it
     // Cornell 2000x2000 1240 vs 1145 Msamples/s, C3 1920x1080 25.5 vs 27.8 ms; 512x512 22.5 vs 21.4 ms, 128x128 13.4 vs 10.0 ms)
     const uint64_t pool_slots = (uint64_t)c->cfg.sm_count * c->cfg.pool_blocks_per_sm * pool_chains_per_cta();
     const bool use_pool = c->pipeline == 2 || (c->pipeline == 3 && t.n_chains >= 2 * pool_slots);
+    nvtxRangePushA(use_pool ? "lisa: tile k_pool" : "lisa: tile k_path");
     if (use_pool) launch_pool(c->scene, c->state, c->cam, t, c->cfg, c->stream);
     else launch_path(c->scene, c->state, c->cam, t, c->cfg, c->stream);
+    nvtxRangePop();
     if (c->profile_stages) { cudaEvent_t e = next_event(c); cudaEventRecord(e, c->stream); cudaEventRecord(next_event(c), c->stream); }
     launch_finalize(c->state, c->cam, t, c->d_accum, c->stream);
     *launches += 2;

@@ -65,7 +65,8 @@ class Stats(ctypes.Structure):
                 ("last_shadow_jobs", ctypes.c_uint64), ("nodes_visited", ctypes.c_uint64),
                 ("triangles_tested", ctypes.c_uint64), ("last_nodes_visited", ctypes.c_uint64),
                 ("last_triangles_tested", ctypes.c_uint64), ("shadow_culled", ctypes.c_uint64),
-                ("last_shadow_culled", ctypes.c_uint64)]
+                ("last_shadow_culled", ctypes.c_uint64), ("build_sort_ms", ctypes.c_float), ("build_hierarchy_ms", ctypes.c_float),
+                ("build_collapse_ms", ctypes.c_float), ("build_pack_ms", ctypes.c_float)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if not k.startswith("_")}
