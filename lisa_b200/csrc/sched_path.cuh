@@ -171,11 +171,13 @@ __global__ void __launch_bounds__(128, LISA_PATH_MIN_BLOCKS) k_path(DScene sc, D
             const int ti = (int)(ws.tg.x + b);
             float tt, uu, vv;
             nt++;
-            if (step_tri_uv(o, ray, sc.tri_v, ti, LISA_TMIN, best_t, tt, uu, vv)) {
-              if (!any_hit) { best_t = tt; best_u = uu; best_v = vv; best_prim = ti; }
-              else if (phase == 0) { best_prim = ti; ws.tg.y = 0; ws.ng.y = 0; stack.clear(); }
-              else occluded = true;
-            }
+            // the outcome, by selects: closest hit so far | first-found emitter (LISA_SHADOW_FIRST_FOUND: stop) | occluder
+            const bool hit = step_tri_uv(o, ray, sc.tri_v, ti, LISA_TMIN, best_t, tt, uu, vv);
+            const bool take = hit & !any_hit, stop0 = hit & any_hit & (phase == 0);
+            best_t = take ? tt : best_t; best_u = take ? uu : best_u; best_v = take ? vv : best_v;
+            best_prim = (take | stop0) ? ti : best_prim;
+            ws.tg.y = stop0 ? 0u : ws.tg.y; ws.ng.y = stop0 ? 0u : ws.ng.y; stack.sp = stop0 ? 0 : stack.sp;
+            occluded |= hit & any_hit & (phase != 0);
           }
         }
         if (!ws.has_tris() && !ws.has_nodes() && !stack.empty() && !occluded) ws.ng = stack.pop();
