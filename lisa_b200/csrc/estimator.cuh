@@ -290,15 +290,15 @@ __device__ __forceinline__ ChainNext chain_event(const DScene& sc, const Tile& t
   //   otherwise: the cone around the sphere that bounds all emitters (q|q| >= cos|cos| v.v).
   // Both are conservative with respect to hits_emitter_bounds(), which confirms the survivors in try order.
   // The job's row of the warp's job buffer is written right here (three float4: N | LCG state, the filter's four
-  // parameters — flat: A0, B0, A2, B2; cone: axis.xyz, cos|cos| — and |dy|, flag bits (sign of dy | 1 = every try passes),
-  // tries left, slack), so that none of it stays live in registers; rows of lanes that stop trying below are never read.
+  // parameters — flat: A0, B0, A2, B2; cone: axis.xyz, cos|cos| — and dy, the threshold for the component towards the plane
+  // (-inf = every try passes), tries left, slack), so that none of it stays live in registers; rows of lanes that stop
+  // trying below are never written.
   bool      nothing = false;                           // no try of this job can reach an emitter
   const int fk = sc.emit_flat;
   if (trying) {
     float4   fpar = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-    float    f_ady = 0.0f, f_sl = 0.0f;
+    float    f_ady = 0.0f, f_sl = 0.0f, f_thr = 0.0f, f_dy = 0.0f;
     float    Nk = c.N.x, N0 = c.N.y, N2 = c.N.z;  // the normal as the loop wants it: permuted (k, k+1, k+2) for flat bounds
-    uint32_t f_bits = 0u;
     if (sc.emit_r2 < 0.0f) nothing = true;             // no emitters at all
     else if (FLAT) {
       // components along the flat axis (k) and along the two axes of the rectangle (k + 1, k + 2 mod 3); fk is uniform
@@ -309,13 +309,14 @@ __device__ __forceinline__ ChainNext chain_event(const DScene& sc, const Tile& t
       const float dy = sc.emit_plane - Pk;
       float A0 = l0 - P0, B0 = h0 - P0, A2 = l2 - P2, B2 = h2 - P2;
       f_ady = fabsf(dy);
+      f_dy = dy;
       const float sum = fabsf(A0) + fabsf(B0) + fabsf(A2) + fabsf(B2) + f_ady;
       const float mrg = 4e-6f * sum;  // hits_emitter_bounds accepts with a relative slack of 1e-6 on its slab distances
       A0 -= mrg; B0 += mrg; A2 -= mrg; B2 += mrg;
       fpar = make_float4(A0, B0, A2, B2);
       f_sl = 1e-6f * sum + sc.emit_hh;  // the draws below are within 2^-23 of the true ones and the test is linear in them; + the slab's half thickness
-      f_bits = __float_as_uint(dy) & 0x80000000u;
-      if (!sc.cull || f_ady <= sc.emit_hh) f_bits |= 1u;  // culling off, or P inside the slab of the light's plane
+      f_thr = -2.4e-7f;
+      if (!sc.cull || f_ady <= sc.emit_hh) { f_thr = -INFINITY; f_sl = INFINITY; }  // culling off, or P inside the slab of the light's plane: every try passes
       else {
         // every try lies in the hemisphere of N: if the whole light is below that horizon no try can reach it
         const float top = fmaxf(N0 * A0, N0 * B0) + fmaxf(N2 * A2, N2 * B2) + Nk * dy + sc.emit_hh * fabsf(Nk);
@@ -334,7 +335,7 @@ __device__ __forceinline__ ChainNext chain_event(const DScene& sc, const Tile& t
     if (!nothing && !(c.flags & F_STICKY)) {  // the lanes that stay in `trying` below
       jb[3 * lane]     = make_float4(Nk, N0, N2, __uint_as_float(c.seed));
       jb[3 * lane + 1] = fpar;
-      jb[3 * lane + 2] = make_float4(f_ady, __uint_as_float(f_bits), __uint_as_float(LISA_SHADOW_TRIES - c.tries), f_sl);
+      jb[3 * lane + 2] = make_float4(f_dy, f_thr, __uint_as_float(LISA_SHADOW_TRIES - c.tries), f_sl);
     }
   }
   if (trying && (c.flags & F_STICKY)) {  // RayState::hit is true (Q1), only at the first try of a bounce: a real ray
@@ -370,7 +371,7 @@ __device__ __forceinline__ ChainNext chain_event(const DScene& sc, const Tile& t
       for (unsigned rem = jobs; rem; rem &= rem - 1u) {
         const int      j  = __ffs(rem) - 1;
         const float4   r0 = jb[3 * j], r1 = jb[3 * j + 1], r2 = jb[3 * j + 2];
-        const uint32_t left = __float_as_uint(r2.z), bits = __float_as_uint(r2.y);
+        const uint32_t left = __float_as_uint(r2.z);
         const uint32_t t0 = my_a * (__float_as_uint(r0.w) << 8) + my_c8;  // shifted LCG state before try (tries_j + lane)
         const float    vk = __uint_as_float(__umulhi(mk * t0 + ck, 0x00800000u) + 0x40000000u) - 3.0f;
         const float    v0 = __uint_as_float(__umulhi(m0 * t0 + c0i, 0x00800000u) + 0x40000000u) - 3.0f;
@@ -378,17 +379,19 @@ __device__ __forceinline__ ChainNext chain_event(const DScene& sc, const Tile& t
         // w = +-v with the sign of v.N (shoot_ray_hemisphere); where that sign is within rounding of zero the try is kept
         const float    sN = fmaf(v2, r0.z, fmaf(v0, r0.y, vk * r0.x));
         const uint32_t sb = __float_as_uint(sN) & 0x80000000u;
-        const float    u  = __uint_as_float(__float_as_uint(vk) ^ sb ^ (bits & 0x80000000u));  // component towards the plane
+        // r2.x = dy: its sign turns w_k into the component towards the plane, its magnitude is |dy|
+        const float    u  = __uint_as_float(__float_as_uint(vk) ^ sb ^ (__float_as_uint(r2.x) & 0x80000000u));
         const float    w0 = __uint_as_float(__float_as_uint(v0) ^ sb), w2 = __uint_as_float(__float_as_uint(v2) ^ sb);
         // |w_i| <= 1 (the draws lie in [-1, 1]), so hh |w_i| <= hh: the half thickness is part of the job's slack
-        const float    c0 = r2.x * w0, c2 = r2.x * w2;
+        const float    c0 = fabsf(r2.x) * w0, c2 = fabsf(r2.x) * w2;
         const float    g1 = fmaf(-r1.x, u, c0);   // |dy| w0 - A0 u  >= -(slack + hh)
         const float    g2 = fmaf(r1.y, u, -c0);   // B0 u - |dy| w0  >= -(slack + hh)
         const float    g3 = fmaf(-r1.z, u, c2);
         const float    g4 = fmaf(r1.w, u, -c2);
         const float    g  = fminf(fminf(g1, g2), fminf(g3, g4));
-        const unsigned keep = ((unsigned)(g >= -r2.w) & (unsigned)(u > -2.4e-7f)) | (unsigned)(fabsf(sN) < 4e-6f) | (bits & 1u);
-        const unsigned m = __ballot_sync(FULL, keep != 0u && lane < left);
+        // "every try passes" (culling off, P inside the light's slab) is in the job's data: threshold -inf, slack +inf
+        const bool     keep = ((g >= -r2.w) & (u > r2.y)) | (fabsf(sN) < 4e-6f);
+        const unsigned m = __ballot_sync(FULL, keep && lane < left);
         if ((int)lane == j) cone_mask = m;
       }
     } else {

@@ -196,7 +196,19 @@ __global__ void __launch_bounds__(128, LISA_PATH_MIN_BLOCKS) k_path(DScene sc, D
           b.cur = (stop || stack.empty()) ? LISA_BIN_NONE : (int)stack.pop().x;
         }
       }
-      if (occluded || (!st.has_nodes() && !st.has_tris())) {
+      if (WIDE) {  // end of a phase, by selects
+        WideState& ws = *reinterpret_cast<WideState*>(&st);
+        const bool done = occluded | (!ws.has_nodes() & !ws.has_tris());
+        // emitters done: now the other triangles in front (if there are any)
+        const bool to1 = done & (phase == 0) & !(any_hit & (best_prim >= 0)) & (sc.root_other >= 0);
+        const bool fin = done & !to1;
+        phase    = (done & (phase == 0) & !(any_hit & (best_prim >= 0))) ? 1 : phase;
+        stack.sp = to1 ? 0 : stack.sp;
+        ws.ng.x = to1 ? (uint32_t)sc.root_other : ws.ng.x; ws.ng.y = to1 ? 0x80000000u : ws.ng.y;
+        ws.tg.x = to1 ? 0u : ws.tg.x;                      ws.tg.y = to1 ? 0u : ws.tg.y;
+        in_flight = !fin;
+        pending   = pending | fin;
+      } else if (occluded || (!st.has_nodes() && !st.has_tris())) {
         if (phase == 0 && !(any_hit && best_prim >= 0)) {  // emitters done: now the other triangles in front
           phase = 1;
           stack.clear();
