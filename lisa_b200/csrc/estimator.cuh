@@ -14,6 +14,18 @@
 #include "traverse.cuh"
 #include "estimator.h"
 
+// Per-lane counters of node visits and triangle tests (lisa_stats::nodes_visited / triangles_tested; one IADD each in the
+// traversal quantum, ~1 % of the issue slots).  A production build can drop them: make EXTRA_NVFLAGS=-DLISA_COUNT_TRAVERSAL=0
+// (the two statistics then read 0; ray and sample counters are kept, they live in the management section).
+#ifndef LISA_COUNT_TRAVERSAL
+#define LISA_COUNT_TRAVERSAL 1
+#endif
+#if LISA_COUNT_TRAVERSAL
+#define LISA_COUNT(x) ((x)++)
+#else
+#define LISA_COUNT(x) ((void)0)
+#endif
+
 #ifndef LISA_STATE_NO_L1
 #define LISA_STATE_NO_L1 0
 #endif

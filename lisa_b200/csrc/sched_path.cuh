@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(128, LISA_PATH_MIN_BLOCKS) k_path(DScene sc, D
     // ---- one traversal quantum
     if (in_flight) {
       if (st.has_nodes() && !st.has_tris()) {
-        nn++;
+        LISA_COUNT(nn);
         if (WIDE) wide_node_step(sc.bvh, o, ray, LISA_TMIN, best_t, *reinterpret_cast<WideState*>(&st), stack);
         else bin_node_step(sc.bvh, o, ray, LISA_TMIN, best_t, *reinterpret_cast<BinState*>(&st), stack);
       }
@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(128, LISA_PATH_MIN_BLOCKS) k_path(DScene sc, D
             ws.tg.y &= ws.tg.y - 1u;
             const int ti = (int)(ws.tg.x + b);
             float tt, uu, vv;
-            nt++;
+            LISA_COUNT(nt);
             // the outcome, by selects: closest hit so far | first-found emitter (LISA_SHADOW_FIRST_FOUND: stop) | occluder
             const bool hit = step_tri_uv(o, ray, sc.tri_v, ti, LISA_TMIN, best_t, tt, uu, vv);
             const bool take = hit & !any_hit, stop0 = hit & any_hit & (phase == 0);
@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(128, LISA_PATH_MIN_BLOCKS) k_path(DScene sc, D
         if (b.has_tris()) {
           const int ti = ~b.cur;
           float tt, uu, vv;
-          nt++;
+          LISA_COUNT(nt);
           bool stop = false;
           if (step_tri_uv(o, ray, sc.tri_v, ti, LISA_TMIN, best_t, tt, uu, vv)) {
             if (!any_hit) { best_t = tt; best_u = uu; best_v = vv; best_prim = ti; }

@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(128, LISA_MIN_BLOCKS) k_extend(DScene sc, DSta
 #endif
     if (in_flight) {
       if (runN && st.has_nodes() && !st.has_tris()) {
-        nn++;
+        LISA_COUNT(nn);
         if (WIDE) wide_node_step(sc.bvh, o, ray, LISA_TMIN, best_t, *reinterpret_cast<WideState*>(&st), stack);
         else bin_node_step(sc.bvh, o, ray, LISA_TMIN, best_t, *reinterpret_cast<BinState*>(&st), stack);
       }
@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(128, LISA_MIN_BLOCKS) k_extend(DScene sc, DSta
             w.tg.y &= w.tg.y - 1u;
             const int ti = (int)(w.tg.x + b);
             float tt, uu, vv;
-            nt++;
+            LISA_COUNT(nt);
             if (step_tri_uv(o, ray, sc.tri_v, ti, LISA_TMIN, best_t, tt, uu, vv)) { best_t = tt; best_u = uu; best_v = vv; best_prim = ti; }
           }
         }
@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(128, LISA_MIN_BLOCKS) k_extend(DScene sc, DSta
         if (b.has_tris()) {
           const int ti = ~b.cur;
           float tt, uu, vv;
-          nt++;
+          LISA_COUNT(nt);
           if (step_tri_uv(o, ray, sc.tri_v, ti, LISA_TMIN, best_t, tt, uu, vv)) { best_t = tt; best_u = uu; best_v = vv; best_prim = ti; }
           b.cur = stack.empty() ? LISA_BIN_NONE : (int)stack.pop().x;
         }
@@ -567,7 +567,7 @@ __global__ void __launch_bounds__(128, LISA_MIN_BLOCKS) k_rays(DScene sc, DState
 #endif
     if (in_flight) {
       if (runN && st.has_nodes() && !st.has_tris()) {
-        nn++;
+        LISA_COUNT(nn);
         if (WIDE) wide_node_step(sc.bvh, P, ray, LISA_TMIN, tlimit, *reinterpret_cast<WideState*>(&st), stack);
         else bin_node_step(sc.bvh, P, ray, LISA_TMIN, tlimit, *reinterpret_cast<BinState*>(&st), stack);
       }
@@ -582,7 +582,7 @@ __global__ void __launch_bounds__(128, LISA_MIN_BLOCKS) k_rays(DScene sc, DState
             w.tg.y &= w.tg.y - 1u;
             const int ti = (int)(w.tg.x + b);
             float tt;
-            nt++;
+            LISA_COUNT(nt);
             if (step_tri(P, ray, sc.tri_v, ti, LISA_TMIN, tlimit, tt)) {
               if (phase == 0 && !sc.shadow_first_found) { tlimit = tt; light_prim = ti; }
               else if (phase == 0) { light_prim = ti; w.tg.y = 0; w.ng.y = 0; stack.clear(); }
@@ -596,7 +596,7 @@ __global__ void __launch_bounds__(128, LISA_MIN_BLOCKS) k_rays(DScene sc, DState
         if (b.has_tris()) {
           const int ti = ~b.cur;
           float tt;
-          nt++;
+          LISA_COUNT(nt);
           if (step_tri(P, ray, sc.tri_v, ti, LISA_TMIN, tlimit, tt)) {
             if (phase == 0 && !sc.shadow_first_found) { tlimit = tt; light_prim = ti; }
             else if (phase == 0) { light_prim = ti; stack.clear(); }
