@@ -147,11 +147,24 @@ __device__ __forceinline__ int shadow_query(const DScene& sc, const float3& o, c
   return 1;
 }
 
-__device__ __forceinline__ float3 shading_normal(const DScene& sc, const Hit& h) {
-  // barycentric_normal (maths.cu:33-57) with the barycentrics of the intersection test
+#ifndef LISA_NORMAL_FROM_P
+#define LISA_NORMAL_FROM_P 0
+#endif
+__device__ __forceinline__ float3 shading_normal(const DScene& sc, const Hit& h, const float3& P) {
   const float4 n0 = __ldg(sc.tri_n + 3 * h.prim), n1 = __ldg(sc.tri_n + 3 * h.prim + 1), n2 = __ldg(sc.tri_n + 3 * h.prim + 2);
+#if LISA_NORMAL_FROM_P
+  // barycentric_normal exactly as maths.cu:33-57: barycentrics recomputed from the hit point by edge dot products
+  const float3 v1 = f3(__ldg(sc.tri_v + 3 * h.prim)), v2 = f3(__ldg(sc.tri_v + 3 * h.prim + 1)), v3 = f3(__ldg(sc.tri_v + 3 * h.prim + 2));
+  const float3 e1 = v2 - v1, e2 = v3 - v1, i = P - v1;
+  const float  d00 = dot(e1, e1), d01 = dot(e1, e2), d11 = dot(e2, e2), d20 = dot(i, e1), d21 = dot(i, e2);
+  const float  denom = d00 * d11 - d01 * d01;
+  const float  w = (d00 * d21 - d01 * d20) / denom, v = (d11 * d20 - d01 * d21) / denom, u = 1.0f - v - w;
+  return normalize(madd(madd(u * f3(n0), v, f3(n1)), w, f3(n2)));
+#else
+  // barycentric_normal (maths.cu:33-57) with the barycentrics of the intersection test
   const float  w0 = 1.0f - h.u - h.v;
   return normalize(madd(madd(w0 * f3(n0), h.u, f3(n1)), h.v, f3(n2)));
+#endif
 }
 
 // camera ray of pixel (x, y) for the chain's next sample (shader.cu:149-152)
@@ -254,7 +267,7 @@ __device__ __forceinline__ ChainNext chain_event(const DScene& sc, const Tile& t
           const float3 P = madd(c.o, ev.t, c.d);  // shader.cu:221
           Hit h;
           h.t = ev.t; h.u = ev.u; h.v = ev.v; h.prim = ev.prim;
-          c.N = shading_normal(sc, h);
+          c.N = shading_normal(sc, h, P);
           if (m.alpha() < 1.0f) {  // dielectric, shader.cu:226-246
             float  cosI = dot(c.d, c.N), eta;
             float3 Nn;

@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(128, LISA_MIN_BLOCKS) k_extend(DScene sc, DSta
             const float3 P = madd(o, best_t, d);  // shader.cu:221
             Hit h;
             h.t = best_t; h.u = best_u; h.v = best_v; h.prim = best_prim;
-            const float3 N = shading_normal(sc, h);
+            const float3 N = shading_normal(sc, h, P);
             uint32_t bounce = (flags & F_BOUNCE_MASK);
             if (m.alpha() < 1.0f) {  // dielectric, shader.cu:226-246
               float  cosI = dot(d, N), eta;
