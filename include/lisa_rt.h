@@ -94,8 +94,14 @@ enum { LISA_FLAG_PROFILE_STAGES = 1, /* CUDA events around every stage launch */
                                         RayState::hit (hit is false and the ray cannot reach any emitter: outside the cone
                                         around the emitter bounds) is resolved without traversal; images are bit-identical
                                         either way and lisa_stats reports how many tries were resolved that way. */
-       LISA_FLAG_WAVEFRONT = 8       /* render with the wavefront pipeline (three kernels per bounce over chain state in HBM)
-                                        instead of the default single persistent kernel per tile; bit-identical images */ };
+       LISA_FLAG_WAVEFRONT = 8,      /* render with the wavefront pipeline (three kernels per bounce over chain state in HBM)
+                                        instead of the default single persistent kernel per tile; bit-identical images */
+       LISA_FLAG_SPLIT_TRIANGLES = 16 /* build the BVH over REFERENCES: a triangle longer than about twice the scene's mean
+                                        triangle spacing is handed to the builder once per cell of a grid over its bounding box,
+                                        each time with the box of the part inside that cell (early split clipping; at most 1.5
+                                        references per triangle on average).  Tighter boxes for long thin triangles; the hits,
+                                        hence the closest-hit images, are those of the unsplit soup.  lisa_stats.num_references
+                                        reports the count.  Off by default. */ };
 
 typedef struct lisa_options {
   uint32_t struct_size;   /* sizeof(lisa_options) */
@@ -125,7 +131,7 @@ typedef struct lisa_stats {
                                               only when options.flags & LISA_FLAG_PROFILE_STAGES or LISA_PROFILE_STAGES=1 */
   uint64_t state_bytes;                  /* device bytes of chain state + queues */
   uint32_t subframes_accumulated;
-  uint32_t _reserved;
+  uint32_t num_references;               /* primitives of the BVH: num_triangles unless LISA_FLAG_SPLIT_TRIANGLES */
   uint64_t last_extend_launches, last_shadow_launches, last_shadow_jobs; /* jobs = opaque hits light-sampled */
   uint64_t nodes_visited, triangles_tested;           /* cumulative traversal work (both stages) */
   uint64_t last_nodes_visited, last_triangles_tested;

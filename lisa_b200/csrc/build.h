@@ -16,14 +16,31 @@ struct BuildInput {
   int                  lbvh;       // 1: plain LBVH hierarchy (fast build), 0: PLOC (default, near-SAH quality)
   int                  ploc_radius;
   int                  rotate_passes;  // SAH tree-rotation passes over the binary hierarchy before the collapse (0 = none)
+  // Triangle splitting (split.cu): when set, the builder's primitives are REFERENCES — num_tris of them — to the triangles
+  // of the soup: reference r is triangle ref_tri[r] with the box [ref_lo[r], ref_hi[r]].  nullptr: one primitive per triangle.
+  const int*           d_ref_tri;
+  const float4*        d_ref_lo;
+  const float4*        d_ref_hi;
 };
+
+struct SplitOutput {
+  int*    d_ref_tri;
+  float4* d_ref_lo;
+  float4* d_ref_hi;
+  int     num_refs;
+  float   cell;  // the grid cell size that was used
+};
+// References for the triangles of a soup (split.cu): at most budget * T + 64 of them.  Returns 0 or a negative lisa_status.
+int  split_triangles(const float* d_verts, int num_tris, float budget, SplitOutput* out, cudaStream_t st, char* err, size_t errlen);
+void split_free(SplitOutput* s);
 
 struct BuildOutput {
   float4* d_nodes;          // node array shared by both BVHs
   float4* d_tri_v;          // 3 float4 per triangle, final order
   float4* d_tri_n;          // 3 float4 per triangle, final order
   int*    d_final_to_orig;  // final index -> caller's triangle index
-  int     num_tris;
+  int     num_tris;        // primitives of the BVH = entries of d_tri_v / d_tri_n / d_final_to_orig (references when the triangles were split)
+  int     num_input_tris;  // triangles of the caller's soup (set by the caller of build_bvh)
   int     num_nodes, nodes_other, nodes_emit;
   int     root_other, root_emit;
   int     num_emit_tris;

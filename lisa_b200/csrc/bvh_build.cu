@@ -52,14 +52,24 @@ __global__ void k_init_bounds(BoundsAcc* b) {
   b->n_emit = 0;
 }
 
-__global__ void k_centroid_bounds(const float* __restrict__ verts, int ntris, BoundsAcc* acc) {
+// centre of primitive t: the triangle's centroid, or the centre of the reference's box when the primitives are references
+__device__ __forceinline__ float3 prim_centre(const float* __restrict__ verts, int t, const float4* __restrict__ ref_lo,
+                                              const float4* __restrict__ ref_hi) {
+  if (ref_lo) {
+    const float4 l = ref_lo[t], h = ref_hi[t];
+    return f3(0.5f * (l.x + h.x), 0.5f * (l.y + h.y), 0.5f * (l.z + h.z));
+  }
+  const float* p = verts + 9ll * t;
+  return f3((p[0] + p[3] + p[6]) * (1.0f / 3.0f), (p[1] + p[4] + p[7]) * (1.0f / 3.0f), (p[2] + p[5] + p[8]) * (1.0f / 3.0f));
+}
+
+__global__ void k_centroid_bounds(const float* __restrict__ verts, int ntris, BoundsAcc* acc, const float4* __restrict__ ref_lo,
+                                  const float4* __restrict__ ref_hi) {
   float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < ntris; t += gridDim.x * blockDim.x) {
-    const float* p = verts + 9ll * t;
-    for (int a = 0; a < 3; a++) {
-      float c = (p[a] + p[3 + a] + p[6 + a]) * (1.0f / 3.0f);
-      lo[a] = fminf(lo[a], c); hi[a] = fmaxf(hi[a], c);
-    }
+    const float3 cc = prim_centre(verts, t, ref_lo, ref_hi);
+    const float  c3[3] = {cc.x, cc.y, cc.z};
+    for (int a = 0; a < 3; a++) { lo[a] = fminf(lo[a], c3[a]); hi[a] = fmaxf(hi[a], c3[a]); }
   }
   for (int a = 0; a < 3; a++) {
     for (int o = 16; o; o >>= 1) {
@@ -82,21 +92,23 @@ __device__ __forceinline__ unsigned long long expand21(unsigned long long v) {
 
 __global__ void k_morton(const float* __restrict__ verts, const int* __restrict__ mat_idx,
                          const unsigned char* __restrict__ mat_emit, int num_mats, int ntris, const BoundsAcc* acc,
-                         unsigned long long* keys, unsigned int* ids, unsigned int* n_emit) {
+                         unsigned long long* keys, unsigned int* ids, unsigned int* n_emit, const int* __restrict__ ref_tri,
+                         const float4* __restrict__ ref_lo, const float4* __restrict__ ref_hi) {
   int          t    = blockIdx.x * blockDim.x + threadIdx.x;
   bool         emit = false;
   if (t < ntris) {
-    const float* p = verts + 9ll * t;
+    const float3 cc = prim_centre(verts, t, ref_lo, ref_hi);
+    const float  c3[3] = {cc.x, cc.y, cc.z};
     unsigned long long q[3];
     for (int a = 0; a < 3; a++) {
       float lo = ord2f(acc->lo[a]), hi = ord2f(acc->hi[a]);
-      float c  = (p[a] + p[3 + a] + p[6 + a]) * (1.0f / 3.0f);
+      float c  = c3[a];
       float e  = hi - lo;
       float x  = e > 0.0f ? (c - lo) / e : 0.0f;
       x        = fminf(fmaxf(x, 0.0f), 1.0f);
       q[a]     = (unsigned long long)fminf(x * 2097152.0f, 2097151.0f);
     }
-    int m = mat_idx[t];
+    int m = mat_idx[ref_tri ? ref_tri[t] : t];
     emit  = (m >= 0 && m < num_mats) ? (mat_emit[m] != 0) : false;
     unsigned long long k = (expand21(q[0]) << 2) | (expand21(q[1]) << 1) | expand21(q[2]);
     keys[t] = k | (emit ? (1ull << 63) : 0ull);
@@ -144,15 +156,23 @@ __global__ void k_karras(const unsigned long long* __restrict__ keys, int n, int
   if (i == 0) parent[0] = -1;
 }
 
+// box of primitive t: the triangle's, or the reference's
+__device__ __forceinline__ void prim_box(const float* __restrict__ verts, unsigned int t, const float4* __restrict__ ref_lo,
+                                         const float4* __restrict__ ref_hi, float3& lo, float3& hi) {
+  if (ref_lo) { lo = f3(ref_lo[t]); hi = f3(ref_hi[t]); return; }
+  const float* p = verts + 9ll * t;
+  lo = f3(fminf(p[0], fminf(p[3], p[6])), fminf(p[1], fminf(p[4], p[7])), fminf(p[2], fminf(p[5], p[8])));
+  hi = f3(fmaxf(p[0], fmaxf(p[3], p[6])), fmaxf(p[1], fmaxf(p[4], p[7])), fmaxf(p[2], fmaxf(p[5], p[8])));
+}
+
 // Leaf boxes, then bottom-up refit.  box_lo/box_hi: 2n-1 entries per partition.
 __global__ void k_refit(const float* __restrict__ verts, const unsigned int* __restrict__ ids, int n,
                         const int2* __restrict__ child, const int* __restrict__ parent, float4* box_lo, float4* box_hi,
-                        int* flags) {
+                        int* flags, const float4* __restrict__ ref_lo, const float4* __restrict__ ref_hi) {
   int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
-  const float* p  = verts + 9ll * ids[j];
-  float3       lo = f3(fminf(p[0], fminf(p[3], p[6])), fminf(p[1], fminf(p[4], p[7])), fminf(p[2], fminf(p[5], p[8])));
-  float3       hi = f3(fmaxf(p[0], fmaxf(p[3], p[6])), fmaxf(p[1], fmaxf(p[4], p[7])), fmaxf(p[2], fmaxf(p[5], p[8])));
+  float3 lo, hi;
+  prim_box(verts, ids[j], ref_lo, ref_hi, lo, hi);
   int          me = (n - 1) + j;
   box_lo[me] = make_float4(lo.x, lo.y, lo.z, 0.0f);
   box_hi[me] = make_float4(hi.x, hi.y, hi.z, 0.0f);
@@ -186,12 +206,12 @@ __global__ void k_refit(const float* __restrict__ verts, const unsigned int* __r
 #define PLOC_TAIL 512
 
 __global__ void k_leaf_records(const float* __restrict__ verts, const unsigned int* __restrict__ ids, int n, float4* box_lo,
-                               float4* box_hi, float4* rec) {
+                               float4* box_hi, float4* rec, const float4* __restrict__ ref_lo, const float4* __restrict__ ref_hi) {
   int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
-  const float* p = verts + 9ll * ids[j];
-  const float4 lo = make_float4(fminf(p[0], fminf(p[3], p[6])), fminf(p[1], fminf(p[4], p[7])), fminf(p[2], fminf(p[5], p[8])), 0.0f);
-  const float4 hi = make_float4(fmaxf(p[0], fmaxf(p[3], p[6])), fmaxf(p[1], fmaxf(p[4], p[7])), fmaxf(p[2], fmaxf(p[5], p[8])), 0.0f);
+  float3 l3, h3;
+  prim_box(verts, ids[j], ref_lo, ref_hi, l3, h3);
+  const float4 lo = make_float4(l3.x, l3.y, l3.z, 0.0f), hi = make_float4(h3.x, h3.y, h3.z, 0.0f);
   box_lo[(n - 1) + j] = lo;
   box_hi[(n - 1) + j] = hi;
   rec[2ll * j]     = make_float4(lo.x, lo.y, lo.z, __int_as_float((n - 1) + j));
@@ -726,10 +746,11 @@ __global__ void k_iota_sorted(unsigned int* final_to_sorted, int n) {
 __global__ void k_pack_triangles(const float* __restrict__ verts, const float* __restrict__ normals,
                                  const int* __restrict__ mat_idx, const unsigned int* __restrict__ sorted_ids,
                                  const unsigned int* __restrict__ final_to_sorted, int ntris, float4* tri_v,
-                                 float4* tri_n, int* final_to_orig) {
+                                 float4* tri_n, int* final_to_orig, const int* __restrict__ ref_tri) {
   int f = blockIdx.x * blockDim.x + threadIdx.x;
   if (f >= ntris) return;
   unsigned int t = sorted_ids[final_to_sorted[f]];
+  if (ref_tri) t = (unsigned int)ref_tri[t];  // a reference: the packed arrays get a full copy of its triangle
   const float* p = verts + 9ll * t;
   const float* q = normals + 9ll * t;
   tri_v[3ll * f + 0] = make_float4(p[0], p[1], p[2], __int_as_float(mat_idx[t]));
@@ -785,9 +806,9 @@ int build_bvh(const BuildInput& in, BuildOutput* out, cudaStream_t st, char* err
   CK(dev_alloc((void**)&d_final_to_sorted, sizeof(unsigned int) * T));
 
   k_init_bounds<<<1, 1, 0, st>>>(d_acc);
-  k_centroid_bounds<<<min(cdiv(T, 256), 148 * 8), 256, 0, st>>>(in.d_verts, T, d_acc);
+  k_centroid_bounds<<<min(cdiv(T, 256), 148 * 8), 256, 0, st>>>(in.d_verts, T, d_acc, in.d_ref_lo, in.d_ref_hi);
   k_morton<<<cdiv(T, 256), 256, 0, st>>>(in.d_verts, in.d_mat_idx, in.d_mat_emit, in.num_mats, T, d_acc, d_keys, d_ids,
-                                         &d_acc->n_emit);
+                                         &d_acc->n_emit, in.d_ref_tri, in.d_ref_lo, in.d_ref_hi);
   const size_t tmp_bytes = radix_sort_temp_bytes((size_t)T);
   void* d_tmp;
   CK(dev_alloc((void**)&d_tmp, tmp_bytes));
@@ -852,10 +873,11 @@ int build_bvh(const BuildInput& in, BuildOutput* out, cudaStream_t st, char* err
         k_karras<<<cdiv(P.n - 1, 256), 256, 0, st>>>(d_keys2 + P.sorted_base, P.n, d_child + P.slice, d_parent + P.slice,
                                                      d_range + P.slice);
       k_refit<<<cdiv(P.n, 256), 256, 0, st>>>(in.d_verts, d_ids2 + P.sorted_base, P.n, d_child + P.slice,
-                                              d_parent + P.slice, d_lo + P.slice, d_hi + P.slice, d_flags + P.slice);
+                                              d_parent + P.slice, d_lo + P.slice, d_hi + P.slice, d_flags + P.slice, in.d_ref_lo, in.d_ref_hi);
       P.root = 0;
     } else {
-      k_leaf_records<<<cdiv(P.n, 256), 256, 0, st>>>(in.d_verts, d_ids2 + P.sorted_base, P.n, d_lo + P.slice, d_hi + P.slice, d_rec[0]);
+      k_leaf_records<<<cdiv(P.n, 256), 256, 0, st>>>(in.d_verts, d_ids2 + P.sorted_base, P.n, d_lo + P.slice, d_hi + P.slice, d_rec[0],
+                                                     in.d_ref_lo, in.d_ref_hi);
       int m = P.n, cur = 0, rounds = 0;
       // stale tile states of the other partition must not be taken for this one's
       CK(cudaMemsetAsync(d_tile_state, 0, sizeof(unsigned long long) * (((size_t)P.n + ploc_tile_size(radius) - 1) / ploc_tile_size(radius)), st));
@@ -997,7 +1019,7 @@ int build_bvh(const BuildInput& in, BuildOutput* out, cudaStream_t st, char* err
   CK(dev_alloc((void**)&d_tri_n, sizeof(float4) * 3 * (size_t)T));
   CK(dev_alloc((void**)&d_final_to_orig, sizeof(int) * (size_t)T));
   k_pack_triangles<<<cdiv(T, 256), 256, 0, st>>>(in.d_verts, in.d_normals, in.d_mat_idx, d_ids2, d_final_to_sorted, T,
-                                                 d_tri_v, d_tri_n, d_final_to_orig);
+                                                 d_tri_v, d_tri_n, d_final_to_orig, in.d_ref_tri);
   CK(cudaStreamSynchronize(st));
   CK(cudaGetLastError());
   tick("pack");

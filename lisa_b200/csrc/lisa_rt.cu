@@ -209,6 +209,7 @@ struct BvhFileHeader {
   uint32_t emit_hash;  // FNV-1a over the materials' emitter flags: the emitter / non-emitter partition is baked into the file
   float    box_other[6], box_emit[6];
   uint64_t file_bytes;
+  uint64_t num_input_tris;  // triangles of the soup the BVH was built from (< num_tris when triangles were split into references)
 };
 static uint32_t emit_flags_hash(const lisa_scene_desc* sd) {
   uint32_t h = 2166136261u;
@@ -225,12 +226,12 @@ static int load_bvh_file(const lisa_scene_desc* sd, const char* path, lisa_ctx* 
   if (!f) return fail(LISA_ERR_IO, "cannot open %s", path);
   struct Closer { FILE* f; ~Closer() { fclose(f); } } closer{f};
   BvhFileHeader h;
-  if (fread(&h, sizeof(h), 1, f) != 1 || memcmp(h.magic, "LISABVH1", 8) != 0 || h.version != 1 || h.header_bytes != sizeof(h))
+  if (fread(&h, sizeof(h), 1, f) != 1 || memcmp(h.magic, "LISABVH1", 8) != 0 || h.version != 2 || h.header_bytes != sizeof(h))
     return fail(LISA_ERR_IO, "%s is not a serialised BVH of this library", path);
   if (fseek(f, 0, SEEK_END) != 0 || (uint64_t)ftell(f) != h.file_bytes || h.file_bytes != bvh_file_bytes(h))
     return fail(LISA_ERR_IO, "%s is truncated or damaged", path);
-  if (sd->num_vertices && (uint64_t)(sd->num_vertices / 3) != h.num_tris)
-    return fail(LISA_ERR_ARG, "%s holds %llu triangles, the scene has %d", path, (unsigned long long)h.num_tris, sd->num_vertices / 3);
+  if (sd->num_vertices && (uint64_t)(sd->num_vertices / 3) != h.num_input_tris)
+    return fail(LISA_ERR_ARG, "%s holds %llu triangles, the scene has %d", path, (unsigned long long)h.num_input_tris, sd->num_vertices / 3);
   if (h.num_materials != sd->num_materials || h.emit_hash != emit_flags_hash(sd))
     return fail(LISA_ERR_ARG, "%s was built for %d materials with other emitter flags (the emitter partition is part of the BVH)", path, h.num_materials);
   fseek(f, (long)sizeof(h), SEEK_SET);
@@ -240,6 +241,7 @@ static int load_bvh_file(const lisa_scene_desc* sd, const char* path, lisa_ctx* 
   b.num_nodes = (int)h.num_nodes; b.nodes_other = h.nodes_other; b.nodes_emit = h.nodes_emit;
   b.root_other = h.root_other; b.root_emit = h.root_emit; b.num_emit_tris = h.num_emit_tris; b.node_bytes = nb;
   b.num_tris = (int)h.num_tris;
+  b.num_input_tris = (int)h.num_input_tris;
   memcpy(b.box_other, h.box_other, sizeof(b.box_other));
   memcpy(b.box_emit, h.box_emit, sizeof(b.box_emit));
   *wide_out = h.wide;
@@ -352,15 +354,26 @@ static int create_impl(const lisa_scene_desc* sd, const lisa_options* opt, lisa_
   if (const char* e = getenv("LISA_PLOC_RADIUS")) radius = std::max(1, atoi(e));
   int rotate = 0;
   if (const char* e = getenv("LISA_BVH_ROTATE")) rotate = std::max(0, std::min(8, atoi(e)));
-  BuildInput bi{d_verts, d_normals, d_mat_idx, d_emit, T, sd->num_materials, wide, lbvh, radius, rotate};
-  int rc = build_bvh(bi, &c->bvh, c->stream, g_err, sizeof(g_err));
+  // triangle splitting (split.cu), opt-in: the builder's primitives become references to the triangles
+  float split_budget = (o.flags & LISA_FLAG_SPLIT_TRIANGLES) ? 1.5f : 0.0f;
+  if (const char* e = getenv("LISA_SPLIT")) { const float v = (float)atof(e); split_budget = v <= 0.0f ? 0.0f : v <= 1.0f ? 1.5f : std::min(v, 8.0f); }
+  const int   T_in = T;
+  SplitOutput sp{};
+  int         rc = 0;
+  if (split_budget > 0.0f && T > 0) {
+    rc = split_triangles(d_verts, T, split_budget, &sp, c->stream, g_err, sizeof(g_err));
+    if (!rc) T = sp.num_refs;
+  }
+  BuildInput bi{d_verts, d_normals, d_mat_idx, d_emit, T, sd->num_materials, wide, lbvh, radius, rotate, sp.d_ref_tri, sp.d_ref_lo, sp.d_ref_hi};
+  if (!rc) rc = build_bvh(bi, &c->bvh, c->stream, g_err, sizeof(g_err));
   if (rc) {  // keep the builder's message: a sticky CUDA error would otherwise be reported by the next call instead
-    dev_free(d_verts); dev_free(d_normals); dev_free(d_mat_idx); dev_free(d_emit);
+    dev_free(d_verts); dev_free(d_normals); dev_free(d_mat_idx); dev_free(d_emit); split_free(&sp);
     return rc;
   }
+  c->bvh.num_input_tris = T_in;
   CU(cudaEventRecord(t2, c->stream));
   CU(cudaStreamSynchronize(c->stream));
-  dev_free(d_verts); dev_free(d_normals); dev_free(d_mat_idx); dev_free(d_emit);
+  dev_free(d_verts); dev_free(d_normals); dev_free(d_mat_idx); dev_free(d_emit); split_free(&sp);
   cudaEventElapsedTime(&c->stats.upload_ms, t0, t1);
   cudaEventElapsedTime(&c->stats.bvh_build_ms, t1, t2);
   c->stats.build_sort_ms = c->bvh.stage_ms[0]; c->stats.build_hierarchy_ms = c->bvh.stage_ms[1];
@@ -414,7 +427,8 @@ static int create_impl(const lisa_scene_desc* sd, const lisa_options* opt, lisa_
   }
 
   c->stats.struct_size = sizeof(lisa_stats);
-  c->stats.num_triangles = (uint32_t)T;
+  c->stats.num_triangles = (uint32_t)c->bvh.num_input_tris;
+  c->stats.num_references = (uint32_t)T;
   c->stats.num_emitter_triangles = (uint32_t)c->bvh.num_emit_tris;
   c->stats.bvh_nodes = (uint32_t)c->bvh.num_nodes;
   c->stats.bvh_emitter_nodes = (uint32_t)c->bvh.nodes_emit;
@@ -528,7 +542,8 @@ extern "C" int lisa_save_bvh(lisa_ctx* c, const char* path) {
   CU(cudaSetDevice(c->device));
   BvhFileHeader h{};
   memcpy(h.magic, "LISABVH1", 8);
-  h.version = 1; h.header_bytes = sizeof(h);
+  h.version = 2; h.header_bytes = sizeof(h);
+  h.num_input_tris = (uint64_t)c->bvh.num_input_tris;
   h.num_tris = (uint64_t)c->scene.num_tris; h.num_nodes = (uint64_t)c->bvh.num_nodes;
   h.nodes_other = c->bvh.nodes_other; h.nodes_emit = c->bvh.nodes_emit;
   h.root_other = c->bvh.root_other; h.root_emit = c->bvh.root_emit;

@@ -25,6 +25,7 @@ FLAG_PROFILE_STAGES = 1
 FLAG_LBVH = 2
 FLAG_NO_CULL = 4
 FLAG_WAVEFRONT = 8
+FLAG_SPLIT_TRIANGLES = 16
 
 
 class Material(ctypes.Structure):
@@ -60,7 +61,7 @@ class Stats(ctypes.Structure):
                 ("last_samples", ctypes.c_uint64), ("last_radiance_rays", ctypes.c_uint64),
                 ("last_shadow_rays", ctypes.c_uint64), ("last_kernel_launches", ctypes.c_uint64),
                 ("last_extend_ms", ctypes.c_double), ("last_shadow_ms", ctypes.c_double),
-                ("state_bytes", ctypes.c_uint64), ("subframes_accumulated", ctypes.c_uint32), ("_reserved", ctypes.c_uint32),
+                ("state_bytes", ctypes.c_uint64), ("subframes_accumulated", ctypes.c_uint32), ("num_references", ctypes.c_uint32),
                 ("last_extend_launches", ctypes.c_uint64), ("last_shadow_launches", ctypes.c_uint64),
                 ("last_shadow_jobs", ctypes.c_uint64), ("nodes_visited", ctypes.c_uint64),
                 ("triangles_tested", ctypes.c_uint64), ("last_nodes_visited", ctypes.c_uint64),

@@ -1,0 +1,79 @@
+#!/usr/bin/env python3
+"""Triangle splitting (csrc/split.cu) on / off: references, build time, render time and traversal work per ray on
+  needles   1,000,000 small triangles + 50,000 long diagonal slivers (the case splitting is for)
+  knot      C3 (871,218 uniformly tessellated triangles + Cornell walls: nothing to split)
+  soup      C4 at 1M (random overlapping triangles of one size)
+One line of JSON per (scene, split) pair."""
+import json, os, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); os.chdir(ROOT)
+import lisa_b200.frontend as fe, lisa_b200.rt as rt
+
+MAT_W = dict(emit=False, alpha=1.0, diffuse=(0.7, 0.7, 0.7), roughness=1.0)
+MAT_L = dict(emit=True, alpha=1.0, emission=(1, 1, 1))
+LIGHT = np.float32([[-1.5, 1.8, -1.5], [1.5, 1.8, -1.5], [1.5, 1.8, 1.5], [-1.5, 1.8, -1.5], [1.5, 1.8, 1.5], [-1.5, 1.8, 1.5]])
+
+
+def needles(T_small=1_000_000, T_long=50_000, seed=11):
+    rng = np.random.default_rng(seed)
+    c = rng.uniform(-1, 1, size=(T_small, 1, 3))
+    v = (c + rng.normal(scale=0.004, size=(T_small, 3, 3))).astype(np.float32).reshape(-1, 3)
+    a = rng.uniform(-1, 1, size=(T_long, 3))
+    b = a + rng.uniform(0.3, 1.2, size=(T_long, 1)) * rng.choice([-1.0, 1.0], size=(T_long, 3))
+    w = rng.normal(scale=0.004, size=(T_long, 3))
+    vl = np.stack([a, b, a + w], axis=1).astype(np.float32).reshape(-1, 3)
+    v = np.concatenate([v, vl, LIGHT])
+    n = np.tile(np.float32([[0, 1, 0]]), (len(v), 1))
+    m = np.concatenate([np.zeros(T_small + T_long, np.int32), np.ones(2, np.int32)])
+    return (v, n, m, [MAT_W, MAT_L], 1024, 1024, (0.0, 0.3, 4.6), (0, 0, 0), 35.0, 4, 7)
+
+
+def knot():
+    sys.path.insert(0, os.path.join(ROOT, "assets"))
+    import gen_knot
+    sc = fe.parse_scene("scenes/cornell_c1.rto")
+    kv, kn = gen_knot.soup_arrays()
+    T0 = len(sc["mat_indices"])
+    keep = np.isin(np.arange(T0), np.r_[0:16, T0 - 2:T0])
+    v = np.concatenate([sc["vertices"].reshape(-1, 3, 3)[keep].reshape(-1, 3), kv])
+    n = np.concatenate([sc["normals"].reshape(-1, 3, 3)[keep].reshape(-1, 3), kn])
+    m = np.concatenate([sc["mat_indices"][keep], np.full(len(kv) // 3, 1, np.int32)])
+    return (v, n, m, sc["materials_packed"], 1920, 1080, sc["camera"]["eye"], sc["camera"]["look_at"], sc["camera"]["fov"], 16, 12)
+
+
+def soup():
+    from oracle.make_golden_gpu import soup as gen   # the C4 generator (test infrastructure; scripts may use it)
+    v, n = gen(1_000_000)
+    q = np.float32([[-0.5, 1.6, -0.5], [1.5, 1.6, -0.5], [1.5, 1.6, 1.5], [-0.5, 1.6, -0.5], [1.5, 1.6, 1.5], [-0.5, 1.6, 1.5]])
+    v = np.concatenate([v, q]); n = np.concatenate([n, np.tile(np.float32([[0, -1, 0]]), (6, 1))])
+    m = np.concatenate([np.zeros(1_000_000, np.int32), np.ones(2, np.int32)])
+    return (v, n, m, [MAT_W, MAT_L], 1024, 1024, (0.5, 0.6, 3.2), (0.5, 0.45, 0.5), 35.0, 4, 7)
+
+
+for name in (sys.argv[1:] or ["needles", "knot", "soup"]):
+    args = dict(needles=needles, knot=knot, soup=soup)[name]()
+    imgs = []
+    for split in (0, 1):
+        best = None
+        for rep in range(3):   # the first build pays the allocator; keep the fastest of three
+            R = rt.Renderer(*args, flags=rt.FLAG_SPLIT_TRIANGLES if split else 0)
+            st = R.stats()
+            if best is None or st["bvh_build_ms"] < best:
+                best = st["bvh_build_ms"]
+            if rep < 2:
+                R.close()
+        spp = args[9]
+        R.render_subframes(0, 1, spp)   # warm-up
+        R.reset_accum()
+        R.render_subframes(0, 1, spp)
+        st = R.stats()
+        rays = st["last_radiance_rays"] + st["last_shadow_rays"] - st["last_shadow_culled"]
+        imgs.append(R.read_accum().copy())
+        print(json.dumps(dict(scene=name, split=split, triangles=st["num_triangles"], references=st["num_references"],
+                              bvh_nodes=st["bvh_nodes"], build_ms=round(best, 2), render_ms=round(st["last_render_ms"], 2),
+                              msamples_per_s=round(st["last_samples"] / st["last_render_ms"] / 1e3, 2),
+                              nodes_per_ray=round(st["last_nodes_visited"] / max(rays, 1), 2),
+                              triangles_per_ray=round(st["last_triangles_tested"] / max(rays, 1), 2))), flush=True)
+        R.close()
+    print(json.dumps(dict(scene=name, images_bit_identical=bool(np.array_equal(imgs[0], imgs[1])))), flush=True)

@@ -332,7 +332,7 @@ def test_serialised_bvh_round_trip(rt, cornell, tmp_path):
     A.save_bvh(path)
     stA = A.stats()
     import os
-    assert os.path.getsize(path) == 120 + stA["bvh_bytes"] + stA["num_triangles"] * 100   # header, nodes, 48 + 48 + 4 bytes per triangle
+    assert os.path.getsize(path) == 128 + stA["bvh_bytes"] + stA["num_triangles"] * 100   # header, nodes, 48 + 48 + 4 bytes per triangle
     B = rt.Renderer.from_bvh(sc, path)
     stB = B.stats()
     for k in ("num_triangles", "num_emitter_triangles", "bvh_nodes", "bvh_emitter_nodes", "bvh_bytes"):
@@ -370,3 +370,101 @@ def test_serialised_bvh_round_trip(rt, cornell, tmp_path):
     swapped["materials"][0], swapped["materials"][4] = swapped["materials"][4], swapped["materials"][0]   # the light becomes material 0
     with pytest.raises(rt.LisaError, match="other emitter flags"):
         rt.Renderer.from_bvh(swapped, path)
+
+
+def _needle_soup(rng, T_small, T_long):
+    """Small triangles plus long thin diagonal ones, whose bounding boxes are almost entirely empty."""
+    v, n = _soup(rng, T_small, size=0.02)
+    a = rng.uniform(-1, 1, size=(T_long, 3))
+    b = a + rng.uniform(0.8, 1.6, size=(T_long, 1)) * rng.choice([-1.0, 1.0], size=(T_long, 3))
+    w = rng.normal(scale=0.01, size=(T_long, 3))
+    vl = np.stack([a, b, a + w], axis=1).astype(np.float32).reshape(-1, 3)
+    nl = rng.normal(size=(T_long * 3, 3)).astype(np.float32)
+    nl /= np.linalg.norm(nl, axis=1, keepdims=True)
+    return np.concatenate([v, vl]), np.concatenate([n, nl])
+
+
+@pytest.mark.parametrize("bvh", [0, 1], ids=["wide8", "binary"])
+def test_split_triangles_same_hits_less_work(rt, orc, bvh):
+    """LISA_FLAG_SPLIT_TRIANGLES (csrc/split.cu): the BVH is built over references with clipped boxes; every ray finds the
+    hit it finds in the unsplit tree and the oracle's, the rendered image is the same bits, the traversal does less work."""
+    rng = np.random.default_rng(77)
+    T_small, T_long = 30000, 1500
+    v, n = _needle_soup(rng, T_small, T_long)
+    T = T_small + T_long
+    m = np.zeros(T, np.int32)
+    m[rng.choice(T_small, 300, replace=False)] = 1
+    m[T_small:T_small + 20] = 1  # some long emitters too: the emitter partition is split as well
+    args = (v, n, m, [MAT_W, MAT_L], 96, 96, (0, 0, 4.5), (0, 0, 0), 40.0, 4, 4)
+    R0 = rt.Renderer(*args, bvh_kind=bvh)
+    R1 = rt.Renderer(*args, bvh_kind=bvh, flags=rt.FLAG_SPLIT_TRIANGLES)
+    s0, s1 = R0.stats(), R1.stats()
+    assert s0["num_references"] == s0["num_triangles"] == T
+    assert s1["num_triangles"] == T and T + T_long < s1["num_references"] <= 1.5 * T + 64
+    assert s1["num_emitter_triangles"] > s0["num_emitter_triangles"] == 320   # references of the emitter partition
+    o, d = _rays(rng, v.min(0), v.max(0), 200000)
+    p0, t0 = R0.trace_closest(o, d)
+    p1, t1 = R1.trace_closest(o, d)
+    same = (p0 == p1)
+    assert (t0[same] == t1[same]).all()
+    assert (~same).sum() <= 2 and np.allclose(t0[~same], t1[~same], rtol=2e-5)  # ties only
+    assert (p1 >= T_small).mean() > 0.02   # the long triangles are hit
+    S = orc.Scene(v, n, m, rt_pack([MAT_W, MAT_L]))
+    bad, _ = _compare_with_oracle(R1, S, o, d, m=2000)
+    assert bad <= 2, bad
+    oc0, l0 = R0.trace_shadow(o, d)
+    oc1, l1 = R1.trace_shadow(o, d)
+    assert (oc0 != oc1).sum() <= 2
+    R0.render(); R1.render()
+    assert np.array_equal(R0.read_accum(), R1.read_accum())
+    w0, w1 = R0.stats(), R1.stats()
+    assert w1["triangles_tested"] < 0.8 * w0["triangles_tested"], (w0["triangles_tested"], w1["triangles_tested"])
+    assert w1["nodes_visited"] < w0["nodes_visited"], (w0["nodes_visited"], w1["nodes_visited"])
+
+
+def test_split_triangles_leaves_short_triangles_alone(rt, cornell, tmp_path):
+    """A soup without long triangles gets one reference per triangle; degenerate and empty soups go through; a split BVH
+    survives lisa_save_bvh / lisa_create_from_bvh."""
+    rng = np.random.default_rng(5)
+    v, n = _soup(rng, 20000, size=0.01)
+    m = np.zeros(20000, np.int32)
+    R = rt.Renderer(v, n, m, [MAT_W], 8, 8, (0, 0, 5), (0, 0, 0), 45.0, 1, 3, flags=rt.FLAG_SPLIT_TRIANGLES)
+    assert R.stats()["num_references"] == 20000
+    # zero-area triangles and one huge triangle
+    v2 = np.zeros((9, 3), np.float32)
+    v2[3:6] = [[-5, -5, 0], [5, -5, 0], [0, 7, 0]]
+    v2[6:9] = [[1, 1, 1], [2, 2, 2], [3, 3, 3]]
+    R2 = rt.Renderer(v2, np.ones((9, 3), np.float32), np.zeros(3, np.int32), [MAT_W], 8, 8, (0, 0, 5), (0, 0, 0), 45.0, 1, 3,
+                     flags=rt.FLAG_SPLIT_TRIANGLES)
+    st = R2.stats()
+    assert st["num_triangles"] == 3 and 3 <= st["num_references"] <= 3 * 64
+    prim, t = R2.trace_closest(np.array([[0.3, 0.2, 3.0], [40.0, 0, 3.0]], np.float32), np.array([[0, 0, -1.0], [0, 0, -1.0]], np.float32))
+    assert prim[0] == 1 and abs(t[0] - 3.0) < 1e-5 and prim[1] == -1
+    R3 = rt.Renderer(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.float32), np.zeros(0, np.int32), [MAT_W], 8, 8, (0, 0, 5),
+                     (0, 0, 0), 45.0, 1, 3, flags=rt.FLAG_SPLIT_TRIANGLES)
+    assert R3.stats()["num_references"] == 0
+    # Cornell: the walls are axis-aligned right triangles, whose boxes are as full as a triangle's box gets -> left alone
+    sc = resized(cornell, 48)
+    A = rt.Renderer.from_scene(sc, flags=rt.FLAG_SPLIT_TRIANGLES)
+    assert A.stats()["num_references"] == A.stats()["num_triangles"] == 1002
+    C = rt.Renderer.from_scene(sc)
+    A.render(); C.render()
+    assert np.array_equal(A.read_accum(), C.read_accum())
+    # a split BVH through lisa_save_bvh / lisa_create_from_bvh: references and images survive
+    v, n = _needle_soup(rng, 5000, 300)
+    m = np.zeros(5300, np.int32); m[:40] = 1
+    sc = dict(vertices=v, normals=n, mat_indices=m, materials=[MAT_W, MAT_L], width=64, height=64,
+              camera=dict(eye=(0, 0, 4.5), look_at=(0, 0, 0), fov=40.0), num_samples=4, num_bounces=4)
+    A = rt.Renderer.from_scene(sc, flags=rt.FLAG_SPLIT_TRIANGLES)
+    sa = A.stats()
+    assert sa["num_triangles"] == 5300 and sa["num_references"] > 5300 + 300
+    path = str(tmp_path / "split.bvh")
+    A.save_bvh(path)
+    B = rt.Renderer.from_bvh(sc, path)
+    sb = B.stats()
+    assert sb["num_triangles"] == 5300 and sb["num_references"] == sa["num_references"]
+    with pytest.raises(rt.LisaError):
+        sc2 = dict(sc, vertices=v[:-3], normals=n[:-3], mat_indices=m[:-1])
+        rt.Renderer.from_bvh(sc2, path, with_geometry=True)   # 5299 triangles against a file built from 5300
+    A.render(); B.render()
+    assert np.array_equal(A.read_accum(), B.read_accum())
