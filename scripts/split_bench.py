@@ -65,7 +65,7 @@ for name in (sys.argv[1:] or ["needles", "knot", "soup"]):
                 R.close()
         spp = args[9]
         R.render_subframes(0, 1, spp)   # warm-up
-        R.reset_accum()
+        R.reset()
         R.render_subframes(0, 1, spp)
         st = R.stats()
         rays = st["last_radiance_rays"] + st["last_shadow_rays"] - st["last_shadow_culled"]
