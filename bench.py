@@ -310,7 +310,7 @@ def main():
     def timed_leg(first_step, spp, sample_clocks):
         """K timed steps of `spp` samples per pixel and rank, bracketed by barrier + synchronize; device time, max over ranks."""
         barrier()
-        clk = ClockSampler(local_rank) if (rank == 0 and sample_clocks) else None
+        clk = ClockSampler(local_rank) if sample_clocks else None   # every rank watches its own GPU
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         agg = dict(render_ms=0.0, shadow_ms=0.0, extend_ms=0.0, shadow_launches=0, extend_launches=0, jobs=0, shadow_rays=0,
                    radiance_rays=0, launches=0, nodes=0, tris=0, culled=0)
@@ -341,7 +341,14 @@ def main():
         if world > 1:
             dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
         T = float(t_ms.item())
-        return dict(T=T, value=world * npix * spp * K / T / 1e3, wall_ms=wall_ms, agg=agg, clocks=clocks)
+        per_rank = None
+        if world > 1 and sample_clocks:
+            # what each rank saw: the slowest one sets the line's time, and its clocks / power say why
+            mine = {"rank": rank, "ms_per_step": round(float(e0.elapsed_time(e1)) / K, 3), "render_ms_per_step": round(agg["render_ms"] / K, 3),
+                    "sm_mhz": (clocks or {}).get("sm_mhz"), "power_w_max": (clocks or {}).get("power_w_max"), "reasons": (clocks or {}).get("reasons")}
+            per_rank = [None] * world
+            dist.all_gather_object(per_rank, mine)
+        return dict(T=T, value=world * npix * spp * K / T / 1e3, wall_ms=wall_ms, agg=agg, clocks=clocks, per_rank=per_rank)
 
     # ---- weak leg: every rank renders its own subframe of S spp each step
     for i in range(W):
@@ -498,6 +505,7 @@ def main():
             "wall_ms_per_step": round(wall_ms / K, 3), "device_render_ms_per_step": round(agg["render_ms"] / K, 3),
             "gpu_launches": int(agg["launches"]),
             "clocks": clocks,
+            **({"per_rank": weak["per_rank"]} if weak.get("per_rank") else {}),
             "e2e": e2e,
             "roofline": roof,
         }
