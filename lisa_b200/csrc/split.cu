@@ -76,13 +76,13 @@ __device__ int clip_plane(const float3* in, int n, float3* out, int axis, float 
 
 // The grid of a triangle: cells of at most L per axis over its bounding box, at most SPLIT_MAX_CELLS in all.
 struct SplitGrid { float lo[3], hi[3], w[3]; int n[3]; };
-__device__ __forceinline__ SplitGrid split_grid(const float* p, float L, float empty) {
+__device__ __forceinline__ SplitGrid split_grid(const float* p, float L, float empty, int max_cells) {
   SplitGrid g;
   float ext[3];
   for (int a = 0; a < 3; a++) {
     const float l = fminf(p[a], fminf(p[3 + a], p[6 + a])), h = fmaxf(p[a], fmaxf(p[3 + a], p[6 + a]));
     g.lo[a] = l; g.hi[a] = h; ext[a] = h - l;
-    g.n[a] = (int)fminf(fmaxf(ceilf(ext[a] / L), 1.0f), (float)SPLIT_MAX_CELLS);
+    g.n[a] = (int)fminf(fmaxf(ceilf(ext[a] / L), 1.0f), (float)max_cells);
   }
   // How empty is the box?  Half its surface area over the triangle's area projected on the three axis planes: 2 for an
   // axis-aligned right triangle (a wall: nothing to gain, and measured: splitting the Cornell walls costs 37 %), unbounded for
@@ -91,9 +91,9 @@ __device__ __forceinline__ SplitGrid split_grid(const float* p, float L, float e
     const float e1[3] = {p[3] - p[0], p[4] - p[1], p[5] - p[2]}, e2[3] = {p[6] - p[0], p[7] - p[1], p[8] - p[2]};
     const float proj = 0.5f * (fabsf(e1[1] * e2[2] - e1[2] * e2[1]) + fabsf(e1[2] * e2[0] - e1[0] * e2[2]) + fabsf(e1[0] * e2[1] - e1[1] * e2[0]));
     const float half = ext[0] * ext[1] + ext[1] * ext[2] + ext[2] * ext[0];
-    if (half <= empty * proj) g.n[0] = g.n[1] = g.n[2] = 1;
+    if (!(half > empty * proj)) g.n[0] = g.n[1] = g.n[2] = 1;  // (NaN from inf * 0: not split either)
   }
-  while (g.n[0] * g.n[1] * g.n[2] > SPLIT_MAX_CELLS) {  // too many cells: coarsen the axis with the smallest cells
+  while (g.n[0] * g.n[1] * g.n[2] > max_cells) {  // too many cells: coarsen the axis with the smallest cells
     int   a = -1;
     float best = FLT_MAX;
     for (int k = 0; k < 3; k++)
@@ -135,12 +135,12 @@ __device__ bool split_cell_box(const float* p, const SplitGrid& g, int ix, int i
 }
 
 template <bool EMIT>
-__global__ void k_split(const float* __restrict__ verts, int ntris, float L, float empty, uint32_t* counts, const uint32_t* __restrict__ first,
+__global__ void k_split(const float* __restrict__ verts, int ntris, float L, float empty, int max_cells, uint32_t* counts, const uint32_t* __restrict__ first,
                         int* ref_tri, float4* ref_lo, float4* ref_hi) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= ntris) return;
   const float* p = verts + 9ll * t;
-  const SplitGrid g = split_grid(p, L, empty);
+  const SplitGrid g = split_grid(p, L, empty, max_cells);
   uint32_t k = 0;
   const uint32_t base = EMIT ? first[t] : 0u;
   if (g.n[0] * g.n[1] * g.n[2] == 1) {  // short enough: the triangle itself, with its own box
@@ -183,18 +183,24 @@ int split_triangles(const float* d_verts, int T, float budget, SplitOutput* out,
     cudaError_t e_ = (x);                                                                                          \
     if (e_ != cudaSuccess) { snprintf(err, errlen, "%s: %s", #x, cudaGetErrorString(e_)); return -2; }             \
   } while (0)
-  SplitBounds* d_b;
-  uint32_t *   d_cnt, *d_first, *d_total;
-  void*        d_tmp;
-  SCK(dev_alloc((void**)&d_b, sizeof(SplitBounds)));
-  SCK(dev_alloc((void**)&d_cnt, sizeof(uint32_t) * (size_t)T));
-  SCK(dev_alloc((void**)&d_first, sizeof(uint32_t) * (size_t)T));
-  SCK(dev_alloc((void**)&d_total, sizeof(uint32_t)));
-  SCK(dev_alloc(&d_tmp, scan_temp_bytes((size_t)T)));
-  k_split_init<<<1, 1, 0, st>>>(d_b);
-  k_split_bounds<<<std::min((T + 255) / 256, 148 * 8), 256, 0, st>>>(d_verts, T, d_b);
+  struct Temps {  // freed on every exit path
+    SplitBounds* b = nullptr;
+    uint32_t *   cnt = nullptr, *first = nullptr, *total = nullptr;
+    void*        tmp = nullptr;
+    ~Temps() { dev_free(b); dev_free(cnt); dev_free(first); dev_free(total); dev_free(tmp); }
+  } d;
+  if ((double)budget * T + 64.0 > 1.0e9) { snprintf(err, errlen, "triangle splitting: %d triangles x %.2f references exceed the builder's 2^30 primitives", T, budget); return -1; }
+  // a triangle gives at most max_cells references: keep the 32-bit total of the scan exact whatever the soup
+  const int max_cells = (int)std::min<long long>(SPLIT_MAX_CELLS, std::max<long long>(1, (1ll << 32) / T - 1));
+  SCK(dev_alloc((void**)&d.b, sizeof(SplitBounds)));
+  SCK(dev_alloc((void**)&d.cnt, sizeof(uint32_t) * (size_t)T));
+  SCK(dev_alloc((void**)&d.first, sizeof(uint32_t) * (size_t)T));
+  SCK(dev_alloc((void**)&d.total, sizeof(uint32_t)));
+  SCK(dev_alloc(&d.tmp, scan_temp_bytes((size_t)T)));
+  k_split_init<<<1, 1, 0, st>>>(d.b);
+  k_split_bounds<<<std::min((T + 255) / 256, 148 * 8), 256, 0, st>>>(d_verts, T, d.b);
   SplitBounds hb;
-  SCK(cudaMemcpyAsync(&hb, d_b, sizeof(hb), cudaMemcpyDeviceToHost, st));
+  SCK(cudaMemcpyAsync(&hb, d.b, sizeof(hb), cudaMemcpyDeviceToHost, st));
   SCK(cudaStreamSynchronize(st));
   float maxext = 0.0f;
   for (int a = 0; a < 3; a++) maxext = std::max(maxext, s_ord2f(hb.hi[a]) - s_ord2f(hb.lo[a]));
@@ -203,10 +209,11 @@ int split_triangles(const float* d_verts, int T, float budget, SplitOutput* out,
   if (const char* e = getenv("LISA_SPLIT_EMPTY")) empty = std::max(0.0f, (float)atof(e));
   if (const char* e = getenv("LISA_SPLIT_CELL")) L = std::max(1e-30f, (float)atof(e)) * maxext;
   uint32_t total = 0;
-  for (int it = 0; it < 12; it++) {
-    k_split<false><<<(T + 127) / 128, 128, 0, st>>>(d_verts, T, L, empty, d_cnt, nullptr, nullptr, nullptr, nullptr);
-    exclusive_scan_u32(d_cnt, d_first, (size_t)T, d_total, d_tmp, st);
-    SCK(cudaMemcpyAsync(&total, d_total, sizeof(total), cudaMemcpyDeviceToHost, st));
+  for (int it = 0; it < 13; it++) {
+    if (it == 12) empty = INFINITY;  // still over budget with cells 280x larger: one reference per triangle
+    k_split<false><<<(T + 127) / 128, 128, 0, st>>>(d_verts, T, L, empty, max_cells, d.cnt, nullptr, nullptr, nullptr, nullptr);
+    exclusive_scan_u32(d.cnt, d.first, (size_t)T, d.total, d.tmp, st);
+    SCK(cudaMemcpyAsync(&total, d.total, sizeof(total), cudaMemcpyDeviceToHost, st));
     SCK(cudaStreamSynchronize(st));
     if ((double)total <= (double)budget * T + 64.0) break;
     L *= 1.6f;  // over budget: coarser cells
@@ -215,12 +222,11 @@ int split_triangles(const float* d_verts, int T, float budget, SplitOutput* out,
   SCK(dev_alloc((void**)&out->d_ref_tri, sizeof(int) * (size_t)total));
   SCK(dev_alloc((void**)&out->d_ref_lo, sizeof(float4) * (size_t)total));
   SCK(dev_alloc((void**)&out->d_ref_hi, sizeof(float4) * (size_t)total));
-  k_split<true><<<(T + 127) / 128, 128, 0, st>>>(d_verts, T, L, empty, nullptr, d_first, out->d_ref_tri, out->d_ref_lo, out->d_ref_hi);
+  k_split<true><<<(T + 127) / 128, 128, 0, st>>>(d_verts, T, L, empty, max_cells, nullptr, d.first, out->d_ref_tri, out->d_ref_lo, out->d_ref_hi);
   SCK(cudaStreamSynchronize(st));
   SCK(cudaGetLastError());
   out->num_refs = (int)total;
   out->cell = L;
-  dev_free(d_b); dev_free(d_cnt); dev_free(d_first); dev_free(d_total); dev_free(d_tmp);
   return 0;
 }
 

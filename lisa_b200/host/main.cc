@@ -4,7 +4,8 @@
 // progressive mode (headless here).  Extra, optional: --gpus N splits num_samples over N GPUs of this box (one context each, in
 // this process) and combines the accumulators with one ncclReduce (lisa_multi_*); --obj-cache keeps a binary copy of each OBJ's triangle soup next to
 // it (<file>.lisasoup) and loads that instead of the text when it is current; --pfm <file> also writes the linear float image; --save-bvh <file> serialises the BVH after the build and
-// --load-bvh <file> starts from such a file instead of loading the OBJ meshes and building (lisa_save_bvh / lisa_create_from_bvh); with -d,
+// --load-bvh <file> starts from such a file instead of loading the OBJ meshes and building (lisa_save_bvh / lisa_create_from_bvh);
+// --split-triangles builds the BVH over references to long thin triangles (LISA_FLAG_SPLIT_TRIANGLES); with -d,
 // --snapshot-every K rewrites the PPM every K subframes, --checkpoint <file> saves the accumulators then (and at the
 // end) and --resume <file> continues an interrupted render from such a file; --stats prints one JSON line with the counters of
 // include/lisa_rt.h:lisa_stats; environment variables LISA_BVH/LISA_SHADOW/LISA_MAX_CHAINS select
@@ -47,7 +48,11 @@ int main(int argc, char** argv) {
       }
     }
     lisa_ctx*       ctx = nullptr;
-    if ((load_bvh ? lisa_create_from_bvh(&params, nullptr, load_bvh, &ctx) : lisa_create(&params, nullptr, &ctx)) != LISA_OK) {
+    lisa_options    opt{};
+    opt.struct_size = sizeof(opt);
+    opt.device = -1;
+    if (cmdOptionExists(argv, argv + argc, "--split-triangles")) opt.flags |= LISA_FLAG_SPLIT_TRIANGLES;
+    if ((load_bvh ? lisa_create_from_bvh(&params, &opt, load_bvh, &ctx) : lisa_create(&params, &opt, &ctx)) != LISA_OK) {
       // the reference throws sutil::Exception out of OptixWrapper's constructor and aborts
       std::cerr << "lisa: " << lisa_last_error() << std::endl;
       return 134;
@@ -70,11 +75,11 @@ int main(int argc, char** argv) {
       lisa_stats s;
       s.struct_size = sizeof(s);
       lisa_get_stats(ctx, &s);
-      printf("{\"triangles\": %u, \"bvh_nodes\": %u, \"upload_ms\": %.3f, \"bvh_build_ms\": %.3f, \"bvh_build_stages_ms\": {\"morton_sort\": %.3f, "
+      printf("{\"triangles\": %u, \"references\": %u, \"bvh_nodes\": %u, \"upload_ms\": %.3f, \"bvh_build_ms\": %.3f, \"bvh_build_stages_ms\": {\"morton_sort\": %.3f, "
              "\"hierarchy\": %.3f, \"collapse\": %.3f, \"pack\": %.3f}, \"render_ms\": %.3f, \"samples\": %llu, "
              "\"radiance_rays\": %llu, \"shadow_rays\": %llu, \"msamples_per_s\": %.3f, \"mrays_per_s\": %.3f, "
              "\"kernel_launches\": %llu}\n",
-             s.num_triangles, s.bvh_nodes, s.upload_ms, s.bvh_build_ms, s.build_sort_ms, s.build_hierarchy_ms, s.build_collapse_ms, s.build_pack_ms,
+             s.num_triangles, s.num_references, s.bvh_nodes, s.upload_ms, s.bvh_build_ms, s.build_sort_ms, s.build_hierarchy_ms, s.build_collapse_ms, s.build_pack_ms,
              s.render_ms, (unsigned long long)s.samples,
              (unsigned long long)s.radiance_rays, (unsigned long long)s.shadow_rays, s.samples / s.render_ms / 1e3,
              (s.radiance_rays + s.shadow_rays) / s.render_ms / 1e3, (unsigned long long)s.kernel_launches);

@@ -39,7 +39,7 @@ def test_render_end_to_end(built, tmp_path):
     import numpy as np
     os.makedirs(os.path.join(ROOT, "out"), exist_ok=True)
     out = os.path.join(ROOT, "out", "cornell_tiny.ppm")
-    for flags in ([], ["-d"]):
+    for flags in ([], ["-d"], ["--split-triangles"]):
         if os.path.exists(out):
             os.remove(out)
         r = _run("-s", "scenes/cornell_tiny.rto", "--stats", *flags)
@@ -47,7 +47,8 @@ def test_render_end_to_end(built, tmp_path):
         so = r.stdout.decode()
         assert "Importing assets/objs/cornell_box/bot.obj...\nDone. Imported 2 triangles.\n" in so
         assert "Starting rendering...\n" in so and "Rendering finished in " in so and " mn.\n" in so
-        if flags:
+        assert '"triangles": 1002, "references": 1002,' in so   # --stats; the Cornell walls are not worth splitting
+        if flags == ["-d"]:
             assert "nb sample   :       16" in so
         raw = open(out, "rb").read()
         assert raw.startswith(b"P6\n64 64\n255\n") and len(raw) == len(b"P6\n64 64\n255\n") + 64 * 64 * 3
