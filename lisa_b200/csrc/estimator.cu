@@ -5,7 +5,6 @@
 #include "sched_wavefront.cuh"
 #include "sched_path.cuh"
 #include "sched_pool.cuh"
-#include "sched_cta.cuh"
 
 namespace lisa {
 
@@ -139,13 +138,6 @@ int configure_kernels(char* err, size_t errlen) {
   path_attr((const void*)k_path<false, true>); path_attr((const void*)k_path<false, false>);
   pool_attr((const void*)k_pool<true, true>); pool_attr((const void*)k_pool<true, false>);
   pool_attr((const void*)k_pool<false, true>); pool_attr((const void*)k_pool<false, false>);
-  const int csm = smem + (int)sizeof(CtaShared);
-  auto cta_attr = [&](const void* f) {
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, csm);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-  };
-  cta_attr((const void*)k_cta<true, true>); cta_attr((const void*)k_cta<true, false>);
-  cta_attr((const void*)k_cta<false, true>); cta_attr((const void*)k_cta<false, false>);
   if (e != cudaSuccess) { snprintf(err, errlen, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -2; }
   return 0;
 }
@@ -165,22 +157,6 @@ void launch_pool(const DScene& sc, const DState& s, const DCamera& cam, const Ti
   const bool flat = sc.emit_flat >= 0;  // each kernel is instantiated with and without the flat-bounds filter of the shadow tries
   auto k = sc.wide ? (flat ? k_pool<true, true> : k_pool<true, false>) : (flat ? k_pool<false, true> : k_pool<false, false>);
   k<<<grid, 128, pool_smem(), st>>>(sc, s, cam, t, (uint32_t)cfg.pool_dry_thresh);
-}
-
-static inline size_t cta_smem() { return stack_smem(128) + sizeof(CtaShared); }
-int cta_occupancy(bool wide) {
-  int n = 0;
-  cudaError_t e = wide ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_cta<true, true>, 128, cta_smem())
-                       : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_cta<false, true>, 128, cta_smem());
-  return (e == cudaSuccess && n > 0) ? n : 1;
-}
-void launch_cta(const DScene& sc, const DState& s, const DCamera& cam, const Tile& t, const LaunchCfg& cfg, cudaStream_t st) {
-  unsigned grid = (unsigned)(cfg.sm_count * min(cfg.pool_blocks_per_sm, cta_occupancy(sc.wide != 0)));
-  grid = min(grid, max(1u, cdiv(t.n_chains, (unsigned)CTA_SLOTS)));
-  cudaMemsetAsync(s.ring, 0, sizeof(unsigned int), st);  // chain fetch cursor
-  const bool flat = sc.emit_flat >= 0;
-  auto k = sc.wide ? (flat ? k_cta<true, true> : k_cta<true, false>) : (flat ? k_cta<false, true> : k_cta<false, false>);
-  k<<<grid, 128, cta_smem(), st>>>(sc, s, cam, t, (uint32_t)cfg.pool_dry_thresh);
 }
 
 int path_occupancy(bool wide, int block) {

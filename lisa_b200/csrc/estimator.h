@@ -64,8 +64,6 @@ int  shadow_occupancy(bool wide, int block);  // resident CTAs of k_rays per SM
 int  extend_occupancy(bool wide, int block);
 int  tries_occupancy(int block);               // resident CTAs of k_tries per SM
 int  path_occupancy(bool wide, int block);     // resident CTAs of k_path per SM
-int  cta_occupancy(bool wide);                 // resident CTAs of k_cta per SM
-void launch_cta(const DScene& sc, const DState& s, const DCamera& cam, const Tile& t, const LaunchCfg& cfg, cudaStream_t st);
 int  pool_occupancy(bool wide);                // resident CTAs of k_pool per SM
 int  pool_chains_per_cta();                    // chains a k_pool CTA keeps in shared memory
 void launch_pool(const DScene& sc, const DState& s, const DCamera& cam, const Tile& t, const LaunchCfg& cfg, cudaStream_t st);

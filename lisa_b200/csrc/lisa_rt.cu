@@ -476,7 +476,7 @@ static int create_impl(const lisa_scene_desc* sd, const lisa_options* opt, lisa_
   }
   c->pipeline = (o.flags & LISA_FLAG_WAVEFRONT) ? 0 : 3;
   if (const char* e2 = getenv("LISA_PIPELINE"))
-    c->pipeline = strcmp(e2, "wavefront") == 0 ? 0 : strcmp(e2, "pool") == 0 ? 2 : strcmp(e2, "path") == 0 ? 1 : strcmp(e2, "cta") == 0 ? 4 : 3;
+    c->pipeline = strcmp(e2, "wavefront") == 0 ? 0 : strcmp(e2, "pool") == 0 ? 2 : strcmp(e2, "path") == 0 ? 1 : 3;
   c->cfg.pool_dry_thresh = 16;
   if (const char* e2 = getenv("LISA_DRY_THRESH")) c->cfg.pool_dry_thresh = std::max(1, std::min(32, atoi(e2)));
   if (const char* e2 = getenv("LISA_POOL_BLOCKS_PER_SM")) c->cfg.pool_blocks_per_sm = std::max(1, std::min(c->cfg.pool_blocks_per_sm, atoi(e2)));
@@ -599,9 +599,8 @@ static int run_tile(lisa_ctx* c, const Tile& t, uint64_t* launches, uint64_t* it
     // Cornell 2000x2000 1240 vs 1145 Msamples/s, C3 1920x1080 25.5 vs 27.8 ms; 512x512 22.5 vs 21.4 ms, 128x128 13.4 vs 10.0 ms)
     const uint64_t pool_slots = (uint64_t)c->cfg.sm_count * c->cfg.pool_blocks_per_sm * pool_chains_per_cta();
     const bool use_pool = c->pipeline == 2 || (c->pipeline == 3 && t.n_chains >= 2 * pool_slots);
-    nvtxRangePushA(c->pipeline == 4 ? "lisa: tile k_cta" : use_pool ? "lisa: tile k_pool" : "lisa: tile k_path");
-    if (c->pipeline == 4) launch_cta(c->scene, c->state, c->cam, t, c->cfg, c->stream);
-    else if (use_pool) launch_pool(c->scene, c->state, c->cam, t, c->cfg, c->stream);
+    nvtxRangePushA(use_pool ? "lisa: tile k_pool" : "lisa: tile k_path");
+    if (use_pool) launch_pool(c->scene, c->state, c->cam, t, c->cfg, c->stream);
     else launch_path(c->scene, c->state, c->cam, t, c->cfg, c->stream);
     nvtxRangePop();
     if (c->profile_stages) { cudaEvent_t e = next_event(c); cudaEventRecord(e, c->stream); cudaEventRecord(next_event(c), c->stream); }
