@@ -139,6 +139,12 @@ typedef struct lisa_stats {
   /* stages of the device BVH build (CUDA events; they add up to bvh_build_ms): Morton keys + radix sort, hierarchy (PLOC rounds
    * or LBVH, optional rotations), collapse to 8-wide nodes, triangle packing */
   float    build_sort_ms, build_hierarchy_ms, build_collapse_ms, build_pack_ms;
+  /* the builder's surface-area estimate of the node visits of a ray that crosses the scene (sum of the 8-wide nodes' surface
+   * areas over their root's; 0 for the binary BVH), and the flavour of the persistent kernel chosen from it: 0 = shallow
+   * (64 chains per warp), 1 = deep (48 chains per warp and a 12-entry traversal stack in shared memory: scenes whose rays
+   * visit tens of nodes).  The flavours give bit-identical images. */
+  float    bvh_sah_nodes_per_ray;
+  uint32_t pool_flavour;
 } lisa_stats;
 
 typedef struct lisa_ctx lisa_ctx;

@@ -16,6 +16,7 @@ struct BuildInput {
   int                  lbvh;       // 1: plain LBVH hierarchy (fast build), 0: PLOC (default, near-SAH quality)
   int                  ploc_radius;
   int                  rotate_passes;  // SAH tree-rotation passes over the binary hierarchy before the collapse (0 = none)
+  float                leaf_sah;   // >= 0: leaves by the surface-area heuristic, the cost of one more child slot in triangle tests (k_collapse8); < 0: every subtree of <= 3 triangles is one leaf
   // Triangle splitting (split.cu): when set, the builder's primitives are REFERENCES — num_tris of them — to the triangles
   // of the soup: reference r is triangle ref_tri[r] with the box [ref_lo[r], ref_hi[r]].  nullptr: one primitive per triangle.
   const int*           d_ref_tri;
@@ -46,6 +47,7 @@ struct BuildOutput {
   int     num_emit_tris;
   size_t  node_bytes;
   float   box_other[6], box_emit[6];  // root bounds (lo.xyz, hi.xyz) of the two partitions
+  float   sah_nodes_per_ray;          // surface-area estimate of the node visits of a ray that crosses the scene: sum of the wide nodes' areas / their root's (0 for the binary BVH)
   float   stage_ms[4];                // CUDA-event time of the build stages: Morton + sort, hierarchy (PLOC / LBVH, rotations), collapse, pack
 };
 

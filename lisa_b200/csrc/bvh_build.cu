@@ -609,18 +609,43 @@ __device__ __forceinline__ int gather_leaves(int node, int n, const int2* __rest
 __global__ void k_collapse8(const WorkItem* __restrict__ in, int n_in, WorkItem* out_q, int n, const int2* __restrict__ child,
                             const int* __restrict__ range, const float4* __restrict__ box_lo,
                             const float4* __restrict__ box_hi, int* counters, float4* nodes,
-                            unsigned int* final_to_sorted, int sorted_base) {
+                            unsigned int* final_to_sorted, int sorted_base, float leaf_sah, int root2,
+                            unsigned long long* sah_acc) {
   int w = blockIdx.x * blockDim.x + threadIdx.x;
+  // surface-area estimate of the node visits per ray (BuildOutput::sah_nodes_per_ray): every wide node adds area / root area,
+  // in 2^-20 fixed point so that the sum does not depend on the order of the atomics; one atomic per warp
+  unsigned long long sah_q = 0ull;
+  if (w < n_in) {
+    const int   node2 = n == 1 ? 0 : in[w].node2, r2 = n == 1 ? 0 : root2;
+    const float ar = half_area(box_lo[r2], box_hi[r2]), an = half_area(box_lo[node2], box_hi[node2]);
+    sah_q = ar > 0.0f ? (unsigned long long)(fminf(an / ar, 1.0f) * 1048576.0f) : 1048576ull;
+  }
+  for (int o = 16; o; o >>= 1) sah_q += __shfl_xor_sync(0xffffffffu, sah_q, o);
+  if ((threadIdx.x & 31) == 0 && sah_q) atomicAdd(sah_acc, sah_q);
   if (w >= n_in) return;
   const WorkItem item = in[w];
   // the children gathered so far, with everything the steps below need of them read ONCE (the kernel waits on these
   // gathers: 10.6 of its stall cycles per instruction were global loads when every step fetched the boxes again)
   int    ch[8], ccnt[8];
   float4 clo[8], chi[8];
+  bool   copen[8];  // a subtree of 2..LEAF_MAX triangles that is better NOT made one leaf (below)
   int    nc = 0;
   float4 plo, phi;
+  // Leaves by the surface-area heuristic (leaf_sah >= 0): a subtree of 2..LEAF_MAX triangles costs, as ONE leaf, a test of
+  // all its triangles whenever its box is hit — count x area(box) — and, opened into its two halves, count_a x area(a) +
+  // count_b x area(b) plus one more child slot in the wide node (leaf_sah x area(box), in units of a triangle test).
+  // Neighbours in a mesh share their box (a quad's two halves: 2A against 2A + slot) and stay one leaf; unrelated
+  // triangles of a soup (merged box ~2.5x each half) are kept apart: 3x fewer triangle tests per ray on the C4 soups.
   auto add_child = [&](int k, int node) {
     ch[k] = node; ccnt[k] = node_count(node, n, range); clo[k] = box_lo[node]; chi[k] = box_hi[node];
+    copen[k] = false;
+    if (leaf_sah >= 0.0f && ccnt[k] >= 2 && ccnt[k] <= LEAF_MAX) {
+      const int2  c2 = child[node];
+      const float am = half_area(clo[k], chi[k]);
+      const float ca = (float)node_count(c2.x, n, range) * half_area(box_lo[c2.x], box_hi[c2.x]);
+      const float cb = (float)node_count(c2.y, n, range) * half_area(box_lo[c2.y], box_hi[c2.y]);
+      copen[k] = ca + cb + leaf_sah * am < (float)ccnt[k] * am;
+    }
   };
   if (n == 1) {  // degenerate partition: one triangle, no binary internal node
     add_child(nc++, 0);
@@ -633,7 +658,7 @@ __global__ void k_collapse8(const WorkItem* __restrict__ in, int n_in, WorkItem*
       int   best = -1;
       float ba   = -1.0f;
       for (int k = 0; k < nc; k++) {
-        if (ccnt[k] <= LEAF_MAX) continue;  // stays a leaf
+        if (ccnt[k] <= LEAF_MAX && !copen[k]) continue;  // stays a leaf
         float a = half_area(clo[k], chi[k]);
         if (a > ba) { ba = a; best = k; }
       }
@@ -973,7 +998,9 @@ int build_bvh(const BuildInput& in, BuildOutput* out, cudaStream_t st, char* err
     int*      d_counters;
     CK(dev_alloc((void**)&d_q[0], sizeof(WorkItem) * max_nodes));
     CK(dev_alloc((void**)&d_q[1], sizeof(WorkItem) * max_nodes));
-    CK(dev_alloc((void**)&d_counters, sizeof(int) * 4));
+    CK(dev_alloc((void**)&d_counters, sizeof(int) * 4 + sizeof(unsigned long long)));
+    unsigned long long* d_sah = reinterpret_cast<unsigned long long*>(d_counters + 4);
+    CK(cudaMemsetAsync(d_sah, 0, sizeof(unsigned long long), st));
     int node_next = 0, tri_next = 0;
     for (int p = 0; p < 2; p++) {
       const Part& P = parts[p];
@@ -989,7 +1016,7 @@ int build_bvh(const BuildInput& in, BuildOutput* out, cudaStream_t st, char* err
         CK(cudaMemcpyAsync(d_counters, h_cnt, sizeof(h_cnt), cudaMemcpyHostToDevice, st));
         k_collapse8<<<cdiv(n_in, 128), 128, 0, st>>>(d_q[cur], n_in, d_q[cur ^ 1], P.n, d_child + P.slice, d_range + P.slice,
                                                      d_lo + P.slice, d_hi + P.slice, d_counters, d_nodes,
-                                                     d_final_to_sorted, P.sorted_base);
+                                                     d_final_to_sorted, P.sorted_base, in.leaf_sah, P.root, d_sah);
         CK(cudaMemcpyAsync(h_cnt, d_counters, sizeof(h_cnt), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         node_next = h_cnt[0]; tri_next = h_cnt[1]; n_in = h_cnt[2];
@@ -1002,6 +1029,10 @@ int build_bvh(const BuildInput& in, BuildOutput* out, cudaStream_t st, char* err
       }
     }
     total_nodes = node_next;
+    unsigned long long h_sah = 0ull;
+    CK(cudaMemcpyAsync(&h_sah, d_sah, sizeof(h_sah), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    out->sah_nodes_per_ray = (float)((double)h_sah / 1048576.0);
     dev_free(d_q[0]); dev_free(d_q[1]); dev_free(d_counters);
     // the node array was sized for the worst case (one wide node per triangle: 8 GB at 100M triangles); keep what is used
     // (typically T / 7 nodes) and hand the rest back

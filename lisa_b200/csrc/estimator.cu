@@ -128,35 +128,43 @@ int configure_kernels(char* err, size_t errlen) {
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_extend<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_rays<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_rays<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  const int psm = smem + 4 * (int)sizeof(PoolWarp);
   auto path_attr = [&](const void* f) { if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); };
-  auto pool_attr = [&](const void* f) {
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, psm);
+  auto pool_attr = [&](const void* f, size_t bytes) {
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   };
   path_attr((const void*)k_path<true, true>); path_attr((const void*)k_path<true, false>);
   path_attr((const void*)k_path<false, true>); path_attr((const void*)k_path<false, false>);
-  pool_attr((const void*)k_pool<true, true>); pool_attr((const void*)k_pool<true, false>);
-  pool_attr((const void*)k_pool<false, true>); pool_attr((const void*)k_pool<false, false>);
+  pool_attr((const void*)k_pool<true, true, false>, PoolShape<false>::smem_bytes); pool_attr((const void*)k_pool<true, false, false>, PoolShape<false>::smem_bytes);
+  pool_attr((const void*)k_pool<false, true, false>, PoolShape<false>::smem_bytes); pool_attr((const void*)k_pool<false, false, false>, PoolShape<false>::smem_bytes);
+  pool_attr((const void*)k_pool<true, true, true>, PoolShape<true>::smem_bytes); pool_attr((const void*)k_pool<true, false, true>, PoolShape<true>::smem_bytes);
   if (e != cudaSuccess) { snprintf(err, errlen, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -2; }
   return 0;
 }
 
-static inline size_t pool_smem() { return stack_smem(128) + 4 * sizeof(PoolWarp); }
-int pool_chains_per_cta() { return POOL_SLOTS * 4; }
-int pool_occupancy(bool wide) {
+// the deep flavour exists for the 8-wide BVH only (the binary BVH is an ablation path)
+static inline bool   pool_deep(const DScene& sc, const LaunchCfg& cfg) { return cfg.pool_deep && sc.wide; }
+int pool_chains_per_cta(bool deep) { return (deep ? PoolShape<true>::SLOTS : PoolShape<false>::SLOTS) * 4; }
+int pool_occupancy(bool wide, bool deep) {
   int n = 0;
-  cudaError_t e = wide ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_pool<true, true>, 128, pool_smem())
-                       : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_pool<false, true>, 128, pool_smem());
+  cudaError_t e = (wide && deep) ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_pool<true, true, true>, 128, PoolShape<true>::smem_bytes)
+                  : wide         ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_pool<true, true, false>, 128, PoolShape<false>::smem_bytes)
+                                 : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_pool<false, true, false>, 128, PoolShape<false>::smem_bytes);
   return (e == cudaSuccess && n > 0) ? n : 1;
 }
 void launch_pool(const DScene& sc, const DState& s, const DCamera& cam, const Tile& t, const LaunchCfg& cfg, cudaStream_t st) {
-  unsigned grid = (unsigned)(cfg.sm_count * cfg.pool_blocks_per_sm);
-  grid = min(grid, max(1u, cdiv(t.n_chains, POOL_SLOTS * 4u)));
+  const bool deep = pool_deep(sc, cfg);
+  unsigned grid = (unsigned)(cfg.sm_count * (deep ? cfg.pool_blocks_per_sm_deep : cfg.pool_blocks_per_sm));
+  grid = min(grid, max(1u, cdiv(t.n_chains, (unsigned)pool_chains_per_cta(deep))));
   cudaMemsetAsync(s.ring, 0, sizeof(unsigned int), st);  // chain fetch cursor
   const bool flat = sc.emit_flat >= 0;  // each kernel is instantiated with and without the flat-bounds filter of the shadow tries
-  auto k = sc.wide ? (flat ? k_pool<true, true> : k_pool<true, false>) : (flat ? k_pool<false, true> : k_pool<false, false>);
-  k<<<grid, 128, pool_smem(), st>>>(sc, s, cam, t, (uint32_t)cfg.pool_dry_thresh);
+  if (deep) {
+    auto k = flat ? k_pool<true, true, true> : k_pool<true, false, true>;
+    k<<<grid, 128, PoolShape<true>::smem_bytes, st>>>(sc, s, cam, t, (uint32_t)cfg.pool_dry_thresh_deep);
+  } else {
+    auto k = sc.wide ? (flat ? k_pool<true, true, false> : k_pool<true, false, false>) : (flat ? k_pool<false, true, false> : k_pool<false, false, false>);
+    k<<<grid, 128, PoolShape<false>::smem_bytes, st>>>(sc, s, cam, t, (uint32_t)cfg.pool_dry_thresh);
+  }
 }
 
 int path_occupancy(bool wide, int block) {

@@ -48,6 +48,8 @@ struct LaunchCfg {
   int path_wait_thresh;    // k_path: lanes that must be waiting before the warp runs its management section
   int pool_blocks_per_sm;  // k_pool: resident CTAs per SM
   int pool_dry_thresh;     // k_pool: pending slots that trigger a management section once the ready queue is empty
+  int pool_deep;           // k_pool: 1 = the deep flavour (48 chains per warp, 12 stack entries in shared memory; sched_pool.cuh)
+  int pool_blocks_per_sm_deep, pool_dry_thresh_deep;
 };
 
 void launch_init_chains(const DState& s, const DCamera& cam, const Tile& t, cudaStream_t st);
@@ -64,8 +66,8 @@ int  shadow_occupancy(bool wide, int block);  // resident CTAs of k_rays per SM
 int  extend_occupancy(bool wide, int block);
 int  tries_occupancy(int block);               // resident CTAs of k_tries per SM
 int  path_occupancy(bool wide, int block);     // resident CTAs of k_path per SM
-int  pool_occupancy(bool wide);                // resident CTAs of k_pool per SM
-int  pool_chains_per_cta();                    // chains a k_pool CTA keeps in shared memory
+int  pool_occupancy(bool wide, bool deep);     // resident CTAs of k_pool per SM
+int  pool_chains_per_cta(bool deep);           // chains a k_pool CTA keeps in shared memory
 void launch_pool(const DScene& sc, const DState& s, const DCamera& cam, const Tile& t, const LaunchCfg& cfg, cudaStream_t st);
 // the whole tile in one persistent launch (chains fetched from a cursor in s.ring[0]; only s.sum, s.ring, s.stats are used)
 void launch_path(const DScene& sc, const DState& s, const DCamera& cam, const Tile& t, const LaunchCfg& cfg, cudaStream_t st);

@@ -26,6 +26,13 @@
 
 #include <nvtx3/nvToolsExt.h>
 
+#ifndef LISA_POOL_DEEP_SAH
+#define LISA_POOL_DEEP_SAH 8.0f
+#endif
+#ifndef LISA_LEAF_SAH_DEFAULT
+#define LISA_LEAF_SAH_DEFAULT 0.5f
+#endif
+
 using namespace lisa;
 
 static thread_local char g_err[512] = "";
@@ -210,6 +217,8 @@ struct BvhFileHeader {
   float    box_other[6], box_emit[6];
   uint64_t file_bytes;
   uint64_t num_input_tris;  // triangles of the soup the BVH was built from (< num_tris when triangles were split into references)
+  float    sah_nodes_per_ray;  // BuildOutput::sah_nodes_per_ray (version 3): chooses k_pool's flavour
+  uint32_t reserved;
 };
 static uint32_t emit_flags_hash(const lisa_scene_desc* sd) {
   uint32_t h = 2166136261u;
@@ -226,7 +235,7 @@ static int load_bvh_file(const lisa_scene_desc* sd, const char* path, lisa_ctx* 
   if (!f) return fail(LISA_ERR_IO, "cannot open %s", path);
   struct Closer { FILE* f; ~Closer() { fclose(f); } } closer{f};
   BvhFileHeader h;
-  if (fread(&h, sizeof(h), 1, f) != 1 || memcmp(h.magic, "LISABVH1", 8) != 0 || h.version != 2 || h.header_bytes != sizeof(h))
+  if (fread(&h, sizeof(h), 1, f) != 1 || memcmp(h.magic, "LISABVH1", 8) != 0 || h.version != 3 || h.header_bytes != sizeof(h))
     return fail(LISA_ERR_IO, "%s is not a serialised BVH of this library", path);
   if (fseek(f, 0, SEEK_END) != 0 || (uint64_t)ftell(f) != h.file_bytes || h.file_bytes != bvh_file_bytes(h))
     return fail(LISA_ERR_IO, "%s is truncated or damaged", path);
@@ -242,6 +251,7 @@ static int load_bvh_file(const lisa_scene_desc* sd, const char* path, lisa_ctx* 
   b.root_other = h.root_other; b.root_emit = h.root_emit; b.num_emit_tris = h.num_emit_tris; b.node_bytes = nb;
   b.num_tris = (int)h.num_tris;
   b.num_input_tris = (int)h.num_input_tris;
+  b.sah_nodes_per_ray = h.sah_nodes_per_ray;
   memcpy(b.box_other, h.box_other, sizeof(b.box_other));
   memcpy(b.box_emit, h.box_emit, sizeof(b.box_emit));
   *wide_out = h.wide;
@@ -282,7 +292,7 @@ static int create_impl(const lisa_scene_desc* sd, const lisa_options* opt, lisa_
   if (o.device >= 0) { CU(cudaSetDevice(o.device)); }
   CU(cudaGetDevice(&c->device));
   // per-device constants are queried once per process (cudaGetDeviceProperties alone can take ~100 ms)
-  struct DevInfo { bool ok = false; int sms = 0, occ_rays[2] = {0, 0}, occ_ext[2] = {0, 0}, occ_path[2] = {0, 0}, occ_pool[2] = {0, 0}, occ_tries = 0; };
+  struct DevInfo { bool ok = false; int sms = 0, occ_rays[2] = {0, 0}, occ_ext[2] = {0, 0}, occ_path[2] = {0, 0}, occ_pool[2] = {0, 0}, occ_pool_deep = 0, occ_tries = 0; };
   static DevInfo dev_info[64];
   DevInfo& di = dev_info[c->device & 63];
   if (!di.ok) {
@@ -364,7 +374,10 @@ static int create_impl(const lisa_scene_desc* sd, const lisa_options* opt, lisa_
     rc = split_triangles(d_verts, T, split_budget, &sp, c->stream, g_err, sizeof(g_err));
     if (!rc) T = sp.num_refs;
   }
-  BuildInput bi{d_verts, d_normals, d_mat_idx, d_emit, T, sd->num_materials, wide, lbvh, radius, rotate, sp.d_ref_tri, sp.d_ref_lo, sp.d_ref_hi};
+  // leaves by the surface-area heuristic (k_collapse8): the cost of one more child slot, in triangle tests; LISA_LEAF_SAH=-1: off
+  float leaf_sah = LISA_LEAF_SAH_DEFAULT;
+  if (const char* e = getenv("LISA_LEAF_SAH")) leaf_sah = (float)atof(e);
+  BuildInput bi{d_verts, d_normals, d_mat_idx, d_emit, T, sd->num_materials, wide, lbvh, radius, rotate, leaf_sah, sp.d_ref_tri, sp.d_ref_lo, sp.d_ref_hi};
   if (!rc) rc = build_bvh(bi, &c->bvh, c->stream, g_err, sizeof(g_err));
   if (rc) {  // keep the builder's message: a sticky CUDA error would otherwise be reported by the next call instead
     dev_free(d_verts); dev_free(d_normals); dev_free(d_mat_idx); dev_free(d_emit); split_free(&sp);
@@ -431,6 +444,7 @@ static int create_impl(const lisa_scene_desc* sd, const lisa_options* opt, lisa_
   c->stats.num_references = (uint32_t)T;
   c->stats.num_emitter_triangles = (uint32_t)c->bvh.num_emit_tris;
   c->stats.bvh_nodes = (uint32_t)c->bvh.num_nodes;
+  c->stats.bvh_sah_nodes_per_ray = c->bvh.sah_nodes_per_ray;
   c->stats.bvh_emitter_nodes = (uint32_t)c->bvh.nodes_emit;
   c->stats.bvh_bytes = c->bvh.node_bytes;
   c->stats.triangle_bytes = (uint64_t)T * 96;
@@ -465,7 +479,8 @@ static int create_impl(const lisa_scene_desc* sd, const lisa_options* opt, lisa_
     const int w = wide != 0;
     if (!di.ok || getenv("LISA_EXTEND_BLOCK") || getenv("LISA_SHADOW_BLOCK")) {
       di.occ_tries = tries_occupancy(256);
-      for (int k = 0; k < 2; k++) { di.occ_ext[k] = extend_occupancy(k != 0, c->cfg.extend_block); di.occ_rays[k] = shadow_occupancy(k != 0, c->cfg.shadow_block); di.occ_path[k] = path_occupancy(k != 0, 128); di.occ_pool[k] = pool_occupancy(k != 0); }
+      for (int k = 0; k < 2; k++) { di.occ_ext[k] = extend_occupancy(k != 0, c->cfg.extend_block); di.occ_rays[k] = shadow_occupancy(k != 0, c->cfg.shadow_block); di.occ_path[k] = path_occupancy(k != 0, 128); di.occ_pool[k] = pool_occupancy(k != 0, false); }
+      di.occ_pool_deep = pool_occupancy(true, true);
       di.ok = true;
     }
     c->cfg.tries_blocks_per_sm = di.occ_tries;
@@ -473,14 +488,25 @@ static int create_impl(const lisa_scene_desc* sd, const lisa_options* opt, lisa_
     c->cfg.shadow_blocks_per_sm = di.occ_rays[w];
     c->cfg.path_blocks_per_sm = di.occ_path[w];
     c->cfg.pool_blocks_per_sm = di.occ_pool[w];
+    c->cfg.pool_blocks_per_sm_deep = di.occ_pool_deep;
   }
   c->pipeline = (o.flags & LISA_FLAG_WAVEFRONT) ? 0 : 3;
   if (const char* e2 = getenv("LISA_PIPELINE"))
     c->pipeline = strcmp(e2, "wavefront") == 0 ? 0 : strcmp(e2, "pool") == 0 ? 2 : strcmp(e2, "path") == 0 ? 1 : 3;
   c->cfg.pool_dry_thresh = 16;
-  if (const char* e2 = getenv("LISA_DRY_THRESH")) c->cfg.pool_dry_thresh = std::max(1, std::min(32, atoi(e2)));
-  if (const char* e2 = getenv("LISA_POOL_BLOCKS_PER_SM")) c->cfg.pool_blocks_per_sm = std::max(1, std::min(c->cfg.pool_blocks_per_sm, atoi(e2)));
-  if (getenv("LISA_DEBUG_TIMING")) fprintf(stderr, "[lisa] pipeline %d, k_path %d CTAs/SM, k_pool %d CTAs/SM\n", c->pipeline, c->cfg.path_blocks_per_sm, c->cfg.pool_blocks_per_sm);
+  c->cfg.pool_dry_thresh_deep = 4;  // measured on the 10M soup (deep flavour): 16 -> 68.6, 8 -> 71.0, 4 -> 72.4 Msamples/s
+  if (const char* e2 = getenv("LISA_DRY_THRESH")) c->cfg.pool_dry_thresh = c->cfg.pool_dry_thresh_deep = std::max(1, std::min(32, atoi(e2)));
+  if (const char* e2 = getenv("LISA_POOL_BLOCKS_PER_SM")) {
+    c->cfg.pool_blocks_per_sm = std::max(1, std::min(c->cfg.pool_blocks_per_sm, atoi(e2)));
+    c->cfg.pool_blocks_per_sm_deep = std::max(1, std::min(c->cfg.pool_blocks_per_sm_deep, atoi(e2)));
+  }
+  // k_pool's flavour (sched_pool.cuh) by the builder's estimate of the node visits per ray: sum of the wide nodes' surface
+  // areas over the root's.  Cornell box 2.3, 871k-triangle knot 2.9, the C4 soups 30-40; the flavours cross over near 8.
+  c->cfg.pool_deep = wide && c->bvh.sah_nodes_per_ray > LISA_POOL_DEEP_SAH;
+  if (const char* e2 = getenv("LISA_POOL_FLAVOUR")) c->cfg.pool_deep = wide && !strcmp(e2, "deep");
+  c->stats.pool_flavour = c->cfg.pool_deep ? 1u : 0u;
+  if (getenv("LISA_DEBUG_TIMING")) fprintf(stderr, "[lisa] pipeline %d, k_path %d CTAs/SM, k_pool %d CTAs/SM (%s flavour: SAH estimate %.2f node visits per ray)\n", c->pipeline, c->cfg.path_blocks_per_sm,
+                                         c->cfg.pool_deep ? c->cfg.pool_blocks_per_sm_deep : c->cfg.pool_blocks_per_sm, c->cfg.pool_deep ? "deep" : "shallow", c->bvh.sah_nodes_per_ray);
   if ((c->width > 65535u || c->height > 65535u) && c->pipeline) c->pipeline = 0;  // k_path packs a chain's pixel as x | y << 16
   c->cfg.path_wait_thresh = 16;  // measured on B200 (Cornell 2000x2000): 8 -> 1057, 12 -> 1090, 16 -> 1115, 20 -> 1107, 24 -> 1073, 28 -> 999 Msamples/s
   if (const char* e2 = getenv("LISA_WAIT_THRESH")) c->cfg.path_wait_thresh = std::max(1, std::min(32, atoi(e2)));
@@ -542,7 +568,8 @@ extern "C" int lisa_save_bvh(lisa_ctx* c, const char* path) {
   CU(cudaSetDevice(c->device));
   BvhFileHeader h{};
   memcpy(h.magic, "LISABVH1", 8);
-  h.version = 2; h.header_bytes = sizeof(h);
+  h.version = 3; h.header_bytes = sizeof(h);
+  h.sah_nodes_per_ray = c->bvh.sah_nodes_per_ray;
   h.num_input_tris = (uint64_t)c->bvh.num_input_tris;
   h.num_tris = (uint64_t)c->scene.num_tris; h.num_nodes = (uint64_t)c->bvh.num_nodes;
   h.nodes_other = c->bvh.nodes_other; h.nodes_emit = c->bvh.nodes_emit;
@@ -597,7 +624,8 @@ static int run_tile(lisa_ctx* c, const Tile& t, uint64_t* launches, uint64_t* it
     if (c->profile_stages) cudaEventRecord(next_event(c), c->stream);
     // k_pool keeps 64 chains per warp: it pays once the tile fills those slots at least twice over (measured on B200:
     // Cornell 2000x2000 1240 vs 1145 Msamples/s, C3 1920x1080 25.5 vs 27.8 ms; 512x512 22.5 vs 21.4 ms, 128x128 13.4 vs 10.0 ms)
-    const uint64_t pool_slots = (uint64_t)c->cfg.sm_count * c->cfg.pool_blocks_per_sm * pool_chains_per_cta();
+    const bool     deep = c->cfg.pool_deep != 0;
+    const uint64_t pool_slots = (uint64_t)c->cfg.sm_count * (deep ? c->cfg.pool_blocks_per_sm_deep : c->cfg.pool_blocks_per_sm) * pool_chains_per_cta(deep);
     const bool use_pool = c->pipeline == 2 || (c->pipeline == 3 && t.n_chains >= 2 * pool_slots);
     nvtxRangePushA(use_pool ? "lisa: tile k_pool" : "lisa: tile k_path");
     if (use_pool) launch_pool(c->scene, c->state, c->cam, t, c->cfg, c->stream);

@@ -29,26 +29,55 @@ namespace lisa {
 #ifndef LISA_POOL_MIN_BLOCKS
 #define LISA_POOL_MIN_BLOCKS 5
 #endif
+// Two flavours of the kernel, chosen per scene by the builder's surface-area estimate of the node visits per ray
+// (BuildOutput::sah_nodes_per_ray, lisa_rt.cu):
+//   shallow  64 chains per warp, POOL_STACK_SM traversal-stack entries per thread in shared memory.  Scenes whose rays visit a
+//            few nodes (the Cornell box: 2, the 871k-triangle knot: 2.2): the management section wants 32 pending slots often.
+//   deep     48 chains per warp and 12 stack entries: scenes whose rays visit tens of nodes (the C4 soups: 30) push deep, and
+//            what does not fit in shared memory spills to the local array — through an L1 that the chain slots leave ~30 KB
+//            of; measured on the 10M soup: 63.7 -> 72.4 Msamples/s, and -9 % on the knot, hence two flavours.
+// Both run 5 CTAs per SM (43.8 KB / 41.4 KB of shared memory per CTA) and are bit-identical in their results.
 #ifndef POOL_SLOTS
-#define POOL_SLOTS 64  // chains per warp (ring positions wrap with % POOL_SLOTS: a power of two costs one AND)
+#define POOL_SLOTS 64  // chains per warp, shallow flavour (ring positions wrap with % SLOTS: a power of two costs one AND)
+#endif
+#ifndef POOL_SLOTS_DEEP
+#define POOL_SLOTS_DEEP 48
+#endif
+#ifndef POOL_STACK_SM
+#define POOL_STACK_SM LISA_STACK_SM
+#endif
+#ifndef POOL_STACK_SM_DEEP
+#define POOL_STACK_SM_DEEP 12
 #endif
 
+template <int SLOTS>
 struct PoolWarp {
-  float4        A[POOL_SLOTS], B[POOL_SLOTS], C[POOL_SLOTS], D[POOL_SLOTS], E[POOL_SLOTS], F[POOL_SLOTS], H[POOL_SLOTS], G[POOL_SLOTS];
-  unsigned char rq[POOL_SLOTS], pq[POOL_SLOTS];
+  float4        A[SLOTS], B[SLOTS], C[SLOTS], D[SLOTS], E[SLOTS], F[SLOTS], H[SLOTS], G[SLOTS];
+  unsigned char rq[SLOTS], pq[SLOTS];
+};
+template <bool DEEP>
+struct PoolShape {
+  static constexpr int SLOTS = DEEP ? POOL_SLOTS_DEEP : POOL_SLOTS;
+  static constexpr int NS0   = DEEP ? POOL_STACK_SM_DEEP : POOL_STACK_SM;
+  static constexpr int NS    = NS0 < LISA_STACK_TOTAL ? NS0 : LISA_STACK_TOTAL - 1;  // (the tiny-stack test build has 5 entries in all)
+  typedef TravStack<uint2, NS, LISA_STACK_TOTAL - NS> Stk;
+  static constexpr size_t smem_bytes = (size_t)NS * 128 * sizeof(uint2) + 4 * sizeof(PoolWarp<SLOTS>);
 };
 
-template <bool WIDE, bool FLAT>
+template <bool WIDE, bool FLAT, bool DEEP>
 __global__ void __launch_bounds__(128, LISA_POOL_MIN_BLOCKS) k_pool(DScene sc, DState s, DCamera cam, Tile t, uint32_t dry_thresh) {
-  extern __shared__ uint2 smem_stack[];  // [LISA_STACK_SM][128] traversal stacks, then 4 x PoolWarp
+  constexpr int POOL_N = PoolShape<DEEP>::SLOTS;
+  typedef typename PoolShape<DEEP>::Stk Stack;
+  typedef lisa::PoolWarp<POOL_N> PoolWarp;
+  extern __shared__ uint2 smem_stack[];  // [NS][128] traversal stacks, then 4 x PoolWarp
   __shared__ uint32_t lcg_a[32], lcg_c[32];  // x -> A^(3k) x + C_(3k): skip k tries
   __shared__ float4   jobbuf[4][96];         // per warp: 32 light-sampling jobs x (N | cos|cos|, cone axis | LCG, tries left)
   Stack          stack(smem_stack);
-  PoolWarp&      pw   = reinterpret_cast<PoolWarp*>(smem_stack + LISA_STACK_SM * 128)[threadIdx.x >> 5];
+  PoolWarp&      pw   = reinterpret_cast<PoolWarp*>(smem_stack + PoolShape<DEEP>::NS * 128)[threadIdx.x >> 5];
   const unsigned lane = lane_id();
   fill_lcg_tables(lcg_a, lcg_c);
   // every slot starts in the pending queue without a chain: the first management sections fetch chains for them
-  for (unsigned k = lane; k < POOL_SLOTS; k += 32) {
+  for (unsigned k = lane; k < POOL_N; k += 32) {
     pw.pq[k] = (unsigned char)k;
     pw.G[k]  = make_float4(__int_as_float(-1), 0.0f, 0.0f, 0.0f);
     pw.F[k]  = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(-1));
@@ -58,7 +87,7 @@ __global__ void __launch_bounds__(128, LISA_POOL_MIN_BLOCKS) k_pool(DScene sc, D
   unsigned int* cursor = &s.ring[0];  // zeroed by the host before the launch
 
   // queues (warp-uniform)
-  unsigned rq_head = 0, rq_cnt = 0, pq_head = 0, pq_cnt = POOL_SLOTS;
+  unsigned rq_head = 0, rq_cnt = 0, pq_head = 0, pq_cnt = POOL_N;
   // ray in flight on this lane
   int      slot = -1;
   bool     in_flight = false, shadow_ray = false, occluded = false;
@@ -82,7 +111,7 @@ __global__ void __launch_bounds__(128, LISA_POOL_MIN_BLOCKS) k_pool(DScene sc, D
     if (freemask && rq_cnt) {
       const unsigned rank = __popc(freemask & lanemask_lt());
       if (!in_flight && rank < rq_cnt) {
-        slot = pw.rq[(rq_head + rank) % POOL_SLOTS];
+        slot = pw.rq[(rq_head + rank) % POOL_N];
         const float4   a4 = pw.A[slot], f4 = pw.F[slot], h4 = pw.H[slot];
         const uint32_t kind = __float_as_uint(pw.E[slot].w);
         o = f3(a4);
@@ -103,7 +132,7 @@ __global__ void __launch_bounds__(128, LISA_POOL_MIN_BLOCKS) k_pool(DScene sc, D
     if (pq_cnt >= 32u || (rq_cnt == 0u && (pq_cnt >= dry_thresh || (fly == 0u && pq_cnt > 0u)))) {
       const unsigned np = min(pq_cnt, 32u);
       const bool     active = lane < np;
-      const int      ms = active ? (int)pw.pq[(pq_head + lane) % POOL_SLOTS] : -1;
+      const int      ms = active ? (int)pw.pq[(pq_head + lane) % POOL_N] : -1;
       pq_head += np; pq_cnt -= np;
       // slot -> registers
       int      chain = -1;
@@ -222,8 +251,8 @@ __global__ void __launch_bounds__(128, LISA_POOL_MIN_BLOCKS) k_pool(DScene sc, D
       }
       {
         const unsigned rm = __ballot_sync(FULL, to_ready), pm = __ballot_sync(FULL, to_pending);
-        if (to_ready) pw.rq[(rq_head + rq_cnt + __popc(rm & lanemask_lt())) % POOL_SLOTS] = (unsigned char)ms;
-        if (to_pending) pw.pq[(pq_head + pq_cnt + __popc(pm & lanemask_lt())) % POOL_SLOTS] = (unsigned char)ms;
+        if (to_ready) pw.rq[(rq_head + rq_cnt + __popc(rm & lanemask_lt())) % POOL_N] = (unsigned char)ms;
+        if (to_pending) pw.pq[(pq_head + pq_cnt + __popc(pm & lanemask_lt())) % POOL_N] = (unsigned char)ms;
         rq_cnt += __popc(rm); pq_cnt += __popc(pm);
       }
       __syncwarp();
@@ -307,7 +336,7 @@ __global__ void __launch_bounds__(128, LISA_POOL_MIN_BLOCKS) k_pool(DScene sc, D
     // the slots whose ray has just finished join the pending queue
     const unsigned fm = __ballot_sync(FULL, finished);
     if (fm) {
-      if (finished) pw.pq[(pq_head + pq_cnt + __popc(fm & lanemask_lt())) % POOL_SLOTS] = (unsigned char)slot;
+      if (finished) pw.pq[(pq_head + pq_cnt + __popc(fm & lanemask_lt())) % POOL_N] = (unsigned char)slot;
       pq_cnt += __popc(fm);
       __syncwarp();
     }

@@ -237,8 +237,9 @@ struct WideState {
 };
 
 // one node visit; precondition st.has_nodes() && !st.has_tris()
+template <class STK>
 __device__ __forceinline__ void wide_node_step(const float4* __restrict__ nodes, const float3& o, const StepRay& r, float tmin,
-                                               float tlimit, WideState& st, Stack& stack) {
+                                               float tlimit, WideState& st, STK& stack) {
   const uint32_t hits_imask      = st.ng.y;
   const uint32_t child_bit_index = 31u - __clz(hits_imask);
   const uint32_t child_base      = st.ng.x;
@@ -306,8 +307,9 @@ struct BinState {
 };
 
 // one node visit; precondition st.has_nodes().  Leaves st.cur = next node / leaf / NONE (after a pop).
+template <class STK>
 __device__ __forceinline__ void bin_node_step(const float4* __restrict__ nodes, const float3& o, const StepRay& r, float tmin,
-                                              float tlimit, BinState& st, Stack& stack) {
+                                              float tlimit, BinState& st, STK& stack) {
   const float4 n0 = __ldg(nodes + 4 * st.cur), n1 = __ldg(nodes + 4 * st.cur + 1), n2 = __ldg(nodes + 4 * st.cur + 2),
                n3 = __ldg(nodes + 4 * st.cur + 3);
   // (plane - o) * idir: one rounding each, so a relative pad is enough

@@ -67,7 +67,8 @@ class Stats(ctypes.Structure):
                 ("triangles_tested", ctypes.c_uint64), ("last_nodes_visited", ctypes.c_uint64),
                 ("last_triangles_tested", ctypes.c_uint64), ("shadow_culled", ctypes.c_uint64),
                 ("last_shadow_culled", ctypes.c_uint64), ("build_sort_ms", ctypes.c_float), ("build_hierarchy_ms", ctypes.c_float),
-                ("build_collapse_ms", ctypes.c_float), ("build_pack_ms", ctypes.c_float)]
+                ("build_collapse_ms", ctypes.c_float), ("build_pack_ms", ctypes.c_float),
+                ("bvh_sah_nodes_per_ray", ctypes.c_float), ("pool_flavour", ctypes.c_uint32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if not k.startswith("_")}

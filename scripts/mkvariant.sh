@@ -7,5 +7,5 @@ name=$1; shift
 mkdir -p variants
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 --use_fast_math -fmad=false -lineinfo -std=c++17 -Xcompiler -fPIC \
   -ccbin "$(command -v /usr/bin/g++ || command -v g++)" "$@" -shared -o variants/liblisa_rt_$name.so \
-  csrc/lisa_rt.cu csrc/bvh_build.cu csrc/estimator.cu csrc/devmem.cu csrc/sort_scan.cu
+  csrc/lisa_rt.cu csrc/bvh_build.cu csrc/estimator.cu csrc/devmem.cu csrc/sort_scan.cu csrc/multi.cu csrc/split.cu -ldl
 echo variants/liblisa_rt_$name.so

@@ -332,11 +332,12 @@ def test_serialised_bvh_round_trip(rt, cornell, tmp_path):
     A.save_bvh(path)
     stA = A.stats()
     import os
-    assert os.path.getsize(path) == 128 + stA["bvh_bytes"] + stA["num_triangles"] * 100   # header, nodes, 48 + 48 + 4 bytes per triangle
+    assert os.path.getsize(path) == 136 + stA["bvh_bytes"] + stA["num_triangles"] * 100   # header (version 3), nodes, 48 + 48 + 4 bytes per triangle
     B = rt.Renderer.from_bvh(sc, path)
     stB = B.stats()
-    for k in ("num_triangles", "num_emitter_triangles", "bvh_nodes", "bvh_emitter_nodes", "bvh_bytes"):
+    for k in ("num_triangles", "num_emitter_triangles", "bvh_nodes", "bvh_emitter_nodes", "bvh_bytes", "bvh_sah_nodes_per_ray", "pool_flavour"):
         assert stA[k] == stB[k], k
+    assert stA["bvh_sah_nodes_per_ray"] > 1.0   # the estimate that chooses k_pool's flavour travels with the file
     assert stB["bvh_build_ms"] == 0.0
     rng = np.random.default_rng(9)
     o, d = _rays(rng, cornell["vertices"].min(0), cornell["vertices"].max(0), 50000)
@@ -468,3 +469,75 @@ def test_split_triangles_leaves_short_triangles_alone(rt, cornell, tmp_path):
         rt.Renderer.from_bvh(sc2, path, with_geometry=True)   # 5299 triangles against a file built from 5300
     A.render(); B.render()
     assert np.array_equal(A.read_accum(), B.read_accum())
+
+
+def _overlap_soup(rng, T):
+    """triangles about as large as their spacing, like the C4 soups: neighbours in Morton order overlap but share no box"""
+    edge = 0.5 * T ** (-1.0 / 3.0)
+    c = rng.random((T, 1, 3))
+    v = (c + (rng.random((T, 3, 3)) - 0.5) * 2 * edge).astype(np.float32).reshape(-1, 3)
+    q = np.float32([[-0.5, 1.6, -0.5], [1.5, 1.6, -0.5], [1.5, 1.6, 1.5], [-0.5, 1.6, -0.5], [1.5, 1.6, 1.5], [-0.5, 1.6, 1.5]])
+    v = np.concatenate([v, q])
+    n = np.tile(np.float32([[0, 1, 0]]), (len(v), 1))
+    m = np.concatenate([np.zeros(T, np.int32), np.ones(2, np.int32)])
+    return v, n, m
+
+
+def test_sah_leaves_same_hits_less_work(rt, orc, cornell, monkeypatch):
+    """Leaves by the surface-area heuristic (k_collapse8, LISA_LEAF_SAH; default on): a subtree of 2-3 triangles becomes ONE leaf
+    only where that costs no more triangle tests than keeping its halves apart.  On a soup of overlapping triangles the
+    traversal tests far fewer triangles and finds the same hits (those of the oracle); on a mesh whose neighbours share
+    their boxes (the Cornell box: quads, a tessellated sphere) the tree stays what it was."""
+    rng = np.random.default_rng(5)
+    T = 60000
+    v, n, m = _overlap_soup(rng, T)
+    args = (v, n, m, [MAT_W, MAT_L], 96, 96, (0.5, 0.6, 3.2), (0.5, 0.45, 0.5), 35.0, 4, 4)
+    R1 = rt.Renderer(*args)
+    monkeypatch.setenv("LISA_LEAF_SAH", "-1")   # every subtree of <= 3 triangles is one leaf
+    R0 = rt.Renderer(*args)
+    monkeypatch.delenv("LISA_LEAF_SAH")
+    assert R1.stats()["bvh_nodes"] > R0.stats()["bvh_nodes"]
+    o, d = _rays(rng, v.min(0), v.max(0), 200000)
+    p0, t0 = R0.trace_closest(o, d)
+    p1, t1 = R1.trace_closest(o, d)
+    same = (p0 == p1)
+    assert (t0[same] == t1[same]).all()
+    assert (~same).sum() <= 4 and np.allclose(t0[~same], t1[~same], rtol=2e-5)  # ties between crossing triangles only
+    S = orc.Scene(v, n, m, rt_pack([MAT_W, MAT_L]))
+    bad, _ = _compare_with_oracle(R1, S, o, d, m=2000)
+    assert bad <= 2, bad
+    R0.render(); R1.render()
+    a0, a1 = R0.read_accum(), R1.read_accum()
+    assert (np.abs(a0 - a1).max(axis=2) > 0).mean() < 1e-3   # a tie resolves by test order; every other pixel is the same bits
+    w0, w1 = R0.stats(), R1.stats()
+    assert w1["triangles_tested"] < 0.75 * w0["triangles_tested"], (w0["triangles_tested"], w1["triangles_tested"])
+    assert w1["nodes_visited"] < 1.1 * w0["nodes_visited"], (w0["nodes_visited"], w1["nodes_visited"])
+    # the Cornell box: the same tree either way, up to a handful of leaves
+    C1 = rt.Renderer.from_scene(resized(cornell, 32))
+    monkeypatch.setenv("LISA_LEAF_SAH", "-1")
+    C0 = rt.Renderer.from_scene(resized(cornell, 32))
+    assert abs(C1.stats()["bvh_nodes"] - C0.stats()["bvh_nodes"]) <= 8
+
+
+def test_pool_flavours_are_bit_identical_and_chosen_by_the_sah_estimate(rt, cornell, monkeypatch):
+    """k_pool's two flavours (sched_pool.cuh: 64 chains per warp and a 4-entry shared-memory stack, or 48 and 12) render the
+    same bits; the library picks the deep one where the builder's surface-area estimate says rays visit many nodes."""
+    rng = np.random.default_rng(6)
+    v, n, m = _overlap_soup(rng, 40000)
+    args = (v, n, m, [MAT_W, MAT_L], 160, 160, (0.5, 0.6, 3.2), (0.5, 0.45, 0.5), 35.0, 2, 5)
+    monkeypatch.setenv("LISA_PIPELINE", "pool")
+    imgs, stats = {}, {}
+    for fl in ("auto", "deep", "shallow"):
+        if fl == "auto": monkeypatch.delenv("LISA_POOL_FLAVOUR", raising=False)
+        else: monkeypatch.setenv("LISA_POOL_FLAVOUR", fl)
+        for name, mk in (("soup", lambda: rt.Renderer(*args)), ("cornell", lambda: rt.Renderer.from_scene(resized(cornell, 160)))):
+            R = mk()
+            R.render_subframes(0, 2, 3)
+            imgs[name, fl], stats[name, fl] = R.read_accum(), R.stats()
+    for name in ("soup", "cornell"):
+        assert np.array_equal(imgs[name, "deep"], imgs[name, "shallow"]) and np.array_equal(imgs[name, "auto"], imgs[name, "deep"])
+        for k in ("radiance_rays", "shadow_rays", "nodes_visited", "triangles_tested", "shadow_culled"):
+            assert stats[name, "deep"][k] == stats[name, "shallow"][k], (name, k)
+        assert stats[name, "deep"]["pool_flavour"] == 1 and stats[name, "shallow"]["pool_flavour"] == 0
+    assert stats["soup", "auto"]["bvh_sah_nodes_per_ray"] > 20 and stats["soup", "auto"]["pool_flavour"] == 1
+    assert stats["cornell", "auto"]["bvh_sah_nodes_per_ray"] < 6 and stats["cornell", "auto"]["pool_flavour"] == 0
