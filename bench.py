@@ -452,9 +452,9 @@ def main():
         # ---- the roofline that binds: instruction issue.  Instruction counts per launch from the committed ncu capture of
         # this very launch (one step of S spp), valid while the kernel sources hash the same; its duration and the SM clock are
         # measured in THIS run.
-        prof, pj = os.path.join(ROOT, "profiles", prof_name), None
-        if not os.path.exists(prof) and prof_name.startswith("r02_"):
-            prof = os.path.join(ROOT, "profiles", "r01_" + prof_name[4:])
+        # the newest capture of that kernel under profiles/ (r03_ = second session of round 2, r02_, r01_)
+        cands = [os.path.join(ROOT, "profiles", tag + prof_name[4:]) for tag in ("r03_", "r02_", "r01_")]
+        prof, pj = next((c for c in cands if os.path.exists(c)), cands[-1]), None
         if os.path.exists(prof):
             try:
                 pj = json.load(open(prof))["launches"][0]

@@ -178,17 +178,17 @@ __global__ void k_refit(const float* __restrict__ verts, const unsigned int* __r
   float3 lo, hi;
   prim_box(verts, ids[j], ref_lo, ref_hi, lo, hi);
   int          me = (n - 1) + j;
-  box_lo[me] = make_float4(lo.x, lo.y, lo.z, 0.0f);
-  box_hi[me] = make_float4(hi.x, hi.y, hi.z, 0.0f);
+  box_lo[2 * (me)] = make_float4(lo.x, lo.y, lo.z, 0.0f);
+  box_hi[2 * (me)] = make_float4(hi.x, hi.y, hi.z, 0.0f);
   if (n == 1) return;
   int cur = parent[me];
   while (cur >= 0) {
     __threadfence();
     if (atomicAdd(&flags[cur], 1) == 0) return;  // first arrival: the sibling will continue
     int2   c  = child[cur];
-    float4 l0 = __ldcg(box_lo + c.x), h0 = __ldcg(box_hi + c.x), l1 = __ldcg(box_lo + c.y), h1 = __ldcg(box_hi + c.y);
-    box_lo[cur] = make_float4(fminf(l0.x, l1.x), fminf(l0.y, l1.y), fminf(l0.z, l1.z), 0.0f);
-    box_hi[cur] = make_float4(fmaxf(h0.x, h1.x), fmaxf(h0.y, h1.y), fmaxf(h0.z, h1.z), 0.0f);
+    float4 l0 = __ldcg(box_lo + 2 * c.x), h0 = __ldcg(box_hi + 2 * c.x), l1 = __ldcg(box_lo + 2 * c.y), h1 = __ldcg(box_hi + 2 * c.y);
+    box_lo[2 * (cur)] = make_float4(fminf(l0.x, l1.x), fminf(l0.y, l1.y), fminf(l0.z, l1.z), 0.0f);
+    box_hi[2 * (cur)] = make_float4(fmaxf(h0.x, h1.x), fmaxf(h0.y, h1.y), fmaxf(h0.z, h1.z), 0.0f);
     cur = parent[cur];
   }
 }
@@ -216,8 +216,8 @@ __global__ void k_leaf_records(const float* __restrict__ verts, const unsigned i
   float3 l3, h3;
   prim_box(verts, ids[j], ref_lo, ref_hi, l3, h3);
   const float4 lo = make_float4(l3.x, l3.y, l3.z, 0.0f), hi = make_float4(h3.x, h3.y, h3.z, 0.0f);
-  box_lo[(n - 1) + j] = lo;
-  box_hi[(n - 1) + j] = hi;
+  box_lo[2 * ((n - 1) + j)] = lo;
+  box_hi[2 * ((n - 1) + j)] = hi;
   rec[2ll * j]     = make_float4(lo.x, lo.y, lo.z, __int_as_float((n - 1) + j));
   rec[2ll * j + 1] = make_float4(hi.x, hi.y, hi.z, __int_as_float(1));
 }
@@ -257,8 +257,8 @@ __device__ __forceinline__ void ploc_make_node(int id, const float4 la, const fl
   const int2 ch = make_int2(__float_as_int(la.w), __float_as_int(lb.w));
   const float4 mlo = make_float4(fminf(la.x, lb.x), fminf(la.y, lb.y), fminf(la.z, lb.z), 0.0f);
   const float4 mhi = make_float4(fmaxf(ha.x, hb.x), fmaxf(ha.y, hb.y), fmaxf(ha.z, hb.z), 0.0f);
-  node_lo[id] = mlo;
-  node_hi[id] = mhi;
+  node_lo[2 * (id)] = mlo;
+  node_hi[2 * (id)] = mhi;
   child[id]   = ch;
   cnt[id]     = c;
   rlo = make_float4(mlo.x, mlo.y, mlo.z, __int_as_float(id));
@@ -518,14 +518,14 @@ __global__ void k_rotate(int n, int2* child, const int* __restrict__ parent, flo
     __threadfence();
     const int2 c = __ldcg(&child[cur]);
     const int  L = c.x, R = c.y;
-    const float4 lL = __ldcg(box_lo + L), hL = __ldcg(box_hi + L), lR = __ldcg(box_lo + R), hR = __ldcg(box_hi + R);
+    const float4 lL = __ldcg(box_lo + 2 * L), hL = __ldcg(box_hi + 2 * L), lR = __ldcg(box_lo + 2 * R), hR = __ldcg(box_hi + 2 * R);
     float best = 0.0f;  // area saved
     int   which = -1;
     int2  cR = make_int2(-1, -1), cL = make_int2(-1, -1);
     float4 lRL, hRL, lRR, hRR, lLL, hLL, lLR, hLR;
     if (R < n - 1) {  // R is internal: L <-> RL (R' = L + RR) or L <-> RR (R' = RL + L)
       cR = __ldcg(&child[R]);
-      lRL = __ldcg(box_lo + cR.x); hRL = __ldcg(box_hi + cR.x); lRR = __ldcg(box_lo + cR.y); hRR = __ldcg(box_hi + cR.y);
+      lRL = __ldcg(box_lo + 2 * cR.x); hRL = __ldcg(box_hi + 2 * cR.x); lRR = __ldcg(box_lo + 2 * cR.y); hRR = __ldcg(box_hi + 2 * cR.y);
       const float aR = union_half_area(lR, hR, lR, hR);
       const float s0 = aR - union_half_area(lL, hL, lRR, hRR), s1 = aR - union_half_area(lRL, hRL, lL, hL);
       if (s0 > best) { best = s0; which = 0; }
@@ -533,7 +533,7 @@ __global__ void k_rotate(int n, int2* child, const int* __restrict__ parent, flo
     }
     if (L < n - 1) {  // L is internal: R <-> LL (L' = R + LR) or R <-> LR (L' = LL + R)
       cL = __ldcg(&child[L]);
-      lLL = __ldcg(box_lo + cL.x); hLL = __ldcg(box_hi + cL.x); lLR = __ldcg(box_lo + cL.y); hLR = __ldcg(box_hi + cL.y);
+      lLL = __ldcg(box_lo + 2 * cL.x); hLL = __ldcg(box_hi + 2 * cL.x); lLR = __ldcg(box_lo + 2 * cL.y); hLR = __ldcg(box_hi + 2 * cL.y);
       const float aL = union_half_area(lL, hL, lL, hL);
       const float s2 = aL - union_half_area(lR, hR, lLR, hLR), s3 = aL - union_half_area(lLL, hLL, lR, hR);
       if (s2 > best) { best = s2; which = 2; }
@@ -542,8 +542,8 @@ __global__ void k_rotate(int n, int2* child, const int* __restrict__ parent, flo
     auto count = [&](int node) { return node >= n - 1 ? 1 : __ldcg(&cnt[node]); };
     auto remake = [&](int node, int a, int b, const float4& la, const float4& ha, const float4& lb, const float4& hb) {
       child[node]  = make_int2(a, b);
-      box_lo[node] = make_float4(fminf(la.x, lb.x), fminf(la.y, lb.y), fminf(la.z, lb.z), 0.0f);
-      box_hi[node] = make_float4(fmaxf(ha.x, hb.x), fmaxf(ha.y, hb.y), fmaxf(ha.z, hb.z), 0.0f);
+      box_lo[2 * (node)] = make_float4(fminf(la.x, lb.x), fminf(la.y, lb.y), fminf(la.z, lb.z), 0.0f);
+      box_hi[2 * (node)] = make_float4(fmaxf(ha.x, hb.x), fmaxf(ha.y, hb.y), fmaxf(ha.z, hb.z), 0.0f);
       cnt[node]    = count(a) + count(b);
     };
     if (which == 0) { remake(R, L, cR.y, lL, hL, lRR, hRR); child[cur] = make_int2(cR.x, R); }
@@ -563,7 +563,7 @@ __global__ void k_emit_binary(int n, const int2* __restrict__ child, const float
   if (i >= max(n - 1, 1)) return;
   float4* o = out + 4ll * (node_base + i);
   if (n == 1) {  // single triangle: child 0 = the leaf, child 1 = empty box
-    float4 l = box_lo[0], h = box_hi[0];
+    float4 l = box_lo[2 * (0)], h = box_hi[2 * (0)];
     o[0] = make_float4(l.x, h.x, l.y, h.y);
     o[1] = make_float4(FLT_MAX, -FLT_MAX, FLT_MAX, -FLT_MAX);
     o[2] = make_float4(l.z, h.z, FLT_MAX, -FLT_MAX);
@@ -571,7 +571,7 @@ __global__ void k_emit_binary(int n, const int2* __restrict__ child, const float
     return;
   }
   int2   c  = child[i];
-  float4 l0 = box_lo[c.x], h0 = box_hi[c.x], l1 = box_lo[c.y], h1 = box_hi[c.y];
+  float4 l0 = box_lo[2 * (c.x)], h0 = box_hi[2 * (c.x)], l1 = box_lo[2 * (c.y)], h1 = box_hi[2 * (c.y)];
   o[0] = make_float4(l0.x, h0.x, l0.y, h0.y);
   o[1] = make_float4(l1.x, h1.x, l1.y, h1.y);
   o[2] = make_float4(l0.z, h0.z, l1.z, h1.z);
@@ -617,7 +617,7 @@ __global__ void k_collapse8(const WorkItem* __restrict__ in, int n_in, WorkItem*
   unsigned long long sah_q = 0ull;
   if (w < n_in) {
     const int   node2 = n == 1 ? 0 : in[w].node2, r2 = n == 1 ? 0 : root2;
-    const float ar = half_area(box_lo[r2], box_hi[r2]), an = half_area(box_lo[node2], box_hi[node2]);
+    const float ar = half_area(box_lo[2 * (r2)], box_hi[2 * (r2)]), an = half_area(box_lo[2 * (node2)], box_hi[2 * (node2)]);
     sah_q = ar > 0.0f ? (unsigned long long)(fminf(an / ar, 1.0f) * 1048576.0f) : 1048576ull;
   }
   for (int o = 16; o; o >>= 1) sah_q += __shfl_xor_sync(0xffffffffu, sah_q, o);
@@ -636,15 +636,21 @@ __global__ void k_collapse8(const WorkItem* __restrict__ in, int n_in, WorkItem*
   // count_b x area(b) plus one more child slot in the wide node (leaf_sah x area(box), in units of a triangle test).
   // Neighbours in a mesh share their box (a quad's two halves: 2A against 2A + slot) and stay one leaf; unrelated
   // triangles of a soup (merged box ~2.5x each half) are kept apart: 3x fewer triangle tests per ray on the C4 soups.
+  // everything about a child is fetched in ONE round of independent loads: its count, its box and (internal nodes) its two
+  // children, which the opening step below and the rule above would otherwise fetch in a second, dependent round
+  int2 cch[8];
   auto add_child = [&](int k, int node) {
-    ch[k] = node; ccnt[k] = node_count(node, n, range); clo[k] = box_lo[node]; chi[k] = box_hi[node];
+    const bool internal = node < n - 1;
+    const int  cnt = internal ? range[node] : 1;
+    const int2 c2  = internal ? child[node] : make_int2(node, node);
+    ch[k] = node; ccnt[k] = cnt; cch[k] = c2; clo[k] = box_lo[2 * (node)]; chi[k] = box_hi[2 * (node)];
     copen[k] = false;
-    if (leaf_sah >= 0.0f && ccnt[k] >= 2 && ccnt[k] <= LEAF_MAX) {
-      const int2  c2 = child[node];
+    if (leaf_sah >= 0.0f && cnt >= 2 && cnt <= LEAF_MAX) {
+      // a subtree of <= 3 triangles: a child that is not a leaf of the binary tree holds all the others
       const float am = half_area(clo[k], chi[k]);
-      const float ca = (float)node_count(c2.x, n, range) * half_area(box_lo[c2.x], box_hi[c2.x]);
-      const float cb = (float)node_count(c2.y, n, range) * half_area(box_lo[c2.y], box_hi[c2.y]);
-      copen[k] = ca + cb + leaf_sah * am < (float)ccnt[k] * am;
+      const float ca = (float)(c2.x >= n - 1 ? 1 : cnt - 1) * half_area(box_lo[2 * (c2.x)], box_hi[2 * (c2.x)]);
+      const float cb = (float)(c2.y >= n - 1 ? 1 : cnt - 1) * half_area(box_lo[2 * (c2.y)], box_hi[2 * (c2.y)]);
+      copen[k] = ca + cb + leaf_sah * am < (float)cnt * am;
     }
   };
   if (n == 1) {  // degenerate partition: one triangle, no binary internal node
@@ -653,7 +659,7 @@ __global__ void k_collapse8(const WorkItem* __restrict__ in, int n_in, WorkItem*
   } else {
     int2 c = child[item.node2];
     add_child(nc++, c.x); add_child(nc++, c.y);
-    plo = box_lo[item.node2]; phi = box_hi[item.node2];
+    plo = box_lo[2 * (item.node2)]; phi = box_hi[2 * (item.node2)];
     while (nc < 8) {
       int   best = -1;
       float ba   = -1.0f;
@@ -663,7 +669,7 @@ __global__ void k_collapse8(const WorkItem* __restrict__ in, int n_in, WorkItem*
         if (a > ba) { ba = a; best = k; }
       }
       if (best < 0) break;
-      int2 c2 = child[ch[best]];
+      const int2 c2 = cch[best];
       add_child(best, c2.x);
       add_child(nc++, c2.y);
     }
@@ -869,12 +875,12 @@ int build_bvh(const BuildInput& in, BuildOutput* out, cudaStream_t st, char* err
   // hierarchy storage for both partitions: partition p uses node slice [base_p, base_p + 2 n_p - 1)
   int2*   d_child;
   int *   d_range, *d_parent = nullptr, *d_flags = nullptr;  // d_range: triangles below each internal node
-  float4 *d_lo, *d_hi;
+  float4 *d_box, *d_lo, *d_hi;  // boxes of the binary nodes, interleaved (lo, hi): one 32-byte sector per box; d_lo[2 i], d_hi[2 i]
   const size_t NN = 2ull * T + 2;
   CK(dev_alloc((void**)&d_child, sizeof(int2) * NN));
   CK(dev_alloc((void**)&d_range, sizeof(int) * NN));
-  CK(dev_alloc((void**)&d_lo, sizeof(float4) * NN));
-  CK(dev_alloc((void**)&d_hi, sizeof(float4) * NN));
+  CK(dev_alloc((void**)&d_box, sizeof(float4) * 2 * NN));
+  d_lo = d_box; d_hi = d_box + 1;
   if (in.lbvh) {
     CK(dev_alloc((void**)&d_parent, sizeof(int) * NN));
     CK(dev_alloc((void**)&d_flags, sizeof(int) * NN));
@@ -902,17 +908,17 @@ int build_bvh(const BuildInput& in, BuildOutput* out, cudaStream_t st, char* err
         k_karras<<<cdiv(P.n - 1, 256), 256, 0, st>>>(d_keys2 + P.sorted_base, P.n, d_child + P.slice, d_parent + P.slice,
                                                      d_range + P.slice);
       k_refit<<<cdiv(P.n, 256), 256, 0, st>>>(in.d_verts, d_ids2 + P.sorted_base, P.n, d_child + P.slice,
-                                              d_parent + P.slice, d_lo + P.slice, d_hi + P.slice, d_flags + P.slice, in.d_ref_lo, in.d_ref_hi);
+                                              d_parent + P.slice, d_lo + 2 * P.slice, d_hi + 2 * P.slice, d_flags + P.slice, in.d_ref_lo, in.d_ref_hi);
       P.root = 0;
     } else {
-      k_leaf_records<<<cdiv(P.n, 256), 256, 0, st>>>(in.d_verts, d_ids2 + P.sorted_base, P.n, d_lo + P.slice, d_hi + P.slice, d_rec[0],
+      k_leaf_records<<<cdiv(P.n, 256), 256, 0, st>>>(in.d_verts, d_ids2 + P.sorted_base, P.n, d_lo + 2 * P.slice, d_hi + 2 * P.slice, d_rec[0],
                                                      in.d_ref_lo, in.d_ref_hi);
       int m = P.n, cur = 0, rounds = 0;
       // stale tile states of the other partition must not be taken for this one's
       CK(cudaMemsetAsync(d_tile_state, 0, sizeof(unsigned long long) * (((size_t)P.n + ploc_tile_size(radius) - 1) / ploc_tile_size(radius)), st));
       while (m > PLOC_TAIL) {
         auto round_kernel = radius == 16 ? k_ploc_round<16> : k_ploc_round<0>;  // the default radius has its own, fully unrolled instance
-        round_kernel<<<cdiv(m, ploc_tile_size(radius)), PLOC_TILE, 0, st>>>(d_rec[cur], m, radius, d_rec[cur ^ 1], d_lo + P.slice, d_hi + P.slice,
+        round_kernel<<<cdiv(m, ploc_tile_size(radius)), PLOC_TILE, 0, st>>>(d_rec[cur], m, radius, d_rec[cur ^ 1], d_lo + 2 * P.slice, d_hi + 2 * P.slice,
                                                                            d_child + P.slice, d_range + P.slice, P.n - m, d_tile_state,
                                                                            (unsigned int*)d_ploc_ctl, d_ploc_ctl + 1, (unsigned)rounds);
         int m2 = 0;
@@ -923,7 +929,7 @@ int build_bvh(const BuildInput& in, BuildOutput* out, cudaStream_t st, char* err
         cur ^= 1;
         rounds++;
       }
-      k_ploc_tail<<<1, PLOC_TAIL, 0, st>>>(d_rec[cur], m, radius, d_lo + P.slice, d_hi + P.slice, d_child + P.slice, d_range + P.slice,
+      k_ploc_tail<<<1, PLOC_TAIL, 0, st>>>(d_rec[cur], m, radius, d_lo + 2 * P.slice, d_hi + 2 * P.slice, d_child + P.slice, d_range + P.slice,
                                           P.n - m, d_ploc_ctl + 2);
       int tail[2] = {0, 0};
       CK(cudaMemcpyAsync(tail, d_ploc_ctl + 2, sizeof(tail), cudaMemcpyDeviceToHost, st));
@@ -949,7 +955,7 @@ int build_bvh(const BuildInput& in, BuildOutput* out, cudaStream_t st, char* err
         if (P.n < 3) continue;
         k_parents<<<cdiv(P.n - 1, 256), 256, 0, st>>>(d_child + P.slice, P.n, P.root, d_par + P.slice);
         CK(cudaMemsetAsync(d_arr + P.slice, 0, sizeof(int) * (size_t)(P.n - 1), st));
-        k_rotate<<<cdiv(P.n, 256), 256, 0, st>>>(P.n, d_child + P.slice, d_par + P.slice, d_lo + P.slice, d_hi + P.slice,
+        k_rotate<<<cdiv(P.n, 256), 256, 0, st>>>(P.n, d_child + P.slice, d_par + P.slice, d_lo + 2 * P.slice, d_hi + 2 * P.slice,
                                                  d_range + P.slice, d_arr + P.slice, d_nrot);
       }
     if (dbg) {
@@ -967,8 +973,8 @@ int build_bvh(const BuildInput& in, BuildOutput* out, cudaStream_t st, char* err
     for (int k = 0; k < 3; k++) { dst[k] = FLT_MAX; dst[3 + k] = -FLT_MAX; }
     if (parts[p].n == 0) continue;
     float4 lo, hi;
-    CK(cudaMemcpyAsync(&lo, d_lo + parts[p].slice + parts[p].root, sizeof(float4), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(&hi, d_hi + parts[p].slice + parts[p].root, sizeof(float4), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&lo, d_lo + 2 * (parts[p].slice + parts[p].root), sizeof(float4), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&hi, d_hi + 2 * (parts[p].slice + parts[p].root), sizeof(float4), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     dst[0] = lo.x; dst[1] = lo.y; dst[2] = lo.z; dst[3] = hi.x; dst[4] = hi.y; dst[5] = hi.z;
   }
@@ -983,7 +989,7 @@ int build_bvh(const BuildInput& in, BuildOutput* out, cudaStream_t st, char* err
     for (int p = 0; p < 2; p++) {
       const Part& P = parts[p];
       if (P.n == 0) continue;
-      k_emit_binary<<<cdiv(nn[p], 256), 256, 0, st>>>(P.n, d_child + P.slice, d_lo + P.slice, d_hi + P.slice, base,
+      k_emit_binary<<<cdiv(nn[p], 256), 256, 0, st>>>(P.n, d_child + P.slice, d_lo + 2 * P.slice, d_hi + 2 * P.slice, base,
                                                       P.sorted_base, d_nodes);
       (p == 0 ? out->root_other : out->root_emit) = base + P.root;
       (p == 0 ? out->nodes_other : out->nodes_emit) = nn[p];
@@ -1015,7 +1021,7 @@ int build_bvh(const BuildInput& in, BuildOutput* out, cudaStream_t st, char* err
         int h_cnt[4] = {node_next, tri_next, 0, 0};
         CK(cudaMemcpyAsync(d_counters, h_cnt, sizeof(h_cnt), cudaMemcpyHostToDevice, st));
         k_collapse8<<<cdiv(n_in, 128), 128, 0, st>>>(d_q[cur], n_in, d_q[cur ^ 1], P.n, d_child + P.slice, d_range + P.slice,
-                                                     d_lo + P.slice, d_hi + P.slice, d_counters, d_nodes,
+                                                     d_lo + 2 * P.slice, d_hi + 2 * P.slice, d_counters, d_nodes,
                                                      d_final_to_sorted, P.sorted_base, in.leaf_sah, P.root, d_sah);
         CK(cudaMemcpyAsync(h_cnt, d_counters, sizeof(h_cnt), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
@@ -1072,7 +1078,7 @@ int build_bvh(const BuildInput& in, BuildOutput* out, cudaStream_t st, char* err
 
   dev_free(d_acc); dev_free(d_keys); dev_free(d_keys2); dev_free(d_ids); dev_free(d_ids2); dev_free(d_final_to_sorted);
   dev_free(d_rec[0]); dev_free(d_rec[1]); dev_free(d_tile_state); dev_free(d_ploc_ctl);
-  dev_free(d_tmp); dev_free(d_child); dev_free(d_range); dev_free(d_parent); dev_free(d_flags); dev_free(d_lo); dev_free(d_hi);
+  dev_free(d_tmp); dev_free(d_child); dev_free(d_range); dev_free(d_parent); dev_free(d_flags); dev_free(d_box);
 
   out->d_nodes = d_nodes;
   out->num_nodes = total_nodes;

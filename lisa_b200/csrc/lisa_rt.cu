@@ -27,7 +27,7 @@
 #include <nvtx3/nvToolsExt.h>
 
 #ifndef LISA_POOL_DEEP_SAH
-#define LISA_POOL_DEEP_SAH 8.0f
+#define LISA_POOL_DEEP_SAH 40.0f
 #endif
 #ifndef LISA_LEAF_SAH_DEFAULT
 #define LISA_LEAF_SAH_DEFAULT 0.5f
@@ -494,14 +494,16 @@ static int create_impl(const lisa_scene_desc* sd, const lisa_options* opt, lisa_
   if (const char* e2 = getenv("LISA_PIPELINE"))
     c->pipeline = strcmp(e2, "wavefront") == 0 ? 0 : strcmp(e2, "pool") == 0 ? 2 : strcmp(e2, "path") == 0 ? 1 : 3;
   c->cfg.pool_dry_thresh = 16;
-  c->cfg.pool_dry_thresh_deep = 4;  // measured on the 10M soup (deep flavour): 16 -> 68.6, 8 -> 71.0, 4 -> 72.4 Msamples/s
+  c->cfg.pool_dry_thresh_deep = 2;  // measured on the 10M soup (deep flavour): 16 -> 68.6, 8 -> 71.0, 4 -> 72.4, 2 -> 73.0 Msamples/s
   if (const char* e2 = getenv("LISA_DRY_THRESH")) c->cfg.pool_dry_thresh = c->cfg.pool_dry_thresh_deep = std::max(1, std::min(32, atoi(e2)));
   if (const char* e2 = getenv("LISA_POOL_BLOCKS_PER_SM")) {
     c->cfg.pool_blocks_per_sm = std::max(1, std::min(c->cfg.pool_blocks_per_sm, atoi(e2)));
     c->cfg.pool_blocks_per_sm_deep = std::max(1, std::min(c->cfg.pool_blocks_per_sm_deep, atoi(e2)));
   }
-  // k_pool's flavour (sched_pool.cuh) by the builder's estimate of the node visits per ray: sum of the wide nodes' surface
-  // areas over the root's.  Cornell box 2.3, 871k-triangle knot 2.9, the C4 soups 30-40; the flavours cross over near 8.
+  // k_pool's flavour (sched_pool.cuh) by the builder's surface-area estimate (sum of the wide nodes' areas over the root's: the
+  // node visits of a LINE through the whole scene, several times what a ray segment that ends at its first hit visits).
+  // Cornell box 3.0, 871k-triangle knot 3.4 (shallow +9 %); soups of overlapping triangles: 3k 15 (shallow +2 %), 10k-100k
+  // 23-52 (equal), 300k 76 (deep +3 %), 1M 116 (deep +10 %), 10M 251 (deep +14 %).
   c->cfg.pool_deep = wide && c->bvh.sah_nodes_per_ray > LISA_POOL_DEEP_SAH;
   if (const char* e2 = getenv("LISA_POOL_FLAVOUR")) c->cfg.pool_deep = wide && !strcmp(e2, "deep");
   c->stats.pool_flavour = c->cfg.pool_deep ? 1u : 0u;

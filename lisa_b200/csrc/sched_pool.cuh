@@ -31,12 +31,12 @@ namespace lisa {
 #endif
 // Two flavours of the kernel, chosen per scene by the builder's surface-area estimate of the node visits per ray
 // (BuildOutput::sah_nodes_per_ray, lisa_rt.cu):
-//   shallow  64 chains per warp, POOL_STACK_SM traversal-stack entries per thread in shared memory.  Scenes whose rays visit a
+//   shallow  64 chains per warp, 5 traversal-stack entries per thread in shared memory.  Scenes whose rays visit a
 //            few nodes (the Cornell box: 2, the 871k-triangle knot: 2.2): the management section wants 32 pending slots often.
 //   deep     48 chains per warp and 12 stack entries: scenes whose rays visit tens of nodes (the C4 soups: 30) push deep, and
 //            what does not fit in shared memory spills to the local array — through an L1 that the chain slots leave ~30 KB
 //            of; measured on the 10M soup: 63.7 -> 72.4 Msamples/s, and -9 % on the knot, hence two flavours.
-// Both run 5 CTAs per SM (43.8 KB / 41.4 KB of shared memory per CTA) and are bit-identical in their results.
+// Both run 5 CTAs per SM (44.8 KB / 43.3 KB of shared memory per CTA) and are bit-identical in their results.
 #ifndef POOL_SLOTS
 #define POOL_SLOTS 64  // chains per warp, shallow flavour (ring positions wrap with % SLOTS: a power of two costs one AND)
 #endif
@@ -44,7 +44,7 @@ namespace lisa {
 #define POOL_SLOTS_DEEP 48
 #endif
 #ifndef POOL_STACK_SM
-#define POOL_STACK_SM LISA_STACK_SM
+#define POOL_STACK_SM 5  // what fits beside 5 CTAs x 64 chains per warp (4 -> 5: knot +1.5 %, Cornell +0.1 %)
 #endif
 #ifndef POOL_STACK_SM_DEEP
 #define POOL_STACK_SM_DEEP 12

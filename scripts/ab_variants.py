@@ -18,7 +18,7 @@ def child(scene, reps):
     import lisa_b200.frontend as fe
     import lisa_b200.rt as rt
     if scene.startswith("soup"):  # the C4 soup of scripts/scale_bench.py
-        T = int(float(scene[4:].replace("m", "e6")))
+        T = int(float(scene[4:].replace("m", "e6").replace("k", "e3")))
         rng = np.random.default_rng(0x5EED)
         edge = 0.5 * T ** (-1.0 / 3.0)
         c = rng.random((T, 1, 3), dtype=np.float32)

@@ -35,6 +35,20 @@ for pipe in ("pool", "path", "wavefront"):
     R.render_subframes(0, 1, 2)
     print("cornell", pipe, float(R.read_accum()[..., :3].mean()))
     R.close()
+# round 2, second session: the deep flavour of k_pool (48 chains per warp, 12 stack entries) on the soup and on the Cornell box,
+# and the collapse with and without the surface-area rule for leaves
+os.environ["LISA_PIPELINE"] = "pool"
+for fl, sah in (("deep", "0.5"), ("shallow", "-1")):
+    os.environ["LISA_POOL_FLAVOUR"] = fl; os.environ["LISA_LEAF_SAH"] = sah
+    R = rt.Renderer(v, n, m, mats, 40, 32, (0, 0, 4), (0, 0, 0), 45.0, 1, 3)
+    R.render_subframes(0, 1, 2)
+    print("soup pool", fl, "leaf_sah", sah, float(R.read_accum()[..., :3].mean()), R.stats()["bvh_nodes"], R.stats()["pool_flavour"])
+    R.close()
+    R = rt.Renderer.from_scene(sc)
+    R.render_subframes(0, 1, 2)
+    print("cornell pool", fl, float(R.read_accum()[..., :3].mean()))
+    R.close()
+os.environ.pop("LISA_POOL_FLAVOUR"); os.environ.pop("LISA_LEAF_SAH")
 os.environ.pop("LISA_PIPELINE")
 R = rt.Renderer(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.float32), np.zeros(0, np.int32), mats, 40, 32, (0, 0, 4), (0, 0, 0), 45.0, 1, 3,
                 _bvh_file="/tmp/sanitize.lisabvh")

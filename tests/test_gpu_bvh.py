@@ -539,5 +539,9 @@ def test_pool_flavours_are_bit_identical_and_chosen_by_the_sah_estimate(rt, corn
         for k in ("radiance_rays", "shadow_rays", "nodes_visited", "triangles_tested", "shadow_culled"):
             assert stats[name, "deep"][k] == stats[name, "shallow"][k], (name, k)
         assert stats[name, "deep"]["pool_flavour"] == 1 and stats[name, "shallow"]["pool_flavour"] == 0
-    assert stats["soup", "auto"]["bvh_sah_nodes_per_ray"] > 20 and stats["soup", "auto"]["pool_flavour"] == 1
+    assert 20 < stats["soup", "auto"]["bvh_sah_nodes_per_ray"] < 40 and stats["soup", "auto"]["pool_flavour"] == 0
     assert stats["cornell", "auto"]["bvh_sah_nodes_per_ray"] < 6 and stats["cornell", "auto"]["pool_flavour"] == 0
+    monkeypatch.delenv("LISA_POOL_FLAVOUR", raising=False)
+    v, n, m = _overlap_soup(rng, 600000)   # deep from an estimate of 40 (measured crossover: lisa_rt.cu)
+    st = rt.Renderer(v, n, m, [MAT_W, MAT_L], 16, 16, (0.5, 0.6, 3.2), (0.5, 0.45, 0.5), 35.0, 1, 3).stats()
+    assert st["bvh_sah_nodes_per_ray"] > 60 and st["pool_flavour"] == 1
