@@ -917,7 +917,8 @@ int build_bvh(const BuildInput& in, BuildOutput* out, cudaStream_t st, char* err
       // stale tile states of the other partition must not be taken for this one's
       CK(cudaMemsetAsync(d_tile_state, 0, sizeof(unsigned long long) * (((size_t)P.n + ploc_tile_size(radius) - 1) / ploc_tile_size(radius)), st));
       while (m > PLOC_TAIL) {
-        auto round_kernel = radius == 16 ? k_ploc_round<16> : k_ploc_round<0>;  // the default radius has its own, fully unrolled instance
+        // the default radius (4) and the former one (16) have their own, fully unrolled instances
+        auto round_kernel = radius == 4 ? k_ploc_round<4> : radius == 16 ? k_ploc_round<16> : k_ploc_round<0>;
         round_kernel<<<cdiv(m, ploc_tile_size(radius)), PLOC_TILE, 0, st>>>(d_rec[cur], m, radius, d_rec[cur ^ 1], d_lo + 2 * P.slice, d_hi + 2 * P.slice,
                                                                            d_child + P.slice, d_range + P.slice, P.n - m, d_tile_state,
                                                                            (unsigned int*)d_ploc_ctl, d_ploc_ctl + 1, (unsigned)rounds);

@@ -359,7 +359,11 @@ static int create_impl(const lisa_scene_desc* sd, const lisa_options* opt, lisa_
   CU(cudaEventRecord(t1, c->stream));
 
   // ---- BVH
-  int lbvh = (o.flags & LISA_FLAG_LBVH) ? 1 : 0, radius = 16;
+  // PLOC search radius, measured on B200 (render Msamples/s at radius 2 / 3 / 4 / 5 / 8 / 16 / 24, one box per group of columns):
+  //   Cornell 1569 / 1563 / 1570 / 1560 / 1564 | 1562 / 1566 / 1560     knot  1639 / 1688 / 1685 / 1702 / 1687 | 1698 / 1675 / 1676
+  //   1M soup 136.0 / 134.0 / 135.9 / 134.4 / 130.8 | 130.6 / 126.1 / 124.2     10M soup 79.3 / 79.0 / 77.9 / 77.7 / 74.6 | 73.4 / 72.1 / 67.1
+  // A wider search buys nothing on meshes and LOSES on overlapping soups; 2 starts to cost on the knot.  4: PLOC 25.8 -> 17.4 ms at 100M triangles.
+  int lbvh = (o.flags & LISA_FLAG_LBVH) ? 1 : 0, radius = 4;
   if (const char* e = getenv("LISA_BUILDER")) lbvh = !strcmp(e, "lbvh");
   if (const char* e = getenv("LISA_PLOC_RADIUS")) radius = std::max(1, atoi(e));
   int rotate = 0;

@@ -59,7 +59,7 @@ template <bool DEEP>
 struct PoolShape {
   static constexpr int SLOTS = DEEP ? POOL_SLOTS_DEEP : POOL_SLOTS;
   static constexpr int NS0   = DEEP ? POOL_STACK_SM_DEEP : POOL_STACK_SM;
-  static constexpr int NS    = NS0 < LISA_STACK_TOTAL ? NS0 : LISA_STACK_TOTAL - 1;  // (the tiny-stack test build has 5 entries in all)
+  static constexpr int NS    = NS0 < LISA_STACK_TOTAL ? NS0 : LISA_STACK_TOTAL - 1;  // (the tiny-stack test build has 3 entries in all)
   typedef TravStack<uint2, NS, LISA_STACK_TOTAL - NS> Stk;
   static constexpr size_t smem_bytes = (size_t)NS * 128 * sizeof(uint2) + 4 * sizeof(PoolWarp<SLOTS>);
 };

@@ -290,7 +290,7 @@ def test_ten_thousand_coincident_triangles(rt, bvh):
 def test_traversal_stack_overflow_is_loud(built, tmp_path):
     """A traversal stack that fills up drops a subtree; the call that ran the kernel must then FAIL (LISA_ERR_STATE) instead
     of returning hits that may be wrong.  The builders do not bound the depth of the tree, so the condition is provoked
-    with a test build of the same sources whose stacks hold 5 entries (make liblisa_rt_tinystack.so): a 50k-triangle soup
+    with a test build of the same sources whose stacks hold 3 entries (make liblisa_rt_tinystack.so): a 50k-triangle soup
     overflows them on most rays, in the diagnostic queries and in the render kernels alike."""
     import os, subprocess, sys
     from conftest import ROOT
@@ -512,11 +512,11 @@ def test_sah_leaves_same_hits_less_work(rt, orc, cornell, monkeypatch):
     w0, w1 = R0.stats(), R1.stats()
     assert w1["triangles_tested"] < 0.75 * w0["triangles_tested"], (w0["triangles_tested"], w1["triangles_tested"])
     assert w1["nodes_visited"] < 1.1 * w0["nodes_visited"], (w0["nodes_visited"], w1["nodes_visited"])
-    # the Cornell box: the same tree either way, up to a handful of leaves
+    # the Cornell box: the same tree either way, up to a handful of leaves (152-169 wide nodes, depending on the PLOC radius)
     C1 = rt.Renderer.from_scene(resized(cornell, 32))
     monkeypatch.setenv("LISA_LEAF_SAH", "-1")
     C0 = rt.Renderer.from_scene(resized(cornell, 32))
-    assert abs(C1.stats()["bvh_nodes"] - C0.stats()["bvh_nodes"]) <= 8
+    assert abs(C1.stats()["bvh_nodes"] - C0.stats()["bvh_nodes"]) <= 0.1 * C0.stats()["bvh_nodes"]
 
 
 def test_pool_flavours_are_bit_identical_and_chosen_by_the_sah_estimate(rt, cornell, monkeypatch):
