@@ -75,11 +75,11 @@ int main(int argc, char** argv) {
       lisa_stats s;
       s.struct_size = sizeof(s);
       lisa_get_stats(ctx, &s);
-      printf("{\"triangles\": %u, \"references\": %u, \"bvh_nodes\": %u, \"upload_ms\": %.3f, \"bvh_build_ms\": %.3f, \"bvh_build_stages_ms\": {\"morton_sort\": %.3f, "
+      printf("{\"triangles\": %u, \"references\": %u, \"bvh_nodes\": %u, \"bvh_sah_nodes_per_ray\": %.2f, \"kernel_flavour\": \"%s\", \"upload_ms\": %.3f, \"bvh_build_ms\": %.3f, \"bvh_build_stages_ms\": {\"morton_sort\": %.3f, "
              "\"hierarchy\": %.3f, \"collapse\": %.3f, \"pack\": %.3f}, \"render_ms\": %.3f, \"samples\": %llu, "
              "\"radiance_rays\": %llu, \"shadow_rays\": %llu, \"msamples_per_s\": %.3f, \"mrays_per_s\": %.3f, "
              "\"kernel_launches\": %llu}\n",
-             s.num_triangles, s.num_references, s.bvh_nodes, s.upload_ms, s.bvh_build_ms, s.build_sort_ms, s.build_hierarchy_ms, s.build_collapse_ms, s.build_pack_ms,
+             s.num_triangles, s.num_references, s.bvh_nodes, s.bvh_sah_nodes_per_ray, s.pool_flavour ? "deep" : "shallow", s.upload_ms, s.bvh_build_ms, s.build_sort_ms, s.build_hierarchy_ms, s.build_collapse_ms, s.build_pack_ms,
              s.render_ms, (unsigned long long)s.samples,
              (unsigned long long)s.radiance_rays, (unsigned long long)s.shadow_rays, s.samples / s.render_ms / 1e3,
              (s.radiance_rays + s.shadow_rays) / s.render_ms / 1e3, (unsigned long long)s.kernel_launches);

@@ -106,3 +106,21 @@ def test_second_bsdf_variant_builds_and_exports(built):
     lib = ctypes.CDLL(os.path.join(ROOT, "lisa_b200", "liblisa_rt_ggx.so"))
     for n in _declared("lisa_rt.h"):
         assert hasattr(lib, n), n
+
+
+def test_stats_and_options_mirror_the_header(rt, tmp_path):
+    """The ctypes mirrors of lisa_stats / lisa_options (lisa_b200/rt.py) against the C header itself: a C program compiled
+    from include/lisa_rt.h prints sizeof and the offsets of the fields added last."""
+    import subprocess
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "lisa_rt.h"\n'
+                   'int main(void) { printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(lisa_stats), offsetof(lisa_stats, bvh_sah_nodes_per_ray),\n'
+                   '  offsetof(lisa_stats, pool_flavour), offsetof(lisa_stats, build_sort_ms), offsetof(lisa_stats, num_references), sizeof(lisa_options)); return 0; }\n')
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
+    size, o_sah, o_flav, o_sort, o_refs, size_opt = map(int, subprocess.check_output([str(exe)]).split())
+    S = rt.Stats
+    assert ctypes.sizeof(S) == size
+    assert S.bvh_sah_nodes_per_ray.offset == o_sah and S.pool_flavour.offset == o_flav
+    assert S.build_sort_ms.offset == o_sort and S.num_references.offset == o_refs
+    assert ctypes.sizeof(rt.Options) == size_opt
