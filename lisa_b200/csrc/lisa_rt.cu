@@ -72,6 +72,7 @@ struct lisa_ctx {
   std::string  output_image;
   uint32_t     emit_hash = 0;       // of the materials' emitter flags (what a serialised BVH is valid for)
   bool         profile_stages = false;
+  float        pool_min_chains_factor = 1.2f;  // k_pool from this many times its slots (run_tile; LISA_POOL_MIN_FACTOR)
   int          pipeline = 3;        // 3: per tile, k_pool when the tile has enough chains to fill its slots twice, else k_path;
                                     // 2: k_pool, 1: k_path (one persistent launch per tile either way), 0: wavefront (three kernels per bounce)
   bool         state_full = false;  // the wavefront arrays are allocated (k_path needs only state.sum)
@@ -511,6 +512,8 @@ static int create_impl(const lisa_scene_desc* sd, const lisa_options* opt, lisa_
   c->cfg.pool_deep = wide && c->bvh.sah_nodes_per_ray > LISA_POOL_DEEP_SAH;
   if (const char* e2 = getenv("LISA_POOL_FLAVOUR")) c->cfg.pool_deep = wide && !strcmp(e2, "deep");
   c->stats.pool_flavour = c->cfg.pool_deep ? 1u : 0u;
+  c->pool_min_chains_factor = 1.2f;
+  if (const char* e2 = getenv("LISA_POOL_MIN_FACTOR")) c->pool_min_chains_factor = (float)atof(e2);
   if (getenv("LISA_DEBUG_TIMING")) fprintf(stderr, "[lisa] pipeline %d, k_path %d CTAs/SM, k_pool %d CTAs/SM (%s flavour: SAH estimate %.2f node visits per ray)\n", c->pipeline, c->cfg.path_blocks_per_sm,
                                          c->cfg.pool_deep ? c->cfg.pool_blocks_per_sm_deep : c->cfg.pool_blocks_per_sm, c->cfg.pool_deep ? "deep" : "shallow", c->bvh.sah_nodes_per_ray);
   if ((c->width > 65535u || c->height > 65535u) && c->pipeline) c->pipeline = 0;  // k_path packs a chain's pixel as x | y << 16
@@ -628,11 +631,13 @@ static int run_tile(lisa_ctx* c, const Tile& t, uint64_t* launches, uint64_t* it
   if (rc) return rc;
   if (c->pipeline >= 1) {
     if (c->profile_stages) cudaEventRecord(next_event(c), c->stream);
-    // k_pool keeps 64 chains per warp: it pays once the tile fills those slots at least twice over (measured on B200:
-    // Cornell 2000x2000 1240 vs 1145 Msamples/s, C3 1920x1080 25.5 vs 27.8 ms; 512x512 22.5 vs 21.4 ms, 128x128 13.4 vs 10.0 ms)
+    // k_pool keeps 64 chains per warp (189,440 on B200): it pays once the tile fills those slots.  Measured, k_pool vs k_path on the
+    // Cornell box (chains / slots): 256x256 (0.35) 11.6 vs 8.1 ms, knot 480x270 (0.68) 24.0 vs 22.9, 512x512 x 64 spp (1.38) 15.3 vs
+    // 16.0, 1280x720 (4.9) 6.8 vs 7.3, 1024x1024 (5.5) 11.6 vs 12.7, 2000x2000 (21) 1564 vs 1254 Msamples/s.  Using fewer slots per
+    // warp so that a tile's rounds are equally full LOSES (512x512: 45 slots 16.6 ms, 32 slots 17.0 ms against 15.3 with all 64).
     const bool     deep = c->cfg.pool_deep != 0;
     const uint64_t pool_slots = (uint64_t)c->cfg.sm_count * (deep ? c->cfg.pool_blocks_per_sm_deep : c->cfg.pool_blocks_per_sm) * pool_chains_per_cta(deep);
-    const bool use_pool = c->pipeline == 2 || (c->pipeline == 3 && t.n_chains >= 2 * pool_slots);
+    const bool use_pool = c->pipeline == 2 || (c->pipeline == 3 && (double)t.n_chains >= (double)c->pool_min_chains_factor * (double)pool_slots);
     nvtxRangePushA(use_pool ? "lisa: tile k_pool" : "lisa: tile k_path");
     if (use_pool) launch_pool(c->scene, c->state, c->cam, t, c->cfg, c->stream);
     else launch_path(c->scene, c->state, c->cam, t, c->cfg, c->stream);

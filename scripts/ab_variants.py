@@ -10,6 +10,10 @@ SCENES = {
     "c2": ("scenes/cornell_c2.rto", 2000, 2000, 50, 4),
     "c1": ("scenes/cornell_c1.rto", 512, 512, 64, 4),
     "c3": ("scenes/c3_knot.rto", 1920, 1080, 16, 4),
+    "c256": ("scenes/cornell_c1.rto", 256, 256, 64, 4),
+    "c720p": ("scenes/cornell_c1.rto", 1280, 720, 16, 4),
+    "c1024": ("scenes/cornell_c1.rto", 1024, 1024, 16, 4),
+    "c3s": ("scenes/c3_knot.rto", 480, 270, 64, 4),
 }
 
 def child(scene, reps):
