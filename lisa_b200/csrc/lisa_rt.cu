@@ -73,7 +73,7 @@ struct lisa_ctx {
   uint32_t     emit_hash = 0;       // of the materials' emitter flags (what a serialised BVH is valid for)
   bool         profile_stages = false;
   float        pool_min_chains_factor = 1.2f;  // k_pool from this many times its slots (run_tile; LISA_POOL_MIN_FACTOR)
-  int          pipeline = 3;        // 3: per tile, k_pool when the tile has enough chains to fill its slots twice, else k_path;
+  int          pipeline = 3;        // 3: per tile, k_pool when the tile has enough chains to fill its slots 1.2 times, else k_path;
                                     // 2: k_pool, 1: k_path (one persistent launch per tile either way), 0: wavefront (three kernels per bounce)
   bool         state_full = false;  // the wavefront arrays are allocated (k_path needs only state.sum)
   std::vector<cudaEvent_t> ev_pool;  // stage profiling: 3 events per iteration (extend start, shadow start, shadow end)

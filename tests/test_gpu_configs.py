@@ -49,8 +49,9 @@ def _render(rt, sc, spp, **kw):
 
 
 def test_c1_config_with_k_pool_forced(rt, cornell, monkeypatch):
-    """BASELINE configs[0] through the bench kernel: 512x512 is below the default switch to k_pool (378,880 chains), so
-    the OptiX-golden tests of test_gpu_parity.py run k_path; here the same comparison with LISA_PIPELINE=pool."""
+    """BASELINE configs[0] through the bench kernel whatever the default switch between k_path and k_pool says for 512x512
+    (227,328 chains since the second session of round 2; 378,880 before): the comparison of test_gpu_parity.py with
+    LISA_PIPELINE=pool.  (test_gpu_properties.py forces each schedule in turn and requires identical bits.)"""
     monkeypatch.setenv("LISA_PIPELINE", "pool")
     acc, st = _render(rt, resized(cornell, 512), 64)
     g64, g1024 = golden("optix_c1"), golden("optix_c1_1024")
