@@ -142,7 +142,8 @@ typedef struct lisa_stats {
   /* the builder's surface-area estimate of the node visits of a ray that crosses the scene (sum of the 8-wide nodes' surface
    * areas over their root's; 0 for the binary BVH), and the flavour of the persistent kernel chosen from it: 0 = shallow
    * (64 chains per warp), 1 = deep (48 chains per warp and a 12-entry traversal stack in shared memory: scenes whose rays
-   * visit tens of nodes).  The flavours give bit-identical images. */
+   * visit tens of nodes).  After a render call that traced >= 100,000 rays the flavour follows the node visits per ray that
+   * call measured (deep above 10, shallow below 8) unless LISA_POOL_FLAVOUR forces one.  The flavours give bit-identical images. */
   float    bvh_sah_nodes_per_ray;
   uint32_t pool_flavour;
 } lisa_stats;

@@ -73,6 +73,7 @@ struct lisa_ctx {
   uint32_t     emit_hash = 0;       // of the materials' emitter flags (what a serialised BVH is valid for)
   bool         profile_stages = false;
   float        pool_min_chains_factor = 1.2f;  // k_pool from this many times its slots (run_tile; LISA_POOL_MIN_FACTOR)
+  bool         pool_flavour_auto = true;       // k_pool's flavour follows the measured node visits per ray (lisa_render_subframes)
   int          pipeline = 3;        // 3: per tile, k_pool when the tile has enough chains to fill its slots 1.2 times, else k_path;
                                     // 2: k_pool, 1: k_path (one persistent launch per tile either way), 0: wavefront (three kernels per bounce)
   bool         state_full = false;  // the wavefront arrays are allocated (k_path needs only state.sum)
@@ -509,8 +510,11 @@ static int create_impl(const lisa_scene_desc* sd, const lisa_options* opt, lisa_
   // node visits of a LINE through the whole scene, several times what a ray segment that ends at its first hit visits).
   // Cornell box 3.0, 871k-triangle knot 3.4 (shallow +9 %); soups of overlapping triangles: 3k 15 (shallow +2 %), 10k-100k
   // 23-52 (equal), 300k 76 (deep +3 %), 1M 116 (deep +10 %), 10M 251 (deep +14 %).
-  c->cfg.pool_deep = wide && c->bvh.sah_nodes_per_ray > LISA_POOL_DEEP_SAH;
-  if (const char* e2 = getenv("LISA_POOL_FLAVOUR")) c->cfg.pool_deep = wide && !strcmp(e2, "deep");
+  float deep_from = LISA_POOL_DEEP_SAH;
+  if (const char* e2 = getenv("LISA_POOL_DEEP_SAH")) deep_from = (float)atof(e2);
+  c->cfg.pool_deep = wide && c->bvh.sah_nodes_per_ray > deep_from;
+  c->pool_flavour_auto = true;
+  if (const char* e2 = getenv("LISA_POOL_FLAVOUR")) { c->cfg.pool_deep = wide && !strcmp(e2, "deep"); c->pool_flavour_auto = false; }
   c->stats.pool_flavour = c->cfg.pool_deep ? 1u : 0u;
   c->pool_min_chains_factor = 1.2f;
   if (const char* e2 = getenv("LISA_POOL_MIN_FACTOR")) c->pool_min_chains_factor = (float)atof(e2);
@@ -750,6 +754,18 @@ extern "C" int lisa_render_subframes(lisa_ctx* c, uint32_t first, uint32_t count
   s.kernel_launches += launches;
   s.iterations += iterations;
   s.subframes_accumulated += count;
+  // The estimate at create time is geometric (a line through the whole scene); once a call has traced enough rays the flavour
+  // follows what they measured.  Crossover on B200 (soups, node visits per traversed ray): 4.1 shallow +2 %, 6.5-9.6 equal,
+  // 10.6 deep +3 %, 27 deep +10 %.  Needs the traversal counters (LISA_COUNT_TRAVERSAL, on by default); same bits either way.
+  if (c->pool_flavour_auto && c->scene.wide && s.last_nodes_visited > 0) {
+    const uint64_t traced = s.last_radiance_rays + s.last_shadow_rays - s.last_shadow_culled;
+    if (traced >= 100000) {
+      const double per_ray = (double)s.last_nodes_visited / (double)traced;
+      if (per_ray > 10.0) c->cfg.pool_deep = 1;
+      else if (per_ray < 8.0) c->cfg.pool_deep = 0;
+      s.pool_flavour = c->cfg.pool_deep ? 1u : 0u;
+    }
+  }
   return LISA_OK;
 }
 

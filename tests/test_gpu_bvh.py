@@ -532,16 +532,25 @@ def test_pool_flavours_are_bit_identical_and_chosen_by_the_sah_estimate(rt, corn
         else: monkeypatch.setenv("LISA_POOL_FLAVOUR", fl)
         for name, mk in (("soup", lambda: rt.Renderer(*args)), ("cornell", lambda: rt.Renderer.from_scene(resized(cornell, 160)))):
             R = mk()
+            stats[name, fl, "created"] = R.stats()
             R.render_subframes(0, 2, 3)
             imgs[name, fl], stats[name, fl] = R.read_accum(), R.stats()
     for name in ("soup", "cornell"):
         assert np.array_equal(imgs[name, "deep"], imgs[name, "shallow"]) and np.array_equal(imgs[name, "auto"], imgs[name, "deep"])
         for k in ("radiance_rays", "shadow_rays", "nodes_visited", "triangles_tested", "shadow_culled"):
             assert stats[name, "deep"][k] == stats[name, "shallow"][k], (name, k)
-        assert stats[name, "deep"]["pool_flavour"] == 1 and stats[name, "shallow"]["pool_flavour"] == 0
-    assert 20 < stats["soup", "auto"]["bvh_sah_nodes_per_ray"] < 40 and stats["soup", "auto"]["pool_flavour"] == 0
+        assert stats[name, "deep"]["pool_flavour"] == 1 and stats[name, "shallow"]["pool_flavour"] == 0   # forced: stays
+    assert 20 < stats["soup", "auto", "created"]["bvh_sah_nodes_per_ray"] < 40 and stats["soup", "auto", "created"]["pool_flavour"] == 0
     assert stats["cornell", "auto"]["bvh_sah_nodes_per_ray"] < 6 and stats["cornell", "auto"]["pool_flavour"] == 0
     monkeypatch.delenv("LISA_POOL_FLAVOUR", raising=False)
-    v, n, m = _overlap_soup(rng, 600000)   # deep from an estimate of 40 (measured crossover: lisa_rt.cu)
-    st = rt.Renderer(v, n, m, [MAT_W, MAT_L], 16, 16, (0.5, 0.6, 3.2), (0.5, 0.45, 0.5), 35.0, 1, 3).stats()
+    v, n, m = _overlap_soup(rng, 1500000)   # deep from an estimate of 40 (measured crossover: lisa_rt.cu)
+    big = (v, n, m, [MAT_W, MAT_L], 128, 128, (0.5, 0.6, 3.2), (0.5, 0.45, 0.5), 35.0, 2, 7)
+    st = rt.Renderer(*big).stats()
     assert st["bvh_sah_nodes_per_ray"] > 60 and st["pool_flavour"] == 1
+    # ... and whatever the estimate said, the flavour follows the node visits per ray a call has measured
+    monkeypatch.setenv("LISA_POOL_DEEP_SAH", "1e9")
+    R = rt.Renderer(*big)
+    assert R.stats()["pool_flavour"] == 0
+    R.render_subframes(0, 1, 2)
+    st = R.stats()
+    assert st["last_nodes_visited"] / (st["last_radiance_rays"] + st["last_shadow_rays"] - st["last_shadow_culled"]) > 10 and st["pool_flavour"] == 1
